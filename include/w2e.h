@@ -1,0 +1,139 @@
+/* libw2e -- C ABI of the B200-native (sm_100a) StyleGAN2 synthesis hot path of Where2edit.
+ *
+ * The reference (Big-Brother-Pikachu/Where2edit) is pure Python/PyTorch and has no FFI of its
+ * own; the boundary it offers for this path is the set of Python callables
+ *   models/stylegan2/op/upfirdn2d.py:11   upfirdn2d(input, kernel, up, down, pad)
+ *   models/stylegan2/op/upfirdn2d.py:19   upfirdn2d_native(input, kernel, 10 ints)
+ *   models/stylegan2/op/fused_act.py:23   fused_leaky_relu(input, bias, negative_slope, scale)
+ *   models/stylegan2/model.py:234         ModulatedConv2d.forward
+ *   models/stylegan2/model.py:334         StyledConv.forward
+ *   models/stylegan2/model.py:353         ToRGB.forward
+ *   attention/attention_model.py:548      region-mask blend inside Generator.forward
+ * Each entry point below names the reference lines it replaces.  A Python binding
+ * (where2edit_b200/_native.py, ctypes) calls these with raw device pointers and the current
+ * CUDA stream; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error (W2E_ERR_*); it never throws and
+ *    never allocates device memory; w2e_last_error_string() describes the last failure of the
+ *    calling thread.
+ *  - all data pointers are DEVICE pointers unless the name says host; tensors are contiguous.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised.
+ *  - dtype: W2E_F32 (float) or W2E_BF16 (__nv_bfloat16) for activation tensors; parameters
+ *    (styles, demod, bias, noise, FIR taps) are always float.
+ */
+#ifndef W2E_H_
+#define W2E_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2E_OK 0
+#define W2E_ERR_INVALID 1      /* bad argument / unsupported shape */
+#define W2E_ERR_CUDA 2         /* a CUDA runtime/driver call failed */
+#define W2E_ERR_UNSUPPORTED 3  /* valid request this build cannot serve (e.g. not sm_100) */
+
+#define W2E_F32 0
+#define W2E_BF16 1
+
+#define W2E_ACT_NONE 0
+#define W2E_ACT_LRELU 1
+
+int w2e_version(void);
+const char* w2e_last_error_string(void);
+/* sm count / compute capability of the current device (host query, no stream work). */
+int w2e_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- upfirdn2d  (models/stylegan2/op/upfirdn2d.py:19-60) ---------------------------------
+ * NCHW planes: x [planes, in_h, in_w] -> y [planes, out_h, out_w], planes = N*C.
+ * taps: host pointer to kh*kw floats, row-major, UNFLIPPED (the reference's `kernel`; the
+ * convolution flips it, upfirdn2d.py:46).  Geometry = the reference's 8 ints.
+ * out_h = (in_h*up_y + py0 + py1 - kh)/down_y + 1 (same for w); the caller allocates y.
+ * Negative pads crop.  A separable 4-tap fast path is selected automatically.            */
+int w2e_upfirdn2d_fwd(const void* x, void* y, const float* host_taps, int64_t planes, int in_h,
+                      int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                      int px0, int px1, int py0, int py1, int dtype, void* stream);
+/* gradient w.r.t. x of the call above: gx [planes,in_h,in_w] from gy [planes,out_h,out_w]
+ * (an upfirdn2d with the flipped kernel and up/down swapped).        */
+int w2e_upfirdn2d_bwd(const void* gy, void* gx, const float* host_taps, int64_t planes, int in_h,
+                      int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                      int px0, int px1, int py0, int py1, int dtype, void* stream);
+
+/* ---- bias + leaky-ReLU * gain  (models/stylegan2/op/fused_act.py:23-39) ------------------
+ * x viewed as [outer, C, inner]; y = lrelu(x + bias[c] + noise_w * noise[.., inner]) * scale.
+ * 2-D [B,C]: outer=B, inner=1.  3-D [B,L,C] (bias on the last dim, fused_act.py:26-32):
+ * outer=B*L, inner=1.  4-D [B,C,H,W]: outer=B, inner=H*W.
+ * noise (optional, may be NULL) implements NoiseInjection (models/stylegan2/model.py:279-290):
+ * float [noise_batch, inner] with noise_batch in {1, outer}; noise_w is a DEVICE pointer to the
+ * scalar NoiseInjection.weight.  bias may be NULL.                                          */
+int w2e_bias_act_fwd(const void* x, const float* bias, const float* noise, const float* noise_w,
+                     int noise_batch, void* y, int64_t outer, int C, int64_t inner, float slope,
+                     float scale, int dtype, void* stream);
+/* gx = gy * scale * (y > 0 ? 1 : slope)  (y = forward output).  If gbias != NULL also
+ * gbias[c] = sum over outer,inner of gx (deterministic two-pass reduction; `workspace` must
+ * hold w2e_bias_act_bwd_workspace(outer, C, inner) bytes).                                   */
+int w2e_bias_act_bwd(const void* gy, const void* y, void* gx, float* gbias, void* workspace,
+                     int64_t outer, int C, int64_t inner, float slope, float scale, int dtype,
+                     void* stream);
+int64_t w2e_bias_act_bwd_workspace(int64_t outer, int C, int64_t inner);
+
+/* ---- style -> demodulation  (models/stylegan2/model.py:239-243, shared-weight form) -----
+ * demod[b,o] = rsqrt(sum_i style[b,i]^2 * wsq[o,i] + 1e-8), wsq[o,i] = sum_k (scale*W[o,i,k])^2 */
+int w2e_style_demod(const float* style, const float* wsq, float* demod, int B, int Cin, int Cout,
+                    void* stream);
+
+/* ---- modulated convolution, exact fp32 engine (models/stylegan2/model.py:249-274) ----------
+ * Direct convolution on CUDA cores, fp32 FMA, NCHW.  One engine serves forward and dgrad:
+ *   y[b,o,oy,ox] = out_scale[b,o] * sum_{c,t} in_scale[b,c] * x[b,c, j*in_stride+dy_t, i*in_stride+dx_t]
+ *                                              * w[t][c][o]            (+ fused epilogue)
+ * with (oy,ox) = (j*out_stride+py, i*out_stride+px) for (j,i) on a grid of grid_h x grid_w.
+ * taps: host array of ntaps*3 ints {dy, dx, weight_slot}; w: float [slots][Cin][Cout].
+ * in_scale / out_scale may be NULL (=1).  Epilogue (act=W2E_ACT_LRELU): + noise_w*noise[oy,ox]
+ * + bias[o], leaky-ReLU(slope 0.2) * sqrt(2)  == NoiseInjection + FusedLeakyReLU.
+ * Forward plain 3x3:  9 taps (dy,dx in -1..1), strides 1.   Forward up x2 (conv_transpose2d,
+ * stride 2): four launches, one per output parity class.       */
+int w2e_conv_engine_f32(const float* x, const float* w, const float* in_scale,
+                        const float* out_scale, const float* bias, const float* noise,
+                        const float* noise_w, int noise_batch, float* y, int B, int Cin, int Cout,
+                        int in_h, int in_w, int out_h, int out_w, int grid_h, int grid_w,
+                        int in_stride, int out_stride, int py, int px, const int* host_taps,
+                        int ntaps, int act, int accumulate, void* stream);
+
+/* ---- row dot / scale helper for the modconv backward ----------------
+ * rows = B*C planes of `inner` pixels: dot[r] = sum_p a[r,p]*b[r,p]; if prod != NULL,
+ * prod[r,p] = a[r,p] * scale[r] (scale may be NULL = 1).                                     */
+int w2e_rowdot_f32(const float* a, const float* b, const float* scale, float* prod, float* dot,
+                   int64_t rows, int64_t inner, void* stream);
+
+/* ---- ToRGB  (models/stylegan2/model.py:353-362) -------------------------------------------
+ * rgb[b,o,p] = sum_c x[b,c,p]*style[b,c]*w[o,c] + bias[o] + upfirdn2d(skip, k4*4, up=2, pad=(2,1))
+ * x: [B,Cin,H,W] (dtype, NCHW) ; w: float [3,Cin] pre-scaled by 1/sqrt(Cin) ; skip: float
+ * [B,3,H/2,W/2] or NULL ; host_taps1d: the 4 taps of the separable skip filter along one axis
+ * (already including the gain, e.g. [1,3,3,1]/8*2) ; rgb: float [B,3,H,W].                   */
+int w2e_torgb_fwd(const void* x, const float* w, const float* style, const float* bias,
+                  const float* skip, const float* host_taps1d, float* rgb, int B, int Cin, int H,
+                  int W, int dtype, void* stream);
+/* backward of the 1x1 modulated part: t[b,c,p] = sum_o g[b,o,p]*w[o,c];
+ * gx = t*style[b,c] ; gstyle[b,c] = sum_p t*x.  (The skip branch's gradient is an
+ * upfirdn2d_bwd of g; the bias gradient a plain reduction -- both done by the caller.)      */
+int w2e_torgb_bwd(const float* g, const float* x, const float* w, const float* style, float* gx,
+                  float* gstyle, int B, int Cin, int H, int W, void* stream);
+
+/* ---- region-mask blend  (attention/attention_model.py:548-549 and siblings) ---------------
+ * out = m*edited + (1-m)*orig, m = mask[b,0,floor(y*mh/H),floor(x*mw/W)] (F.interpolate
+ * nearest, integer-exact), broadcast over C; the [B,C,H,W] mask is never materialised.      */
+int w2e_mask_blend_fwd(const void* edited, const void* orig, const float* mask, void* out, int B,
+                       int C, int H, int W, int mh, int mw, int dtype, void* stream);
+/* g_edited = m*g ; g_mask[b,0,y',x'] = sum_c sum_{(y,x)->(y',x')} g*(edited-orig)
+ * (no gradient to orig: callers compute it under no_grad, run_attention.py:1195-1203).       */
+int w2e_mask_blend_bwd(const float* g, const float* edited, const float* orig, const float* mask,
+                       float* g_edited, float* g_mask, float* workspace /* B*H*W floats */, int B,
+                       int C, int H, int W, int mh, int mw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2E_H_ */

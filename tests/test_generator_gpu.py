@@ -1,0 +1,142 @@
+"""End-to-end GPU parity of Generator.forward (fp32 mode) against the reference goldens and the
+oracle: images, captured features, styles, blends, z/truncation/mixing paths, gradients."""
+import numpy as np
+import pytest
+import torch
+
+import where2edit_b200 as w2e
+from conftest import max_abs
+from oracle import make_golden as mg
+from oracle import stylegan2_oracle as orc
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4   # north_star: fp32 mode <= 1e-4 max-abs
+
+
+@pytest.fixture(scope="module")
+def g32():
+    sd = synth.make_state_dict(32, seed=0, perturbed=True)
+    gen = w2e.Generator(32, 512, 8)
+    gen.load_state_dict(sd, strict=True)
+    return gen.to(DEV).eval(), sd, synth.make_wplus(2, 8, seed=2)
+
+
+def test_wplus_forward_features_styles(g32, golden_g32):
+    gen, sd, wplus = g32
+    g = golden_g32
+    with torch.no_grad():
+        out = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+    assert len(out) == 4
+    img, latent, styles, feats = out
+    assert max_abs(img.cpu(), g["img_wplus"]) <= TOL
+    assert torch.equal(latent.cpu(), wplus)
+    assert len(feats) == 11 and len(styles) == 11
+    for i, f in enumerate(feats):
+        assert max_abs(mg.sub(f.cpu()), g[f"feat_{i}_sub"]) <= TOL, i
+    for i, s in enumerate(styles):
+        assert tuple(s.shape) == g[f"style_{i}"].shape
+        assert max_abs(s.cpu(), g[f"style_{i}"]) <= 1e-5
+    with torch.no_grad():
+        two = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False)
+        three = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_latents=True)
+    assert len(two) == 2 and two[1] is None and len(three) == 3
+
+
+def test_stylespace_and_blend_paths(g32, golden_g32):
+    gen, sd, wplus = g32
+    g = golden_g32
+    ref_styles = [torch.from_numpy(g[f"style_{i}"]).to(DEV) for i in range(11)]
+    with torch.no_grad():
+        img_ss, _ = gen([ref_styles], input_is_stylespace=True, randomize_noise=False)
+        assert max_abs(img_ss.cpu(), g["img_stylespace"]) <= TOL
+        _, _, _, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+        edited = [s * (1 + 0.05 * synth.make_tensor(tuple(s.shape), 500 + i).to(DEV)) for i, s in enumerate(ref_styles)]
+        img_ed, _ = gen([edited], input_is_stylespace=True, randomize_noise=False)
+        assert max_abs(img_ed.cpu(), g["img_edited"]) <= TOL
+        for tag, layer, msize, binary in [("a", 7, 16, False), ("b", 6, 8, False), ("c", 9, 12, True), ("d", 1, 4, False)]:
+            mask = synth.make_mask(2, msize, seed=3 + layer, binary=binary).to(DEV)
+            img_b, _, _, feats_b = gen([edited], input_is_stylespace=True, randomize_noise=False,
+                                       return_features=True, attention_layer=layer, attention_map=mask,
+                                       feature_map=feats)
+            assert max_abs(img_b.cpu(), g[f"img_blend_{tag}"]) <= TOL, tag
+            got = np.stack([mg.stats(f.cpu()) for f in feats_b])
+            np.testing.assert_allclose(got, g[f"blend_{tag}_feat_stats"], rtol=5e-5, atol=2e-3)
+        mask = synth.make_mask(2, 16, seed=10).to(DEV)
+        w_ed = (wplus + 0.1 * synth.make_tensor(tuple(wplus.shape), 600)).to(DEV)
+        img_bw, _, _, _ = gen([w_ed], input_is_latent=True, randomize_noise=False, return_features=True,
+                              attention_layer=7, attention_map=mask, feature_map=feats)
+        assert max_abs(img_bw.cpu(), g["img_blend_wplus"]) <= TOL
+
+
+def test_z_truncation_mixing_noise(g32, golden_g32):
+    gen, sd, wplus = g32
+    g = golden_g32
+    z, z2 = synth.make_z(2, seed=2).to(DEV), synth.make_z(2, seed=3).to(DEV)
+    with torch.no_grad():
+        mean_w = gen.style(synth.make_z(64, seed=9).to(DEV)).mean(0, keepdim=True)
+        assert max_abs(mean_w.cpu(), g["mean_w"]) <= 1e-5
+        img, lat, sv = gen([z], truncation=0.7, truncation_latent=mean_w, randomize_noise=False, return_latents=True)
+        assert max_abs(lat.cpu(), g["latent_z_trunc"]) <= 1e-5
+        assert max_abs(img.cpu(), g["img_z_trunc"]) <= TOL
+        img_mix, _ = gen([z, z2], inject_index=3, randomize_noise=False)
+        assert max_abs(img_mix.cpu(), g["img_z_mix"]) <= TOL
+        noise = [synth.make_tensor((1, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)), 700 + i).to(DEV) for i in range(7)]
+        img_n, _ = gen([wplus.to(DEV)], input_is_latent=True, noise=noise)
+        assert max_abs(img_n.cpu(), g["img_noise_list"]) <= TOL
+        # randomize_noise=True (the reference default) draws per-sample noise: just shape/finite checks
+        img_r, _ = gen([wplus.to(DEV)], input_is_latent=True)
+        assert img_r.shape == (2, 3, 32, 32) and torch.isfinite(img_r).all()
+
+
+def test_gradients_match_reference_autograd(g32, golden_g32):
+    gen, sd, wplus = g32
+    g = golden_g32
+    upstream = (synth.make_tensor((2, 3, 32, 32), 4) / (2 * 3 * 32 * 32)).to(DEV)
+    wp = wplus.to(DEV).requires_grad_(True)
+    img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+    (img * upstream).sum().backward()
+    scale = np.abs(g["grad_wplus"]).max()
+    assert max_abs(wp.grad.cpu(), g["grad_wplus"]) <= 2e-4 * scale
+    with torch.no_grad():
+        _, _, _, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+    ref_styles = [torch.from_numpy(g[f"style_{i}"]) for i in range(11)]
+    edited = [(s * (1 + 0.05 * synth.make_tensor(tuple(s.shape), 500 + i))).to(DEV).requires_grad_(True)
+              for i, s in enumerate(ref_styles)]
+    mask = synth.make_mask(2, 16, seed=10).to(DEV).requires_grad_(True)
+    img, _, _, _ = gen([edited], input_is_stylespace=True, randomize_noise=False, return_features=True,
+                       attention_layer=7, attention_map=mask, feature_map=feats)
+    (img * upstream).sum().backward()
+    for i, s in enumerate(edited):
+        ref = g[f"grad_style_{i}"]
+        assert max_abs(s.grad.cpu(), ref) <= 2e-4 * max(np.abs(ref).max(), 1e-6), i
+    assert max_abs(mask.grad.cpu(), g["grad_mask"]) <= 2e-4 * np.abs(g["grad_mask"]).max()
+
+
+def test_generator128_channel_changing_layers(golden_g128):
+    sd = synth.make_state_dict(128, channel_multiplier=1, seed=5, perturbed=True)
+    gen = w2e.Generator(128, 512, 8, channel_multiplier=1)
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.to(DEV).eval()
+    wplus = synth.make_wplus(1, 12, seed=6).to(DEV)
+    with torch.no_grad():
+        img, _, _, feats = gen([wplus], input_is_latent=True, randomize_noise=False, return_features=True)
+    assert max_abs(img.cpu(), golden_g128["img_wplus"]) <= TOL
+    got = np.stack([mg.stats(f.cpu()) for f in feats])
+    np.testing.assert_allclose(got, golden_g128["feat_stats"], rtol=5e-5, atol=2e-3)
+
+
+def test_batch_invariance_and_ragged_batch():
+    """each image depends only on its own latent: a batch of 3 equals three batches of 1 (bitwise)"""
+    sd = synth.make_state_dict(16, seed=3, perturbed=True)
+    gen = w2e.Generator(16, 512, 8)
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV).eval()
+    wplus = synth.make_wplus(3, 6, seed=4).to(DEV)
+    with torch.no_grad():
+        full, _ = gen([wplus], input_is_latent=True, randomize_noise=False)
+        singles = torch.cat([gen([wplus[i:i + 1]], input_is_latent=True, randomize_noise=False)[0] for i in range(3)])
+    assert torch.equal(full, singles)
+    ref, _ = orc.generator_forward_ref(sd, [wplus.cpu()], 16, input_is_latent=True)
+    assert max_abs(full.cpu(), ref) <= TOL

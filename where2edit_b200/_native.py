@@ -1,0 +1,124 @@
+"""ctypes binding of libw2e.so (C ABI in include/w2e.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing or a call fails,
+a RuntimeError is raised.  Tensors cross the boundary as raw device pointers (`data_ptr()`); the
+stream is torch's current CUDA stream, so the calls compose with torch ops and CUDA graphs.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU = 0, 1
+
+# name -> (restype, argtypes)   -- must mirror include/w2e.h exactly (tests check every symbol)
+PROTOTYPES = {
+    "w2e_version": (_I, []),
+    "w2e_last_error_string": (ctypes.c_char_p, []),
+    "w2e_device_info": (_I, [_P, _P, _P]),
+    "w2e_upfirdn2d_fwd": (_I, [_P, _P, _P, _L] + [_I] * 12 + [_I, _P]),
+    "w2e_upfirdn2d_bwd": (_I, [_P, _P, _P, _L] + [_I] * 12 + [_I, _P]),
+    "w2e_bias_act_fwd": (_I, [_P, _P, _P, _P, _I, _P, _L, _I, _L, _F, _F, _I, _P]),
+    "w2e_bias_act_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _L, _F, _F, _I, _P]),
+    "w2e_bias_act_bwd_workspace": (_L, [_L, _I, _L]),
+    "w2e_style_demod": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "w2e_conv_engine_f32": (_I, [_P] * 7 + [_I, _P] + [_I] * 13 + [_P, _I, _I, _I, _P]),
+    "w2e_rowdot_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _P]),
+    "w2e_torgb_fwd": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),
+    "w2e_torgb_bwd": (_I, [_P] * 6 + [_I, _I, _I, _I, _P]),
+    "w2e_mask_blend_fwd": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_I, _P]),
+    "w2e_mask_blend_bwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the in-tree library is stale and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if not os.path.exists(path) or (os.environ.get("W2E_REBUILD") == "1"):
+            path = _build.build(force=True)
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as e:  # fail loudly: there is no other implementation
+            raise RuntimeError(f"where2edit_b200: cannot load the CUDA library {path}: {e}") from e
+        for name, (res, args) in PROTOTYPES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise RuntimeError(f"where2edit_b200: {path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    msg = load().w2e_last_error_string()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"libw2e {what} failed (code {code}): {last_error()}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("where2edit_b200 has no CPU path: tensor must live on a CUDA device")
+    if not t.is_contiguous():
+        raise RuntimeError("where2edit_b200: tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"where2edit_b200: unsupported dtype {t.dtype} (float32 or bfloat16)")
+
+
+def host_floats(values):
+    arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def host_ints(values):
+    arr = (ctypes.c_int * len(values))(*[int(v) for v in values])
+    return arr
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "where2edit_b200 has no CPU path (the reference's CPU implementation is only kept as "
+                "the test oracle): move the model and its inputs to a CUDA device")

@@ -1,0 +1,278 @@
+"""Differentiable building blocks of the fp32 ("exact") synthesis path, each a thin
+torch.autograd.Function around libw2e kernels.  Math: SURVEY.md appendix C (shared-weight form of
+models/stylegan2/model.py:239-274 and its backward).  No CPU path.
+"""
+import torch
+
+from . import _native as N
+from .op.fused_act import _BiasAct
+from .op.upfirdn2d import _UpFirDn2d, kernel_taps
+
+
+# --------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------
+class PackedWeight:
+    """Batch-shared layouts of one ModulatedConv2d weight [1,Cout,Cin,k,k], pre-multiplied by the
+    equalised-lr scale 1/sqrt(Cin*k*k) (model.py:216-217):
+        fwd  [k*k, Cin, Cout]  engine layout for the forward convolution
+        dgr  [k*k, Cout, Cin]  engine layout for dgrad (roles of Cin/Cout swapped)
+        wsq  [Cout, Cin]       sum over taps of (scale*W)^2 -> demodulation without per-sample weights
+    """
+
+    def __init__(self, weight, scale, key):
+        self.key = key
+        w = weight[0].to(torch.float32) * scale          # [Cout,Cin,k,k]
+        cout, cin, k, _ = w.shape
+        self.cin, self.cout, self.k = cin, cout, k
+        self.fwd = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).contiguous()
+        self.dgr = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous()
+        self.wsq = w.pow(2).sum((2, 3)).contiguous()
+        self.rgb = w.reshape(cout, cin).contiguous() if k == 1 else None
+        self.tc = None  # bf16 tensor-core layout, filled lazily by the engine
+
+
+def demod_coefficients(s, wsq):
+    """d[b,o] = rsqrt(sum_i s[b,i]^2 * wsq[o,i] + 1e-8) (model.py:242).  Uses libw2e's kernel when no
+    gradient is needed, plain torch ops (tiny [B,C] algebra) when autograd must see it."""
+    if torch.is_grad_enabled() and s.requires_grad:
+        return torch.rsqrt((s * s) @ wsq.t() + 1e-8)
+    s = s.contiguous()
+    d = torch.empty((s.shape[0], wsq.shape[0]), device=s.device, dtype=torch.float32)
+    N.check(N.load().w2e_style_demod(N.ptr(s), N.ptr(wsq), N.ptr(d), s.shape[0], s.shape[1], wsq.shape[0],
+                                     N.stream_ptr()), "style_demod")
+    return d
+
+
+# --------------------------------------------------------------------------------------------
+# convolution engine launches
+# --------------------------------------------------------------------------------------------
+def _taps_plain(k, flip=False):
+    taps = []
+    for ky in range(k):
+        for kx in range(k):
+            dy, dx = ky - k // 2, kx - k // 2
+            taps += [(-dy if flip else dy), (-dx if flip else dx), ky * k + kx]
+    return taps
+
+
+# conv_transpose2d(stride 2, k=3): output parity class p uses taps ky in {0,2} (input offsets 0,-1)
+# when p == 0 and ky == 1 (offset 0) when p == 1.
+_UP_AXIS = {0: [(0, 0), (-1, 2)], 1: [(0, 1)]}
+
+
+def _engine(x, w, in_scale, out_scale, y, cin, cout, in_hw, out_hw, grid_hw, in_stride, out_stride, py, px, taps,
+            bias=None, noise=None, noise_w=None, act=N.ACT_NONE):
+    nb = 0 if noise is None else noise.shape[0]
+    N.check(N.load().w2e_conv_engine_f32(
+        N.ptr(x), N.ptr(w), N.ptr(in_scale), N.ptr(out_scale), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
+        N.ptr(y), x.shape[0], cin, cout, in_hw[0], in_hw[1], out_hw[0], out_hw[1], grid_hw[0], grid_hw[1],
+        in_stride, out_stride, py, px, N.host_ints(taps), len(taps) // 3, act, 0, N.stream_ptr()), "conv_engine")
+
+
+def conv_forward(x, s, d, pw, k, upsample, bias=None, noise=None, noise_w=None, act=N.ACT_NONE):
+    """y = d * conv(x*s, W) [ + fused noise/bias/act ].  Up: (2H+1)x(2W+1) pre-blur tensor."""
+    b, cin, h, w = x.shape
+    if not upsample:
+        y = torch.empty((b, pw.cout, h, w), device=x.device, dtype=torch.float32)
+        _engine(x, pw.fwd, s, d, y, cin, pw.cout, (h, w), (h, w), (h, w), 1, 1, 0, 0, _taps_plain(k), bias, noise,
+                noise_w, act)
+        return y
+    oh, ow = 2 * h + 1, 2 * w + 1
+    y = torch.empty((b, pw.cout, oh, ow), device=x.device, dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for dy, ky in _UP_AXIS[py]:
+                for dx, kx in _UP_AXIS[px]:
+                    taps += [dy, dx, ky * 3 + kx]
+            _engine(x, pw.fwd, s, d, y, cin, pw.cout, (h, w), (oh, ow), (h + 1 - py, w + 1 - px), 1, 2, py, px, taps)
+    return y
+
+
+def conv_dgrad(gy, d, pw, k, upsample, in_hw):
+    """gxs = conv^T(gy*d, W): gradient w.r.t. the MODULATED input x*s."""
+    b = gy.shape[0]
+    h, w = in_hw
+    gxs = torch.empty((b, pw.cin, h, w), device=gy.device, dtype=torch.float32)
+    if not upsample:
+        _engine(gy, pw.dgr, d, None, gxs, pw.cout, pw.cin, (h, w), (h, w), (h, w), 1, 1, 0, 0, _taps_plain(k, flip=True))
+    else:
+        taps = []
+        for ky in range(3):
+            for kx in range(3):
+                taps += [ky, kx, ky * 3 + kx]
+        _engine(gy, pw.dgr, d, None, gxs, pw.cout, pw.cin, (gy.shape[2], gy.shape[3]), (h, w), (h, w), 2, 1, 0, 0, taps)
+    return gxs
+
+
+def _rowdot(a, b, scale=None, want_prod=False):
+    rows = a.shape[0] * a.shape[1]
+    inner = a[0, 0].numel()
+    dot = torch.empty((a.shape[0], a.shape[1]), device=a.device, dtype=torch.float32)
+    prod = torch.empty_like(a) if want_prod else None
+    N.check(N.load().w2e_rowdot_f32(N.ptr(a), N.ptr(b), N.ptr(scale), N.ptr(prod), N.ptr(dot), rows, inner,
+                                    N.stream_ptr()), "rowdot")
+    return dot, prod
+
+
+class _ModConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, d, pw, k, upsample):
+        y = conv_forward(x, s, d, pw, k, upsample)
+        ctx.save_for_backward(x, s, d if d is not None else x.new_zeros(0), y)
+        ctx.cfg = (pw, k, upsample, d is not None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, s, d, y = ctx.saved_tensors
+        pw, k, upsample, has_d = ctx.cfg
+        gy = gy.contiguous()
+        d_or_none = d if has_d else None
+        gx = gs = gd = None
+        if has_d and ctx.needs_input_grad[2]:
+            dot, _ = _rowdot(gy, y)                 # sum_p gy*y = d * sum_p gy*z
+            gd = dot / d
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gxs = conv_dgrad(gy, d_or_none, pw, k, upsample, (x.shape[2], x.shape[3]))
+            gs, gx = _rowdot(gxs, x, scale=s.contiguous(), want_prod=True)   # gs = sum_p gxs*x ; gx = gxs*s
+        return gx, gs, gd, None, None, None
+
+
+def modulated_conv2d(x, s, d, pw, k, upsample):
+    """x [B,Cin,H,W] fp32, s [B,Cin], d [B,Cout] or None -> [B,Cout,H,W] (or (2H+1)^2 pre-blur)."""
+    x = x.to(torch.float32).contiguous()
+    s = s.contiguous()
+    if d is not None:
+        d = d.contiguous()
+    if torch.is_grad_enabled() and (x.requires_grad or s.requires_grad or (d is not None and d.requires_grad)):
+        return _ModConv.apply(x, s, d, pw, k, upsample)
+    return conv_forward(x, s, d, pw, k, upsample)
+
+
+# --------------------------------------------------------------------------------------------
+# noise + bias + activation
+# --------------------------------------------------------------------------------------------
+def noise_bias_act(x, bias, noise, noise_w, slope, scale):
+    """NoiseInjection + FusedLeakyReLU in one pass (model.py:279-290 + op/fused_act.py:23-39)."""
+    noise = noise.to(torch.float32).contiguous()
+    return _BiasAct.apply(x.contiguous(), bias.detach().to(torch.float32).contiguous(), noise,
+                          noise_w.detach().to(torch.float32).contiguous(), float(slope), float(scale))
+
+
+# --------------------------------------------------------------------------------------------
+# ToRGB
+# --------------------------------------------------------------------------------------------
+def separable_taps(kernel2d):
+    """1-D factor of a separable 4x4 FIR kernel given as a flat tuple (row-major)."""
+    n = int(round(len(kernel2d) ** 0.5))
+    rows = [kernel2d[i * n:(i + 1) * n] for i in range(n)]
+    total = sum(kernel2d)
+    col = [sum(r) for r in rows]
+    row = [sum(rows[i][j] for i in range(n)) for j in range(n)]
+    # k = outer(col, row) / total  for a rank-1 kernel; split the gain evenly
+    g = abs(total) ** 0.5
+    kv = [c / g for c in col]
+    kh = [r / g * (1 if total >= 0 else -1) for r in row]
+    for i in range(n):
+        for j in range(n):
+            if abs(kv[i] * kh[j] - rows[i][j]) > 1e-6 * max(abs(v) for v in kernel2d):
+                return None
+    if any(abs(a - b) > 1e-7 for a, b in zip(kv, kh)):
+        return None
+    return kv
+
+
+class _ToRGB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, skip, w_rgb, bias, taps2d, taps1d):
+        b, cin, h, w = x.shape
+        rgb = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
+        N.check(N.load().w2e_torgb_fwd(N.ptr(x), N.ptr(w_rgb), N.ptr(s), N.ptr(bias), N.ptr(skip),
+                                       N.host_floats(taps1d) if skip is not None else None, N.ptr(rgb), b, cin, h,
+                                       w, N.dtype_code(x), N.stream_ptr()), "torgb_fwd")
+        ctx.save_for_backward(x, s)
+        ctx.cfg = (w_rgb, taps2d, skip is not None)
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        w_rgb, taps2d, has_skip = ctx.cfg
+        g = g.contiguous()
+        b, cin, h, w = x.shape
+        gx = gs = gskip = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx = torch.empty_like(x, dtype=torch.float32)
+            gs = torch.empty((b, cin), device=x.device, dtype=torch.float32)
+            N.check(N.load().w2e_torgb_bwd(N.ptr(g), N.ptr(x), N.ptr(w_rgb), N.ptr(s), N.ptr(gx), N.ptr(gs), b, cin,
+                                           h, w, N.stream_ptr()), "torgb_bwd")
+        if has_skip and ctx.needs_input_grad[2]:
+            gskip = torch.empty((b, 3, h // 2, w // 2), device=x.device, dtype=torch.float32)
+            N.check(N.load().w2e_upfirdn2d_bwd(N.ptr(g), N.ptr(gskip), N.host_floats(taps2d), b * 3, h // 2, w // 2,
+                                               4, 4, 2, 2, 1, 1, 2, 1, 2, 1, N.F32, N.stream_ptr()), "upfirdn2d_bwd")
+        return gx, gs, gskip, None, None, None, None
+
+
+def to_rgb(x, s, pw, bias, skip, up_kernel):
+    """rgb = conv1x1(x*s, W) + bias + Upsample(skip)  (model.py:353-362), fused."""
+    x = x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    s = s.contiguous()
+    taps2d = taps1d = None
+    if skip is not None:
+        taps2d = kernel_taps(up_kernel)
+        taps1d = separable_taps(taps2d) if len(taps2d) == 16 else None
+        if taps1d is None:  # unusual (non-separable / non-4x4) filter: generic upfirdn2d + add
+            rgb = _ToRGB.apply(x, s, None, pw.rgb, bias.detach().reshape(3).contiguous(), None, None)
+            p = up_kernel.shape[0] - 2
+            return rgb + _UpFirDn2d.apply(skip.contiguous(), taps2d, up_kernel.shape[0], up_kernel.shape[1],
+                                          (2, 2, 1, 1, (p + 1) // 2 + 1, p // 2, (p + 1) // 2 + 1, p // 2))
+        skip = skip.to(torch.float32).contiguous()
+    return _ToRGB.apply(x, s, skip, pw.rgb, bias.detach().reshape(3).to(torch.float32).contiguous(), taps2d, taps1d)
+
+
+# --------------------------------------------------------------------------------------------
+# region-mask blend
+# --------------------------------------------------------------------------------------------
+class _MaskBlend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, edited, orig, mask):
+        b, c, h, w = edited.shape
+        out = torch.empty_like(edited)
+        N.check(N.load().w2e_mask_blend_fwd(N.ptr(edited), N.ptr(orig), N.ptr(mask), N.ptr(out), b, c, h, w,
+                                            mask.shape[2], mask.shape[3], N.dtype_code(edited), N.stream_ptr()),
+                "mask_blend_fwd")
+        ctx.save_for_backward(edited, orig, mask)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        edited, orig, mask = ctx.saved_tensors
+        b, c, h, w = edited.shape
+        g = g.contiguous().float()
+        ge = torch.empty_like(g)
+        gm = torch.empty_like(mask)
+        ws = torch.empty((b, h, w), device=g.device, dtype=torch.float32)
+        N.check(N.load().w2e_mask_blend_bwd(N.ptr(g), N.ptr(edited), N.ptr(orig), N.ptr(mask), N.ptr(ge), N.ptr(gm),
+                                            N.ptr(ws), b, c, h, w, mask.shape[2], mask.shape[3], N.stream_ptr()),
+                "mask_blend_bwd")
+        return ge, None, gm
+
+
+def mask_blend(edited, orig, mask):
+    """m*edited + (1-m)*orig with m = nearest-resized [B,1,h,w] mask broadcast over channels
+    (attention/attention_model.py:548-549); the resized/repeated mask is never materialised."""
+    N.require_cuda(edited, orig, mask)
+    if mask.ndim != 4 or mask.shape[1] != 1 or mask.shape[0] != edited.shape[0]:
+        raise ValueError(f"attention_map must be [B,1,h,w], got {tuple(mask.shape)}")
+    if orig.shape != edited.shape:
+        raise ValueError(f"feature_map entry {tuple(orig.shape)} does not match layer output {tuple(edited.shape)}")
+    edited = edited.to(torch.float32).contiguous()
+    orig = orig.detach().to(torch.float32).contiguous()
+    return _MaskBlend.apply(edited, orig, mask.to(torch.float32).contiguous())
