@@ -1,5 +1,7 @@
 """upfirdn2d -- same signature and result as models/stylegan2/op/upfirdn2d.py:11-60, executed by
 libw2e's CUDA kernels (csrc/upfirdn2d.cu).  There is no CPU implementation here."""
+import weakref
+
 import torch
 
 from .. import _native as N
@@ -8,18 +10,20 @@ _TAPS_CACHE = {}
 
 
 def kernel_taps(kernel):
-    """Host copy of the (tiny) FIR kernel as a flat tuple; cached per tensor version so the
+    """Host copy of the (tiny) FIR kernel as a flat tuple; cached per tensor object + version so the
     device->host read happens once (it would be illegal inside CUDA-graph capture)."""
-    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), str(kernel.device))
+    key = id(kernel)
     hit = _TAPS_CACHE.get(key)
-    if hit is None:
-        if kernel.ndim != 2:
-            raise ValueError(f"upfirdn2d: kernel must be 2-D, got shape {tuple(kernel.shape)}")
-        hit = tuple(kernel.detach().to("cpu", torch.float32).reshape(-1).tolist())
-        if len(_TAPS_CACHE) > 256:
-            _TAPS_CACHE.clear()
-        _TAPS_CACHE[key] = hit
-    return hit
+    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version:
+        return hit[2]
+    if kernel.ndim != 2:
+        raise ValueError(f"upfirdn2d: kernel must be 2-D, got shape {tuple(kernel.shape)}")
+    taps = tuple(kernel.detach().to("cpu", torch.float32).reshape(-1).tolist())
+    if len(_TAPS_CACHE) > 512:
+        for k in [k for k, v in _TAPS_CACHE.items() if v[0]() is None]:
+            del _TAPS_CACHE[k]
+    _TAPS_CACHE[key] = (weakref.ref(kernel), kernel._version, taps)
+    return taps
 
 
 def out_size(in_size, up, down, pad0, pad1, k):
