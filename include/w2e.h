@@ -133,6 +133,58 @@ int w2e_mask_blend_bwd(const float* g, const float* edited, const float* orig, c
                        float* g_edited, float* g_mask, float* workspace /* B*H*W floats */, int B,
                        int C, int H, int W, int mh, int mw, void* stream);
 
+/* ==== bf16 tensor-core path: channels-last (NHWC) bf16 activations ==========================
+ *
+ * ---- modulated convolution on tcgen05 tensor cores (models/stylegan2/model.py:249-274) ------
+ * Implicit GEMM, one launch per "class" of output pixels:
+ *   acc[b,j,i,o] = sum_{t<ntaps} sum_c xs[b, j+dy_t, i+dx_t, c] * w[slot_t][o][c]     (fp32 accumulate)
+ *   v = acc * out_scale[b,o]                                  (demodulation, model.py:242-243)
+ *   act == W2E_ACT_LRELU:  v = lrelu(v + noise_w*noise[oy,ox] + bias[o], 0.2) * sqrt(2)
+ *   out[b,oy,ox,o] = v ;  out_mod[b,oy,ox,o] = v * next_scale[b,o]
+ * with (oy,ox) = (j*out_stride+py, i*out_stride+px), (j,i) on a grid_h x grid_w grid.
+ *   xs:  bf16 [B,in_h,in_w,Cin]  -- the input ALREADY multiplied by this layer's style (its
+ *        producer wrote it through out_mod/next_scale), so all samples share one weight tensor;
+ *        reads outside the image are zero (= the convolution padding, done by TMA).
+ *   w:   bf16 [nslots][Cout][Cin], pre-scaled by 1/sqrt(Cin*k*k) (model.py:216-217).
+ *   host_taps: ntaps x {dy, dx, slot} ints.  Plain 3x3: 9 taps, out_stride 1.  Transposed x2
+ *   (conv_transpose2d stride 2): four launches with 4/2/2/1 taps, out_stride 2, (py,px) the parity.
+ *   out / out_mod: bf16 [B,out_h,out_w,Cout]; either may be NULL.  error_flag: device int set to 1
+ *   if the kernel's pipeline timed out (never expected; turns a hang into a reportable error).
+ * Requires Cin % 32 == 0, Cout % 16 == 0, 16-byte aligned tensors, an sm_100 device.          */
+int w2e_modconv_tc_supported(void);
+int w2e_modconv_tc(const void* xs, const void* w, const float* out_scale, const float* bias,
+                   const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                   void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
+                   int in_w, int out_h, int out_w, int grid_h, int grid_w, int out_stride, int py,
+                   int px, const int* host_taps, int ntaps, int nslots, int act, void* stream);
+
+/* ---- layout transforms ----------------------------------------------------------------------
+ * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],
+ * multiplied by style[b,c] when style != NULL.                                                */
+int w2e_nchw_to_nhwc_mod(const float* x, const float* style, void* y, int B, int Bx, int C,
+                         int64_t HW, void* stream);
+/* x bf16 [B,HW,C] -> y fp32 [B,C,HW]  (feature capture, attention_model.py:542-543).          */
+int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, void* stream);
+
+/* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
+ * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->
+ * [B,out_h,out_w,C]; then the same epilogue as w2e_modconv_tc (no demodulation).              */
+int w2e_blur_act_nhwc(const void* z, const float* host_taps, const float* bias, const float* noise,
+                      const float* noise_w, int noise_batch, const float* next_scale, void* out,
+                      void* out_mod, int B, int C, int in_h, int in_w, int py0, int px0, int out_h,
+                      int out_w, int act, void* stream);
+
+/* ---- ToRGB, channels-last input (model.py:353-362): as w2e_torgb_fwd with x bf16 [B,H,W,C]. */
+int w2e_torgb_nhwc(const void* x, const float* w, const float* style, const float* bias,
+                   const float* skip, const float* host_taps1d, float* rgb, int B, int C, int H,
+                   int W, void* stream);
+
+/* ---- region-mask blend, channels-last bf16 (attention_model.py:548-549) ---------------------
+ * out = m*edited + (1-m)*orig ; out_mod = out*next_scale[b,c].                                */
+int w2e_blend_nhwc(const void* edited, const void* orig, const float* mask, const float* next_scale,
+                   void* out, void* out_mod, int B, int C, int H, int W, int mh, int mw,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,204 @@
+"""bf16 tensor-core path (tcgen05 modulated convolution + channels-last kernels) against the CPU
+oracle.  Tolerances are the north-star's bf16 bar: <= 2e-2 max-abs and >= 45 dB PSNR (peak-to-peak
+2) after both images are divided by c = max|reference| (random-init images are not in [-1,1],
+SURVEY.md section 0.6); per-op checks use the same normalisation with a tighter 1e-2 bound."""
+import numpy as np
+import pytest
+import torch
+
+import where2edit_b200 as w2e
+from oracle import stylegan2_oracle as orc
+from oracle import synth
+from where2edit_b200 import _native as N
+from where2edit_b200 import engine as E
+from where2edit_b200 import functional as K
+
+from conftest import max_abs, psnr_db
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def norm_err(test, ref):
+    c = float(torch.as_tensor(ref).abs().max())
+    return max_abs(torch.as_tensor(test).double() / c, torch.as_tensor(ref).double() / c)
+
+
+class _Layer:
+    """A StyledConv of the product package driven directly through the engine's launchers."""
+
+    def __init__(self, cin, cout, up, seed):
+        self.m = w2e.StyledConv(cin, cout, 3, 16, upsample=up)
+        self.weight = synth.make_tensor((1, cout, cin, 3, 3), seed)
+        with torch.no_grad():
+            self.m.conv.weight.copy_(self.weight)
+            self.m.noise.weight.fill_(0.3)
+            self.m.activate.bias.copy_(0.2 * synth.make_tensor((cout,), seed + 1))
+        self.m = self.m.to(DEV)
+
+
+def run_layer(eng, layer, x, s, noise, nxt, act=True):
+    """x fp32 NCHW, s [B,Cin] -> (out NCHW fp32, out_mod NCHW fp32) through the bf16 kernels."""
+    m = layer.m
+    b, cin, h, w = x.shape
+    pw = eng._tc_weight(m.conv)
+    d = K.demod_coefficients(s.to(DEV), pw.wsq)
+    xs = eng._to_nhwc(x.to(DEV), s.to(DEV).contiguous(), b)
+    nz = noise.to(DEV) if noise is not None else None
+    nw = m.noise.weight.detach()
+    bias = m.activate.bias.detach()
+    nxt_d = nxt.to(DEV).contiguous() if nxt is not None else None
+    if not m.conv.upsample:
+        out, out_mod = eng._conv(xs, pw, d, nz, nw, bias, nxt_d, True, nxt is not None, E._TAPS_PLAIN, (h, w), (h, w),
+                                 (h, w), 1, 0, 0, N.ACT_LRELU if act else N.ACT_NONE)
+    else:
+        zh, zw = 2 * h + 1, 2 * w + 1
+        z = torch.full((b, zh, zw, pw.cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+        for (py, px), taps in E._TAPS_UP.items():
+            eng._conv(xs, pw, d, None, None, None, None, True, False, taps, (h, w), (zh, zw), (h + 1 - py, w + 1 - px),
+                      2, py, px, N.ACT_NONE, out=z)
+        out, out_mod = eng._blur(z, m.conv.blur.kernel, m.conv.blur.pad, bias, nz, nw, nxt_d, True, nxt is not None,
+                                 (2 * h, 2 * w))
+    eng.assert_ok()
+    return eng._to_nchw(out).cpu(), (eng._to_nchw(out_mod).cpu() if out_mod is not None else None)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    gen = w2e.Generator(8, 512, 1).to(DEV)
+    return E.SynthesisEngine(gen)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,up", [
+    (2, 64, 64, 16, False),     # BK 64, one pixel tile per image row block
+    (1, 32, 32, 40, False),     # BK 32 (64-byte swizzle), ragged 40x40 grid
+    (3, 128, 48, 8, False),     # two images per tile, BN 16
+    (9, 64, 32, 4, False),      # eight images per tile, ragged batch
+    (1, 512, 512, 8, False),    # BN 256 x 2 column tiles, 72 pipeline iterations
+    (2, 256, 128, 16, False),   # BN 128
+    (2, 64, 64, 8, True),       # transposed x2: four parity classes + blur
+    (1, 128, 64, 20, True),
+    (5, 512, 512, 4, True),
+])
+def test_styled_conv_tc_matches_oracle(eng, b, cin, cout, h, up):
+    layer = _Layer(cin, cout, up, 31)
+    x = synth.make_tensor((b, cin, h, h), 32)
+    s = 1 + 0.3 * synth.make_tensor((b, cin), 33)
+    oh = 2 * h if up else h
+    noise = synth.make_tensor((1, 1, oh, oh), 34)
+    nxt = 1 + 0.3 * synth.make_tensor((b, cout), 35)
+    got, got_mod = run_layer(eng, layer, x, s, noise, nxt)
+    blur = synth.blur_kernel_2d(gain=4.0)
+    ref, _ = orc.modulated_conv2d_ref(x.double(), s.double().reshape(b, 1, cin, 1, 1), layer.weight.double(), None,
+                                      None, True, up, blur.double(), input_is_stylespace=True)
+    ref = ref + 0.3 * noise.double()
+    ref = orc.fused_leaky_relu_ref(ref, layer.m.activate.bias.detach().cpu().double())
+    assert got.shape == ref.shape
+    assert norm_err(got, ref) <= 1e-2
+    assert norm_err(got_mod, ref * nxt.double().reshape(b, cout, 1, 1)) <= 1e-2
+
+
+def test_torgb_nhwc_and_layouts(eng):
+    b, c, h = 2, 64, 16
+    x = synth.make_tensor((b, c, h, h), 41)
+    s = 1 + 0.3 * synth.make_tensor((b, c), 42)
+    skip = synth.make_tensor((b, 3, h // 2, h // 2), 43)
+    m = w2e.ToRGB(c, 16)
+    w = synth.make_tensor((1, 3, c, 1, 1), 44)
+    with torch.no_grad():
+        m.conv.weight.copy_(w)
+        m.bias.copy_(0.1 * synth.make_tensor((1, 3, 1, 1), 45))
+    m = m.to(DEV)
+    xh = eng._to_nhwc(x.to(DEV), None, b)
+    # layout round trip is exact up to the bf16 rounding of the input
+    back = eng._to_nchw(xh).cpu()
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+    rgb = eng._torgb(xh, m, s.to(DEV).contiguous(), skip.to(DEV)).cpu()
+    sd = {"p.conv.weight": w, "p.bias": m.bias.detach().cpu(), "p.upsample.kernel": synth.blur_kernel_2d(gain=4.0)}
+    ref, _ = orc._to_rgb({k: v.double() for k, v in sd.items()} | {"p.conv.modulation.weight": None,
+                                                                   "p.conv.modulation.bias": None},
+                         "p", x.to(torch.bfloat16).double(), s.double().reshape(b, 1, c, 1, 1), skip.double(), True)
+    assert norm_err(rgb, ref) <= 1e-5
+    rgb0 = eng._torgb(xh, m, s.to(DEV).contiguous(), None).cpu()
+    ref0, _ = orc._to_rgb({k: v.double() for k, v in sd.items()} | {"p.conv.modulation.weight": None,
+                                                                    "p.conv.modulation.bias": None},
+                          "p", x.to(torch.bfloat16).double(), s.double().reshape(b, 1, c, 1, 1), None, True)
+    assert norm_err(rgb0, ref0) <= 1e-5
+
+
+def _check_image(img, ref):
+    c = float(ref.abs().max())
+    assert max_abs(img.double() / c, ref.double() / c) <= 2e-2
+    assert psnr_db(img.double() / c, ref.double() / c, peak=2.0) >= 45.0
+
+
+@pytest.mark.parametrize("size,cm,batch", [(32, 2, 3), (128, 2, 2)])
+def test_generator_bf16_matches_oracle(size, cm, batch):
+    sd = synth.make_state_dict(size, seed=0, perturbed=True, channel_multiplier=cm)
+    gen = w2e.Generator(size, 512, 8, channel_multiplier=cm, precision="bf16")
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV).eval()
+    wplus = synth.make_wplus(batch, gen.n_latent, seed=2)
+    ref, _, ref_styles, ref_feats = orc.generator_forward_ref(sd, [wplus], size, input_is_latent=True,
+                                                              return_features=True)
+    with torch.no_grad():
+        img, latent, styles, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False,
+                                         return_features=True)
+    gen._engine.assert_ok()
+    assert img.dtype == torch.float32 and tuple(img.shape) == tuple(ref.shape)
+    _check_image(img.cpu(), ref)
+    assert len(feats) == len(ref_feats) and len(styles) == len(ref_styles)
+    for i, (f, r) in enumerate(zip(feats, ref_feats)):
+        assert tuple(f.shape) == tuple(r.shape), i
+        assert norm_err(f.cpu(), r) <= 3e-2, i
+    for s, r in zip(styles, ref_styles):
+        assert max_abs(s.cpu(), r) <= 1e-4 * max(1.0, float(r.abs().max()))
+    # stylespace input reproduces the W+ image bit-exactly (same kernels, same styles)
+    with torch.no_grad():
+        img_ss, _ = gen([styles], input_is_stylespace=True, randomize_noise=False)
+    assert torch.equal(img_ss, img)
+
+
+def test_generator_bf16_blend_path():
+    size = 32
+    sd = synth.make_state_dict(size, seed=0, perturbed=True)
+    gen = w2e.Generator(size, 512, 8, precision="bf16")
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV).eval()
+    wplus = synth.make_wplus(2, gen.n_latent, seed=2)
+    _, _, ref_styles, ref_feats = orc.generator_forward_ref(sd, [wplus], size, input_is_latent=True,
+                                                            return_features=True)
+    edited = [s * (1 + 0.05 * synth.make_tensor(tuple(s.shape), 500 + i)) for i, s in enumerate(ref_styles)]
+    mask = synth.make_mask(2, 16, seed=10)
+    ref, _, _, ref_new = orc.generator_forward_ref(sd, [edited], size, input_is_stylespace=True, return_features=True,
+                                                   attention_layer=7, attention_map=mask, feature_map=ref_feats)
+    with torch.no_grad():
+        img, _, _, new = gen([[s.to(DEV) for s in edited]], input_is_stylespace=True, randomize_noise=False,
+                             return_features=True, attention_layer=7, attention_map=mask.to(DEV),
+                             feature_map=[f.to(DEV) for f in ref_feats])
+    gen._engine.assert_ok()
+    _check_image(img.cpu(), ref)
+    assert norm_err(new[6].cpu(), ref_new[6]) <= 3e-2
+    # a mask of ones leaves the edited image, a mask of zeros restores the original features downstream
+    with torch.no_grad():
+        full, _ = gen([[s.to(DEV) for s in edited]], input_is_stylespace=True, randomize_noise=False)
+        ones, _ = gen([[s.to(DEV) for s in edited]], input_is_stylespace=True, randomize_noise=False,
+                      attention_layer=7, attention_map=torch.ones(2, 1, 16, 16, device=DEV),
+                      feature_map=[f.to(DEV) for f in ref_feats])
+    assert norm_err(ones.cpu(), full.cpu()) <= 2e-2
+
+
+def test_bf16_batch_invariance():
+    """no cross-sample term and no split-K: a batch of 3 equals three batches of 1, bitwise"""
+    sd = synth.make_state_dict(32, seed=3, perturbed=True)
+    gen = w2e.Generator(32, 512, 8, precision="bf16")
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV).eval()
+    wplus = synth.make_wplus(3, gen.n_latent, seed=4).to(DEV)
+    with torch.no_grad():
+        _, _, styles = gen([wplus], input_is_latent=True, randomize_noise=False, return_latents=True)
+        full, _ = gen([styles], input_is_stylespace=True, randomize_noise=False)
+        singles = torch.cat([gen([[s[i:i + 1] for s in styles]], input_is_stylespace=True,
+                                 randomize_noise=False)[0] for i in range(3)])
+    gen._engine.assert_ok()
+    assert torch.equal(full, singles)

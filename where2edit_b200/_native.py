@@ -37,7 +37,69 @@ PROTOTYPES = {
     "w2e_torgb_bwd": (_I, [_P] * 6 + [_I, _I, _I, _I, _P]),
     "w2e_mask_blend_fwd": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_I, _P]),
     "w2e_mask_blend_bwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
+    "w2e_modconv_tc_supported": (_I, []),
+    "w2e_modconv_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 12 + [_P, _I, _I, _I, _P]),
+    "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
+    "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),
+    "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 9 + [_P]),
+    "w2e_torgb_nhwc": (_I, [_P] * 7 + [_I, _I, _I, _I, _P]),
+    "w2e_blend_nhwc": (_I, [_P] * 6 + [_I] * 6 + [_P]),
 }
+
+# entry points that enqueue no kernel (host queries)
+_HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace",
+              "w2e_modconv_tc_supported"}
+
+
+class Stats:
+    """Launch accounting of the C-ABI calls: `launches[name]` counts kernel-enqueueing calls; when
+    `trace` is a list, every call appends (name, note, start_event, end_event) with CUDA events
+    recorded on the current stream around the call (bench.py's per-kernel roofline pass)."""
+
+    def __init__(self):
+        self.launches = {}
+        self.trace = None
+        self.note = None
+
+    def total(self):
+        return sum(self.launches.values())
+
+    def reset(self):
+        self.launches = {}
+
+
+STATS = Stats()
+
+
+def note(**work):
+    """Attach algorithmic work (flops=..., bytes=..., tag=...) to the next C-ABI call (tracing only)."""
+    if STATS.trace is not None:
+        STATS.note = work
+
+
+def _wrap(name, fn):
+    if name in _HOST_ONLY:
+        return fn
+
+    def call(*args):
+        st = STATS
+        st.launches[name] = st.launches.get(name, 0) + 1
+        if st.trace is None:
+            return fn(*args)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        st.trace.append((name, st.note, e0, e1))
+        st.note = None
+        return rc
+
+    return call
+
+
+class _Lib:
+    pass
 
 _lib = None
 _lock = threading.Lock()
@@ -69,7 +131,11 @@ def load():
                 raise RuntimeError(f"where2edit_b200: {path} does not export {name}") from e
             fn.restype = res
             fn.argtypes = args
-        _lib = lib
+        proxy = _Lib()
+        proxy.cdll = lib
+        for name in PROTOTYPES:
+            setattr(proxy, name, _wrap(name, getattr(lib, name)))
+        _lib = proxy
     return _lib
 
 

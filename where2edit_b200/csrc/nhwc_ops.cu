@@ -1,0 +1,400 @@
+// Channels-last bf16 kernels around the tensor-core modulated convolution (modconv_tc.cu).
+// All are HBM-bound; every activation is touched once per kernel with 128-bit accesses.
+//
+//  * nchw_to_nhwc_mod   fp32 NCHW (constant input / caller feature maps) -> bf16 NHWC, times the
+//                       consumer's style (modulation folded into the producer, model.py:238-239)
+//  * nhwc_to_nchw_f32   bf16 NHWC -> fp32 NCHW (feature capture, attention_model.py:542-543)
+//  * blur_act_nhwc      Blur after the up-convolution (model.py:200-206,260 = upfirdn2d with the
+//                       4x4 separable kernel, pad (1,1)) fused with NoiseInjection + FusedLeakyReLU
+//                       (model.py:279-290, op/fused_act.py:23-39) and the next layer's modulation.
+//                       Algorithmic bytes: B*C*((H+1)*(W+1) + H*W*n_out)*2.
+//  * torgb_nhwc         ToRGB (model.py:353-362): 1x1 modulated conv to 3 channels + bias +
+//                       polyphase x2 skip upsample + add, reading bf16 NHWC, writing fp32 NCHW.
+//  * blend_nhwc         region-mask blend (attention_model.py:548-549) on bf16 NHWC.
+#include "common.cuh"
+
+namespace w2e {
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// ------------------------------------------------------------------------------ layout transforms
+// x [Bx, C, HW] fp32 (Bx = 1 broadcasts over the batch) -> y [B, HW, C] bf16 * style[b, c]
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ style, __nv_bfloat16* __restrict__ y,
+                        int Bx, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* xb = x + (Bx == 1 ? 0 : (int64_t)b * C * HW);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? __ldg(xb + (int64_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    if (p < HW && c < C) {
+      float v = tile[tx][r];
+      if (style) v *= __ldg(style + (int64_t)b * C + c);
+      y[((int64_t)b * HW + p) * C + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// x [B, HW, C] bf16 -> y [B, C, HW] fp32
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    tile[r][tx] = (p < HW && c < C) ? __bfloat162float(x[((int64_t)b * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    if (c < C && p < HW) y[((int64_t)b * C + c) * HW + p] = tile[tx][r];
+  }
+}
+
+// ------------------------------------------------------------------------------ blur + noise + bias + act
+// One thread = 8 channels of one output column, walking down ROWS output rows with a sliding
+// window of horizontally filtered rows in registers.
+constexpr int kBlurRows = 16;
+
+struct BlurParams {
+  const __nv_bfloat16* z;   // [B, IH, IW, C]
+  const float* bias;        // [C] or null
+  const float* noise;       // [noise_batch, H*W] or null
+  const float* noise_w;     // device scalar
+  const float* next_scale;  // [B, C] or null
+  __nv_bfloat16* out;       // [B, H, W, C] or null
+  __nv_bfloat16* out_mod;   // [B, H, W, C] or null
+  int noise_per_sample;
+  int B, C, IH, IW, H, W, py0, px0;
+  int act;
+  float fv[4], fh[4];       // flipped 1-D taps (vertical, horizontal)
+};
+
+__global__ void __launch_bounds__(256)
+blur_act_nhwc_kernel(const __grid_constant__ BlurParams P) {
+  const int cg = P.C >> 3;  // channel groups of 8
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_strip = (int64_t)P.W * cg;
+  const int strips = (P.H + kBlurRows - 1) / kBlurRows;
+  if (idx >= (int64_t)P.B * strips * per_strip) return;
+  const int g = (int)(idx % cg);
+  const int ox = (int)((idx / cg) % P.W);
+  const int strip = (int)((idx / per_strip) % strips);
+  const int b = (int)(idx / (per_strip * strips));
+  const int oy0 = strip * kBlurRows;
+  const int rows = min(kBlurRows, P.H - oy0);
+  const int c0 = g * 8;
+
+  float bias[8], nsc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    bias[e] = P.bias ? __ldg(P.bias + c0 + e) : 0.f;
+    nsc[e] = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + e) : 1.f;
+  }
+  const float nw = P.noise ? __ldg(P.noise_w) : 0.f;
+  const float* noise = P.noise ? P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0) : nullptr;
+  const __nv_bfloat16* zb = P.z + (int64_t)b * P.IH * P.IW * P.C + c0;
+
+  float win[4][8];  // horizontally filtered input rows iy0-? .. (ring)
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) win[r][e] = 0.f;
+
+  // output row oy needs input rows oy - py0 + {0..3}; walk input rows iy = oy0 - py0 .. oy0 - py0 + rows + 2
+  const int iy_first = oy0 - P.py0;
+  for (int t = 0; t < rows + 3; ++t) {
+    const int iy = iy_first + t;
+    float h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = 0.f;
+    if (iy >= 0 && iy < P.IH) {
+      const __nv_bfloat16* zr = zb + (int64_t)iy * P.IW * P.C;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ix = ox - P.px0 + k;
+        if (ix >= 0 && ix < P.IW) {
+          const bf16x8 v = *reinterpret_cast<const bf16x8*>(zr + (int64_t)ix * P.C);
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = fmaf(P.fh[k], f[e], h[e]);
+        }
+      }
+    }
+    // shift the window (fully unrolled register moves) and append
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      win[0][e] = win[1][e];
+      win[1][e] = win[2][e];
+      win[2][e] = win[3][e];
+      win[3][e] = h[e];
+    }
+    if (t >= 3) {
+      const int oy = oy0 + t - 3;
+      float v[8];
+      const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = P.fv[0] * win[0][e];
+        a = fmaf(P.fv[1], win[1][e], a);
+        a = fmaf(P.fv[2], win[2][e], a);
+        a = fmaf(P.fv[3], win[3][e], a);
+        if (P.act == W2E_ACT_LRELU) a = lrelu_gain(a + nz + bias[e], 0.2f, 1.41421356237309515f);
+        else a += bias[e];
+        v[e] = a;
+      }
+      const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
+      if (P.out) *reinterpret_cast<bf16x8*>(P.out + o) = pack8(v);
+      if (P.out_mod) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
+        *reinterpret_cast<bf16x8*>(P.out_mod + o) = pack8(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ ToRGB (NHWC in, NCHW out)
+// LP lanes share one pixel (8 channels per lane per step); a warp covers 32/LP pixels per step.
+template <int LP>
+__global__ void __launch_bounds__(256)
+torgb_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ style,
+                  const float* __restrict__ bias, const float* __restrict__ skip, float4 kf, float* __restrict__ rgb,
+                  int C, int H, int W, int pix_per_block) {
+  extern __shared__ float wm[];  // [3][C] per-sample modulated weights
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < 3 * C; e += blockDim.x)
+    wm[e] = __ldg(w + e) * __ldg(style + (int64_t)b * C + (e % C));
+  __syncthreads();
+  constexpr int PPW = 32 / LP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int sub = lane % LP, grp = lane / LP;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = min(HW, p_begin + pix_per_block);
+  const __nv_bfloat16* xb = x + (int64_t)b * HW * C;
+  const float kfa[4] = {kf.x, kf.y, kf.z, kf.w};
+  for (int64_t p0 = p_begin + (int64_t)warp * PPW; p0 < p_end; p0 += (int64_t)nwarps * PPW) {
+    const int64_t p = p0 + grp;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (p < p_end) {
+      for (int c = sub * 8; c < C; c += LP * 8) {
+        const bf16x8 v = *reinterpret_cast<const bf16x8*>(xb + p * C + c);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a0 = fmaf(f[e], wm[c + e], a0);
+          a1 = fmaf(f[e], wm[C + c + e], a1);
+          a2 = fmaf(f[e], wm[2 * C + c + e], a2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (p < p_end && sub < 3) {
+      float v = sub == 0 ? a0 : (sub == 1 ? a1 : a2);
+      if (bias) v += __ldg(bias + sub);
+      if (skip) {
+        // upfirdn2d(skip, k, up=2, pad=(2,1)) as a polyphase filter: 2 taps per axis
+        const int oy = (int)(p / W), ox = (int)(p % W);
+        const int h = H / 2, wd = W / 2;
+        const int ya = (oy & 1) ? (oy - 1) / 2 : oy / 2 - 1, xa = (ox & 1) ? (ox - 1) / 2 : ox / 2 - 1;
+        const float cy0 = kfa[(oy & 1)], cy1 = kfa[(oy & 1) + 2];
+        const float cx0 = kfa[(ox & 1)], cx1 = kfa[(ox & 1) + 2];
+        const float* sp = skip + ((int64_t)b * 3 + sub) * h * wd;
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const int iy = ya + dy;
+          if (iy < 0 || iy >= h) continue;
+          float row = 0.f;
+          if (xa >= 0) row = cx0 * __ldg(sp + (int64_t)iy * wd + xa);
+          if (xa + 1 < wd) row = fmaf(cx1, __ldg(sp + (int64_t)iy * wd + xa + 1), row);
+          acc = fmaf(dy ? cy1 : cy0, row, acc);
+        }
+        v += acc;
+      }
+      rgb[((int64_t)b * 3 + sub) * HW + p] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ blend (NHWC bf16)
+// out = m*edited + (1-m)*orig ; out_mod = out * next_scale.  8 channels per thread.
+__global__ void __launch_bounds__(256)
+blend_nhwc_kernel(const __nv_bfloat16* __restrict__ edited, const __nv_bfloat16* __restrict__ orig,
+                  const float* __restrict__ mask, const float* __restrict__ next_scale,
+                  __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_mod, int64_t total8, int C, int H,
+                  int W, int mh, int mw) {
+  const int cg = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int64_t pix = i / cg;
+    const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
+    const int64_t b = pix / ((int64_t)W * H);
+    const int my = (int)(((int64_t)yy * mh) / H), mx = (int)(((int64_t)xx * mw) / W);
+    const float m = __ldg(mask + (b * mh + my) * mw + mx);
+    float e[8], o[8], v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(edited + i * 8), e);
+    unpack8(*reinterpret_cast<const bf16x8*>(orig + i * 8), o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __fadd_rn(__fmul_rn(m, e[k]), __fmul_rn(__fsub_rn(1.f, m), o[k]));
+    if (out) *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
+    if (out_mod) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= __ldg(next_scale + b * C + g * 8 + k);
+      *reinterpret_cast<bf16x8*>(out_mod + i * 8) = pack8(v);
+    }
+  }
+}
+
+}  // namespace w2e
+
+using namespace w2e;
+
+extern "C" int w2e_nchw_to_nhwc_mod(const float* x, const float* style, void* y, int B, int Bx, int C, int64_t HW,
+                                    void* stream) {
+  W2E_CHECK_ARG(x && y, "nchw_to_nhwc_mod: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && (Bx == 1 || Bx == B), "nchw_to_nhwc_mod: bad shape");
+  W2E_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "nchw_to_nhwc_mod: batch/channels above 65535");
+  if (B == 0) return W2E_OK;
+  dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+  nchw_to_nhwc_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, style, (__nv_bfloat16*)y, Bx, C, HW);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, void* stream) {
+  W2E_CHECK_ARG(x && y, "nhwc_to_nchw_f32: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && B <= 65535, "nhwc_to_nchw_f32: bad shape");
+  if (B == 0) return W2E_OK;
+  dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+  nhwc_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const float* bias, const float* noise,
+                                 const float* noise_w, int noise_batch, const float* next_scale, void* out,
+                                 void* out_mod, int B, int C, int in_h, int in_w, int py0, int px0, int out_h,
+                                 int out_w, int act, void* stream) {
+  W2E_CHECK_ARG(z && host_taps && (out || out_mod), "blur_act_nhwc: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && C % 8 == 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0,
+                "blur_act_nhwc: bad shape (C must be a multiple of 8)");
+  W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "blur_act_nhwc: out_mod needs next_scale");
+  W2E_CHECK_ARG(noise == nullptr || (noise_w != nullptr && (noise_batch == 1 || noise_batch == B)),
+                "blur_act_nhwc: noise");
+  // separable factorisation of the 4x4 kernel (rank-1 check as in upfirdn2d.cu)
+  int bi = 0, bj = 0;
+  float best = 0.f;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (fabsf(host_taps[i * 4 + j]) > best) best = fabsf(host_taps[i * 4 + j]), bi = i, bj = j;
+  W2E_CHECK_ARG(best > 0.f, "blur_act_nhwc: zero kernel");
+  float kv[4], kh[4];
+  for (int i = 0; i < 4; ++i) kv[i] = host_taps[i * 4 + bj];
+  for (int j = 0; j < 4; ++j) kh[j] = host_taps[bi * 4 + j] / host_taps[bi * 4 + bj];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      W2E_CHECK_ARG(fabsf(host_taps[i * 4 + j] - kv[i] * kh[j]) <= 1e-6f * best,
+                    "blur_act_nhwc: the 4x4 kernel is not separable");
+  if (B == 0) return W2E_OK;
+  BlurParams P;
+  P.z = (const __nv_bfloat16*)z; P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.next_scale = next_scale;
+  P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod;
+  P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
+  P.B = B; P.C = C; P.IH = in_h; P.IW = in_w; P.H = out_h; P.W = out_w; P.py0 = py0; P.px0 = px0; P.act = act;
+  for (int i = 0; i < 4; ++i) { P.fv[i] = kv[3 - i]; P.fh[i] = kh[3 - i]; }
+  const int strips = ceil_div(out_h, kBlurRows);
+  const int64_t threads = (int64_t)B * strips * out_w * (C / 8);
+  blur_act_nhwc_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(P);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_torgb_nhwc(const void* x, const float* w, const float* style, const float* bias,
+                              const float* skip, const float* host_taps1d, float* rgb, int B, int C, int H, int W,
+                              void* stream) {
+  W2E_CHECK_ARG(x && w && style && rgb, "torgb_nhwc: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C >= 32 && C % 8 == 0 && H > 0 && W > 0 && B <= 65535, "torgb_nhwc: bad shape");
+  W2E_CHECK_ARG(skip == nullptr || (host_taps1d != nullptr && H % 2 == 0 && W % 2 == 0), "torgb_nhwc: skip needs taps and even H, W");
+  if (B == 0) return W2E_OK;
+  float4 kf = make_float4(0, 0, 0, 0);
+  if (skip) kf = make_float4(host_taps1d[3], host_taps1d[2], host_taps1d[1], host_taps1d[0]);
+  const int64_t HW = (int64_t)H * W;
+  // enough blocks to fill the machine, at least 256 pixels per block
+  int64_t want_blocks = (int64_t)sm_count() * 8 / (B > 0 ? B : 1) + 1;
+  int64_t ppb = ceil_div64(HW, want_blocks);
+  if (ppb < 256) ppb = 256;
+  ppb = ceil_div64(ppb, 32) * 32;
+  dim3 grid((unsigned)ceil_div64(HW, ppb), (unsigned)B);
+  const size_t smem = (size_t)3 * C * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
+#define W2E_RGB_CASE(lp) torgb_nhwc_kernel<lp><<<grid, 256, smem, s>>>(xp, w, style, bias, skip, kf, rgb, C, H, W, (int)ppb)
+  if (C >= 256) W2E_RGB_CASE(32);
+  else if (C >= 128) W2E_RGB_CASE(16);
+  else if (C >= 64) W2E_RGB_CASE(8);
+  else W2E_RGB_CASE(4);
+#undef W2E_RGB_CASE
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_blend_nhwc(const void* edited, const void* orig, const float* mask, const float* next_scale,
+                              void* out, void* out_mod, int B, int C, int H, int W, int mh, int mw, void* stream) {
+  W2E_CHECK_ARG(edited && orig && mask && (out || out_mod), "blend_nhwc: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && mh > 0 && mw > 0, "blend_nhwc: bad shape");
+  W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "blend_nhwc: out_mod needs next_scale");
+  const int64_t total8 = (int64_t)B * H * W * (C / 8);
+  if (total8 == 0) return W2E_OK;
+  const int64_t blocks = ceil_div64(total8, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  blend_nhwc_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)edited, (const __nv_bfloat16*)orig, mask, next_scale, (__nv_bfloat16*)out,
+      (__nv_bfloat16*)out_mod, total8, C, H, W, mh, mw);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}

@@ -1,0 +1,244 @@
+"""bf16 tensor-core synthesis engine: the no-grad fast path behind `Generator.forward` when
+`precision == "bf16"` (attention/attention_model.py:473-676 semantics).
+
+Data layout in HBM: activations are channels-last bf16 `[B,H,W,C]` (C innermost = the K dimension
+of the implicit GEMM, so TMA boxes land directly in the UMMA operand layout).  Every producer
+kernel writes its result ALREADY multiplied by the style of the layer that will consume it
+(`out_mod`), which is how the style modulation of models/stylegan2/model.py:238-239 is folded
+into the activation path: all samples share one bf16 weight tensor `[9][Cout][Cin]` per layer and
+the demodulation (model.py:242-243) is a per-(sample, channel) scale in the GEMM epilogue.
+
+Per resolution block (model.py:306-362):
+    up-conv   4 polyphase launches of w2e_modconv_tc (conv_transpose2d stride 2) -> z [(2h+1)^2]
+    blur      w2e_blur_act_nhwc: 4x4 FIR + noise + bias + lrelu*sqrt2, writes act * s_conv
+    conv      w2e_modconv_tc (9 taps) + demod + noise + bias + lrelu*sqrt2, writes act (for ToRGB /
+              feature capture) and act * s_next_up
+    ToRGB     w2e_torgb_nhwc: 1x1 modulated conv + bias + polyphase skip upsample, fp32 NCHW
+Styles, demodulation coefficients and the tiny modulation linears stay fp32.
+"""
+import torch
+
+from . import _native as N
+from . import functional as K
+from .op.upfirdn2d import kernel_taps
+
+_UP_AXIS = {0: [(0, 0), (-1, 2)], 1: [(0, 1)]}
+
+
+def _taps_plain():
+    taps = []
+    for ky in range(3):
+        for kx in range(3):
+            taps += [ky - 1, kx - 1, ky * 3 + kx]
+    return taps
+
+
+def _taps_up(py, px):
+    taps = []
+    for dy, ky in _UP_AXIS[py]:
+        for dx, kx in _UP_AXIS[px]:
+            taps += [dy, dx, ky * 3 + kx]
+    return taps
+
+
+_TAPS_PLAIN = _taps_plain()
+_TAPS_UP = {(py, px): _taps_up(py, px) for py in (0, 1) for px in (0, 1)}
+
+
+class SynthesisEngine:
+    def __init__(self, gen):
+        self.gen = gen
+        self._w = {}
+        self._err = None
+        if not N.load().w2e_modconv_tc_supported():
+            raise RuntimeError("where2edit_b200: precision='bf16' needs an sm_100 (B200) device and a driver with "
+                               "cuTensorMapEncodeTiled; there is no fallback -- use precision='fp32'")
+
+    # ------------------------------------------------------------------ cached derived weights
+    def _tc_weight(self, conv):
+        """bf16 [k*k][Cout][Cin] with the equalised-lr scale folded in (model.py:216-217)."""
+        pw = conv.packed()
+        if pw.tc is None:
+            pw.tc = pw.dgr.to(torch.bfloat16).contiguous()
+        return pw
+
+    def error_flag(self, device):
+        if self._err is None or self._err.device != device:
+            self._err = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._err
+
+    def assert_ok(self):
+        """Synchronising check of the pipeline-timeout flag of the tensor-core kernels."""
+        if self._err is not None and int(self._err.item()) != 0:
+            self._err.zero_()
+            raise RuntimeError("where2edit_b200: a tcgen05 pipeline wait timed out (libw2e modconv_tc)")
+
+    # ------------------------------------------------------------------ kernel launches
+    def _conv(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, taps, in_hw, out_hw, grid_hw,
+              out_stride, py, px, act, out=None):
+        b = xs.shape[0]
+        dev = xs.device
+        nslots = pw.tc.shape[0]
+        if out is None and want_out:
+            out = torch.empty((b, out_hw[0], out_hw[1], pw.cout), device=dev, dtype=torch.bfloat16)
+        out_mod = torch.empty((b, out_hw[0], out_hw[1], pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
+        nb = 0 if noise is None else noise.shape[0]
+        ntaps = len(taps) // 3
+        N.note(kind="modconv", flops=2.0 * ntaps * pw.cin * pw.cout * b * grid_hw[0] * grid_hw[1],
+               tag=f"{pw.cin}->{pw.cout}@{grid_hw[0]}x{grid_hw[1]}x{ntaps}")
+        N.check(N.load().w2e_modconv_tc(
+            N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
+            N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, in_hw[0], in_hw[1],
+            out_hw[0], out_hw[1], grid_hw[0], grid_hw[1], out_stride, py, px, N.host_ints(taps), ntaps, nslots, act,
+            N.stream_ptr()), "modconv_tc")
+        return out, out_mod
+
+    def _blur(self, z, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod, out_hw):
+        b, ih, iw, c = z.shape
+        dev = z.device
+        out = torch.empty((b, out_hw[0], out_hw[1], c), device=dev, dtype=torch.bfloat16) if want_out else None
+        out_mod = torch.empty((b, out_hw[0], out_hw[1], c), device=dev, dtype=torch.bfloat16) if want_mod else None
+        nb = 0 if noise is None else noise.shape[0]
+        n_out = int(want_out) + int(want_mod)
+        N.note(kind="upfirdn2d", bytes=2.0 * b * c * (ih * iw + out_hw[0] * out_hw[1] * n_out),
+               tag=f"blur {c}@{out_hw[0]}")
+        N.check(N.load().w2e_blur_act_nhwc(
+            N.ptr(z), N.host_floats(kernel_taps(blur_kernel)), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
+            N.ptr(next_scale), N.ptr(out), N.ptr(out_mod), b, c, ih, iw, pad[0], pad[0], out_hw[0], out_hw[1],
+            N.ACT_LRELU, N.stream_ptr()), "blur_act_nhwc")
+        return out, out_mod
+
+    def _to_nchw(self, x):
+        b, h, w, c = x.shape
+        y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+        N.note(kind="layout", bytes=6.0 * x.numel(), tag=f"nhwc->nchw {c}@{h}")
+        N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.stream_ptr()), "nhwc_to_nchw_f32")
+        return y
+
+    def _to_nhwc(self, x, style, batch):
+        bx, c, h, w = x.shape
+        x = x.to(torch.float32).contiguous()
+        y = torch.empty((batch, h, w, c), device=x.device, dtype=torch.bfloat16)
+        N.note(kind="layout", bytes=4.0 * x.numel() + 2.0 * y.numel(), tag=f"nchw->nhwc {c}@{h}")
+        N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(style), N.ptr(y), batch, bx, c, h * w, N.stream_ptr()),
+                "nchw_to_nhwc_mod")
+        return y
+
+    def _torgb(self, x, module, s, skip):
+        b, h, w, c = x.shape
+        pw = module.conv.packed()
+        rgb = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
+        taps1d = None
+        if skip is not None:
+            taps2d = kernel_taps(module.upsample.kernel)
+            taps1d = K.separable_taps(taps2d) if len(taps2d) == 16 else None
+            if taps1d is None:
+                raise RuntimeError("where2edit_b200 bf16 engine: the ToRGB upsample kernel must be a separable 4x4 FIR")
+            skip = skip.contiguous()
+        bias = module.bias.detach().reshape(3).to(torch.float32).contiguous()
+        N.note(kind="torgb", bytes=b * h * w * (2.0 * c + 12.0 + (3.0 if skip is not None else 0.0)),
+               tag=f"torgb {c}@{h}")
+        N.check(N.load().w2e_torgb_nhwc(N.ptr(x), N.ptr(pw.rgb), N.ptr(s), N.ptr(bias), N.ptr(skip),
+                                        N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb), b, c, h, w,
+                                        N.stream_ptr()), "torgb_nhwc")
+        return rgb
+
+    def _blend(self, out, orig_nchw, mask, next_scale, want_mod):
+        b, h, w, c = out.shape
+        if tuple(orig_nchw.shape) != (b, c, h, w):
+            raise ValueError(f"feature_map entry {tuple(orig_nchw.shape)} does not match layer output {(b, c, h, w)}")
+        if mask.ndim != 4 or mask.shape[1] != 1 or mask.shape[0] != b:
+            raise ValueError(f"attention_map must be [B,1,h,w], got {tuple(mask.shape)}")
+        orig = self._to_nhwc(orig_nchw.detach(), None, b)
+        mask = mask.detach().to(torch.float32).contiguous()
+        new = torch.empty_like(out)
+        new_mod = torch.empty_like(out) if want_mod else None
+        N.note(kind="blend", bytes=2.0 * out.numel() * (3 + int(want_mod)), tag=f"blend {c}@{h}")
+        N.check(N.load().w2e_blend_nhwc(N.ptr(out), N.ptr(orig), N.ptr(mask), N.ptr(next_scale), N.ptr(new),
+                                        N.ptr(new_mod), b, c, h, w, mask.shape[2], mask.shape[3], N.stream_ptr()),
+                "blend_nhwc")
+        return new, new_mod
+
+    # ------------------------------------------------------------------ the forward
+    @torch.no_grad()
+    def run(self, latent, stylespace, noise, want_features=False, attention_layer=0, attention_map=None,
+            feature_map=None):
+        gen = self.gen
+        layers = gen.styled_layers()
+        rows = gen.latent_rows(stylespace)
+        pick = (lambda r: latent[r]) if stylespace else (lambda r: latent[:, r])
+        batch = (latent[0] if stylespace else latent).shape[0]
+        dev = gen.input.input.device
+        N.require_cuda(latent[0] if stylespace else latent)
+
+        # styles and demodulation coefficients of all layers up front (tiny fp32 work)
+        styles, demods = [], []
+        for (module, kind), row in zip(layers, rows):
+            s = module.conv.styles(pick(row), stylespace).to(torch.float32).contiguous()
+            styles.append(s)
+            if kind == "rgb":
+                demods.append(None)
+            else:
+                pw = self._tc_weight(module.conv)
+                demods.append(K.demod_coefficients(s, pw.wsq))
+
+        def consumer_style(idx):
+            """style of the next 3x3 conv after layer idx (None after the last one)."""
+            for j in range(idx + 1, len(layers)):
+                if layers[j][1] != "rgb":
+                    return styles[j]
+            return None
+
+        captured, style_vector = [], []
+        carry = False
+        skip = None
+        noise_idx = 0
+        xs = self._to_nhwc(gen.input.input.detach(), styles[0], batch)   # ConstantInput * s_conv1
+        act = None
+        hw = (gen.input.input.shape[2], gen.input.input.shape[3])
+        for idx, ((module, kind), s) in enumerate(zip(layers, styles)):
+            layer = idx + 1
+            blend_here = bool(attention_layer) and layer == attention_layer
+            if kind == "rgb":
+                skip = self._torgb(act, module, s, skip)
+                if attention_layer and (blend_here or carry):
+                    carry = False
+                    skip = K.mask_blend(skip, feature_map[layer - 1], attention_map)
+                captured.append(skip)
+                style_vector.append(s.reshape(batch, 1, -1, 1, 1))
+                continue
+            conv = module.conv
+            pw = self._tc_weight(conv)
+            nz = noise[noise_idx]
+            noise_idx += 1
+            if nz is None:  # model.py:286-288: fresh per-sample noise
+                f = 2 if kind == "up" else 1
+                nz = torch.empty((batch, 1, hw[0] * f, hw[1] * f), device=dev, dtype=torch.float32).normal_()
+            nz = nz.to(torch.float32).contiguous()
+            noise_w = module.noise.weight.detach().to(torch.float32).contiguous()
+            bias = module.activate.bias.detach().to(torch.float32).contiguous()
+            nxt = consumer_style(idx)
+            next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
+            need_out = next_is_rgb or want_features or blend_here
+            need_mod = nxt is not None and not blend_here
+            if kind == "conv":
+                act, xs_next = self._conv(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
+                                          _TAPS_PLAIN, hw, hw, hw, 1, 0, 0, N.ACT_LRELU)
+            else:
+                h, w = hw
+                zh, zw = 2 * h + 1, 2 * w + 1
+                z = torch.empty((batch, zh, zw, pw.cout), device=dev, dtype=torch.bfloat16)
+                for (py, px), taps in _TAPS_UP.items():
+                    self._conv(xs, pw, demods[idx], None, None, None, None, True, False, taps, (h, w), (zh, zw),
+                               (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
+                hw = (2 * h, 2 * w)
+                act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, need_out,
+                                          need_mod, hw)
+            if blend_here:
+                carry = True
+                act, xs_next = self._blend(act, feature_map[layer - 1], attention_map, nxt, nxt is not None)
+            xs = xs_next
+            if want_features:
+                captured.append(self._to_nchw(act))
+            style_vector.append(s.reshape(batch, 1, -1, 1, 1))
+        return skip, style_vector, captured
