@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the Where2edit StyleGAN2 synthesis hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one `Generator.forward` over a batch of synthetic W+ latents (configs[1] of
+BASELINE.json: FFHQ-1024 generator, batch 32 per GPU, bf16 tensor-core mode, fixed noise buffers).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "1024x1024 edited images/sec"
+UNIT = "images/s"
+# algorithmic work per image of the 1024^2 generator (SURVEY.md appendix A / BASELINE.md section 4)
+MODCONV_GFLOP_PER_IMAGE = 148.13
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.25] or [l for (_, l) in self.lines]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_generator(size, precision, device):
+    """Random-init generator of the reference architecture (no checkpoints exist offline); the
+    zero-initialised noise weights / biases are perturbed so those code paths do real work."""
+    import where2edit_b200 as w2e
+    torch.manual_seed(0)
+    gen = w2e.Generator(size, 512, 8, channel_multiplier=2, precision=precision)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in gen.named_parameters():
+            if name.endswith("noise.weight") or name.endswith("activate.bias") or (name.endswith(".bias") and p.ndim == 4):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    return gen.to(device).eval()
+
+
+def cpu_forward_images_per_s(state_dict, size, n_latent, batch, threads):
+    """The reference's CPU algorithm (oracle port of models/stylegan2/model.py + op/) timed on the
+    host cores: one warm-up image, then `batch` images."""
+    from oracle import stylegan2_oracle as orc
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        orc.generator_forward_ref(state_dict, [torch.randn(1, n_latent, 512, generator=g)], size, input_is_latent=True)
+        w = torch.randn(batch, n_latent, 512, generator=g)
+        t0 = time.perf_counter()
+        orc.generator_forward_ref(state_dict, [w], size, input_is_latent=True)
+        dt = time.perf_counter() - t0
+    return batch / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (it ships no native
+    code and its Python cannot travel to the GPU box, so the pinned oracle port is timed) on all
+    host cores; every step is a bounded sample of the workload (one 1024^2 image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import stylegan2_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    import where2edit_b200 as w2e
+    gen = w2e.Generator(args.size, 512, 8, channel_multiplier=2)
+    sd = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    sample_batch = 1
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            orc.generator_forward_ref(sd, [torch.randn(sample_batch, gen.n_latent, 512, generator=g)], args.size,
+                                      input_is_latent=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.generator_forward_ref(sd, [torch.randn(sample_batch, gen.n_latent, 512, generator=g)], args.size,
+                                      input_is_latent=True)
+        dt = time.perf_counter() - t0
+    value = sample_batch * args.steps / dt
+    sample = f"{sample_batch} image(s) of the {args.size}^2 generator per step, fp32, torch CPU ops, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"StyleGAN2 FFHQ-{args.size} generator forward (random init), CPU sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def summarise_trace(trace, peaks):
+    """Per-kernel-kind totals from the traced step: algorithmic work / CUDA-event time."""
+    kinds = {}
+    layers = []
+    for name, note, e0, e1 in trace:
+        ms = e0.elapsed_time(e1)
+        kind = (note or {}).get("kind", name)
+        k = kinds.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        k["ms"] += ms
+        k["launches"] += 1
+        k["flops"] += (note or {}).get("flops", 0.0)
+        k["bytes"] += (note or {}).get("bytes", 0.0)
+        layers.append({"call": name, "tag": (note or {}).get("tag"), "ms": ms, "flops": (note or {}).get("flops"),
+                       "bytes": (note or {}).get("bytes")})
+    return kinds, layers
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images of the CPU-baseline sample (0 = skip)")
+    ap.add_argument("--layers-out", default=None, help="write the per-launch trace of one step to this JSON file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU implementation")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from where2edit_b200 import _native as N
+    gen = make_generator(args.size, args.precision, dev)
+    B, K_, W_ = args.batch, args.steps, args.warmup
+    peaks = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    g = torch.Generator().manual_seed(2 + rank)
+    n_lat = gen.n_latent
+    host_w = [torch.randn(B, n_lat, 512, generator=g).pin_memory() for _ in range(2)]
+    dev_w = [w.to(dev) for w in host_w]
+    comm_stream = torch.cuda.Stream() if dist is not None else None
+    gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=torch.bfloat16) for _ in range(2)] \
+        if dist is not None else None
+
+    def step(i, w):
+        """One pass of the hot path; at N>1 the images are all-gathered (bf16) on a side stream so the
+        collective of step i overlaps the kernels of step i+1."""
+        with torch.no_grad():
+            img, _ = gen([w], input_is_latent=True, randomize_noise=False)
+        if dist is not None:
+            small = img.to(torch.bfloat16)
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(gathered[i % 2], small)
+            small.record_stream(comm_stream)
+        return img
+
+    # ---------------- device-resident throughput (`value`)
+    for i in range(W_):
+        step(i, dev_w[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    N.STATS.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(K_):
+        step(i, dev_w[i % 2])
+    if comm_stream is not None:
+        torch.cuda.current_stream().wait_stream(comm_stream)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    launches = N.STATS.total()
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if gen._engine is not None:
+        gen._engine.assert_ok()
+    value = world * B * K_ / (total_ms / 1e3)
+
+    # ---------------- end to end through the public API with host buffers (`e2e`)
+    copy_stream = torch.cuda.Stream()
+    host_img = [torch.empty((B, 3, args.size, args.size), dtype=torch.float32).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_step(i):
+        w = host_w[i % 2].to(dev, non_blocking=True)            # H2D of this step's latents (pinned)
+        img = step(i, w)
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        done[i % 2].synchronize()                               # host buffer i%2 free again
+        with torch.cuda.stream(copy_stream):
+            host_img[i % 2].copy_(img, non_blocking=True)       # D2H of the step's images
+            done[i % 2].record(copy_stream)
+        img.record_stream(copy_stream)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(K_):
+        e2e_step(i)
+    torch.cuda.current_stream().wait_stream(copy_stream)
+    if comm_stream is not None:
+        torch.cuda.current_stream().wait_stream(comm_stream)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K_ / (float(ms2.item()) / 1e3)
+    h2d = host_w[0].numel() * 4
+    d2h = host_img[0].numel() * 4
+
+    # ---------------- per-kernel roofline from one traced step (CUDA events around every launch)
+    roofline = roofline_up = None
+    kinds = {}
+    if rank == 0:
+        step(0, dev_w[0])
+        torch.cuda.synchronize()
+        N.STATS.trace = []
+        step(1, dev_w[1])
+        torch.cuda.synchronize()
+        trace, N.STATS.trace = N.STATS.trace, None
+        kinds, layers = summarise_trace(trace, peaks)
+        traced_ms = sum(k["ms"] for k in kinds.values())
+        if "modconv" in kinds and kinds["modconv"]["ms"] > 0:
+            k = kinds["modconv"]
+            ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "modconv_tc_kernel (all 3x3 modulated-conv launches of a step)",
+                        "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                        "launches": k["launches"], "share_of_step": k["ms"] / traced_ms}
+        if "upfirdn2d" in kinds and kinds["upfirdn2d"]["ms"] > 0:
+            k = kinds["upfirdn2d"]
+            ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+            roofline_up = {"bound": "hbm", "kernel": "blur_act_nhwc_kernel (all blur launches of a step)",
+                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                           "traffic": None, "peak_source": peaks["source"] + " hbm_gbs", "launches": k["launches"],
+                           "share_of_step": k["ms"] / traced_ms}
+        if args.layers_out:
+            with open(args.layers_out, "w") as fh:
+                json.dump({"batch": B, "size": args.size, "precision": args.precision, "launches": layers,
+                           "kinds": kinds}, fh, indent=1)
+
+    # ---------------- CPU baseline (rank 0, N == 1 only): the reference algorithm on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        threads = os.cpu_count() or 1
+        sd = {k: v.detach().cpu().float() for k, v in gen.state_dict().items()}
+        v, dt = cpu_forward_images_per_s(sd, args.size, n_lat, args.cpu_sample, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_sample} images of the same {args.size}^2 generator forward in one batch "
+                         f"({dt:.1f} s), fp32 torch CPU ops via the oracle port, after a 1-image warm-up"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
+            "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"StyleGAN2 FFHQ-{args.size} generator forward (random init, channel_multiplier 2), "
+                                   f"batch {B} per GPU from W+ latents, fixed noise buffers, {args.precision} mode",
+                       "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"batch sharded over {world} GPU(s)"
+                                      + (", bf16 all-gather of images overlapped on a side stream" if world > 1 else ""),
+                       "l2": "inputs larger than L2: every step streams multi-GB activations (no flush needed)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_upfirdn2d": roofline_up,
+            "modconv_tflops_per_step_algorithmic": MODCONV_GFLOP_PER_IMAGE * B / 1e3 if args.size == 1024 else None,
+            "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in kinds.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

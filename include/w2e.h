@@ -158,6 +158,19 @@ int w2e_modconv_tc(const void* xs, const void* w, const float* out_scale, const 
                    int in_w, int out_h, int out_w, int grid_h, int grid_w, int out_stride, int py,
                    int px, const int* host_taps, int ntaps, int nslots, int act, void* stream);
 
+/* Persistent v2 of the kernel above (haloed input tile shared by all 9 taps, double-buffered TMEM
+ * accumulators, the four parity classes of the transposed convolution fused into one pass).
+ * transposed == 0: plain 3x3, padding 1: xs [B,in_h,in_w,Cin] -> out [B,in_h,in_w,Cout].
+ * transposed == 1: conv_transpose2d stride 2: -> out [B,2*in_h+1,2*in_w+1,Cout] (the pre-blur tensor).
+ * Same epilogue, operands and constraints as w2e_modconv_tc.                                  */
+int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
+                    const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                    void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
+                    int in_w, int transposed, int act, void* stream);
+/* tuning/diagnostic knobs of w2e_modconv_tc2: pitch of the haloed tile in pixels (10..32), whether
+ * the UMMA descriptors carry the base-offset field, and a cap on the number of CTAs (0 = none). */
+void w2e_modconv_tc2_knobs(int pitch, int base_offset_mode, int max_ctas);
+
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],
  * multiplied by style[b,c] when style != NULL.                                                */

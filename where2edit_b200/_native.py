@@ -39,6 +39,8 @@ PROTOTYPES = {
     "w2e_mask_blend_bwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
     "w2e_modconv_tc_supported": (_I, []),
     "w2e_modconv_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 12 + [_P, _I, _I, _I, _P]),
+    "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P]),
+    "w2e_modconv_tc2_knobs": (None, [_I, _I, _I]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),
     "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 9 + [_P]),
@@ -48,7 +50,7 @@ PROTOTYPES = {
 
 # entry points that enqueue no kernel (host queries)
 _HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace",
-              "w2e_modconv_tc_supported"}
+              "w2e_modconv_tc_supported", "w2e_modconv_tc2_knobs"}
 
 
 class Stats:

@@ -21,101 +21,9 @@
 // tcgen05.commit releases stages and publishes the accumulator.
 //
 // Algorithmic FLOPs per launch: 2 * ntaps * Cin * Cout * B * grid_h * grid_w.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace w2e {
-
-// ----------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a hang (bad descriptor, lost arrive) becomes an error flag instead of a dead GPU.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if ((spin & 1023u) == 1023u && *abort_flag) return false;
-  }
-  *abort_flag = 1;
-  return false;
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(0) | SBO>>4 << 32 |
-// version 1 << 46 | layout << 61, layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  SBO = 8 rows.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t row_bytes) {
-  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
-  d |= 1ull << 46;
-  d |= layout << 61;
-  return d;
-}
 
 // ----------------------------------------------------------------------------------------- kernel
 constexpr int kTcMaxTaps = 9;
@@ -305,11 +213,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -321,9 +225,9 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int row_bytes) {
-  EncodeTiledFn fn = encode_fn();
+int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, int row_bytes) {
+  EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return set_error(W2E_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -357,7 +261,7 @@ extern "C" int w2e_modconv_tc_supported(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
-  return (major == 10 && encode_fn() != nullptr) ? 1 : 0;
+  return (major == 10 && tensor_map_encoder() != nullptr) ? 1 : 0;
 }
 
 extern "C" int w2e_modconv_tc(const void* xs, const void* w, const float* out_scale, const float* bias,
@@ -405,14 +309,14 @@ extern "C" int w2e_modconv_tc(const void* xs, const void* w, const float* out_sc
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)in_w * Cin * 2, (uint64_t)in_h * in_w * Cin * 2};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)P.tw, (uint32_t)P.th, (uint32_t)P.nb};
-    int rc = make_map(&ma, xs, 4, dims, strides, box, BK * 2);
+    int rc = make_bf16_map(&ma, xs, 4, dims, strides, box, BK * 2);
     if (rc) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)nslots};
     const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
     const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1u};
-    int rc = make_map(&mb, w, 3, dims, strides, box, BK * 2);
+    int rc = make_bf16_map(&mb, w, 3, dims, strides, box, BK * 2);
     if (rc) return rc;
   }
   dim3 grid((unsigned)(P.tiles_x * P.tiles_y * tiles_n), (unsigned)(Cout / BN));

@@ -1,0 +1,463 @@
+// Persistent, warp-specialised tensor-core modulated convolution for sm_100a (v2 of modconv_tc.cu).
+// Replaces the grouped F.conv2d / F.conv_transpose2d of models/stylegan2/model.py:249-274 in bf16
+// mode.  SURVEY.md section 2.2 kernels K1a (plain 3x3) and K1b (transposed x2).
+//
+// What changed against v1 (one 128-pixel tile per CTA, 9 shifted TMA fetches of the input):
+//  * HALOED INPUT TILE.  One TMA box {BK channels, P pixels, TH+2 rows} of the (already
+//    style-modulated) NHWC input is loaded ONCE per K-chunk; all 9 filter taps read it in place
+//    through shifted UMMA shared-memory descriptors: an output tile is 8 pixels wide, so one
+//    8-row core-matrix group = one image-row segment, the group stride (SBO) is the pitch of the
+//    haloed tile and a tap (dy,dx) is a start-address offset of (dy*P+dx) rows.  L2->SM traffic
+//    for the activation drops from 9x to ~1.4x.
+//  * PERSISTENT CTAs with a static tile schedule, an smem ring for the weight blocks (or the
+//    whole weight resident in smem when it is small), and double-buffered TMEM accumulators, so
+//    TMA, MMA and the epilogue of consecutive tiles overlap.
+//  * Up to 256 pixels x 256 channels per tile (two M=128 accumulators share every weight block).
+//  * The transposed (x2) convolution computes its four output-parity classes in ONE pass: the 9
+//    taps accumulate into 4 TMEM accumulators (class = parity of (ky,kx)) from the same input tile.
+//
+// Warp roles (320 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 also
+// owns the TMEM allocation), warps 2..9 = epilogue (TMEM -> registers -> global; one accumulator
+// row = one output pixel per thread, two warps per TMEM lane quarter splitting the columns):
+// * demodulation, + noise, + bias, leaky-ReLU * sqrt(2), and the next layer's style (out_mod) -- so
+// the whole batch shares one weight tensor.  Per-channel constants are staged in shared memory
+// once per tile.
+//
+// Algorithmic FLOPs per launch: 2 * taps * Cin * Cout * B * (pixels of the class grids).
+#include "tc_ptx.cuh"
+
+namespace w2e {
+
+constexpr int kT2Threads = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kT2EpiThreads = 256;
+constexpr int kT2MaxA = 4, kT2MaxB = 16, kT2MaxAcc = 2;
+constexpr int kTileW = 8, kSubTileH = 16;  // one M=128 sub-tile = 16 rows x 8 pixels
+
+struct Tc2Params {
+  const float* out_scale;   // [B,Cout] demodulation or null
+  const float* bias;        // [Cout] or null
+  const float* noise;       // [noise_batch, OH*OW] or null
+  const float* noise_w;     // device scalar
+  const float* next_scale;  // [B,Cout] or null
+  __nv_bfloat16* out;       // [B,OH,OW,Cout] or null
+  __nv_bfloat16* out_mod;   // [B,OH,OW,Cout] or null
+  int* error_flag;
+  int noise_per_sample;
+  int B, Cin, Cout, OH, OW;
+  int grid_h, grid_w, out_stride;
+  int tiles_x, tiles_y, tiles_n, ntiles;
+  int bn, bk, mt, ng, wres, nbuf;
+  int pitch, box_rows, a_stages, b_stages;
+  int a_stage_bytes, a_box_bytes, b_block_bytes;
+  int tmem_cols;
+  int use_base_offset;
+  int act;
+  int ntaps;
+  int tap_off[9], tap_slot[9], tap_acc[9];
+  int acc_py[4], acc_px[4];
+};
+
+struct Tc2Bars {
+  uint64_t a_full[kT2MaxA], a_empty[kT2MaxA];
+  uint64_t b_full[kT2MaxB], b_empty[kT2MaxB];
+  uint64_t acc_full[kT2MaxAcc], acc_empty[kT2MaxAcc];
+  uint64_t w_full;
+  uint32_t tmem_slot;
+  int abort_flag;
+  // per-tile epilogue constants, double-buffered by tile parity: scale (demod*gain), shift (bias*gain), next style
+  alignas(16) float ep_scale[2][256];
+  alignas(16) float ep_shift[2][256];
+  alignas(16) float ep_next[2][256];
+};
+
+// K-major swizzled operand descriptor with an explicit group stride (SBO) and optional base offset.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t row_bytes, uint32_t sbo_bytes, int base_off_mode) {
+  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  if (base_off_mode) d |= (uint64_t)((addr >> 7) & 7u) << 49;
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1)
+modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ Tc2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)P.a_stages * P.a_stage_bytes;
+  const int n_bblocks = P.wres ? P.ntaps * (P.Cin / P.bk) : P.b_stages;
+  Tc2Bars* bars = reinterpret_cast<Tc2Bars*>(b_base + (size_t)n_bblocks * P.b_block_bytes);
+  volatile int* abort_flag = &bars->abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = P.Cin / P.bk;
+  const int row_bytes = P.bk * 2;
+  const int tiles_per_n = P.tiles_x * P.tiles_y * P.B;
+
+  if (threadIdx.x == 0) {
+    bars->abort_flag = 0;
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
+      for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
+      for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], kT2EpiThreads); }
+      mbar_init(&bars->w_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_slot, (uint32_t)P.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (P.wres) {
+        mbar_arrive_expect_tx(&bars->w_full, (uint32_t)(n_bblocks * P.b_block_bytes));
+        for (int kc = 0; kc < kchunks; ++kc)
+          for (int t = 0; t < P.ntaps; ++t)
+            tma_load_3d(b_base + (size_t)(kc * P.ntaps + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * P.bk, 0,
+                        P.tap_slot[t]);
+      }
+      uint32_t ai = 0, bi = 0;  // running stage counters
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
+        const int tn = tile / tiles_per_n;
+        int rem = tile - tn * tiles_per_n;
+        const int b = rem / (P.tiles_x * P.tiles_y);
+        rem -= b * (P.tiles_x * P.tiles_y);
+        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+        const int j0 = ty * (kSubTileH * P.mt), i0 = tx * kTileW, co0 = tn * P.bn;
+        for (int kc = 0; kc < kchunks && ok; ++kc) {
+          const int as = ai % P.a_stages;
+          ok = mbar_wait(&bars->a_empty[as], ((ai / P.a_stages) & 1u) ^ 1u, abort_flag);
+          if (!ok) break;
+          mbar_arrive_expect_tx(&bars->a_full[as], (uint32_t)P.a_box_bytes);
+          tma_load_4d(a_base + (size_t)as * P.a_stage_bytes, &map_a, &bars->a_full[as], kc * P.bk, i0 - 1, j0 - 1, b);
+          ++ai;
+          if (!P.wres) {
+            for (int t = 0; t < P.ntaps; ++t) {
+              const int bs = bi % P.b_stages;
+              ok = mbar_wait(&bars->b_empty[bs], ((bi / P.b_stages) & 1u) ^ 1u, abort_flag);
+              if (!ok) break;
+              mbar_arrive_expect_tx(&bars->b_full[bs], (uint32_t)P.b_block_bytes);
+              tma_load_3d(b_base + (size_t)bs * P.b_block_bytes, &map_b, &bars->b_full[bs], kc * P.bk, co0,
+                          P.tap_slot[t]);
+              ++bi;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((128u >> 4) << 24);
+      const int ksteps = P.bk / 16;
+      const uint32_t a_sbo = (uint32_t)(P.pitch * row_bytes);
+      const uint32_t b_sbo = (uint32_t)(8 * row_bytes);
+      uint32_t ai = 0, bi = 0, acc_it = 0;
+      bool ok = true;
+      if (P.wres) {
+        ok = mbar_wait(&bars->w_full, 0, abort_flag);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, ++acc_it) {
+        const int buf = acc_it % P.nbuf;
+        ok = mbar_wait(&bars->acc_empty[buf], ((acc_it / P.nbuf) & 1u) ^ 1u, abort_flag);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t acc_base = tmem_base + (uint32_t)(buf * P.ng * P.mt * P.bn);
+        uint32_t inited = 0;
+        for (int kc = 0; kc < kchunks && ok; ++kc) {
+          const int as = ai % P.a_stages;
+          ok = mbar_wait(&bars->a_full[as], (ai / P.a_stages) & 1u, abort_flag);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + (size_t)as * P.a_stage_bytes);
+          for (int t = 0; t < P.ntaps; ++t) {
+            uint32_t b_addr;
+            int bs = 0;
+            if (P.wres) {
+              b_addr = smem_u32(b_base + (size_t)(kc * P.ntaps + t) * P.b_block_bytes);
+            } else {
+              bs = bi % P.b_stages;
+              ok = mbar_wait(&bars->b_full[bs], (bi / P.b_stages) & 1u, abort_flag);
+              if (!ok) break;
+              tc_fence_after();
+              b_addr = smem_u32(b_base + (size_t)bs * P.b_block_bytes);
+            }
+            const int g = P.tap_acc[t];
+            const bool fresh = !((inited >> g) & 1u);
+            inited |= 1u << g;
+            for (int m = 0; m < P.mt; ++m) {
+              const uint32_t a_tap = a_addr + (uint32_t)((P.tap_off[t] + m * kSubTileH * P.pitch) * row_bytes);
+              const uint32_t d_tmem = acc_base + (uint32_t)((g * P.mt + m) * P.bn);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adesc = make_desc(a_tap + k * 32, row_bytes, a_sbo, P.use_base_offset);
+                const uint64_t bdesc = make_desc(b_addr + k * 32, row_bytes, b_sbo, 0);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (fresh && k == 0) ? 0u : 1u);
+              }
+            }
+            if (!P.wres) {
+              umma_commit(&bars->b_empty[bs]);
+              ++bi;
+            }
+          }
+          umma_commit(&bars->a_empty[as]);
+          ++ai;
+        }
+        umma_commit(&bars->acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warps 2..9
+    // warp w reads TMEM lane quarter w%4 (hardware rule); warps 2..5 take the first half of the
+    // tile's BN columns, warps 6..9 the second half.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
+    const int r = q * 32 + lane;      // accumulator row == pixel inside the sub-tile
+    const int sy = r >> 3, sx = r & 7;
+    const bool lrelu = P.act == W2E_ACT_LRELU;
+    const float gain = lrelu ? 1.41421356237309515f : 1.f;
+    const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
+    const int c_begin = (P.bn >= 32) ? half * (P.bn >> 1) : 0;
+    const int c_end = (P.bn >= 32) ? c_begin + (P.bn >> 1) : (half == 0 ? P.bn : 0);
+    uint32_t acc_it = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++acc_it) {
+      const int tn = tile / tiles_per_n;
+      int rem = tile - tn * tiles_per_n;
+      const int b = rem / (P.tiles_x * P.tiles_y);
+      rem -= b * (P.tiles_x * P.tiles_y);
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      const int j0 = ty * (kSubTileH * P.mt), i0 = tx * kTileW, co0 = tn * P.bn;
+      const int buf = acc_it % P.nbuf;
+      // stage this tile's per-channel constants (one named barrier per tile; see Tc2Bars)
+      const int cb = acc_it & 1;
+      for (int c = et; c < P.bn; c += kT2EpiThreads) {
+        const int64_t bc = (int64_t)b * P.Cout + co0 + c;
+        bars->ep_scale[cb][c] = (P.out_scale ? __ldg(P.out_scale + bc) : 1.f) * gain;
+        bars->ep_shift[cb][c] = (P.bias ? __ldg(P.bias + co0 + c) : 0.f) * gain;
+        bars->ep_next[cb][c] = P.next_scale ? __ldg(P.next_scale + bc) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kT2EpiThreads) : "memory");
+      if (ok) ok = mbar_wait(&bars->acc_full[buf], (acc_it / P.nbuf) & 1u, abort_flag);
+      tc_fence_after();
+      const float* sc = bars->ep_scale[cb];
+      const float* sh = bars->ep_shift[cb];
+      const float* nx = bars->ep_next[cb];
+      for (int g = 0; g < P.ng; ++g) {
+        for (int m = 0; m < P.mt; ++m) {
+          const int j = j0 + m * kSubTileH + sy, i = i0 + sx;
+          const int oy = j * P.out_stride + P.acc_py[g], ox = i * P.out_stride + P.acc_px[g];
+          const bool valid = ok && j < P.grid_h && i < P.grid_w && oy < P.OH && ox < P.OW;
+          const int64_t pix = valid ? ((int64_t)b * P.OH + oy) * P.OW + ox : 0;
+          float nz = 0.f;
+          if (valid && P.noise)
+            nz = nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox);
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                  (uint32_t)(buf * P.ng * P.mt * P.bn + (g * P.mt + m) * P.bn);
+          __nv_bfloat16* o_row = P.out ? P.out + pix * P.Cout + co0 : nullptr;
+          __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix * P.Cout + co0 : nullptr;
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (valid) {
+              float f[16];
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(sc + c + 4 * e4);
+                const float4 b4 = *reinterpret_cast<const float4*>(sh + c + 4 * e4);
+                f[4 * e4 + 0] = fmaf(__uint_as_float(v[4 * e4 + 0]), a4.x, b4.x + nz);
+                f[4 * e4 + 1] = fmaf(__uint_as_float(v[4 * e4 + 1]), a4.y, b4.y + nz);
+                f[4 * e4 + 2] = fmaf(__uint_as_float(v[4 * e4 + 2]), a4.z, b4.z + nz);
+                f[4 * e4 + 3] = fmaf(__uint_as_float(v[4 * e4 + 3]), a4.w, b4.w + nz);
+              }
+              if (lrelu) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.2f * f[e]);
+              }
+              if (o_row) {
+                uint4 pk[2];
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(o_row + c);
+                dst[0] = pk[0];
+                dst[1] = pk[1];
+              }
+              if (m_row) {
+                uint4 pk[2];
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 n4 = *reinterpret_cast<const float4*>(nx + c + 4 * e4);
+                  h[2 * e4] = __floats2bfloat162_rn(f[4 * e4] * n4.x, f[4 * e4 + 1] * n4.y);
+                  h[2 * e4 + 1] = __floats2bfloat162_rn(f[4 * e4 + 2] * n4.z, f[4 * e4 + 3] * n4.w);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(m_row + c);
+                dst[0] = pk[0];
+                dst[1] = pk[1];
+              }
+            }
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&bars->acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && bars->abort_flag && P.error_flag) *P.error_flag = 1;
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// debug / tuning knobs (tests flip them to validate the shifted-descriptor scheme on hardware)
+static int g_pitch = 10;
+static int g_base_offset = 0;
+static int g_max_ctas = 0;
+
+}  // namespace w2e
+
+using namespace w2e;
+
+extern "C" void w2e_modconv_tc2_knobs(int pitch, int base_offset_mode, int max_ctas) {
+  if (pitch >= 10 && pitch <= 32) g_pitch = pitch;
+  g_base_offset = base_offset_mode ? 1 : 0;
+  g_max_ctas = max_ctas;
+}
+
+extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
+                               const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                               void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
+                               int transposed, int act, void* stream) {
+  W2E_CHECK_ARG(xs && w && (out || out_mod), "modconv_tc2: null pointer");
+  W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
+  W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
+  W2E_CHECK_ARG(Cin % 32 == 0 && Cout % 16 == 0, "modconv_tc2: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
+  W2E_CHECK_ARG(noise == nullptr || (noise_w != nullptr && (noise_batch == 1 || noise_batch == B)), "modconv_tc2: noise");
+  W2E_CHECK_ARG(((uintptr_t)xs & 15) == 0 && ((uintptr_t)w & 15) == 0, "modconv_tc2: operands must be 16-byte aligned");
+  if (!w2e_modconv_tc_supported()) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2: device is not sm_100");
+
+  Tc2Params P;
+  memset(&P, 0, sizeof(P));
+  P.out_scale = out_scale; P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.next_scale = next_scale;
+  P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod; P.error_flag = error_flag;
+  P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
+  P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
+  P.use_base_offset = g_base_offset;
+  P.pitch = g_pitch;
+  P.ntaps = 9;
+  if (!transposed) {
+    P.OH = in_h; P.OW = in_w; P.grid_h = in_h; P.grid_w = in_w; P.out_stride = 1; P.ng = 1;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int t = ky * 3 + kx;
+        P.tap_off[t] = ky * P.pitch + kx; P.tap_slot[t] = t; P.tap_acc[t] = 0;
+      }
+  } else {
+    // conv_transpose2d(stride 2, k 3): out[2j+py, 2i+px] gets x[j - (ky==2), i - (kx==2)] * W[ky,kx], py = ky&1
+    P.OH = 2 * in_h + 1; P.OW = 2 * in_w + 1; P.grid_h = in_h + 1; P.grid_w = in_w + 1; P.out_stride = 2; P.ng = 4;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int t = ky * 3 + kx;
+        P.tap_off[t] = (ky == 2 ? 0 : 1) * P.pitch + (kx == 2 ? 0 : 1);
+        P.tap_slot[t] = t; P.tap_acc[t] = (ky & 1) * 2 + (kx & 1);
+      }
+    for (int g = 0; g < 4; ++g) { P.acc_py[g] = g >> 1; P.acc_px[g] = g & 1; }
+  }
+  P.bk = (Cin % 64 == 0) ? 64 : 32;
+  const int row_bytes = P.bk * 2;
+  P.mt = (P.grid_h > kSubTileH) ? 2 : 1;
+  const int bn_max = transposed ? 128 : 256;
+  P.bn = 16;
+  for (int cand : {256, 128, 64, 32, 16})
+    if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
+  if (P.ng * P.mt * P.bn > 512) P.mt = 1;
+  P.nbuf = (P.ng * P.mt * P.bn * 2 <= 512) ? 2 : 1;
+  int cols = P.ng * P.mt * P.bn * P.nbuf;
+  P.tmem_cols = 32;
+  while (P.tmem_cols < cols) P.tmem_cols <<= 1;
+  P.box_rows = kSubTileH * P.mt + 2;
+  P.a_box_bytes = P.box_rows * P.pitch * row_bytes;
+  P.a_stage_bytes = (P.a_box_bytes + 1023) / 1024 * 1024;
+  P.b_block_bytes = P.bn * row_bytes;
+  P.tiles_x = ceil_div(P.grid_w, kTileW);
+  P.tiles_y = ceil_div(P.grid_h, kSubTileH * P.mt);
+  P.tiles_n = Cout / P.bn;
+  const int64_t ntiles = (int64_t)P.tiles_x * P.tiles_y * P.tiles_n * B;
+  W2E_CHECK_ARG(ntiles < (1ll << 31), "modconv_tc2: too many tiles");
+  P.ntiles = (int)ntiles;
+  const int kchunks = Cin / P.bk;
+
+  // shared-memory plan: resident weights when small, else a ring of weight blocks
+  const int smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(Tc2Bars);
+  const int w_bytes = 9 * kchunks * P.b_block_bytes;
+  P.wres = (P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
+  P.a_stages = kchunks == 1 ? 3 : 2;
+  int b_bytes;
+  if (P.wres) {
+    P.b_stages = 1;
+    b_bytes = w_bytes;
+  } else {
+    int avail = smem_limit - P.a_stages * P.a_stage_bytes;
+    P.b_stages = avail / P.b_block_bytes;
+    if (P.b_stages > kT2MaxB) P.b_stages = kT2MaxB;
+    W2E_CHECK_ARG(P.b_stages >= 2, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
+    b_bytes = P.b_stages * P.b_block_bytes;
+  }
+  const int smem_bytes = P.a_stages * P.a_stage_bytes + b_bytes + (int)sizeof(Tc2Bars) + 1024;
+  W2E_CHECK_ARG(smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
+
+  CUtensorMap ma, mb;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)in_w * Cin * 2, (uint64_t)in_h * in_w * Cin * 2};
+    const uint32_t box[4] = {(uint32_t)P.bk, (uint32_t)P.pitch, (uint32_t)P.box_rows, 1u};
+    int rc = make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)P.bn, 1u};
+    int rc = make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
+    if (rc) return rc;
+  }
+  static int configured_smem = 0;
+  if (smem_bytes > configured_smem) {
+    W2E_CUDA_OK(cudaFuncSetAttribute(modconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_smem = 227 * 1024;
+  }
+  int per_sm = (227 * 1024) / smem_bytes;
+  if (per_sm * P.tmem_cols > 512) per_sm = 512 / P.tmem_cols;
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int ctas = sm_count() * per_sm;
+  if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
+  if (ctas > P.ntiles) ctas = P.ntiles;
+  modconv_tc2_kernel<<<ctas, kT2Threads, smem_bytes, (cudaStream_t)stream>>>(ma, mb, P);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}

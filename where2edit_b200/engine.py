@@ -16,6 +16,8 @@ Per resolution block (model.py:306-362):
     ToRGB     w2e_torgb_nhwc: 1x1 modulated conv + bias + polyphase skip upsample, fp32 NCHW
 Styles, demodulation coefficients and the tiny modulation linears stay fp32.
 """
+import os
+
 import torch
 
 from . import _native as N
@@ -50,6 +52,8 @@ class SynthesisEngine:
         self.gen = gen
         self._w = {}
         self._err = None
+        # W2E_TC_V1=1 selects the first-generation kernel (one tile per CTA, 9 shifted TMA loads)
+        self.v1 = os.environ.get("W2E_TC_V1", "0") == "1"
         if not N.load().w2e_modconv_tc_supported():
             raise RuntimeError("where2edit_b200: precision='bf16' needs an sm_100 (B200) device and a driver with "
                                "cuTensorMapEncodeTiled; there is no fallback -- use precision='fp32'")
@@ -91,6 +95,23 @@ class SynthesisEngine:
             N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, in_hw[0], in_hw[1],
             out_hw[0], out_hw[1], grid_hw[0], grid_hw[1], out_stride, py, px, N.host_ints(taps), ntaps, nslots, act,
             N.stream_ptr()), "modconv_tc")
+        return out, out_mod
+
+    def _conv2(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, transposed, act):
+        """Persistent v2 kernel: plain 3x3 (transposed=False) or the fused 4-class conv_transpose x2."""
+        b, h, w, _ = xs.shape
+        dev = xs.device
+        oh, ow = (2 * h + 1, 2 * w + 1) if transposed else (h, w)
+        out = torch.empty((b, oh, ow, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
+        out_mod = torch.empty((b, oh, ow, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
+        nb = 0 if noise is None else noise.shape[0]
+        gh, gw = (h, w)
+        N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * gh * gw,
+               tag=f"{'up ' if transposed else ''}{pw.cin}->{pw.cout}@{gh}x{gw}")
+        N.check(N.load().w2e_modconv_tc2(
+            N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
+            N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w, int(transposed), act,
+            N.stream_ptr()), "modconv_tc2")
         return out, out_mod
 
     def _blur(self, z, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod, out_hw):
@@ -222,15 +243,22 @@ class SynthesisEngine:
             need_out = next_is_rgb or want_features or blend_here
             need_mod = nxt is not None and not blend_here
             if kind == "conv":
-                act, xs_next = self._conv(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
-                                          _TAPS_PLAIN, hw, hw, hw, 1, 0, 0, N.ACT_LRELU)
+                if self.v1:
+                    act, xs_next = self._conv(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
+                                              _TAPS_PLAIN, hw, hw, hw, 1, 0, 0, N.ACT_LRELU)
+                else:
+                    act, xs_next = self._conv2(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
+                                               False, N.ACT_LRELU)
             else:
                 h, w = hw
-                zh, zw = 2 * h + 1, 2 * w + 1
-                z = torch.empty((batch, zh, zw, pw.cout), device=dev, dtype=torch.bfloat16)
-                for (py, px), taps in _TAPS_UP.items():
-                    self._conv(xs, pw, demods[idx], None, None, None, None, True, False, taps, (h, w), (zh, zw),
-                               (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
+                if self.v1:
+                    zh, zw = 2 * h + 1, 2 * w + 1
+                    z = torch.empty((batch, zh, zw, pw.cout), device=dev, dtype=torch.bfloat16)
+                    for (py, px), taps in _TAPS_UP.items():
+                        self._conv(xs, pw, demods[idx], None, None, None, None, True, False, taps, (h, w), (zh, zw),
+                                   (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
+                else:
+                    z, _ = self._conv2(xs, pw, demods[idx], None, None, None, None, True, False, True, N.ACT_NONE)
                 hw = (2 * h, 2 * w)
                 act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, need_out,
                                           need_mod, hw)
