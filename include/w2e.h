@@ -167,9 +167,8 @@ int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const
                     const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                     int in_w, int transposed, int act, void* stream);
-/* tuning/diagnostic knobs of w2e_modconv_tc2: pitch of the haloed tile in pixels (10..32), whether
- * the UMMA descriptors carry the base-offset field, and a cap on the number of CTAs (0 = none). */
-void w2e_modconv_tc2_knobs(int pitch, int base_offset_mode, int max_ctas);
+/* tuning knob of w2e_modconv_tc2: cap on the number of persistent CTAs (0 = one or two per SM). */
+void w2e_modconv_tc2_knobs(int max_ctas);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],

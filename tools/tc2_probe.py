@@ -44,7 +44,7 @@ for (b, cin, cout, h, tr) in SHAPES:
                                  0, 0, N.ACT_LRELU)
     eng.assert_ok()
     for pitch, boff in itertools.product((10, 16), (0, 1)):
-        lib.w2e_modconv_tc2_knobs(pitch, boff, 0)
+        lib.w2e_modconv_tc2_knobs(0)
         try:
             if tr:
                 got, _ = eng._conv2(xs, pw, d, None, None, None, None, True, False, True, N.ACT_NONE)
@@ -61,4 +61,4 @@ for (b, cin, cout, h, tr) in SHAPES:
                   f"(scale {scale:.3g}) nan {nan}", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"shape {(b, cin, cout, h, tr)} pitch {pitch} base_off {boff}: FAILED {e}", flush=True)
-lib.w2e_modconv_tc2_knobs(10, 0, 0)
+lib.w2e_modconv_tc2_knobs(0)

@@ -50,11 +50,8 @@ struct Tc2Params {
   int pitch, box_rows, a_stages, b_stages;
   int a_stage_bytes, a_box_bytes, b_block_bytes;
   int tmem_cols;
-  int use_base_offset;
   int act;
   int ntaps;
-  int tap_off[9], tap_slot[9], tap_acc[9];
-  int acc_py[4], acc_px[4];
 };
 
 struct Tc2Bars {
@@ -70,32 +67,62 @@ struct Tc2Bars {
   alignas(16) float ep_next[2][256];
 };
 
-// K-major swizzled operand descriptor with an explicit group stride (SBO) and optional base offset.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t row_bytes, uint32_t sbo_bytes, int base_off_mode) {
-  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
-  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;
-  if (base_off_mode) d |= (uint64_t)((addr >> 7) & 7u) << 49;
-  d |= layout << 61;
-  return d;
+constexpr int kPitch = 10;  // pixels per row of the haloed tile (8 + 2 halo columns)
+
+// Upper 32 bits of a K-major swizzled UMMA shared-memory descriptor: SBO (bytes >> 4) @32,
+// version 1 @46, layout @61 (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); the lower word is the start
+// address >> 4.  Hardware fact validated by tools/tc2_probe.py: the swizzle is an XOR on absolute
+// shared-memory address bits, so ANY 16-byte aligned start inside a TMA-written swizzled tile and
+// any SBO are legal, with the base-offset field left at 0.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t addr_bytes) {
+  return ((uint64_t)hi << 32) | (uint64_t)((addr_bytes & 0x3FFFFu) >> 4);
 }
 
+// tap t = ky*3+kx.  Plain 3x3: reads haloed pixel (y+ky, x+kx), one accumulator.  Transposed x2:
+// out[2j+py, 2i+px] += x[j-(ky==2), i-(kx==2)] * W[ky,kx] with class (py,px) = (ky&1, kx&1).
+template <bool TR>
+__device__ __forceinline__ constexpr int tap_rows(int t) {
+  const int ky = t / 3, kx = t % 3;
+  return TR ? ((ky == 2 ? 0 : 1) * kPitch + (kx == 2 ? 0 : 1)) : (ky * kPitch + kx);
+}
+template <bool TR>
+__device__ __forceinline__ constexpr int tap_group(int t) {
+  return TR ? ((t / 3) & 1) * 2 + ((t % 3) & 1) : 0;
+}
+template <bool TR>
+__device__ __forceinline__ constexpr bool tap_first(int t) {  // first tap (in issue order) of its accumulator
+  return TR ? (t == 0 || t == 1 || t == 3 || t == 4) : (t == 0);
+}
+
+struct Ring {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+};
+
+template <bool TR, int MT, int KSTEPS, bool WRES>
 __global__ void __launch_bounds__(kT2Threads, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ Tc2Params P) {
+  constexpr int NG = TR ? 4 : 1;
+  constexpr int kRowBytes = KSTEPS * 32;  // BK * 2 bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  constexpr int kBK = KSTEPS * 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;
   uint8_t* b_base = smem + (size_t)P.a_stages * P.a_stage_bytes;
-  const int n_bblocks = P.wres ? P.ntaps * (P.Cin / P.bk) : P.b_stages;
+  const int kchunks = P.Cin / kBK;
+  const int n_bblocks = WRES ? 9 * kchunks : P.b_stages;
   Tc2Bars* bars = reinterpret_cast<Tc2Bars*>(b_base + (size_t)n_bblocks * P.b_block_bytes);
   volatile int* abort_flag = &bars->abort_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = P.Cin / P.bk;
-  const int row_bytes = P.bk * 2;
-  const int tiles_per_n = P.tiles_x * P.tiles_y * P.B;
+  const int tiles_xy = P.tiles_x * P.tiles_y;
+  const int tiles_per_n = tiles_xy * P.B;
 
   if (threadIdx.x == 0) {
     bars->abort_flag = 0;
@@ -121,112 +148,121 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
-      if (P.wres) {
+      if (WRES) {
         mbar_arrive_expect_tx(&bars->w_full, (uint32_t)(n_bblocks * P.b_block_bytes));
         for (int kc = 0; kc < kchunks; ++kc)
-          for (int t = 0; t < P.ntaps; ++t)
-            tma_load_3d(b_base + (size_t)(kc * P.ntaps + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * P.bk, 0,
-                        P.tap_slot[t]);
+          for (int t = 0; t < 9; ++t)
+            tma_load_3d(b_base + (size_t)(kc * 9 + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * kBK, 0, t);
       }
-      uint32_t ai = 0, bi = 0;  // running stage counters
+      Ring ar, br;
       bool ok = true;
       for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
         const int tn = tile / tiles_per_n;
         int rem = tile - tn * tiles_per_n;
-        const int b = rem / (P.tiles_x * P.tiles_y);
-        rem -= b * (P.tiles_x * P.tiles_y);
+        const int b = rem / tiles_xy;
+        rem -= b * tiles_xy;
         const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-        const int j0 = ty * (kSubTileH * P.mt), i0 = tx * kTileW, co0 = tn * P.bn;
+        const int j0 = ty * (kSubTileH * MT), i0 = tx * kTileW, co0 = tn * P.bn;
         for (int kc = 0; kc < kchunks && ok; ++kc) {
-          const int as = ai % P.a_stages;
-          ok = mbar_wait(&bars->a_empty[as], ((ai / P.a_stages) & 1u) ^ 1u, abort_flag);
+          ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
           if (!ok) break;
-          mbar_arrive_expect_tx(&bars->a_full[as], (uint32_t)P.a_box_bytes);
-          tma_load_4d(a_base + (size_t)as * P.a_stage_bytes, &map_a, &bars->a_full[as], kc * P.bk, i0 - 1, j0 - 1, b);
-          ++ai;
-          if (!P.wres) {
-            for (int t = 0; t < P.ntaps; ++t) {
-              const int bs = bi % P.b_stages;
-              ok = mbar_wait(&bars->b_empty[bs], ((bi / P.b_stages) & 1u) ^ 1u, abort_flag);
+          mbar_arrive_expect_tx(&bars->a_full[ar.idx], (uint32_t)P.a_box_bytes);
+          tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
+                      j0 - 1, b);
+          ar.advance(P.a_stages);
+          if (!WRES) {
+            for (int t = 0; t < 9; ++t) {
+              ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
-              mbar_arrive_expect_tx(&bars->b_full[bs], (uint32_t)P.b_block_bytes);
-              tma_load_3d(b_base + (size_t)bs * P.b_block_bytes, &map_b, &bars->b_full[bs], kc * P.bk, co0,
-                          P.tap_slot[t]);
-              ++bi;
+              mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
+              tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
+              br.advance(P.b_stages);
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((128u >> 4) << 24);
-      const int ksteps = P.bk / 16;
-      const uint32_t a_sbo = (uint32_t)(P.pitch * row_bytes);
-      const uint32_t b_sbo = (uint32_t)(8 * row_bytes);
-      uint32_t ai = 0, bi = 0, acc_it = 0;
-      bool ok = true;
-      if (P.wres) {
-        ok = mbar_wait(&bars->w_full, 0, abort_flag);
-        tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, ++acc_it) {
-        const int buf = acc_it % P.nbuf;
-        ok = mbar_wait(&bars->acc_empty[buf], ((acc_it / P.nbuf) & 1u) ^ 1u, abort_flag);
+    // -------------------------------------------------------------------- MMA issuer
+    // The whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform
+    // registers); only tcgen05.mma / tcgen05.commit are issued, by one elected lane.
+    // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = desc_hi(kRowBytes, kPitch * kRowBytes);
+    const uint32_t b_hi = desc_hi(kRowBytes, 8 * kRowBytes);
+    const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
+    Ring ar, br, cr;
+    bool ok = true;
+    if (WRES) {
+      ok = mbar_wait_warp(&bars->w_full, 0, abort_flag);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
+      ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t acc_base = tmem_base + cr.idx * (uint32_t)(NG * MT) * (uint32_t)P.bn;
+      for (int kc = 0; kc < kchunks && ok; ++kc) {
+        ok = mbar_wait_warp(&bars->a_full[ar.idx], ar.phase, abort_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t acc_base = tmem_base + (uint32_t)(buf * P.ng * P.mt * P.bn);
-        uint32_t inited = 0;
-        for (int kc = 0; kc < kchunks && ok; ++kc) {
-          const int as = ai % P.a_stages;
-          ok = mbar_wait(&bars->a_full[as], (ai / P.a_stages) & 1u, abort_flag);
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + (size_t)as * P.a_stage_bytes);
-          for (int t = 0; t < P.ntaps; ++t) {
-            uint32_t b_addr;
-            int bs = 0;
-            if (P.wres) {
-              b_addr = smem_u32(b_base + (size_t)(kc * P.ntaps + t) * P.b_block_bytes);
-            } else {
-              bs = bi % P.b_stages;
-              ok = mbar_wait(&bars->b_full[bs], (bi / P.b_stages) & 1u, abort_flag);
-              if (!ok) break;
-              tc_fence_after();
-              b_addr = smem_u32(b_base + (size_t)bs * P.b_block_bytes);
-            }
-            const int g = P.tap_acc[t];
-            const bool fresh = !((inited >> g) & 1u);
-            inited |= 1u << g;
-            for (int m = 0; m < P.mt; ++m) {
-              const uint32_t a_tap = a_addr + (uint32_t)((P.tap_off[t] + m * kSubTileH * P.pitch) * row_bytes);
-              const uint32_t d_tmem = acc_base + (uint32_t)((g * P.mt + m) * P.bn);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adesc = make_desc(a_tap + k * 32, row_bytes, a_sbo, P.use_base_offset);
-                const uint64_t bdesc = make_desc(b_addr + k * 32, row_bytes, b_sbo, 0);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (fresh && k == 0) ? 0u : 1u);
+        const uint32_t a_addr = a_smem + ar.idx * (uint32_t)P.a_stage_bytes;
+        const uint32_t first = (kc == 0) ? 0u : 1u;  // 0 => the first MMA of an accumulator overwrites it
+        if (WRES) {
+          const uint32_t b_chunk = b_smem + (uint32_t)(kc * 9 * P.b_block_bytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t b_addr = b_chunk + (uint32_t)(t * P.b_block_bytes);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint32_t a_tap = a_addr + (uint32_t)((tap_rows<TR>(t) + m * kSubTileH * kPitch) * kRowBytes);
+                const uint32_t d_tmem = acc_base + (uint32_t)(tap_group<TR>(t) * MT + m) * (uint32_t)P.bn;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, desc64(a_hi, a_tap + k * 32), desc64(b_hi, b_addr + k * 32), idesc,
+                            (tap_first<TR>(t) && k == 0) ? first : 1u);
               }
             }
-            if (!P.wres) {
-              umma_commit(&bars->b_empty[bs]);
-              ++bi;
-            }
+            umma_commit(&bars->a_empty[ar.idx]);
           }
-          umma_commit(&bars->a_empty[as]);
-          ++ai;
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b_addr = b_smem + br.idx * (uint32_t)P.b_block_bytes;
+            if (elect_one()) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint32_t a_tap = a_addr + (uint32_t)((tap_rows<TR>(t) + m * kSubTileH * kPitch) * kRowBytes);
+                const uint32_t d_tmem = acc_base + (uint32_t)(tap_group<TR>(t) * MT + m) * (uint32_t)P.bn;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, desc64(a_hi, a_tap + k * 32), desc64(b_hi, b_addr + k * 32), idesc,
+                            (tap_first<TR>(t) && k == 0) ? first : 1u);
+              }
+              umma_commit(&bars->b_empty[br.idx]);
+              if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
+            }
+            __syncwarp();
+            br.advance(P.b_stages);
+          }
         }
-        umma_commit(&bars->acc_full[buf]);
+        ar.advance(P.a_stages);
       }
+      if (ok && elect_one()) umma_commit(&bars->acc_full[cr.idx]);
+      __syncwarp();
+      cr.advance(P.nbuf);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: warps 2..9
     // warp w reads TMEM lane quarter w%4 (hardware rule); warps 2..5 take the first half of the
     // tile's BN columns, warps 6..9 the second half.
-    const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0..255
     const int r = q * 32 + lane;      // accumulator row == pixel inside the sub-tile
     const int sy = r >> 3, sx = r & 7;
@@ -235,92 +271,105 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
     const int c_begin = (P.bn >= 32) ? half * (P.bn >> 1) : 0;
     const int c_end = (P.bn >= 32) ? c_begin + (P.bn >> 1) : (half == 0 ? P.bn : 0);
-    uint32_t acc_it = 0;
+    constexpr int out_stride = TR ? 2 : 1;
+    Ring cr;
+    uint32_t parity = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++acc_it) {
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const int tn = tile / tiles_per_n;
       int rem = tile - tn * tiles_per_n;
-      const int b = rem / (P.tiles_x * P.tiles_y);
-      rem -= b * (P.tiles_x * P.tiles_y);
+      const int b = rem / tiles_xy;
+      rem -= b * tiles_xy;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-      const int j0 = ty * (kSubTileH * P.mt), i0 = tx * kTileW, co0 = tn * P.bn;
-      const int buf = acc_it % P.nbuf;
+      const int j0 = ty * (kSubTileH * MT), i0 = tx * kTileW, co0 = tn * P.bn;
       // stage this tile's per-channel constants (one named barrier per tile; see Tc2Bars)
-      const int cb = acc_it & 1;
+      const int cb = parity;
+      parity ^= 1u;
       for (int c = et; c < P.bn; c += kT2EpiThreads) {
         const int64_t bc = (int64_t)b * P.Cout + co0 + c;
         bars->ep_scale[cb][c] = (P.out_scale ? __ldg(P.out_scale + bc) : 1.f) * gain;
         bars->ep_shift[cb][c] = (P.bias ? __ldg(P.bias + co0 + c) : 0.f) * gain;
         bars->ep_next[cb][c] = P.next_scale ? __ldg(P.next_scale + bc) : 0.f;
       }
+      // output coordinates and noise of this thread's NG*MT pixels, fetched before the accumulator wait
+      int64_t pix[NG * MT];
+      float nz[NG * MT];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int j = j0 + m * kSubTileH + sy, i = i0 + sx;
+          const int oy = j * out_stride + (TR ? (g >> 1) : 0), ox = i * out_stride + (TR ? (g & 1) : 0);
+          const bool valid = j < P.grid_h && i < P.grid_w && oy < P.OH && ox < P.OW;
+          pix[g * MT + m] = valid ? ((int64_t)b * P.OH + oy) * P.OW + ox : -1;
+          nz[g * MT + m] = (valid && P.noise)
+              ? nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox)
+              : 0.f;
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kT2EpiThreads) : "memory");
-      if (ok) ok = mbar_wait(&bars->acc_full[buf], (acc_it / P.nbuf) & 1u, abort_flag);
+      if (ok) ok = mbar_wait(&bars->acc_full[cr.idx], cr.phase, abort_flag);
       tc_fence_after();
       const float* sc = bars->ep_scale[cb];
       const float* sh = bars->ep_shift[cb];
       const float* nx = bars->ep_next[cb];
-      for (int g = 0; g < P.ng; ++g) {
-        for (int m = 0; m < P.mt; ++m) {
-          const int j = j0 + m * kSubTileH + sy, i = i0 + sx;
-          const int oy = j * P.out_stride + P.acc_py[g], ox = i * P.out_stride + P.acc_px[g];
-          const bool valid = ok && j < P.grid_h && i < P.grid_w && oy < P.OH && ox < P.OW;
-          const int64_t pix = valid ? ((int64_t)b * P.OH + oy) * P.OW + ox : 0;
-          float nz = 0.f;
-          if (valid && P.noise)
-            nz = nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox);
-          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                  (uint32_t)(buf * P.ng * P.mt * P.bn + (g * P.mt + m) * P.bn);
-          __nv_bfloat16* o_row = P.out ? P.out + pix * P.Cout + co0 : nullptr;
-          __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix * P.Cout + co0 : nullptr;
+      const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + cr.idx * (uint32_t)(NG * MT) * (uint32_t)P.bn;
+#pragma unroll
+      for (int gm = 0; gm < NG * MT; ++gm) {
+        const bool valid = ok && pix[gm] >= 0;
+        const float nzv = nz[gm];
+        const uint32_t t_addr = t_tile + (uint32_t)gm * (uint32_t)P.bn;
+        __nv_bfloat16* o_row = P.out ? P.out + pix[gm] * P.Cout + co0 : nullptr;
+        __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix[gm] * P.Cout + co0 : nullptr;
 #pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_addr + (uint32_t)c, v);
-            tmem_ld_wait();
-            if (valid) {
-              float f[16];
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(sc + c + 4 * e4);
+              const float4 b4 = *reinterpret_cast<const float4*>(sh + c + 4 * e4);
+              f[4 * e4 + 0] = fmaf(__uint_as_float(v[4 * e4 + 0]), a4.x, b4.x + nzv);
+              f[4 * e4 + 1] = fmaf(__uint_as_float(v[4 * e4 + 1]), a4.y, b4.y + nzv);
+              f[4 * e4 + 2] = fmaf(__uint_as_float(v[4 * e4 + 2]), a4.z, b4.z + nzv);
+              f[4 * e4 + 3] = fmaf(__uint_as_float(v[4 * e4 + 3]), a4.w, b4.w + nzv);
+            }
+            if (lrelu) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.2f * f[e]);
+            }
+            if (o_row) {
+              uint4 pk[2];
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              uint4* dst = reinterpret_cast<uint4*>(o_row + c);
+              dst[0] = pk[0];
+              dst[1] = pk[1];
+            }
+            if (m_row) {
+              uint4 pk[2];
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 a4 = *reinterpret_cast<const float4*>(sc + c + 4 * e4);
-                const float4 b4 = *reinterpret_cast<const float4*>(sh + c + 4 * e4);
-                f[4 * e4 + 0] = fmaf(__uint_as_float(v[4 * e4 + 0]), a4.x, b4.x + nz);
-                f[4 * e4 + 1] = fmaf(__uint_as_float(v[4 * e4 + 1]), a4.y, b4.y + nz);
-                f[4 * e4 + 2] = fmaf(__uint_as_float(v[4 * e4 + 2]), a4.z, b4.z + nz);
-                f[4 * e4 + 3] = fmaf(__uint_as_float(v[4 * e4 + 3]), a4.w, b4.w + nz);
+                const float4 n4 = *reinterpret_cast<const float4*>(nx + c + 4 * e4);
+                h[2 * e4] = __floats2bfloat162_rn(f[4 * e4] * n4.x, f[4 * e4 + 1] * n4.y);
+                h[2 * e4 + 1] = __floats2bfloat162_rn(f[4 * e4 + 2] * n4.z, f[4 * e4 + 3] * n4.w);
               }
-              if (lrelu) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.2f * f[e]);
-              }
-              if (o_row) {
-                uint4 pk[2];
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(o_row + c);
-                dst[0] = pk[0];
-                dst[1] = pk[1];
-              }
-              if (m_row) {
-                uint4 pk[2];
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                  const float4 n4 = *reinterpret_cast<const float4*>(nx + c + 4 * e4);
-                  h[2 * e4] = __floats2bfloat162_rn(f[4 * e4] * n4.x, f[4 * e4 + 1] * n4.y);
-                  h[2 * e4 + 1] = __floats2bfloat162_rn(f[4 * e4 + 2] * n4.z, f[4 * e4 + 3] * n4.w);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(m_row + c);
-                dst[0] = pk[0];
-                dst[1] = pk[1];
-              }
+              uint4* dst = reinterpret_cast<uint4*>(m_row + c);
+              dst[0] = pk[0];
+              dst[1] = pk[1];
             }
           }
         }
       }
       // accumulator buffer drained: hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&bars->acc_empty[buf]);
+      mbar_arrive(&bars->acc_empty[cr.idx]);
+      cr.advance(P.nbuf);
     }
   }
 
@@ -333,20 +382,36 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+template <bool TR, int MT, int KSTEPS, bool WRES>
+static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, int smem_bytes, int max_ctas,
+                      cudaStream_t s) {
+  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES>;
+  static bool configured = false;
+  if (!configured) {
+    W2E_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int per_sm = 1;
+  W2E_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT2Threads, smem_bytes));
+  if (per_sm * P.tmem_cols > 512) per_sm = 512 / P.tmem_cols;
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int ctas = sm_count() * per_sm;
+  if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  if (ctas > P.ntiles) ctas = P.ntiles;
+  kern<<<ctas, kT2Threads, smem_bytes, s>>>(ma, mb, P);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
 // debug / tuning knobs (tests flip them to validate the shifted-descriptor scheme on hardware)
-static int g_pitch = 10;
-static int g_base_offset = 0;
 static int g_max_ctas = 0;
 
 }  // namespace w2e
 
 using namespace w2e;
 
-extern "C" void w2e_modconv_tc2_knobs(int pitch, int base_offset_mode, int max_ctas) {
-  if (pitch >= 10 && pitch <= 32) g_pitch = pitch;
-  g_base_offset = base_offset_mode ? 1 : 0;
-  g_max_ctas = max_ctas;
-}
+extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 
 extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
                                const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
@@ -366,26 +431,12 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
   P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod; P.error_flag = error_flag;
   P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
   P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
-  P.use_base_offset = g_base_offset;
-  P.pitch = g_pitch;
+  P.pitch = kPitch;
   P.ntaps = 9;
   if (!transposed) {
     P.OH = in_h; P.OW = in_w; P.grid_h = in_h; P.grid_w = in_w; P.out_stride = 1; P.ng = 1;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        const int t = ky * 3 + kx;
-        P.tap_off[t] = ky * P.pitch + kx; P.tap_slot[t] = t; P.tap_acc[t] = 0;
-      }
   } else {
-    // conv_transpose2d(stride 2, k 3): out[2j+py, 2i+px] gets x[j - (ky==2), i - (kx==2)] * W[ky,kx], py = ky&1
     P.OH = 2 * in_h + 1; P.OW = 2 * in_w + 1; P.grid_h = in_h + 1; P.grid_w = in_w + 1; P.out_stride = 2; P.ng = 4;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        const int t = ky * 3 + kx;
-        P.tap_off[t] = (ky == 2 ? 0 : 1) * P.pitch + (kx == 2 ? 0 : 1);
-        P.tap_slot[t] = t; P.tap_acc[t] = (ky & 1) * 2 + (kx & 1);
-      }
-    for (int g = 0; g < 4; ++g) { P.acc_py[g] = g >> 1; P.acc_px[g] = g & 1; }
   }
   P.bk = (Cin % 64 == 0) ? 64 : 32;
   const int row_bytes = P.bk * 2;
@@ -445,19 +496,17 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
     int rc = make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    W2E_CUDA_OK(cudaFuncSetAttribute(modconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured_smem = 227 * 1024;
-  }
-  int per_sm = (227 * 1024) / smem_bytes;
-  if (per_sm * P.tmem_cols > 512) per_sm = 512 / P.tmem_cols;
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  int ctas = sm_count() * per_sm;
-  if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
-  if (ctas > P.ntiles) ctas = P.ntiles;
-  modconv_tc2_kernel<<<ctas, kT2Threads, smem_bytes, (cudaStream_t)stream>>>(ma, mb, P);
-  W2E_LAUNCH_OK();
-  return W2E_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ks = P.bk / 16;
+#define W2E_TC2_CASE(TR_, MT_, KS_, WR_) \
+  if ((transposed != 0) == TR_ && P.mt == MT_ && ks == KS_ && (P.wres != 0) == WR_) \
+    return launch_tc2<TR_, MT_, KS_, WR_>(ma, mb, P, smem_bytes, g_max_ctas, st);
+  W2E_TC2_CASE(false, 1, 4, false) W2E_TC2_CASE(false, 2, 4, false) W2E_TC2_CASE(false, 1, 2, false)
+  W2E_TC2_CASE(false, 2, 2, false) W2E_TC2_CASE(false, 1, 4, true) W2E_TC2_CASE(false, 2, 4, true)
+  W2E_TC2_CASE(false, 1, 2, true) W2E_TC2_CASE(false, 2, 2, true)
+  W2E_TC2_CASE(true, 1, 4, false) W2E_TC2_CASE(true, 2, 4, false) W2E_TC2_CASE(true, 1, 2, false)
+  W2E_TC2_CASE(true, 2, 2, false) W2E_TC2_CASE(true, 1, 4, true) W2E_TC2_CASE(true, 2, 4, true)
+  W2E_TC2_CASE(true, 1, 2, true) W2E_TC2_CASE(true, 2, 2, true)
+#undef W2E_TC2_CASE
+  return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2: no kernel variant");
 }
