@@ -19,6 +19,17 @@ struct __align__(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+// 128-bit global accesses (a struct copy of four bfloat162 compiles to four 32-bit loads)
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  bf16x8 r;
+  *reinterpret_cast<uint4*>(&r) = u;
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -88,9 +99,13 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
 }
 
 // ------------------------------------------------------------------------------ blur + noise + bias + act
-// One thread = 8 channels of one output column, walking down ROWS output rows with a sliding
-// window of horizontally filtered rows in registers.
+// One thread = 8 channels of kBlurPx adjacent output columns, walking down kBlurRows output rows.
+// Per input row it loads kBlurPx+3 pixels (128-bit each), filters them horizontally in registers
+// and keeps the last four filtered rows in a register ring (compile-time slots, no moves); each
+// new row completes one output row.  HBM sees every input element once (the 3-row / 3-column halo
+// re-reads hit L1/L2).
 constexpr int kBlurRows = 16;
+constexpr int kBlurPx = 2;
 
 struct BlurParams {
   const __nv_bfloat16* z;   // [B, IH, IW, C]
@@ -106,86 +121,90 @@ struct BlurParams {
   float fv[4], fh[4];       // flipped 1-D taps (vertical, horizontal)
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 blur_act_nhwc_kernel(const __grid_constant__ BlurParams P) {
   const int cg = P.C >> 3;  // channel groups of 8
+  const int xblocks = (P.W + kBlurPx - 1) / kBlurPx;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per_strip = (int64_t)P.W * cg;
+  const int64_t per_strip = (int64_t)xblocks * cg;
   const int strips = (P.H + kBlurRows - 1) / kBlurRows;
   if (idx >= (int64_t)P.B * strips * per_strip) return;
   const int g = (int)(idx % cg);
-  const int ox = (int)((idx / cg) % P.W);
+  const int ox0 = (int)((idx / cg) % xblocks) * kBlurPx;
   const int strip = (int)((idx / per_strip) % strips);
   const int b = (int)(idx / (per_strip * strips));
   const int oy0 = strip * kBlurRows;
   const int rows = min(kBlurRows, P.H - oy0);
   const int c0 = g * 8;
+  const bool lrelu = P.act == W2E_ACT_LRELU;
+  const float gain = lrelu ? 1.41421356237309515f : 1.f;
 
   float bias[8], nsc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    bias[e] = P.bias ? __ldg(P.bias + c0 + e) : 0.f;
+    bias[e] = (P.bias ? __ldg(P.bias + c0 + e) : 0.f) * gain;
     nsc[e] = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + e) : 1.f;
   }
-  const float nw = P.noise ? __ldg(P.noise_w) : 0.f;
+  const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
   const float* noise = P.noise ? P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0) : nullptr;
   const __nv_bfloat16* zb = P.z + (int64_t)b * P.IH * P.IW * P.C + c0;
+  const float fv0 = P.fv[0] * gain, fv1 = P.fv[1] * gain, fv2 = P.fv[2] * gain, fv3 = P.fv[3] * gain;
+  const float fh0 = P.fh[0], fh1 = P.fh[1], fh2 = P.fh[2], fh3 = P.fh[3];
 
-  float win[4][8];  // horizontally filtered input rows iy0-? .. (ring)
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) win[r][e] = 0.f;
-
-  // output row oy needs input rows oy - py0 + {0..3}; walk input rows iy = oy0 - py0 .. oy0 - py0 + rows + 2
+  float win[4][kBlurPx][8];
+  // output row oy needs input rows oy - py0 + {0..3}: walk input rows t = 0 .. rows + 2
   const int iy_first = oy0 - P.py0;
-  for (int t = 0; t < rows + 3; ++t) {
-    const int iy = iy_first + t;
-    float h[8];
+  const int ix_first = ox0 - P.px0;
+  for (int t0 = 0; t0 < rows + 3; t0 += 4) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = 0.f;
-    if (iy >= 0 && iy < P.IH) {
-      const __nv_bfloat16* zr = zb + (int64_t)iy * P.IW * P.C;
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t < rows + 3) {
+        const int iy = iy_first + t;
+        float f[kBlurPx + 3][8];
+        const bool row_ok = iy >= 0 && iy < P.IH;
+        const __nv_bfloat16* zr = zb + (int64_t)iy * P.IW * P.C;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ix = ox - P.px0 + k;
-        if (ix >= 0 && ix < P.IW) {
-          const bf16x8 v = *reinterpret_cast<const bf16x8*>(zr + (int64_t)ix * P.C);
-          float f[8];
-          unpack8(v, f);
+        for (int k = 0; k < kBlurPx + 3; ++k) {
+          const int ix = ix_first + k;
+          if (row_ok && ix >= 0 && ix < P.IW) {
+            unpack8(ld8(zr + (int64_t)ix * P.C), f[k]);
+          } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = fmaf(P.fh[k], f[e], h[e]);
+            for (int e = 0; e < 8; ++e) f[k][e] = 0.f;
+          }
         }
-      }
-    }
-    // shift the window (fully unrolled register moves) and append
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      win[0][e] = win[1][e];
-      win[1][e] = win[2][e];
-      win[2][e] = win[3][e];
-      win[3][e] = h[e];
-    }
-    if (t >= 3) {
-      const int oy = oy0 + t - 3;
-      float v[8];
-      const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+        for (int px = 0; px < kBlurPx; ++px)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float a = P.fv[0] * win[0][e];
-        a = fmaf(P.fv[1], win[1][e], a);
-        a = fmaf(P.fv[2], win[2][e], a);
-        a = fmaf(P.fv[3], win[3][e], a);
-        if (P.act == W2E_ACT_LRELU) a = lrelu_gain(a + nz + bias[e], 0.2f, 1.41421356237309515f);
-        else a += bias[e];
-        v[e] = a;
-      }
-      const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
-      if (P.out) *reinterpret_cast<bf16x8*>(P.out + o) = pack8(v);
-      if (P.out_mod) {
+          for (int e = 0; e < 8; ++e)
+            win[u][px][e] = fmaf(fh3, f[px + 3][e], fmaf(fh2, f[px + 2][e], fmaf(fh1, f[px + 1][e], fh0 * f[px][e])));
+        if (t >= 3) {
+          const int oy = oy0 + t - 3;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
-        *reinterpret_cast<bf16x8*>(P.out_mod + o) = pack8(v);
+          for (int px = 0; px < kBlurPx; ++px) {
+            const int ox = ox0 + px;
+            if (ox < P.W) {
+              const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                // rows t-3 .. t live in slots (u+1)&3, (u+2)&3, (u+3)&3, u
+                float a = fmaf(fv3, win[u][px][e],
+                               fmaf(fv2, win[(u + 3) & 3][px][e],
+                                    fmaf(fv1, win[(u + 2) & 3][px][e], fmaf(fv0, win[(u + 1) & 3][px][e], bias[e] + nz))));
+                v[e] = lrelu ? fmaxf(a, 0.2f * a) : a;
+              }
+              const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
+              if (P.out) st8(P.out + o, pack8(v));
+              if (P.out_mod) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
+                st8(P.out_mod + o, pack8(v));
+              }
+            }
+          }
+        }
       }
     }
   }
@@ -211,52 +230,77 @@ torgb_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   const int64_t p_end = min(HW, p_begin + pix_per_block);
   const __nv_bfloat16* xb = x + (int64_t)b * HW * C;
   const float kfa[4] = {kf.x, kf.y, kf.z, kf.w};
-  for (int64_t p0 = p_begin + (int64_t)warp * PPW; p0 < p_end; p0 += (int64_t)nwarps * PPW) {
-    const int64_t p = p0 + grp;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (p < p_end) {
-      for (int c = sub * 8; c < C; c += LP * 8) {
-        const bf16x8 v = *reinterpret_cast<const bf16x8*>(xb + p * C + c);
-        float f[8];
-        unpack8(v, f);
+  constexpr int U = 4;  // independent pixels in flight per lane group
+  for (int64_t p0 = p_begin + (int64_t)warp * PPW * U; p0 < p_end; p0 += (int64_t)nwarps * PPW * U) {
+    float a0[U], a1[U], a2[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          a0 = fmaf(f[e], wm[c + e], a0);
-          a1 = fmaf(f[e], wm[C + c + e], a1);
-          a2 = fmaf(f[e], wm[2 * C + c + e], a2);
+    for (int u = 0; u < U; ++u) a0[u] = a1[u] = a2[u] = 0.f;
+    for (int c = sub * 8; c < C; c += LP * 8) {
+      bf16x8 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = p0 + u * PPW + grp;
+        if (p < p_end) v[u] = ld8(xb + p * C + c);
+      }
+      float w0[8], w1[8], w2[8];
+#pragma unroll
+      for (int e4 = 0; e4 < 2; ++e4) {
+        const float4 t0 = *reinterpret_cast<const float4*>(wm + c + 4 * e4);
+        const float4 t1 = *reinterpret_cast<const float4*>(wm + C + c + 4 * e4);
+        const float4 t2 = *reinterpret_cast<const float4*>(wm + 2 * C + c + 4 * e4);
+        w0[4 * e4] = t0.x; w0[4 * e4 + 1] = t0.y; w0[4 * e4 + 2] = t0.z; w0[4 * e4 + 3] = t0.w;
+        w1[4 * e4] = t1.x; w1[4 * e4 + 1] = t1.y; w1[4 * e4 + 2] = t1.z; w1[4 * e4 + 3] = t1.w;
+        w2[4 * e4] = t2.x; w2[4 * e4 + 1] = t2.y; w2[4 * e4 + 2] = t2.z; w2[4 * e4 + 3] = t2.w;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = p0 + u * PPW + grp;
+        if (p < p_end) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a0[u] = fmaf(f[e], w0[e], a0[u]);
+            a1[u] = fmaf(f[e], w1[e], a1[u]);
+            a2[u] = fmaf(f[e], w2[e], a2[u]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = LP >> 1; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (p < p_end && sub < 3) {
-      float v = sub == 0 ? a0 : (sub == 1 ? a1 : a2);
-      if (bias) v += __ldg(bias + sub);
-      if (skip) {
-        // upfirdn2d(skip, k, up=2, pad=(2,1)) as a polyphase filter: 2 taps per axis
-        const int oy = (int)(p / W), ox = (int)(p % W);
-        const int h = H / 2, wd = W / 2;
-        const int ya = (oy & 1) ? (oy - 1) / 2 : oy / 2 - 1, xa = (ox & 1) ? (ox - 1) / 2 : ox / 2 - 1;
-        const float cy0 = kfa[(oy & 1)], cy1 = kfa[(oy & 1) + 2];
-        const float cx0 = kfa[(ox & 1)], cx1 = kfa[(ox & 1) + 2];
-        const float* sp = skip + ((int64_t)b * 3 + sub) * h * wd;
-        float acc = 0.f;
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-          const int iy = ya + dy;
-          if (iy < 0 || iy >= h) continue;
-          float row = 0.f;
-          if (xa >= 0) row = cx0 * __ldg(sp + (int64_t)iy * wd + xa);
-          if (xa + 1 < wd) row = fmaf(cx1, __ldg(sp + (int64_t)iy * wd + xa + 1), row);
-          acc = fmaf(dy ? cy1 : cy0, row, acc);
-        }
-        v += acc;
+      for (int o = LP >> 1; o > 0; o >>= 1) {
+        a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
+        a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
+        a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
       }
-      rgb[((int64_t)b * 3 + sub) * HW + p] = v;
+      const int64_t p = p0 + u * PPW + grp;
+      if (p < p_end && sub < 3) {
+        float v = sub == 0 ? a0[u] : (sub == 1 ? a1[u] : a2[u]);
+        if (bias) v += __ldg(bias + sub);
+        if (skip) {
+          // upfirdn2d(skip, k, up=2, pad=(2,1)) as a polyphase filter: 2 taps per axis
+          const int oy = (int)(p / W), ox = (int)(p % W);
+          const int h = H / 2, wd = W / 2;
+          const int ya = (oy & 1) ? (oy - 1) / 2 : oy / 2 - 1, xa = (ox & 1) ? (ox - 1) / 2 : ox / 2 - 1;
+          const float cy0 = kfa[(oy & 1)], cy1 = kfa[(oy & 1) + 2];
+          const float cx0 = kfa[(ox & 1)], cx1 = kfa[(ox & 1) + 2];
+          const float* sp = skip + ((int64_t)b * 3 + sub) * h * wd;
+          float acc = 0.f;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const int iy = ya + dy;
+            if (iy < 0 || iy >= h) continue;
+            float row = 0.f;
+            if (xa >= 0) row = cx0 * __ldg(sp + (int64_t)iy * wd + xa);
+            if (xa + 1 < wd) row = fmaf(cx1, __ldg(sp + (int64_t)iy * wd + xa + 1), row);
+            acc = fmaf(dy ? cy1 : cy0, row, acc);
+          }
+          v += acc;
+        }
+        rgb[((int64_t)b * 3 + sub) * HW + p] = v;
+      }
     }
   }
 }
@@ -277,15 +321,15 @@ blend_nhwc_kernel(const __nv_bfloat16* __restrict__ edited, const __nv_bfloat16*
     const int my = (int)(((int64_t)yy * mh) / H), mx = (int)(((int64_t)xx * mw) / W);
     const float m = __ldg(mask + (b * mh + my) * mw + mx);
     float e[8], o[8], v[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(edited + i * 8), e);
-    unpack8(*reinterpret_cast<const bf16x8*>(orig + i * 8), o);
+    unpack8(ld8(edited + i * 8), e);
+    unpack8(ld8(orig + i * 8), o);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = __fadd_rn(__fmul_rn(m, e[k]), __fmul_rn(__fsub_rn(1.f, m), o[k]));
-    if (out) *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(v);
+    if (out) st8(out + i * 8, pack8(v));
     if (out_mod) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] *= __ldg(next_scale + b * C + g * 8 + k);
-      *reinterpret_cast<bf16x8*>(out_mod + i * 8) = pack8(v);
+      st8(out_mod + i * 8, pack8(v));
     }
   }
 }
@@ -348,8 +392,8 @@ extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const fl
   P.B = B; P.C = C; P.IH = in_h; P.IW = in_w; P.H = out_h; P.W = out_w; P.py0 = py0; P.px0 = px0; P.act = act;
   for (int i = 0; i < 4; ++i) { P.fv[i] = kv[3 - i]; P.fh[i] = kh[3 - i]; }
   const int strips = ceil_div(out_h, kBlurRows);
-  const int64_t threads = (int64_t)B * strips * out_w * (C / 8);
-  blur_act_nhwc_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(P);
+  const int64_t threads = (int64_t)B * strips * ceil_div(out_w, kBlurPx) * (C / 8);
+  blur_act_nhwc_kernel<<<(unsigned)ceil_div64(threads, 128), 128, 0, (cudaStream_t)stream>>>(P);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
