@@ -230,7 +230,8 @@ int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return set_error(W2E_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                   reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

@@ -11,7 +11,7 @@
 //  * torgb_nhwc         ToRGB (model.py:353-362): 1x1 modulated conv to 3 channels + bias +
 //                       polyphase x2 skip upsample + add, reading bf16 NHWC, writing fp32 NCHW.
 //  * blend_nhwc         region-mask blend (attention_model.py:548-549) on bf16 NHWC.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace w2e {
 
@@ -104,9 +104,6 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
 // and keeps the last four filtered rows in a register ring (compile-time slots, no moves); each
 // new row completes one output row.  HBM sees every input element once (the 3-row / 3-column halo
 // re-reads hit L1/L2).
-constexpr int kBlurRows = 16;
-constexpr int kBlurPx = 2;
-
 struct BlurParams {
   const __nv_bfloat16* z;   // [B, IH, IW, C]
   const float* bias;        // [C] or null
@@ -121,24 +118,51 @@ struct BlurParams {
   float fv[4], fh[4];       // flipped 1-D taps (vertical, horizontal)
 };
 
+// Tile = kBlurTY rows x TX columns x CT channels of the output, TX = 1024 / CT (CT = min(C, 128)):
+// 128 threads = 2 row groups x (TX/2 column pairs) x (CT/8 channel groups).  The haloed input tile
+// (kBlurTY+3) x (TX+3) x CT arrives in shared memory through ONE TMA box per CTA; out-of-image
+// coordinates are zero-filled by the TMA unit, which is exactly upfirdn2d's padding
+// (op/upfirdn2d.py:32-34), so the compute loop has no boundary logic.  Several CTAs per SM overlap
+// one CTA's load with another's arithmetic.
+constexpr int kBlurTY = 16;
+constexpr int kBlurRG = 2;                    // row groups per tile
+constexpr int kBlurRows = kBlurTY / kBlurRG;  // output rows walked by one thread
+constexpr int kBlurPx = 2;
+
+struct BlurTile {
+  int ct, tx, tiles_x, tiles_y, tiles_c;
+};
+
 __global__ void __launch_bounds__(128)
-blur_act_nhwc_kernel(const __grid_constant__ BlurParams P) {
-  const int cg = P.C >> 3;  // channel groups of 8
-  const int xblocks = (P.W + kBlurPx - 1) / kBlurPx;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per_strip = (int64_t)xblocks * cg;
-  const int strips = (P.H + kBlurRows - 1) / kBlurRows;
-  if (idx >= (int64_t)P.B * strips * per_strip) return;
-  const int g = (int)(idx % cg);
-  const int ox0 = (int)((idx / cg) % xblocks) * kBlurPx;
-  const int strip = (int)((idx / per_strip) % strips);
-  const int b = (int)(idx / (per_strip * strips));
-  const int oy0 = strip * kBlurRows;
-  const int rows = min(kBlurRows, P.H - oy0);
-  const int c0 = g * 8;
+blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ BlurParams P,
+                     const __grid_constant__ BlurTile T) {
+  extern __shared__ uint8_t blur_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(blur_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  int tile = blockIdx.x;
+  const int tcx = tile % T.tiles_c; tile /= T.tiles_c;
+  const int tx_i = tile % T.tiles_x; tile /= T.tiles_x;
+  const int ty_i = tile % T.tiles_y;
+  const int b = tile / T.tiles_y;
+  const int ox_t = tx_i * T.tx, oy_t = ty_i * kBlurTY, c_t = tcx * T.ct;
+  const int sw = T.tx + 3;                 // smem tile width in pixels
+  const int pix_bytes = T.ct * 2;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&bar, (uint32_t)((kBlurTY + 3) * sw * pix_bytes));
+    tma_load_4d(smem, &map_z, &bar, c_t, ox_t - P.px0, oy_t - P.py0, b);
+  }
+  const int cg = T.ct >> 3;
+  const int g = tid % cg;
+  const int xb = (tid / cg) % (T.tx / kBlurPx);
+  const int rg = tid / (cg * (T.tx / kBlurPx));
+  const int c0 = c_t + g * 8;
+  const int ox0 = ox_t + xb * kBlurPx;
+  const int oy0 = oy_t + rg * kBlurRows;
   const bool lrelu = P.act == W2E_ACT_LRELU;
   const float gain = lrelu ? 1.41421356237309515f : 1.f;
-
   float bias[8], nsc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -147,61 +171,57 @@ blur_act_nhwc_kernel(const __grid_constant__ BlurParams P) {
   }
   const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
   const float* noise = P.noise ? P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0) : nullptr;
-  const __nv_bfloat16* zb = P.z + (int64_t)b * P.IH * P.IW * P.C + c0;
   const float fv0 = P.fv[0] * gain, fv1 = P.fv[1] * gain, fv2 = P.fv[2] * gain, fv3 = P.fv[3] * gain;
   const float fh0 = P.fh[0], fh1 = P.fh[1], fh2 = P.fh[2], fh3 = P.fh[3];
+  __syncthreads();  // barrier initialised
+  {
+    uint32_t spin = 0;
+    while (!mbar_try_wait(&bar, 0))
+      if (++spin > (1u << 26)) __trap();  // a lost TMA completion becomes a launch failure, not a hang
+  }
+  const uint8_t* col = smem + ((size_t)(rg * kBlurRows) * sw + xb * kBlurPx) * pix_bytes + g * 16;
 
   float win[4][kBlurPx][8];
-  // output row oy needs input rows oy - py0 + {0..3}: walk input rows t = 0 .. rows + 2
-  const int iy_first = oy0 - P.py0;
-  const int ix_first = ox0 - P.px0;
-  for (int t0 = 0; t0 < rows + 3; t0 += 4) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + u;
-      if (t < rows + 3) {
-        const int iy = iy_first + t;
-        float f[kBlurPx + 3][8];
-        const bool row_ok = iy >= 0 && iy < P.IH;
-        const __nv_bfloat16* zr = zb + (int64_t)iy * P.IW * P.C;
+  for (int t = 0; t < kBlurRows + 3; ++t) {
+    const int u = t & 3;
+    float f[kBlurPx + 3][8];
+    const uint8_t* row = col + (size_t)t * sw * pix_bytes;
 #pragma unroll
-        for (int k = 0; k < kBlurPx + 3; ++k) {
-          const int ix = ix_first + k;
-          if (row_ok && ix >= 0 && ix < P.IW) {
-            unpack8(ld8(zr + (int64_t)ix * P.C), f[k]);
-          } else {
+    for (int k = 0; k < kBlurPx + 3; ++k) {
+      bf16x8 v;
+      *reinterpret_cast<uint4*>(&v) = *reinterpret_cast<const uint4*>(row + k * pix_bytes);
+      unpack8(v, f[k]);
+    }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[k][e] = 0.f;
-          }
-        }
+    for (int px = 0; px < kBlurPx; ++px)
 #pragma unroll
-        for (int px = 0; px < kBlurPx; ++px)
+      for (int e = 0; e < 8; ++e)
+        win[u][px][e] = fmaf(fh3, f[px + 3][e], fmaf(fh2, f[px + 2][e], fmaf(fh1, f[px + 1][e], fh0 * f[px][e])));
+    if (t >= 3) {
+      const int oy = oy0 + t - 3;
+      if (oy < P.H) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            win[u][px][e] = fmaf(fh3, f[px + 3][e], fmaf(fh2, f[px + 2][e], fmaf(fh1, f[px + 1][e], fh0 * f[px][e])));
-        if (t >= 3) {
-          const int oy = oy0 + t - 3;
+        for (int px = 0; px < kBlurPx; ++px) {
+          const int ox = ox0 + px;
+          if (ox < P.W) {
+            const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+            float v[8];
 #pragma unroll
-          for (int px = 0; px < kBlurPx; ++px) {
-            const int ox = ox0 + px;
-            if (ox < P.W) {
-              const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
-              float v[8];
+            for (int e = 0; e < 8; ++e) {
+              // rows t-3 .. t live in slots (u+1)&3, (u+2)&3, (u+3)&3, u
+              const float a = fmaf(fv3, win[u][px][e],
+                                   fmaf(fv2, win[(u + 3) & 3][px][e],
+                                        fmaf(fv1, win[(u + 2) & 3][px][e],
+                                             fmaf(fv0, win[(u + 1) & 3][px][e], bias[e] + nz))));
+              v[e] = lrelu ? fmaxf(a, 0.2f * a) : a;
+            }
+            const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
+            if (P.out) st8(P.out + o, pack8(v));
+            if (P.out_mod) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                // rows t-3 .. t live in slots (u+1)&3, (u+2)&3, (u+3)&3, u
-                float a = fmaf(fv3, win[u][px][e],
-                               fmaf(fv2, win[(u + 3) & 3][px][e],
-                                    fmaf(fv1, win[(u + 2) & 3][px][e], fmaf(fv0, win[(u + 1) & 3][px][e], bias[e] + nz))));
-                v[e] = lrelu ? fmaxf(a, 0.2f * a) : a;
-              }
-              const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
-              if (P.out) st8(P.out + o, pack8(v));
-              if (P.out_mod) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
-                st8(P.out_mod + o, pack8(v));
-              }
+              for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
+              st8(P.out_mod + o, pack8(v));
             }
           }
         }
@@ -391,9 +411,30 @@ extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const fl
   P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
   P.B = B; P.C = C; P.IH = in_h; P.IW = in_w; P.H = out_h; P.W = out_w; P.py0 = py0; P.px0 = px0; P.act = act;
   for (int i = 0; i < 4; ++i) { P.fv[i] = kv[3 - i]; P.fh[i] = kh[3 - i]; }
-  const int strips = ceil_div(out_h, kBlurRows);
-  const int64_t threads = (int64_t)B * strips * ceil_div(out_w, kBlurPx) * (C / 8);
-  blur_act_nhwc_kernel<<<(unsigned)ceil_div64(threads, 128), 128, 0, (cudaStream_t)stream>>>(P);
+  BlurTile T;
+  T.ct = C >= 128 ? 128 : C;
+  W2E_CHECK_ARG((T.ct & (T.ct - 1)) == 0 && T.ct >= 8 && C % T.ct == 0,
+                "blur_act_nhwc: C must be 8, 16, 32, 64 or a multiple of 128 (got %d)", C);
+  T.tx = 1024 / T.ct;
+  T.tiles_x = ceil_div(out_w, T.tx); T.tiles_y = ceil_div(out_h, kBlurTY); T.tiles_c = C / T.ct;
+  const int64_t blocks = (int64_t)T.tiles_x * T.tiles_y * T.tiles_c * B;
+  W2E_CHECK_ARG(blocks < (1ll << 31), "blur_act_nhwc: too many tiles");
+  W2E_CHECK_ARG(((uintptr_t)z & 15) == 0, "blur_act_nhwc: input must be 16-byte aligned");
+  CUtensorMap mz;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)in_w * C * 2, (uint64_t)in_h * in_w * C * 2};
+    const uint32_t box[4] = {(uint32_t)T.ct, (uint32_t)(T.tx + 3), (uint32_t)(kBlurTY + 3), 1u};
+    int rc = make_bf16_map(&mz, z, 4, dims, strides, box, 0 /* no swizzle */);
+    if (rc) return rc;
+  }
+  const int smem_bytes = (kBlurTY + 3) * (T.tx + 3) * T.ct * 2 + 128;
+  static bool configured = false;
+  if (!configured) {
+    W2E_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  blur_act_nhwc_kernel<<<(unsigned)blocks, 128, smem_bytes, (cudaStream_t)stream>>>(mz, P, T);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

@@ -123,7 +123,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();  // modconv_tc.cu
-// bf16 tiled tensor map; row_bytes (inner box extent in bytes) selects the swizzle: 128 -> 128B, 64 -> 64B
+// bf16 tiled tensor map; row_bytes selects the swizzle: 128 -> 128B, 64 -> 64B, anything else -> none
 int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int row_bytes);
 
