@@ -167,6 +167,19 @@ int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const
                     const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                     int in_w, int transposed, int act, void* stream);
+/* Plain 3x3 variant with the following ToRGB (models/stylegan2/model.py:353-362) fused into the
+ * epilogue: every epilogue thread holds one pixel's full channel row, so
+ *   rgb[b,o,y,x] = sum_c act[b,y,x,c]*rgb_style[b,c]*rgb_w[o,c] + rgb_bias[o] + upsample2(rgb_skip)[b,o,y,x]
+ * is produced without re-reading the activation; out and out_mod may then both be NULL.
+ * rgb_w: float [3,Cout] pre-scaled by 1/sqrt(Cout); rgb_skip: float [B,3,in_h/2,in_w/2] or NULL;
+ * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: float [B,3,in_h,in_w].
+ * Needs Cout <= 256 and in_h > 16.                                                             */
+int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
+                        const float* noise, const float* noise_w, int noise_batch,
+                        const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
+                        int Cin, int Cout, int in_h, int in_w, int act, const float* rgb_w,
+                        const float* rgb_style, const float* rgb_bias, const float* rgb_skip,
+                        const float* host_taps1d, float* rgb, void* stream);
 /* tuning knob of w2e_modconv_tc2: cap on the number of persistent CTAs (0 = one or two per SM). */
 void w2e_modconv_tc2_knobs(int max_ctas);
 

@@ -212,3 +212,46 @@ def test_bf16_batch_invariance():
                                  randomize_noise=False)[0] for i in range(3)])
     gen._engine.assert_ok()
     assert torch.equal(full, singles)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,with_skip,want_out", [
+    (2, 64, 64, 32, True, True), (1, 32, 32, 40, False, False), (2, 128, 256, 24, True, False),
+    (1, 64, 32, 72, True, True),
+])
+def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, want_out):
+    """StyledConv + ToRGB in one launch (w2e_modconv_tc2_rgb) vs the oracle's two modules"""
+    layer = _Layer(cin, cout, False, 51)
+    rgbm = w2e.ToRGB(cout, 16)
+    wr = synth.make_tensor((1, 3, cout, 1, 1), 52)
+    with torch.no_grad():
+        rgbm.conv.weight.copy_(wr)
+        rgbm.bias.copy_(0.1 * synth.make_tensor((1, 3, 1, 1), 53))
+    rgbm = rgbm.to(DEV)
+    x = synth.make_tensor((b, cin, h, h), 54)
+    s = 1 + 0.3 * synth.make_tensor((b, cin), 55)
+    s_rgb = 1 + 0.3 * synth.make_tensor((b, cout), 56)
+    nxt = 1 + 0.3 * synth.make_tensor((b, cout), 57)
+    noise = synth.make_tensor((1, 1, h, h), 58)
+    skip = synth.make_tensor((b, 3, h // 2, h // 2), 59) if with_skip else None
+    m = layer.m
+    pw = eng._tc_weight(m.conv)
+    d = K.demod_coefficients(s.to(DEV), pw.wsq)
+    xs = eng._to_nhwc(x.to(DEV), s.to(DEV).contiguous(), b)
+    out, out_mod, rgb = eng._conv2_rgb(xs, pw, d, noise.to(DEV), m.noise.weight.detach(), m.activate.bias.detach(),
+                                       nxt.to(DEV).contiguous(), want_out, True, rgbm, s_rgb.to(DEV).contiguous(),
+                                       skip.to(DEV) if skip is not None else None)
+    eng.assert_ok()
+    ref, _ = orc.modulated_conv2d_ref(x.double(), s.double().reshape(b, 1, cin, 1, 1), layer.weight.double(), None,
+                                      None, True, False, None, input_is_stylespace=True)
+    ref = orc.fused_leaky_relu_ref(ref + 0.3 * noise.double(), m.activate.bias.detach().cpu().double())
+    sd = {"p.conv.weight": wr.double(), "p.bias": rgbm.bias.detach().cpu().double(),
+          "p.upsample.kernel": synth.blur_kernel_2d(gain=4.0).double(), "p.conv.modulation.weight": None,
+          "p.conv.modulation.bias": None}
+    ref_rgb, _ = orc._to_rgb(sd, "p", ref, s_rgb.double().reshape(b, 1, cout, 1, 1),
+                             skip.double() if skip is not None else None, True)
+    assert norm_err(rgb.cpu(), ref_rgb) <= 1e-2
+    assert norm_err(eng._to_nchw(out_mod).cpu(), ref * nxt.double().reshape(b, cout, 1, 1)) <= 1e-2
+    if want_out:
+        assert norm_err(eng._to_nchw(out).cpu(), ref) <= 1e-2
+    else:
+        assert out is None

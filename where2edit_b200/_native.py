@@ -40,6 +40,7 @@ PROTOTYPES = {
     "w2e_modconv_tc_supported": (_I, []),
     "w2e_modconv_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 12 + [_P, _I, _I, _I, _P]),
     "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P]),
+    "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 7),
     "w2e_modconv_tc2_knobs": (None, [_I]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),

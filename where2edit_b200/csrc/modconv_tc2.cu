@@ -42,6 +42,13 @@ struct Tc2Params {
   __nv_bfloat16* out;       // [B,OH,OW,Cout] or null
   __nv_bfloat16* out_mod;   // [B,OH,OW,Cout] or null
   int* error_flag;
+  // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
+  const float* rgb_w;       // [3,Cout] 1x1 weight * 1/sqrt(Cout)
+  const float* rgb_style;   // [B,Cout]
+  const float* rgb_bias;    // [3] or null
+  const float* rgb_skip;    // [B,3,OH/2,OW/2] fp32 NCHW or null
+  float* rgb;               // [B,3,OH,OW] fp32 NCHW
+  float kf[4];              // flipped 1-D taps of the skip upsample filter
   int noise_per_sample;
   int B, Cin, Cout, OH, OW;
   int grid_h, grid_w, out_stride;
@@ -65,6 +72,7 @@ struct Tc2Bars {
   alignas(16) float ep_scale[2][256];
   alignas(16) float ep_shift[2][256];
   alignas(16) float ep_next[2][256];
+  alignas(16) float ep_rgb[2][3][256];  // per-sample modulated ToRGB weights
 };
 
 constexpr int kPitch = 10;  // pixels per row of the haloed tile (8 + 2 halo columns)
@@ -104,11 +112,12 @@ struct Ring {
   }
 };
 
-template <bool TR, int MT, int KSTEPS, bool WRES>
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB>
 __global__ void __launch_bounds__(kT2Threads, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ Tc2Params P) {
   constexpr int NG = TR ? 4 : 1;
+  static_assert(!RGB || (!TR && MT == 2), "fused ToRGB needs the plain conv with two sub-tiles");
   constexpr int kRowBytes = KSTEPS * 32;  // BK * 2 bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   constexpr int kBK = KSTEPS * 16;
   extern __shared__ uint8_t smem_raw[];
@@ -260,67 +269,137 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else {
     // ------------------------------------------------------------------ epilogue: warps 2..9
     // warp w reads TMEM lane quarter w%4 (hardware rule); warps 2..5 take the first half of the
-    // tile's BN columns, warps 6..9 the second half.
+    // tile's BN columns, warps 6..9 the second half.  With the fused ToRGB (RGB) a thread needs its
+    // pixel's whole channel row, so warps 2..5 take sub-tile 0 and warps 6..9 sub-tile 1 instead.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;  // 0..255
+    const int et = threadIdx.x - 64;  // 0..255; also the channel whose constants this thread stages
     const int r = q * 32 + lane;      // accumulator row == pixel inside the sub-tile
     const int sy = r >> 3, sx = r & 7;
     const bool lrelu = P.act == W2E_ACT_LRELU;
     const float gain = lrelu ? 1.41421356237309515f : 1.f;
     const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
-    const int c_begin = (P.bn >= 32) ? half * (P.bn >> 1) : 0;
-    const int c_end = (P.bn >= 32) ? c_begin + (P.bn >> 1) : (half == 0 ? P.bn : 0);
+    const int c_begin = RGB ? 0 : ((P.bn >= 32) ? half * (P.bn >> 1) : 0);
+    const int c_end = RGB ? P.bn : ((P.bn >= 32) ? c_begin + (P.bn >> 1) : (half == 0 ? P.bn : 0));
     constexpr int out_stride = TR ? 2 : 1;
+    constexpr int NPIX = RGB ? 1 : NG * MT;   // pixels this thread finishes per tile
+
+    // Everything a tile's epilogue needs from global memory, fetched ONE TILE AHEAD into registers
+    // so that its latency hides behind the current tile's arithmetic.
+    struct Pre {
+      int b, j0, i0, co0;
+      float scale, shift, next, rgbw[3];  // constants of channel `et` (published to smem per tile)
+      float nz[NPIX];                     // noise_w * noise at this thread's pixels (already * gain)
+      float rgbi[3];                      // ToRGB bias + upsampled skip at this thread's pixel
+    };
+    auto pixel_of = [&](const Pre& t, int gm, int& oy, int& ox) -> bool {
+      const int g = gm / MT, m = RGB ? half : gm % MT;
+      const int j = t.j0 + m * kSubTileH + sy, i = t.i0 + sx;
+      oy = j * out_stride + (TR ? (g >> 1) : 0);
+      ox = i * out_stride + (TR ? (g & 1) : 0);
+      return j < P.grid_h && i < P.grid_w && oy < P.OH && ox < P.OW;
+    };
+    auto prefetch = [&](int tile) -> Pre {
+      Pre t;
+      const int tn = tile / tiles_per_n;
+      int rem = tile - tn * tiles_per_n;
+      t.b = rem / tiles_xy;
+      rem -= t.b * tiles_xy;
+      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
+      t.j0 = ty * (kSubTileH * MT); t.i0 = tx * kTileW; t.co0 = tn * P.bn;
+      t.scale = gain; t.shift = 0.f; t.next = 0.f; t.rgbw[0] = t.rgbw[1] = t.rgbw[2] = 0.f;
+      if (et < P.bn) {
+        const int64_t bc = (int64_t)t.b * P.Cout + t.co0 + et;
+        if (P.out_scale) t.scale = __ldg(P.out_scale + bc) * gain;
+        if (P.bias) t.shift = __ldg(P.bias + t.co0 + et) * gain;
+        if (P.next_scale) t.next = __ldg(P.next_scale + bc);
+        if (RGB) {
+          const float rs = __ldg(P.rgb_style + bc);
+#pragma unroll
+          for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + et) * rs;
+        }
+      }
+#pragma unroll
+      for (int gm = 0; gm < NPIX; ++gm) {
+        int oy, ox;
+        const bool valid = pixel_of(t, gm, oy, ox);
+        t.nz[gm] = (valid && P.noise)
+            ? nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)t.b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox)
+            : 0.f;
+      }
+      t.rgbi[0] = t.rgbi[1] = t.rgbi[2] = 0.f;
+      if (RGB) {
+        int oy, ox;
+        if (pixel_of(t, 0, oy, ox)) {
+          // bias + polyphase x2 upsample of the running skip image (upfirdn2d up=2 pad=(2,1): 2 taps per axis)
+#pragma unroll
+          for (int o = 0; o < 3; ++o) t.rgbi[o] = P.rgb_bias ? __ldg(P.rgb_bias + o) : 0.f;
+          if (P.rgb_skip) {
+            const int h = P.OH >> 1, wd = P.OW >> 1;
+            const int ya = (oy & 1) ? (oy - 1) / 2 : oy / 2 - 1, xa = (ox & 1) ? (ox - 1) / 2 : ox / 2 - 1;
+            const float cy0 = (oy & 1) ? P.kf[1] : P.kf[0], cy1 = (oy & 1) ? P.kf[3] : P.kf[2];
+            const float cx0 = (ox & 1) ? P.kf[1] : P.kf[0], cx1 = (ox & 1) ? P.kf[3] : P.kf[2];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float* sp = P.rgb_skip + ((int64_t)t.b * 3 + o) * h * wd;
+              float acc = 0.f;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy) {
+                const int iy = ya + dy;
+                if (iy < 0 || iy >= h) continue;
+                float row = 0.f;
+                if (xa >= 0) row = cx0 * __ldg(sp + (int64_t)iy * wd + xa);
+                if (xa + 1 < wd) row = fmaf(cx1, __ldg(sp + (int64_t)iy * wd + xa + 1), row);
+                acc = fmaf(dy ? cy1 : cy0, row, acc);
+              }
+              t.rgbi[o] += acc;
+            }
+          }
+        }
+      }
+      return t;
+    };
+
     Ring cr;
     uint32_t parity = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      const int tn = tile / tiles_per_n;
-      int rem = tile - tn * tiles_per_n;
-      const int b = rem / tiles_xy;
-      rem -= b * tiles_xy;
-      const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-      const int j0 = ty * (kSubTileH * MT), i0 = tx * kTileW, co0 = tn * P.bn;
-      // stage this tile's per-channel constants (one named barrier per tile; see Tc2Bars)
+    int tile = blockIdx.x;
+    Pre cur;
+    if (tile < P.ntiles) cur = prefetch(tile);
+    for (; tile < P.ntiles; tile += gridDim.x) {
+      // publish this tile's per-channel constants (double-buffered by tile parity: the single named
+      // barrier per tile also orders the reuse of the other buffer)
       const int cb = parity;
       parity ^= 1u;
-      for (int c = et; c < P.bn; c += kT2EpiThreads) {
-        const int64_t bc = (int64_t)b * P.Cout + co0 + c;
-        bars->ep_scale[cb][c] = (P.out_scale ? __ldg(P.out_scale + bc) : 1.f) * gain;
-        bars->ep_shift[cb][c] = (P.bias ? __ldg(P.bias + co0 + c) : 0.f) * gain;
-        bars->ep_next[cb][c] = P.next_scale ? __ldg(P.next_scale + bc) : 0.f;
-      }
-      // output coordinates and noise of this thread's NG*MT pixels, fetched before the accumulator wait
-      int64_t pix[NG * MT];
-      float nz[NG * MT];
+      if (et < P.bn) {
+        bars->ep_scale[cb][et] = cur.scale;
+        bars->ep_shift[cb][et] = cur.shift;
+        bars->ep_next[cb][et] = cur.next;
+        if (RGB) {
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const int j = j0 + m * kSubTileH + sy, i = i0 + sx;
-          const int oy = j * out_stride + (TR ? (g >> 1) : 0), ox = i * out_stride + (TR ? (g & 1) : 0);
-          const bool valid = j < P.grid_h && i < P.grid_w && oy < P.OH && ox < P.OW;
-          pix[g * MT + m] = valid ? ((int64_t)b * P.OH + oy) * P.OW + ox : -1;
-          nz[g * MT + m] = (valid && P.noise)
-              ? nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox)
-              : 0.f;
+          for (int o = 0; o < 3; ++o) bars->ep_rgb[cb][o][et] = cur.rgbw[o];
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kT2EpiThreads) : "memory");
+      const Pre me = cur;
+      if (tile + (int)gridDim.x < P.ntiles) cur = prefetch(tile + gridDim.x);  // in flight during this tile
       if (ok) ok = mbar_wait(&bars->acc_full[cr.idx], cr.phase, abort_flag);
       tc_fence_after();
       const float* sc = bars->ep_scale[cb];
       const float* sh = bars->ep_shift[cb];
       const float* nx = bars->ep_next[cb];
       const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + cr.idx * (uint32_t)(NG * MT) * (uint32_t)P.bn;
+      float rgb_acc[3] = {me.rgbi[0], me.rgbi[1], me.rgbi[2]};
 #pragma unroll
-      for (int gm = 0; gm < NG * MT; ++gm) {
-        const bool valid = ok && pix[gm] >= 0;
-        const float nzv = nz[gm];
+      for (int gmi = 0; gmi < NPIX; ++gmi) {
+        const int gm = RGB ? half : gmi;   // accumulator index inside the tile
+        int oy, ox;
+        const bool valid = pixel_of(me, gmi, oy, ox) && ok;
+        const int64_t pix = valid ? ((int64_t)me.b * P.OH + oy) * P.OW + ox : 0;
+        const float nzv = me.nz[gmi];
         const uint32_t t_addr = t_tile + (uint32_t)gm * (uint32_t)P.bn;
-        __nv_bfloat16* o_row = P.out ? P.out + pix[gm] * P.Cout + co0 : nullptr;
-        __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix[gm] * P.Cout + co0 : nullptr;
+        __nv_bfloat16* o_row = P.out ? P.out + pix * P.Cout + me.co0 : nullptr;
+        __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix * P.Cout + me.co0 : nullptr;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; c += 16) {
           uint32_t v[16];
@@ -340,6 +419,20 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (lrelu) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.2f * f[e]);
+            }
+            if (RGB) {
+              const float* w0 = bars->ep_rgb[cb][0] + c;
+              const float* w1 = bars->ep_rgb[cb][1] + c;
+              const float* w2 = bars->ep_rgb[cb][2] + c;
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 x0 = *reinterpret_cast<const float4*>(w0 + 4 * e4);
+                const float4 x1 = *reinterpret_cast<const float4*>(w1 + 4 * e4);
+                const float4 x2 = *reinterpret_cast<const float4*>(w2 + 4 * e4);
+                rgb_acc[0] = fmaf(f[4 * e4 + 3], x0.w, fmaf(f[4 * e4 + 2], x0.z, fmaf(f[4 * e4 + 1], x0.y, fmaf(f[4 * e4], x0.x, rgb_acc[0]))));
+                rgb_acc[1] = fmaf(f[4 * e4 + 3], x1.w, fmaf(f[4 * e4 + 2], x1.z, fmaf(f[4 * e4 + 1], x1.y, fmaf(f[4 * e4], x1.x, rgb_acc[1]))));
+                rgb_acc[2] = fmaf(f[4 * e4 + 3], x2.w, fmaf(f[4 * e4 + 2], x2.z, fmaf(f[4 * e4 + 1], x2.y, fmaf(f[4 * e4], x2.x, rgb_acc[2]))));
+              }
             }
             if (o_row) {
               uint4 pk[2];
@@ -365,6 +458,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
           }
         }
+        if (RGB && valid) {
+#pragma unroll
+          for (int o = 0; o < 3; ++o) P.rgb[(((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox] = rgb_acc[o];
+        }
       }
       // accumulator buffer drained: hand it back to the MMA warp
       tc_fence_before();
@@ -382,10 +479,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-template <bool TR, int MT, int KSTEPS, bool WRES>
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, int smem_bytes, int max_ctas,
                       cudaStream_t s) {
-  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES>;
+  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB>;
   static bool configured = false;
   if (!configured) {
     W2E_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -413,11 +510,15 @@ using namespace w2e;
 
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 
-extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
-                               const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
-                               void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
-                               int transposed, int act, void* stream) {
-  W2E_CHECK_ARG(xs && w && (out || out_mod), "modconv_tc2: null pointer");
+struct RgbArgs {
+  const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
+};
+
+static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
+                   const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
+                   int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
+                   const RgbArgs* rgb, void* stream) {
+  W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
   W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
   W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
   W2E_CHECK_ARG(Cin % 32 == 0 && Cout % 16 == 0, "modconv_tc2: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
@@ -431,6 +532,16 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
   P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod; P.error_flag = error_flag;
   P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
   P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
+  if (rgb) {
+    W2E_CHECK_ARG(rgb->w && rgb->style && rgb->rgb, "modconv_tc2_rgb: null pointer");
+    W2E_CHECK_ARG(!transposed && Cout <= 256 && in_h > kSubTileH,
+                  "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 256 and more than %d rows", kSubTileH);
+    W2E_CHECK_ARG(rgb->skip == nullptr || (rgb->host_taps1d && in_h % 2 == 0 && in_w % 2 == 0),
+                  "modconv_tc2_rgb: skip needs taps and even H, W");
+    P.rgb_w = rgb->w; P.rgb_style = rgb->style; P.rgb_bias = rgb->bias; P.rgb_skip = rgb->skip; P.rgb = rgb->rgb;
+    if (rgb->skip)
+      for (int i = 0; i < 4; ++i) P.kf[i] = rgb->host_taps1d[3 - i];
+  }
   P.pitch = kPitch;
   P.ntaps = 9;
   if (!transposed) {
@@ -498,9 +609,16 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int ks = P.bk / 16;
+  if (rgb) {
+    W2E_CHECK_ARG(P.mt == 2 && P.tiles_n == 1, "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
+#define W2E_TC2_RGB(KS_, WR_) \
+  if (ks == KS_ && (P.wres != 0) == WR_) return launch_tc2<false, 2, KS_, WR_, true>(ma, mb, P, smem_bytes, g_max_ctas, st);
+    W2E_TC2_RGB(4, false) W2E_TC2_RGB(4, true) W2E_TC2_RGB(2, false) W2E_TC2_RGB(2, true)
+#undef W2E_TC2_RGB
+  }
 #define W2E_TC2_CASE(TR_, MT_, KS_, WR_) \
   if ((transposed != 0) == TR_ && P.mt == MT_ && ks == KS_ && (P.wres != 0) == WR_) \
-    return launch_tc2<TR_, MT_, KS_, WR_>(ma, mb, P, smem_bytes, g_max_ctas, st);
+    return launch_tc2<TR_, MT_, KS_, WR_, false>(ma, mb, P, smem_bytes, g_max_ctas, st);
   W2E_TC2_CASE(false, 1, 4, false) W2E_TC2_CASE(false, 2, 4, false) W2E_TC2_CASE(false, 1, 2, false)
   W2E_TC2_CASE(false, 2, 2, false) W2E_TC2_CASE(false, 1, 4, true) W2E_TC2_CASE(false, 2, 4, true)
   W2E_TC2_CASE(false, 1, 2, true) W2E_TC2_CASE(false, 2, 2, true)
@@ -509,4 +627,22 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
   W2E_TC2_CASE(true, 1, 2, true) W2E_TC2_CASE(true, 2, 2, true)
 #undef W2E_TC2_CASE
   return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2: no kernel variant");
+}
+
+extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
+                               const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                               void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
+                               int transposed, int act, void* stream) {
+  return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
+                 in_h, in_w, transposed, act, nullptr, stream);
+}
+
+extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
+                                   const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                                   void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
+                                   int in_w, int act, const float* rgb_w, const float* rgb_style, const float* rgb_bias,
+                                   const float* rgb_skip, const float* host_taps1d, float* rgb, void* stream) {
+  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb};
+  return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
+                 in_h, in_w, 0, act, &a, stream);
 }

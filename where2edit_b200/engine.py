@@ -54,6 +54,8 @@ class SynthesisEngine:
         self._err = None
         # W2E_TC_V1=1 selects the first-generation kernel (one tile per CTA, 9 shifted TMA loads)
         self.v1 = os.environ.get("W2E_TC_V1", "0") == "1"
+        # W2E_FUSE_RGB=0 keeps ToRGB as its own kernel (w2e_torgb_nhwc) instead of the conv epilogue
+        self.fuse_rgb = os.environ.get("W2E_FUSE_RGB", "1") == "1"
         if not N.load().w2e_modconv_tc_supported():
             raise RuntimeError("where2edit_b200: precision='bf16' needs an sm_100 (B200) device and a driver with "
                                "cuTensorMapEncodeTiled; there is no fallback -- use precision='fp32'")
@@ -113,6 +115,31 @@ class SynthesisEngine:
             N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w, int(transposed), act,
             N.stream_ptr()), "modconv_tc2")
         return out, out_mod
+
+    def _conv2_rgb(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, rgb_module, rgb_style, skip):
+        """Plain 3x3 StyledConv with the following ToRGB fused into its epilogue."""
+        b, h, w, _ = xs.shape
+        dev = xs.device
+        out = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
+        out_mod = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
+        rgb = torch.empty((b, 3, h, w), device=dev, dtype=torch.float32)
+        rpw = rgb_module.conv.packed()
+        taps1d = None
+        if skip is not None:
+            taps2d = kernel_taps(rgb_module.upsample.kernel)
+            taps1d = K.separable_taps(taps2d) if len(taps2d) == 16 else None
+            if taps1d is None:
+                raise RuntimeError("where2edit_b200 bf16 engine: the ToRGB upsample kernel must be a separable 4x4 FIR")
+            skip = skip.contiguous()
+        rbias = rgb_module.bias.detach().reshape(3).to(torch.float32).contiguous()
+        nb = 0 if noise is None else noise.shape[0]
+        N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"{pw.cin}->{pw.cout}@{h}x{w}+rgb")
+        N.check(N.load().w2e_modconv_tc2_rgb(
+            N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
+            N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w, N.ACT_LRELU,
+            N.ptr(rpw.rgb), N.ptr(rgb_style), N.ptr(rbias), N.ptr(skip),
+            N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb), N.stream_ptr()), "modconv_tc2_rgb")
+        return out, out_mod, rgb
 
     def _blur(self, z, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod, out_hw):
         b, ih, iw, c = z.shape
@@ -211,6 +238,7 @@ class SynthesisEngine:
             return None
 
         captured, style_vector = [], []
+        fused_rgb = None
         carry = False
         skip = None
         noise_idx = 0
@@ -221,7 +249,10 @@ class SynthesisEngine:
             layer = idx + 1
             blend_here = bool(attention_layer) and layer == attention_layer
             if kind == "rgb":
-                skip = self._torgb(act, module, s, skip)
+                if fused_rgb is not None:
+                    skip, fused_rgb = fused_rgb, None
+                else:
+                    skip = self._torgb(act, module, s, skip)
                 if attention_layer and (blend_here or carry):
                     carry = False
                     skip = K.mask_blend(skip, feature_map[layer - 1], attention_map)
@@ -242,7 +273,13 @@ class SynthesisEngine:
             next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
             need_out = next_is_rgb or want_features or blend_here
             need_mod = nxt is not None and not blend_here
-            if kind == "conv":
+            fuse = (kind == "conv" and next_is_rgb and not self.v1 and self.fuse_rgb and pw.cout <= 256
+                    and hw[0] > 16 and not (attention_layer and attention_layer in (layer, layer + 1)))
+            if fuse:
+                act, xs_next, fused_rgb = self._conv2_rgb(xs, pw, demods[idx], nz, noise_w, bias, nxt,
+                                                          want_features, need_mod, layers[idx + 1][0],
+                                                          styles[idx + 1], skip)
+            elif kind == "conv":
                 if self.v1:
                     act, xs_next = self._conv(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
                                               _TAPS_PLAIN, hw, hw, hw, 1, 0, 0, N.ACT_LRELU)
