@@ -286,11 +286,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     // Everything a tile's epilogue needs from global memory, fetched ONE TILE AHEAD into registers
     // so that its latency hides behind the current tile's arithmetic.
-    struct Pre {
-      int b, j0, i0, co0;
-      float scale, shift, next, rgbw[3];  // constants of channel `et` (published to smem per tile)
-      float nz[NPIX];                     // noise_w * noise at this thread's pixels (already * gain)
-      float rgbi[3];                      // ToRGB bias + upsampled skip at this thread's pixel
+    struct Pre {                          // RAW loaded values only: nothing here may be consumed
+      int b, j0, i0, co0;                 // arithmetically until the tile becomes current
+      float scale, shift, next, rgbs, rgbw[3];
+      float nz[NPIX];
+      float rgbb[3], tap[3][4];           // ToRGB bias and the 2x2 skip taps of this thread's pixel
     };
     auto pixel_of = [&](const Pre& t, int gm, int& oy, int& ox) -> bool {
       const int g = gm / MT, m = RGB ? half : gm % MT;
@@ -307,16 +307,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       rem -= t.b * tiles_xy;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
       t.j0 = ty * (kSubTileH * MT); t.i0 = tx * kTileW; t.co0 = tn * P.bn;
-      t.scale = gain; t.shift = 0.f; t.next = 0.f; t.rgbw[0] = t.rgbw[1] = t.rgbw[2] = 0.f;
+      t.scale = 1.f; t.shift = 0.f; t.next = 0.f; t.rgbs = 0.f; t.rgbw[0] = t.rgbw[1] = t.rgbw[2] = 0.f;
       if (et < P.bn) {
         const int64_t bc = (int64_t)t.b * P.Cout + t.co0 + et;
-        if (P.out_scale) t.scale = __ldg(P.out_scale + bc) * gain;
-        if (P.bias) t.shift = __ldg(P.bias + t.co0 + et) * gain;
+        if (P.out_scale) t.scale = __ldg(P.out_scale + bc);
+        if (P.bias) t.shift = __ldg(P.bias + t.co0 + et);
         if (P.next_scale) t.next = __ldg(P.next_scale + bc);
         if (RGB) {
-          const float rs = __ldg(P.rgb_style + bc);
+          t.rgbs = __ldg(P.rgb_style + bc);
 #pragma unroll
-          for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + et) * rs;
+          for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + et);
         }
       }
 #pragma unroll
@@ -324,35 +324,34 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int oy, ox;
         const bool valid = pixel_of(t, gm, oy, ox);
         t.nz[gm] = (valid && P.noise)
-            ? nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)t.b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox)
+            ? __ldg(P.noise + (P.noise_per_sample ? (int64_t)t.b * P.OH * P.OW : 0) + (int64_t)oy * P.OW + ox)
             : 0.f;
       }
-      t.rgbi[0] = t.rgbi[1] = t.rgbi[2] = 0.f;
       if (RGB) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          t.rgbb[o] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t.tap[o][k] = 0.f;
+        }
         int oy, ox;
         if (pixel_of(t, 0, oy, ox)) {
-          // bias + polyphase x2 upsample of the running skip image (upfirdn2d up=2 pad=(2,1): 2 taps per axis)
 #pragma unroll
-          for (int o = 0; o < 3; ++o) t.rgbi[o] = P.rgb_bias ? __ldg(P.rgb_bias + o) : 0.f;
+          for (int o = 0; o < 3; ++o) t.rgbb[o] = P.rgb_bias ? __ldg(P.rgb_bias + o) : 0.f;
           if (P.rgb_skip) {
+            // upfirdn2d(skip, up=2, pad=(2,1)) is a 2x2-tap polyphase filter: rows ya, ya+1, columns xa, xa+1
             const int h = P.OH >> 1, wd = P.OW >> 1;
-            const int ya = (oy & 1) ? (oy - 1) / 2 : oy / 2 - 1, xa = (ox & 1) ? (ox - 1) / 2 : ox / 2 - 1;
-            const float cy0 = (oy & 1) ? P.kf[1] : P.kf[0], cy1 = (oy & 1) ? P.kf[3] : P.kf[2];
-            const float cx0 = (ox & 1) ? P.kf[1] : P.kf[0], cx1 = (ox & 1) ? P.kf[3] : P.kf[2];
+            const int ya = ((oy + 1) >> 1) - 1, xa = ((ox + 1) >> 1) - 1;
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
               const float* sp = P.rgb_skip + ((int64_t)t.b * 3 + o) * h * wd;
-              float acc = 0.f;
 #pragma unroll
-              for (int dy = 0; dy < 2; ++dy) {
-                const int iy = ya + dy;
-                if (iy < 0 || iy >= h) continue;
-                float row = 0.f;
-                if (xa >= 0) row = cx0 * __ldg(sp + (int64_t)iy * wd + xa);
-                if (xa + 1 < wd) row = fmaf(cx1, __ldg(sp + (int64_t)iy * wd + xa + 1), row);
-                acc = fmaf(dy ? cy1 : cy0, row, acc);
-              }
-              t.rgbi[o] += acc;
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                  const int iy = ya + dy, ix = xa + dx;
+                  if (iy >= 0 && iy < h && ix >= 0 && ix < wd) t.tap[o][dy * 2 + dx] = __ldg(sp + (int64_t)iy * wd + ix);
+                }
             }
           }
         }
@@ -372,12 +371,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int cb = parity;
       parity ^= 1u;
       if (et < P.bn) {
-        bars->ep_scale[cb][et] = cur.scale;
-        bars->ep_shift[cb][et] = cur.shift;
+        bars->ep_scale[cb][et] = cur.scale * gain;
+        bars->ep_shift[cb][et] = cur.shift * gain;
         bars->ep_next[cb][et] = cur.next;
         if (RGB) {
 #pragma unroll
-          for (int o = 0; o < 3; ++o) bars->ep_rgb[cb][o][et] = cur.rgbw[o];
+          for (int o = 0; o < 3; ++o) bars->ep_rgb[cb][o][et] = cur.rgbw[o] * cur.rgbs;
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kT2EpiThreads) : "memory");
@@ -389,14 +388,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const float* sh = bars->ep_shift[cb];
       const float* nx = bars->ep_next[cb];
       const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + cr.idx * (uint32_t)(NG * MT) * (uint32_t)P.bn;
-      float rgb_acc[3] = {me.rgbi[0], me.rgbi[1], me.rgbi[2]};
+      float rgb_acc[3] = {0.f, 0.f, 0.f};
+      if (RGB) {
+        int oy, ox;
+        pixel_of(me, 0, oy, ox);
+        const float cy0 = (oy & 1) ? P.kf[1] : P.kf[0], cy1 = (oy & 1) ? P.kf[3] : P.kf[2];
+        const float cx0 = (ox & 1) ? P.kf[1] : P.kf[0], cx1 = (ox & 1) ? P.kf[3] : P.kf[2];
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+          rgb_acc[o] = me.rgbb[o] + cy0 * fmaf(cx1, me.tap[o][1], cx0 * me.tap[o][0]) +
+                       cy1 * fmaf(cx1, me.tap[o][3], cx0 * me.tap[o][2]);
+      }
 #pragma unroll
       for (int gmi = 0; gmi < NPIX; ++gmi) {
         const int gm = RGB ? half : gmi;   // accumulator index inside the tile
         int oy, ox;
         const bool valid = pixel_of(me, gmi, oy, ox) && ok;
         const int64_t pix = valid ? ((int64_t)me.b * P.OH + oy) * P.OW + ox : 0;
-        const float nzv = me.nz[gmi];
+        const float nzv = nw * me.nz[gmi];
         const uint32_t t_addr = t_tile + (uint32_t)gm * (uint32_t)P.bn;
         __nv_bfloat16* o_row = P.out ? P.out + pix * P.Cout + me.co0 : nullptr;
         __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix * P.Cout + me.co0 : nullptr;
