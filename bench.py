@@ -28,6 +28,29 @@ UNIT = "images/s"
 MODCONV_GFLOP_PER_IMAGE = 148.13
 
 
+def workload_config(size, batch, precision, world):
+    return {"workload": f"StyleGAN2 FFHQ-{size} generator forward (random init, channel_multiplier 2), "
+                        f"batch {batch} per GPU from W+ latents, fixed noise buffers, {precision} mode",
+            "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": f"batch sharded over {world} GPU(s)"
+                           + (", bf16 all-gather of images overlapped on a side stream" if world > 1 else ""),
+            "l2": "inputs larger than L2: every step streams multi-GB activations (no flush needed)"}
+
+
+def ncu_traffic(kernel_substr):
+    """dram bytes (read+write) per step of a kernel, from the committed `ncu --set full` capture of all
+    its launches in one step (profiles/*_traffic.json, key '<round>_step_<kernel>'); None if absent."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        with open(path) as fh:
+            data = json.load(fh)
+        for name, launches in data.items():
+            if "_step_" in name and kernel_substr in name:
+                best = sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in launches)
+    return best
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -148,7 +171,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"StyleGAN2 FFHQ-{args.size} generator forward (random init), CPU sample"},
+        "config": workload_config(args.size, args.batch, args.precision, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -203,6 +226,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from where2edit_b200 import _native as N
+    from where2edit_b200 import parallel
     gen = make_generator(args.size, args.precision, dev)
     B, K_, W_ = args.batch, args.steps, args.warmup
     peaks = measured_peaks()
@@ -229,7 +253,7 @@ def main():
             small = img.to(torch.bfloat16)
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered[i % 2], small)
+                parallel.gather_images(small, out=gathered[i % 2])
             small.record_stream(comm_stream)
         return img
 
@@ -311,17 +335,19 @@ def main():
         if "modconv" in kinds and kinds["modconv"]["ms"] > 0:
             k = kinds["modconv"]
             ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "modconv_tc_kernel (all 3x3 modulated-conv launches of a step)",
+            roofline = {"bound": "tensor", "kernel": "modconv_tc2_kernel (all 3x3 modulated-conv launches of a step)",
                         "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                        "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                        "frac": ach / peaks["bf16_tflops_sustained"],
+                        "traffic": ncu_traffic("modconv") if (B == 32 and args.size == 1024) else None,
+                        "peak_source": peaks["source"] + " bf16_tflops_sustained", "algorithmic_flops": k["flops"],
                         "launches": k["launches"], "share_of_step": k["ms"] / traced_ms}
         if "upfirdn2d" in kinds and kinds["upfirdn2d"]["ms"] > 0:
             k = kinds["upfirdn2d"]
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
             roofline_up = {"bound": "hbm", "kernel": "blur_act_nhwc_kernel (all blur launches of a step)",
                            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                           "traffic": None, "peak_source": peaks["source"] + " hbm_gbs", "launches": k["launches"],
+                           "traffic": ncu_traffic("blur") if (B == 32 and args.size == 1024) else None,
+                           "algorithmic_bytes": k["bytes"], "peak_source": peaks["source"] + " hbm_gbs", "launches": k["launches"],
                            "share_of_step": k["ms"] / traced_ms}
         if args.layers_out:
             with open(args.layers_out, "w") as fh:
@@ -343,12 +369,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
             "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"StyleGAN2 FFHQ-{args.size} generator forward (random init, channel_multiplier 2), "
-                                   f"batch {B} per GPU from W+ latents, fixed noise buffers, {args.precision} mode",
-                       "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"batch sharded over {world} GPU(s)"
-                                      + (", bf16 all-gather of images overlapped on a side stream" if world > 1 else ""),
-                       "l2": "inputs larger than L2: every step streams multi-GB activations (no flush needed)"},
+            "config": workload_config(args.size, B, args.precision, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

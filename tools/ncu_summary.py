@@ -19,6 +19,11 @@ KEYS = [
 ]
 
 
+SUBSTR = ["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+          "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+          "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active"]
+
+
 def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -28,7 +33,7 @@ def main(path):
         print("=" * 100)
         print(row[name_col][:90], "| grid", row[hdr.index("Grid Size")] if "Grid Size" in hdr else "")
         for h, u, v in zip(hdr, units, row):
-            if h in KEYS or "stall" in h and "pct" in h and v not in ("0", ""):
+            if h in KEYS or any(k in h for k in SUBSTR):
                 print(f"  {h:90s} {v:>16s} {u}")
 
 
