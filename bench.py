@@ -223,7 +223,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
     from where2edit_b200 import _native as N
     from where2edit_b200 import parallel
@@ -244,12 +245,12 @@ def main():
     gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=torch.bfloat16) for _ in range(2)] \
         if dist is not None else None
 
-    def step(i, w):
+    def step(i, w, gather=True):
         """One pass of the hot path; at N>1 the images are all-gathered (bf16) on a side stream so the
         collective of step i overlaps the kernels of step i+1."""
         with torch.no_grad():
             img, _ = gen([w], input_is_latent=True, randomize_noise=False)
-        if dist is not None:
+        if dist is not None and gather:
             small = img.to(torch.bfloat16)
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
@@ -324,10 +325,10 @@ def main():
     roofline = roofline_up = None
     kinds = {}
     if rank == 0:
-        step(0, dev_w[0])
+        step(0, dev_w[0], gather=False)   # rank-0 only: must not enter a collective
         torch.cuda.synchronize()
         N.STATS.trace = []
-        step(1, dev_w[1])
+        step(1, dev_w[1], gather=False)
         torch.cuda.synchronize()
         trace, N.STATS.trace = N.STATS.trace, None
         kinds, layers = summarise_trace(trace, peaks)
