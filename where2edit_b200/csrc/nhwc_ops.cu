@@ -139,6 +139,7 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
   extern __shared__ uint8_t blur_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(blur_smem_raw) + 127) & ~uintptr_t(127));
   __shared__ uint64_t bar;
+  __shared__ float s_noise[kBlurTY][128];  // noise_w * gain * noise of the tile (TX <= 128)
   const int tid = threadIdx.x;
   int tile = blockIdx.x;
   const int tcx = tile % T.tiles_c; tile /= T.tiles_c;
@@ -154,6 +155,18 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
     mbar_arrive_expect_tx(&bar, (uint32_t)((kBlurTY + 3) * sw * pix_bytes));
     tma_load_4d(smem, &map_z, &bar, c_t, ox_t - P.px0, oy_t - P.py0, b);
   }
+  const bool lrelu = P.act == W2E_ACT_LRELU;
+  const float gain = lrelu ? 1.41421356237309515f : 1.f;
+  // while the TMA box is in flight: the tile's noise patch and this thread's per-channel constants
+  if (P.noise) {
+    const float nw = __ldg(P.noise_w) * gain;
+    const float* noise = P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0);
+    for (int e = tid; e < kBlurTY * T.tx; e += 128) {
+      const int yy = e / T.tx, xx = e - yy * T.tx;
+      const int oy = oy_t + yy, ox = ox_t + xx;
+      s_noise[yy][xx] = (oy < P.H && ox < P.W) ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+    }
+  }
   const int cg = T.ct >> 3;
   const int g = tid % cg;
   const int xb = (tid / cg) % (T.tx / kBlurPx);
@@ -161,36 +174,42 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
   const int c0 = c_t + g * 8;
   const int ox0 = ox_t + xb * kBlurPx;
   const int oy0 = oy_t + rg * kBlurRows;
-  const bool lrelu = P.act == W2E_ACT_LRELU;
-  const float gain = lrelu ? 1.41421356237309515f : 1.f;
   float bias[8], nsc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     bias[e] = (P.bias ? __ldg(P.bias + c0 + e) : 0.f) * gain;
     nsc[e] = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + e) : 1.f;
   }
-  const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
-  const float* noise = P.noise ? P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0) : nullptr;
   const float fv0 = P.fv[0] * gain, fv1 = P.fv[1] * gain, fv2 = P.fv[2] * gain, fv3 = P.fv[3] * gain;
   const float fh0 = P.fh[0], fh1 = P.fh[1], fh2 = P.fh[2], fh3 = P.fh[3];
-  __syncthreads();  // barrier initialised
+  const bool has_noise = P.noise != nullptr;
+  // output pointers of this thread's first row; advanced by one image row per output row
+  const int64_t o_first = (((int64_t)b * P.H + oy0) * P.W + ox0) * P.C + c0;
+  __nv_bfloat16* o_ptr = P.out ? P.out + o_first : nullptr;
+  __nv_bfloat16* m_ptr = P.out_mod ? P.out_mod + o_first : nullptr;
+  const int64_t row_stride = (int64_t)P.W * P.C;
+  const int rows_ok = min(kBlurRows, P.H - oy0);          // may be <= 0 on a ragged bottom edge
+  bool px_ok[kBlurPx];
+#pragma unroll
+  for (int px = 0; px < kBlurPx; ++px) px_ok[px] = ox0 + px < P.W;
+  __syncthreads();  // barrier initialised, noise patch visible
   {
     uint32_t spin = 0;
     while (!mbar_try_wait(&bar, 0))
       if (++spin > (1u << 26)) __trap();  // a lost TMA completion becomes a launch failure, not a hang
   }
   const uint8_t* col = smem + ((size_t)(rg * kBlurRows) * sw + xb * kBlurPx) * pix_bytes + g * 16;
+  const int row_bytes = sw * pix_bytes;
 
   float win[4][kBlurPx][8];
 #pragma unroll
   for (int t = 0; t < kBlurRows + 3; ++t) {
     const int u = t & 3;
     float f[kBlurPx + 3][8];
-    const uint8_t* row = col + (size_t)t * sw * pix_bytes;
 #pragma unroll
     for (int k = 0; k < kBlurPx + 3; ++k) {
       bf16x8 v;
-      *reinterpret_cast<uint4*>(&v) = *reinterpret_cast<const uint4*>(row + k * pix_bytes);
+      *reinterpret_cast<uint4*>(&v) = *reinterpret_cast<const uint4*>(col + t * row_bytes + k * pix_bytes);
       unpack8(v, f[k]);
     }
 #pragma unroll
@@ -199,13 +218,12 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
       for (int e = 0; e < 8; ++e)
         win[u][px][e] = fmaf(fh3, f[px + 3][e], fmaf(fh2, f[px + 2][e], fmaf(fh1, f[px + 1][e], fh0 * f[px][e])));
     if (t >= 3) {
-      const int oy = oy0 + t - 3;
-      if (oy < P.H) {
+      const int r = t - 3;
+      if (r < rows_ok) {
 #pragma unroll
         for (int px = 0; px < kBlurPx; ++px) {
-          const int ox = ox0 + px;
-          if (ox < P.W) {
-            const float nz = noise ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+          if (px_ok[px]) {
+            const float nz = has_noise ? s_noise[rg * kBlurRows + r][xb * kBlurPx + px] : 0.f;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -216,16 +234,17 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
                                              fmaf(fv0, win[(u + 1) & 3][px][e], bias[e] + nz))));
               v[e] = lrelu ? fmaxf(a, 0.2f * a) : a;
             }
-            const int64_t o = (((int64_t)b * P.H + oy) * P.W + ox) * P.C + c0;
-            if (P.out) st8(P.out + o, pack8(v));
-            if (P.out_mod) {
+            if (o_ptr) st8(o_ptr + px * P.C, pack8(v));
+            if (m_ptr) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
-              st8(P.out_mod + o, pack8(v));
+              st8(m_ptr + px * P.C, pack8(v));
             }
           }
         }
       }
+      if (o_ptr) o_ptr += row_stride;
+      if (m_ptr) m_ptr += row_stride;
     }
   }
 }
