@@ -182,6 +182,9 @@ int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, c
                         const float* host_taps1d, float* rgb, void* stream);
 /* tuning knob of w2e_modconv_tc2: cap on the number of persistent CTAs (0 = one or two per SM). */
 void w2e_modconv_tc2_knobs(int max_ctas);
+/* epilogue selection of w2e_modconv_tc2[_rgb]: 1 (default) = shared-memory-staged TMA-store epilogue
+ * whenever the shape is eligible, 0 = always the direct-store epilogue (A/B tests). */
+void w2e_modconv_tc2_epilogue(int ts_mode);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],

@@ -240,6 +240,19 @@ int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   return W2E_OK;
 }
 
+int make_f32_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+  EncodeTiledFn fn = tensor_map_encoder();
+  if (!fn) return set_error(W2E_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                  reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(W2E_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return W2E_OK;
+}
+
 template <int BN, int BK, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, cudaStream_t s) {
   using L = TcSmem<BN, BK, STAGES>;

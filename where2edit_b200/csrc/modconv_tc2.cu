@@ -23,12 +23,22 @@
 // the whole batch shares one weight tensor.  Per-channel constants are staged in shared memory
 // once per tile.
 //
+// TS epilogue (template flag TS; tiles with <= 64-channel staging units, i.e. the >= 256^2 layers
+// whose time is the epilogue, not the MMA): the bf16 result tile is staged in 128B/64B-swizzled
+// shared memory (conflict-free 128-bit writes, one accumulator row = one pixel per thread) and
+// leaves through ONE TMA store per 128-pixel x 64-channel unit (the four output-parity classes of
+// the transposed conv through four strided tensor maps); the noise patch and the 2x2-tap patch of
+// the ToRGB skip image arrive through TMA boxes issued by the producer warp one tile ahead
+// (out-of-bounds zero fill = the image borders), so the epilogue threads do no global-memory
+// address arithmetic at all; per-element math is packed fp32x2 (FFMA2/FMUL2/FADD2).
+//
 // Algorithmic FLOPs per launch: 2 * taps * Cin * Cout * B * (pixels of the class grids).
 #include "tc_ptx.cuh"
 
 namespace w2e {
 
-constexpr int kT2Threads = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kT2Threads = 320;    // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kT2ThreadsTS = 576;  // TS flavour: two groups of 8 epilogue warps (one per accumulator buffer)
 constexpr int kT2EpiThreads = 256;
 constexpr int kT2MaxA = 4, kT2MaxB = 16, kT2MaxAcc = 2;
 constexpr int kTileW = 8, kSubTileH = 16;  // one M=128 sub-tile = 16 rows x 8 pixels
@@ -59,6 +69,17 @@ struct Tc2Params {
   int tmem_cols;
   int act;
   int ntaps;
+  // TS epilogue: staging units of 128 pixels x ts_unit_ch channels, ts_slots per epilogue half
+  int ts_unit_ch, ts_unit_bytes, ts_slots, ts_off;
+  int e_off, e_stage_bytes, e_noise_bytes, e_bytes, use_e;   // TMA-staged epilogue inputs (noise, skip)
+  int bars_off;
+};
+
+// tensor maps of the TS epilogue
+struct alignas(64) Tc2Maps {
+  CUtensorMap noise;   // fp32 {OW, OH, noise_batch}, box {8, 16*MT, 1}
+  CUtensorMap skip;    // fp32 {OW/2, OH/2, B*3}, box {12, 10, 3}
+  CUtensorMap st[4];   // bf16 stores, box {unit_ch, 8, 16, 1}: plain [0] = out, [1] = out_mod; transposed [g] = class g of out
 };
 
 struct Tc2Bars {
@@ -66,6 +87,7 @@ struct Tc2Bars {
   uint64_t b_full[kT2MaxB], b_empty[kT2MaxB];
   uint64_t acc_full[kT2MaxAcc], acc_empty[kT2MaxAcc];
   uint64_t w_full;
+  uint64_t e_full[2], e_empty[2];
   uint32_t tmem_slot;
   int abort_flag;
   // per-tile epilogue constants, double-buffered by tile parity: scale (demod*gain), shift (bias*gain), next style
@@ -73,9 +95,37 @@ struct Tc2Bars {
   alignas(16) float ep_shift[2][256];
   alignas(16) float ep_next[2][256];
   alignas(16) float ep_rgb[2][3][256];  // per-sample modulated ToRGB weights
+  // TS flavour: the same 3072 floats viewed as [group][parity][6 = scale, shift, next, rgb0..2][128]
+  __device__ __forceinline__ float* ts_consts(int group, int cb) { return &ep_scale[0][0] + (group * 2 + cb) * 768; }
+};
+static_assert(offsetof(Tc2Bars, ep_rgb) - offsetof(Tc2Bars, ep_scale) == 3 * 512 * sizeof(float), "ep arrays must be contiguous");
+
+// Tile coordinates advanced without divisions: tile = ((tn*B + b)*tiles_y + ty)*tiles_x + tx and
+// the per-CTA stride is decomposed once in the same mixed radix.
+struct TileWalk {
+  int tx, ty, b, tn, dtx, dty, db, dtn;
+  __device__ __forceinline__ void init(int tile, int stride, const Tc2Params& P) {
+    tx = tile % P.tiles_x; tile /= P.tiles_x;
+    ty = tile % P.tiles_y; tile /= P.tiles_y;
+    b = tile % P.B; tn = tile / P.B;
+    dtx = stride % P.tiles_x; stride /= P.tiles_x;
+    dty = stride % P.tiles_y; stride /= P.tiles_y;
+    db = stride % P.B; dtn = stride / P.B;
+  }
+  __device__ __forceinline__ void next(const Tc2Params& P) {
+    tx += dtx;
+    if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
+    ty += dty;
+    if (ty >= P.tiles_y) { ty -= P.tiles_y; ++b; }
+    b += db;
+    if (b >= P.B) { b -= P.B; ++tn; }
+    tn += dtn;
+  }
 };
 
 constexpr int kPitch = 10;  // pixels per row of the haloed tile (8 + 2 halo columns)
+// skip-image patch of one sub-tile (fused ToRGB, TS epilogue): 3 planes x 10 rows x 12 columns fp32
+constexpr int kSkipBoxW = 12, kSkipBoxBytes = 1536;
 
 // Upper 32 bits of a K-major swizzled UMMA shared-memory descriptor: SBO (bytes >> 4) @32,
 // version 1 @46, layout @61 (2 = SWIZZLE_128B, 4 = SWIZZLE_64B); the lower word is the start
@@ -112,10 +162,10 @@ struct Ring {
   }
 };
 
-template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB>
-__global__ void __launch_bounds__(kT2Threads, 1)
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
+__global__ void __launch_bounds__(TS ? kT2ThreadsTS : kT2Threads, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const __grid_constant__ Tc2Params P) {
+                   const __grid_constant__ Tc2Params P, const __grid_constant__ Tc2Maps M) {
   constexpr int NG = TR ? 4 : 1;
   static_assert(!RGB || (!TR && MT == 2), "fused ToRGB needs the plain conv with two sub-tiles");
   constexpr int kRowBytes = KSTEPS * 32;  // BK * 2 bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
@@ -126,7 +176,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* b_base = smem + (size_t)P.a_stages * P.a_stage_bytes;
   const int kchunks = P.Cin / kBK;
   const int n_bblocks = WRES ? 9 * kchunks : P.b_stages;
-  Tc2Bars* bars = reinterpret_cast<Tc2Bars*>(b_base + (size_t)n_bblocks * P.b_block_bytes);
+  Tc2Bars* bars = reinterpret_cast<Tc2Bars*>(smem + P.bars_off);
+  (void)n_bblocks;
   volatile int* abort_flag = &bars->abort_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,6 +195,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], kT2EpiThreads); }
       mbar_init(&bars->w_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->e_full[s], 1); mbar_init(&bars->e_empty[s], kT2EpiThreads); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -163,15 +215,28 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int t = 0; t < 9; ++t)
             tma_load_3d(b_base + (size_t)(kc * 9 + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * kBK, 0, t);
       }
-      Ring ar, br;
+      Ring ar, br, er;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
-        const int tn = tile / tiles_per_n;
-        int rem = tile - tn * tiles_per_n;
-        const int b = rem / tiles_xy;
-        rem -= b * tiles_xy;
-        const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
-        const int j0 = ty * (kSubTileH * MT), i0 = tx * kTileW, co0 = tn * P.bn;
+      TileWalk wk;
+      wk.init(blockIdx.x, gridDim.x, P);
+      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
+        const int b = wk.b;
+        const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW, co0 = wk.tn * P.bn;
+        if (TS && P.use_e) {
+          // epilogue inputs of this tile: noise patch and (fused ToRGB) the skip-image patch of each sub-tile
+          ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
+          if (!ok) break;
+          uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
+          mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);
+          if (P.noise) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
+          if (RGB && P.rgb_skip) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
+                          ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
+          }
+          er.advance(2);
+        }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
           if (!ok) break;
@@ -265,6 +330,252 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (ok && elect_one()) umma_commit(&bars->acc_full[cr.idx]);
       __syncwarp();
       cr.advance(P.nbuf);
+    }
+
+  } else if constexpr (TS) {
+    // ------------------------------------------------------------------ epilogue, TS flavour
+    // 16 epilogue warps = two groups of 8; group g drains the tiles that land in accumulator
+    // buffer g (tile parity), so one group's TMEM/shared-memory latencies hide behind the other's
+    // arithmetic (with a single accumulator buffer only group 0 works).  Inside a group, thread
+    // (q, lane) owns accumulator row r = pixel (sy, sx) of a sub-tile; work units are
+    // (accumulator, <=64-channel chunk) and the group's two halves take alternate units (fused
+    // ToRGB: half = sub-tile, because a thread then needs its pixel's whole channel row).
+    const int ew = warp - 2;
+    const int group = ew >> 3;
+    const int half = (ew >> 2) & 1;
+    const int q = warp & 3;
+    const int gt = (int)threadIdx.x - 64 - group * kT2EpiThreads;   // 0..255 inside the group
+    if (group < P.nbuf) {
+      const int r = q * 32 + lane;
+      const int sy = r >> 3, sx = r & 7;
+      const bool leader = (gt & 127) == 0;
+      const int UC = P.ts_unit_ch;
+      const int chunks = P.bn / UC;
+      constexpr int NACC = NG * MT;
+      const bool has_out = P.out != nullptr, has_mod = P.out_mod != nullptr;
+      const int n_out = (has_out ? 1 : 0) + (has_mod ? 1 : 0);
+      const bool one_in_flight = n_out == 1 && P.ts_slots == 2;
+      const bool lrelu = P.act == W2E_ACT_LRELU;
+      const float gain = lrelu ? 1.41421356237309515f : 1.f;
+      const float slope = lrelu ? 0.2f : 1.f;
+      const uint64_t slope2 = pack2(slope, slope);
+      const bool has_noise = P.noise != nullptr, has_skip = RGB && P.rgb_skip != nullptr;
+      const float nw = has_noise ? __ldg(P.noise_w) * gain : 0.f;
+      const uint32_t stage0 =
+          smem_u32(smem + P.ts_off) + (uint32_t)((group * 2 + half) * P.ts_slots * P.ts_unit_bytes);
+      const uint32_t row_off = (uint32_t)(r * UC * 2);
+      const uint32_t swz = (UC == 64) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+      const uint32_t e_base = smem_u32(smem + P.e_off);
+      const int bar_group = 1 + group * 3, bar_half = 2 + group * 3 + half;
+      const int stride = (int)gridDim.x * P.nbuf;
+      const int64_t plane = (int64_t)P.OH * P.OW;
+      // skip-upsample polyphase taps of this thread's pixel (parity of (sy, sx): tile origins are even)
+      const float cy0 = (sy & 1) ? P.kf[1] : P.kf[0], cy1 = (sy & 1) ? P.kf[3] : P.kf[2];
+      const float cx0 = (sx & 1) ? P.kf[1] : P.kf[0], cx1 = (sx & 1) ? P.kf[3] : P.kf[2];
+      const uint32_t skip_off = (uint32_t)P.e_noise_bytes +
+                                (uint32_t)(half * kSkipBoxBytes + (((sy + 1) >> 1) * kSkipBoxW + ((sx + 1) >> 1) + 3) * 4);
+      const uint32_t noise_off = (uint32_t)((sy * kTileW + sx) * 4);
+
+      struct Cst { float scale, shift, next, rgbs, rgbw[3]; };
+      auto load_consts = [&](int b, int tn) -> Cst {   // raw loads only; consumed one tile later
+        Cst t;
+        t.scale = 1.f; t.shift = 0.f; t.next = 0.f; t.rgbs = 0.f; t.rgbw[0] = t.rgbw[1] = t.rgbw[2] = 0.f;
+        if (gt < P.bn) {
+          const int c = tn * P.bn + gt, bc = b * P.Cout + c;
+          if (P.out_scale) t.scale = __ldg(P.out_scale + bc);
+          if (P.bias) t.shift = __ldg(P.bias + c);
+          if (P.next_scale) t.next = __ldg(P.next_scale + bc);
+          if (RGB) {
+            t.rgbs = __ldg(P.rgb_style + bc);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + gt);
+          }
+        }
+        return t;
+      };
+
+      float rgbb[3] = {0.f, 0.f, 0.f};
+      if (RGB && P.rgb_bias) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) rgbb[o] = __ldg(P.rgb_bias + o);
+      }
+      TileWalk wk;
+      int tile = (int)blockIdx.x + group * (int)gridDim.x;
+      wk.init(tile < P.ntiles ? tile : 0, stride, P);
+      Cst cur;
+      if (tile < P.ntiles) cur = load_consts(wk.b, wk.tn);
+      uint32_t un = 0;
+      bool ok = true;
+      for (uint32_t k = 0; tile < P.ntiles; tile += stride, ++k) {
+        const int b = wk.b;
+        const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW, co0 = wk.tn * P.bn;
+        wk.next(P);
+        const uint32_t cb = k & 1u;
+        const uint32_t seq = k * (uint32_t)P.nbuf + (uint32_t)group;   // position in the CTA's tile sequence
+        float* cst = bars->ts_consts(group, (int)cb);
+        if (gt < P.bn) {
+          cst[gt] = cur.scale * gain;
+          cst[128 + gt] = cur.shift * gain;
+          cst[256 + gt] = cur.next;
+          if (RGB) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) cst[384 + o * 128 + gt] = cur.rgbw[o] * cur.rgbs;
+          }
+        }
+        named_bar_sync(bar_group, kT2EpiThreads);
+        if (tile + stride < P.ntiles) cur = load_consts(wk.b, wk.tn);
+        const uint32_t sc_a = smem_u32(cst);
+
+        // epilogue inputs staged by the producer's TMA boxes
+        float nzm[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) nzm[m] = 0.f;
+        uint64_t racc[3] = {0ull, 0ull, 0ull};
+        float rgb_init[3] = {rgbb[0], rgbb[1], rgbb[2]};
+        if (P.use_e) {
+          const uint32_t es = seq & 1u;
+          if (ok) ok = mbar_wait(&bars->e_full[es], (seq >> 1) & 1u, abort_flag);
+          const uint32_t eb = e_base + es * (uint32_t)P.e_stage_bytes;
+          if (has_noise) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) nzm[m] = nw * lds_f32(eb + noise_off + (uint32_t)(m * kSubTileH * kTileW * 4));
+          }
+          if (has_skip) {
+            // upfirdn2d(skip, up=2, pad=(2,1)) = a 2x2-tap polyphase filter on rows ya, ya+1 / columns xa, xa+1.
+            // The box starts one row and FOUR columns before the sub-tile's first source pixel: the innermost
+            // start coordinate of a TMA box must be 16-byte aligned (x0 - 1 faults with an illegal instruction).
+            const uint32_t sb = eb + skip_off;
+            constexpr int kPlane = 10 * kSkipBoxW * 4, kRow = kSkipBoxW * 4;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float t00 = lds_f32(sb + o * kPlane), t01 = lds_f32(sb + o * kPlane + 4);
+              const float t10 = lds_f32(sb + o * kPlane + kRow), t11 = lds_f32(sb + o * kPlane + kRow + 4);
+              rgb_init[o] += cy0 * fmaf(cx1, t01, cx0 * t00) + cy1 * fmaf(cx1, t11, cx0 * t10);
+            }
+          }
+          mbar_arrive(&bars->e_empty[es]);
+        }
+
+        const uint32_t ci = seq % (uint32_t)P.nbuf;   // accumulator buffer of this tile
+        if (ok) ok = mbar_wait(&bars->acc_full[ci], k & 1u, abort_flag);
+        tc_fence_after();
+        const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + ci * (uint32_t)(NACC * P.bn);
+        const int nunits = RGB ? chunks : NACC * chunks;
+        bool released = false;
+        for (int ui = RGB ? 0 : half; ui < nunits; ui += RGB ? 1 : 2) {
+          const int acc = RGB ? half : ui / chunks;
+          const int chunk = RGB ? ui : ui - acc * chunks;
+          const int m = acc % MT;
+          const uint32_t t_addr = t_tile + (uint32_t)(acc * P.bn + chunk * UC);
+          float nzv = nzm[0];
+          if (MT == 2 && m == 1) nzv = nzm[MT - 1];
+          const uint64_t nz2 = pack2(nzv, nzv);
+          const uint32_t slot_o = stage0 + (uint32_t)((n_out == 2 ? 0 : (int)(un & (uint32_t)(P.ts_slots - 1))) * P.ts_unit_bytes);
+          const uint32_t slot_m = has_out ? stage0 + (uint32_t)P.ts_unit_bytes : slot_o;
+          const bool last_unit = ui + (RGB ? 1 : 2) >= nunits;
+          for (int c16 = 0; c16 < UC; c16 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + (uint32_t)c16, v);
+            tmem_ld_wait();
+            if (last_unit && c16 + 16 >= UC) {   // this thread's last TMEM read of the tile: hand the buffer back
+              tc_fence_before();
+              mbar_arrive(&bars->acc_empty[ci]);
+              released = true;
+            }
+            const uint32_t ca = sc_a + (uint32_t)((chunk * UC + c16) * 4);
+            uint32_t po[8], pm[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint64_t a01, a23, f01, f23;
+              lds_2x2(ca + e * 16, a01, a23);
+              if (TR) {
+                f01 = mul2(pack2u(v[4 * e], v[4 * e + 1]), a01);
+                f23 = mul2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23);
+              } else {
+                uint64_t b01, b23;
+                lds_2x2(ca + 512 + e * 16, b01, b23);
+                f01 = add2(fma2(pack2u(v[4 * e], v[4 * e + 1]), a01, b01), nz2);
+                f23 = add2(fma2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23, b23), nz2);
+                const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
+                float x0, x1, x2, x3, y0, y1, y2, y3;
+                unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                unpack2(g01, y0, y1); unpack2(g23, y2, y3);
+                f01 = pack2(fmaxf(x0, y0), fmaxf(x1, y1));
+                f23 = pack2(fmaxf(x2, y2), fmaxf(x3, y3));
+              }
+              if (RGB) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                  uint64_t w01, w23;
+                  lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01, w23);
+                  racc[o] = fma2(f23, w23, fma2(f01, w01, racc[o]));
+                }
+              }
+              if (has_out) {
+                float x0, x1, x2, x3;
+                unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                po[2 * e] = cvt_bf16x2(x0, x1);
+                po[2 * e + 1] = cvt_bf16x2(x2, x3);
+              }
+              if (has_mod) {
+                uint64_t n01, n23;
+                lds_2x2(ca + 1024 + e * 16, n01, n23);
+                float x0, x1, x2, x3;
+                unpack2(mul2(f01, n01), x0, x1); unpack2(mul2(f23, n23), x2, x3);
+                pm[2 * e] = cvt_bf16x2(x0, x1);
+                pm[2 * e + 1] = cvt_bf16x2(x2, x3);
+              }
+            }
+            if (n_out) {
+              if (c16 == 0) {
+                // slot acquire: the TMA store that last read these slots must have drained
+                if (leader) {
+                  if (one_in_flight) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                }
+                named_bar_sync(bar_half, 128);
+              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t col = (((uint32_t)(c16 >> 3) + j) ^ swz) << 4;
+                if (has_out) sts_128(slot_o + row_off + col, po[4 * j], po[4 * j + 1], po[4 * j + 2], po[4 * j + 3]);
+                if (has_mod) sts_128(slot_m + row_off + col, pm[4 * j], pm[4 * j + 1], pm[4 * j + 2], pm[4 * j + 3]);
+              }
+            }
+          }
+          if (n_out) {
+            fence_proxy_async_smem();
+            named_bar_sync(bar_half, 128);
+            if (leader) {
+              const int cc = co0 + chunk * UC, yy = j0 + m * kSubTileH;
+              if (TR) {
+                tma_store_4d(&M.st[acc / MT], slot_o, cc, i0, yy, b);
+              } else {
+                if (has_out) tma_store_4d(&M.st[0], slot_o, cc, i0, yy, b);
+                if (has_mod) tma_store_4d(&M.st[1], slot_m, cc, i0, yy, b);
+              }
+              bulk_commit();
+            }
+            ++un;
+          }
+        }
+        if (!released) {
+          tc_fence_before();
+          mbar_arrive(&bars->acc_empty[ci]);
+        }
+        if (RGB) {
+          const int oy = j0 + half * kSubTileH + sy, ox = i0 + sx;
+          if (oy < P.OH && ox < P.OW && ok) {
+            float* dst = P.rgb + ((int64_t)b * 3 * P.OH + oy) * P.OW + ox;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              float lo, hi;
+              unpack2(racc[o], lo, hi);
+              dst[o * plane] = rgb_init[o] + (lo + hi);
+            }
+          }
+        }
+      }
+      if (leader) bulk_wait_all();
     }
   } else {
     // ------------------------------------------------------------------ epilogue: warps 2..9
@@ -488,36 +799,39 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB>
-static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, int smem_bytes, int max_ctas,
-                      cudaStream_t s) {
-  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB>;
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
+static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, const Tc2Maps& M, int smem_bytes,
+                      int max_ctas, cudaStream_t s) {
+  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB, TS>;
   static bool configured = false;
   if (!configured) {
     W2E_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   int per_sm = 1;
-  W2E_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT2Threads, smem_bytes));
+  constexpr int kThreads = TS ? kT2ThreadsTS : kT2Threads;
+  W2E_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes));
   if (per_sm * P.tmem_cols > 512) per_sm = 512 / P.tmem_cols;
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int ctas = sm_count() * per_sm;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > P.ntiles) ctas = P.ntiles;
-  kern<<<ctas, kT2Threads, smem_bytes, s>>>(ma, mb, P);
+  kern<<<ctas, kThreads, smem_bytes, s>>>(ma, mb, P, M);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
 
 // debug / tuning knobs (tests flip them to validate the shifted-descriptor scheme on hardware)
 static int g_max_ctas = 0;
+static int g_ts_mode = 1;   // 0 = never use the TS epilogue, 1 = whenever eligible
 
 }  // namespace w2e
 
 using namespace w2e;
 
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
+extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -582,24 +896,68 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.ntiles = (int)ntiles;
   const int kchunks = Cin / P.bk;
 
-  // shared-memory plan: resident weights when small, else a ring of weight blocks
-  const int smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - (int)sizeof(Tc2Bars);
+  // TS epilogue eligibility (see the header): staging units of <= 64 channels, TMA-able strides
+  const int n_out = (out ? 1 : 0) + (out_mod ? 1 : 0);
+  bool ts = g_ts_mode != 0 && P.mt == 2 && P.bn >= 32 && P.bn <= 128;
+  if (transposed) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
+  if (noise) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
+  if (rgb && rgb->skip) ts = ts && ((P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
+  if (out) ts = ts && (((uintptr_t)out & 15) == 0);
+  if (out_mod) ts = ts && (((uintptr_t)out_mod & 15) == 0);
+  if (rgb && P.bn != Cout) ts = false;
+
+  // shared-memory plan: resident weights when small, else a ring of weight blocks; with the TS
+  // epilogue also the output staging slots (per epilogue group and half) and the two stages of
+  // epilogue inputs.  TS candidates in order of preference: 64-channel units with two slots, one
+  // slot, then 32-channel units; if none fits the direct-store epilogue is used.
+  const int kBarsBytes = ((int)sizeof(Tc2Bars) + 15) / 16 * 16;
   const int w_bytes = 9 * kchunks * P.b_block_bytes;
-  P.wres = (P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
-  P.a_stages = kchunks == 1 ? 3 : 2;
-  int b_bytes;
-  if (P.wres) {
-    P.b_stages = 1;
-    b_bytes = w_bytes;
-  } else {
-    int avail = smem_limit - P.a_stages * P.a_stage_bytes;
-    P.b_stages = avail / P.b_block_bytes;
-    if (P.b_stages > kT2MaxB) P.b_stages = kT2MaxB;
-    W2E_CHECK_ARG(P.b_stages >= 2, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
-    b_bytes = P.b_stages * P.b_block_bytes;
+  int smem_bytes = 0;
+  struct Cand { int unit_ch, slots; };
+  const Cand cands[5] = {{64, 2}, {64, 1}, {32, 2}, {32, 1}, {0, 0}};
+  for (int ci = ts ? 0 : 4; ci < 5 && smem_bytes == 0; ++ci) {
+    const bool use_ts = cands[ci].unit_ch != 0;
+    int extra = 0, ts_bytes = 0;
+    if (use_ts) {
+      P.ts_unit_ch = P.bn < cands[ci].unit_ch ? P.bn : cands[ci].unit_ch;
+      if (ci >= 2 && P.bn <= 32) continue;   // same unit as candidates 0/1
+      P.ts_slots = cands[ci].slots;
+      if (n_out > P.ts_slots) continue;
+      P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
+      P.use_e = (noise || (rgb && rgb->skip)) ? 1 : 0;
+      P.e_noise_bytes = 1024;
+      P.e_stage_bytes = P.use_e ? 1024 + 2 * kSkipBoxBytes : 0;
+      P.e_bytes = (noise ? kTileW * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * kSkipBoxW * 4 : 0);
+      ts_bytes = n_out ? P.nbuf * 2 * P.ts_slots * P.ts_unit_bytes : 0;
+      extra = 1024 /*alignment of the staging area*/ + 2 * P.e_stage_bytes;
+    } else {
+      P.ts_unit_ch = P.ts_unit_bytes = P.ts_slots = P.use_e = P.e_stage_bytes = P.e_bytes = 0;
+    }
+    const int smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - kBarsBytes - extra;
+    P.a_stages = kchunks == 1 ? 3 : 2;
+    P.wres = (P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
+    int b_bytes = 0;
+    if (P.wres) {
+      while (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit && P.a_stages > 2) --P.a_stages;
+      if (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit) continue;
+      P.b_stages = 1;
+      b_bytes = w_bytes;
+    } else {
+      const int avail = smem_limit - P.a_stages * P.a_stage_bytes - ts_bytes;
+      P.b_stages = avail / P.b_block_bytes;
+      if (P.b_stages > kT2MaxB) P.b_stages = kT2MaxB;
+      if (P.b_stages < (use_ts ? 6 : 2)) continue;
+      b_bytes = P.b_stages * P.b_block_bytes;
+    }
+    const int ab = P.a_stages * P.a_stage_bytes + b_bytes;
+    P.ts_off = (ab + 1023) / 1024 * 1024;
+    P.e_off = P.ts_off + ts_bytes;
+    P.bars_off = use_ts ? P.e_off + 2 * P.e_stage_bytes : (ab + 15) / 16 * 16;
+    smem_bytes = P.bars_off + kBarsBytes + 1024;
+    ts = use_ts;
   }
-  const int smem_bytes = P.a_stages * P.a_stage_bytes + b_bytes + (int)sizeof(Tc2Bars) + 1024;
-  W2E_CHECK_ARG(smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
+  W2E_CHECK_ARG(smem_bytes > 0, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
+  W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
   {
@@ -616,18 +974,71 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     int rc = make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
+  Tc2Maps M;
+  memset(&M, 0, sizeof(M));
+  if (ts) {
+    if (noise) {
+      const uint64_t dims[3] = {(uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)noise_batch};
+      const uint64_t strides[2] = {(uint64_t)P.OW * 4, (uint64_t)P.OH * P.OW * 4};
+      const uint32_t box[3] = {(uint32_t)kTileW, (uint32_t)(kSubTileH * P.mt), 1u};
+      int rc = make_f32_map(&M.noise, noise, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (rgb && rgb->skip) {
+      const uint64_t h2 = (uint64_t)P.OH / 2, w2 = (uint64_t)P.OW / 2;
+      const uint64_t dims[3] = {w2, h2, (uint64_t)B * 3};
+      const uint64_t strides[2] = {w2 * 4, h2 * w2 * 4};
+      const uint32_t box[3] = {(uint32_t)kSkipBoxW, 10u, 3u};
+      int rc = make_f32_map(&M.skip, rgb->skip, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    const uint32_t sbox[4] = {(uint32_t)P.ts_unit_ch, (uint32_t)kTileW, (uint32_t)kSubTileH, 1u};
+    if (!transposed) {
+      const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)P.OW * Cout * 2, (uint64_t)P.OH * P.OW * Cout * 2};
+      if (out) {
+        int rc = make_bf16_map(&M.st[0], out, 4, dims, strides, sbox, P.ts_unit_ch * 2);
+        if (rc) return rc;
+      }
+      if (out_mod) {
+        int rc = make_bf16_map(&M.st[1], out_mod, 4, dims, strides, sbox, P.ts_unit_ch * 2);
+        if (rc) return rc;
+      }
+    } else {
+      // class (py, px): pixels (2j+py, 2i+px) of the (2h+1) x (2w+1) output as a strided [B, rows, cols, C] view
+      for (int g = 0; g < 4; ++g) {
+        const int py = g >> 1, px = g & 1;
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)((P.OW - px + 1) / 2), (uint64_t)((P.OH - py + 1) / 2), (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cout * 4, (uint64_t)P.OW * Cout * 4, (uint64_t)P.OH * P.OW * Cout * 2};
+        const __nv_bfloat16* base = (const __nv_bfloat16*)out + ((int64_t)py * P.OW + px) * Cout;
+        int rc = make_bf16_map(&M.st[g], base, 4, dims, strides, sbox, P.ts_unit_ch * 2);
+        if (rc) return rc;
+      }
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int ks = P.bk / 16;
   if (rgb) {
     W2E_CHECK_ARG(P.mt == 2 && P.tiles_n == 1, "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
 #define W2E_TC2_RGB(KS_, WR_) \
-  if (ks == KS_ && (P.wres != 0) == WR_) return launch_tc2<false, 2, KS_, WR_, true>(ma, mb, P, smem_bytes, g_max_ctas, st);
+  if (ks == KS_ && (P.wres != 0) == WR_) { \
+    if (ts) return launch_tc2<false, 2, KS_, WR_, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st); \
+    return launch_tc2<false, 2, KS_, WR_, true, false>(ma, mb, P, M, smem_bytes, g_max_ctas, st); \
+  }
     W2E_TC2_RGB(4, false) W2E_TC2_RGB(4, true) W2E_TC2_RGB(2, false) W2E_TC2_RGB(2, true)
 #undef W2E_TC2_RGB
   }
+  if (ts) {
+#define W2E_TC2_TS(TR_, KS_, WR_) \
+  if ((transposed != 0) == TR_ && ks == KS_ && (P.wres != 0) == WR_) \
+    return launch_tc2<TR_, 2, KS_, WR_, false, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
+    W2E_TC2_TS(false, 4, false) W2E_TC2_TS(false, 4, true) W2E_TC2_TS(false, 2, false) W2E_TC2_TS(false, 2, true)
+    W2E_TC2_TS(true, 4, false) W2E_TC2_TS(true, 4, true) W2E_TC2_TS(true, 2, false) W2E_TC2_TS(true, 2, true)
+#undef W2E_TC2_TS
+  }
 #define W2E_TC2_CASE(TR_, MT_, KS_, WR_) \
   if ((transposed != 0) == TR_ && P.mt == MT_ && ks == KS_ && (P.wres != 0) == WR_) \
-    return launch_tc2<TR_, MT_, KS_, WR_, false>(ma, mb, P, smem_bytes, g_max_ctas, st);
+    return launch_tc2<TR_, MT_, KS_, WR_, false, false>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
   W2E_TC2_CASE(false, 1, 4, false) W2E_TC2_CASE(false, 2, 4, false) W2E_TC2_CASE(false, 1, 2, false)
   W2E_TC2_CASE(false, 2, 2, false) W2E_TC2_CASE(false, 1, 4, true) W2E_TC2_CASE(false, 2, 4, true)
   W2E_TC2_CASE(false, 1, 2, true) W2E_TC2_CASE(false, 2, 2, true)

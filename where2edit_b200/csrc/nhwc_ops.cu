@@ -133,7 +133,7 @@ struct BlurTile {
   int ct, tx, tiles_x, tiles_y, tiles_c;
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ BlurParams P,
                      const __grid_constant__ BlurTile T) {
   extern __shared__ uint8_t blur_smem_raw[];
