@@ -165,6 +165,9 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ void lds_2x2(uint32_t addr, uint64_t& p0, uint64_t& p1) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "r"(addr));
 }
+__device__ __forceinline__ void lds_4i(uint32_t addr, int& a, int& b, int& c, int& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
