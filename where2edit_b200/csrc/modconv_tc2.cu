@@ -42,7 +42,8 @@ namespace w2e {
 constexpr int kT2Threads = 320;    // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kT2ThreadsTS = 576;  // TS flavour: two groups of 8 epilogue warps (one per accumulator buffer)
 constexpr int kT2EpiThreads = 256;
-constexpr int kT2MaxA = 4, kT2MaxB = 16, kT2MaxAcc = 2;
+constexpr int kT2MaxA = 8, kT2MaxB = 16, kT2MaxAcc = 2;
+constexpr int kEStages = 4;   // epilogue-input ring (TS flavour): deep enough not to throttle the A-tile prefetch
 constexpr int kTileW = 8, kSubTileH = 16;  // one M=128 sub-tile = 16 rows x 8 pixels
 
 struct Tc2Params {
@@ -89,7 +90,7 @@ struct Tc2Bars {
   uint64_t b_full[kT2MaxB], b_empty[kT2MaxB];
   uint64_t acc_full[kT2MaxAcc], acc_empty[kT2MaxAcc];
   uint64_t w_full;
-  uint64_t e_full[2], e_empty[2];
+  uint64_t e_full[kEStages], e_empty[kEStages];
   uint32_t tmem_slot;
   int abort_flag;
   // per-tile epilogue constants, double-buffered by tile parity: scale (demod*gain), shift (bias*gain), next style
@@ -197,7 +198,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], kT2EpiThreads); }
       mbar_init(&bars->w_full, 1);
-      for (int s = 0; s < 2; ++s) { mbar_init(&bars->e_full[s], 1); mbar_init(&bars->e_empty[s], kT2EpiThreads); }
+      for (int s = 0; s < kEStages; ++s) { mbar_init(&bars->e_full[s], 1); mbar_init(&bars->e_empty[s], kT2EpiThreads); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -239,7 +240,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
                           ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
           }
-          er.advance(2);
+          er.advance(kEStages);
         }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
@@ -268,7 +269,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hi = desc_hi(kRowBytes, kPitch * kRowBytes);
     const uint32_t b_hi = desc_hi(kRowBytes, 8 * kRowBytes);
-    const uint32_t a_smem = smem_u32(a_base), b_smem = smem_u32(b_base);
+    // descriptor low words (start address >> 4) are LINEAR in the address: one add per operand per MMA
+    const uint32_t a_lo0 = (smem_u32(a_base) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(b_base) & 0x3FFFFu) >> 4;
+    const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4, b_block16 = (uint32_t)P.b_block_bytes >> 4;
+    const uint32_t bn = (uint32_t)P.bn;
     Ring ar, br, cr;
     bool ok = true;
     if (WRES) {
@@ -279,28 +283,31 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t acc_base = tmem_base + cr.idx * (uint32_t)(NG * MT) * (uint32_t)P.bn;
+      uint32_t dcol[NG * MT];   // TMEM column of every accumulator of this tile
+      dcol[0] = tmem_base + cr.idx * (uint32_t)(NG * MT) * bn;
+#pragma unroll
+      for (int i = 1; i < NG * MT; ++i) dcol[i] = dcol[i - 1] + bn;
       for (int kc = 0; kc < kchunks && ok; ++kc) {
         ok = mbar_wait_warp(&bars->a_full[ar.idx], ar.phase, abort_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t a_addr = a_smem + ar.idx * (uint32_t)P.a_stage_bytes;
+        const uint32_t a_lo = a_lo0 + ar.idx * a_stage16;
         const uint32_t first = (kc == 0) ? 0u : 1u;  // 0 => the first MMA of an accumulator overwrites it
         if (WRES) {
-          const uint32_t b_chunk = b_smem + (uint32_t)(kc * 9 * P.b_block_bytes);
+          uint32_t b_lo = b_lo0 + (uint32_t)(kc * 9) * b_block16;
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const uint32_t b_addr = b_chunk + (uint32_t)(t * P.b_block_bytes);
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
-                const uint32_t a_tap = a_addr + (uint32_t)((tap_rows<TR>(t) + m * kSubTileH * kPitch) * kRowBytes);
-                const uint32_t d_tmem = acc_base + (uint32_t)(tap_group<TR>(t) * MT + m) * (uint32_t)P.bn;
+                constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16(d_tmem, desc64(a_hi, a_tap + k * 32), desc64(b_hi, b_addr + k * 32), idesc,
-                            (tap_first<TR>(t) && k == 0) ? first : 1u);
+                  umma_bf16_lohi(dcol[tap_group<TR>(t) * MT + m], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                 (tap_first<TR>(t) && k == 0) ? first : 1u);
               }
+              b_lo += b_block16;
             }
             umma_commit(&bars->a_empty[ar.idx]);
           }
@@ -311,16 +318,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
             if (!ok) break;
             tc_fence_after();
-            const uint32_t b_addr = b_smem + br.idx * (uint32_t)P.b_block_bytes;
+            const uint32_t b_lo = b_lo0 + br.idx * b_block16;
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
-                const uint32_t a_tap = a_addr + (uint32_t)((tap_rows<TR>(t) + m * kSubTileH * kPitch) * kRowBytes);
-                const uint32_t d_tmem = acc_base + (uint32_t)(tap_group<TR>(t) * MT + m) * (uint32_t)P.bn;
+                constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16(d_tmem, desc64(a_hi, a_tap + k * 32), desc64(b_hi, b_addr + k * 32), idesc,
-                            (tap_first<TR>(t) && k == 0) ? first : 1u);
+                  umma_bf16_lohi(dcol[tap_group<TR>(t) * MT + m], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                 (tap_first<TR>(t) && k == 0) ? first : 1u);
               }
               umma_commit(&bars->b_empty[br.idx]);
               if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
@@ -395,8 +402,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t k = 0;
       for (int tile = (int)blockIdx.x + group * (int)gridDim.x; tile < P.ntiles; tile += stride, ++k) {
         const uint32_t seq = k * (uint32_t)P.nbuf + (uint32_t)group;   // position in the CTA's tile sequence
-        const uint32_t es = seq & 1u;
-        if (ok) ok = mbar_wait(&bars->e_full[es], (seq >> 1) & 1u, abort_flag);
+        const uint32_t es = seq % (uint32_t)kEStages;
+        if (ok) ok = mbar_wait(&bars->e_full[es], (seq / (uint32_t)kEStages) & 1u, abort_flag);
         const uint32_t eb = e_base + es * (uint32_t)P.e_stage_bytes;
         int b, j0, i0, tn;
         lds_4i(eb + (uint32_t)P.e_info_off, b, j0, i0, tn);
@@ -929,11 +936,11 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
       P.use_e = 1;
       P.e_noise_bytes = 1024;
-      P.e_info_off = 1024 + 2 * kSkipBoxBytes;
+      P.e_info_off = 1024 + ((rgb && rgb->skip) ? 2 * kSkipBoxBytes : 0);
       P.e_stage_bytes = P.e_info_off + 128;
       P.e_bytes = (noise ? kTileW * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * kSkipBoxW * 4 : 0);
       ts_bytes = n_out ? P.nbuf * 2 * P.ts_slots * P.ts_unit_bytes : 0;
-      extra = 1024 /*alignment of the staging area*/ + 2 * P.e_stage_bytes;
+      extra = 1024 /*alignment of the staging area*/ + kEStages * P.e_stage_bytes;
     } else {
       P.ts_unit_ch = P.ts_unit_bytes = P.ts_slots = P.use_e = P.e_stage_bytes = P.e_bytes = 0;
     }
@@ -942,6 +949,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     P.wres = (P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
     int b_bytes = 0;
     if (P.wres) {
+      if (use_ts) P.a_stages = kT2MaxA;   // epilogue-bound layers: a deep A ring hides the DRAM latency of the tile loads
       while (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit && P.a_stages > 2) --P.a_stages;
       if (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit) continue;
       P.b_stages = 1;
@@ -956,7 +964,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     const int ab = P.a_stages * P.a_stage_bytes + b_bytes;
     P.ts_off = (ab + 1023) / 1024 * 1024;
     P.e_off = P.ts_off + ts_bytes;
-    P.bars_off = use_ts ? P.e_off + 2 * P.e_stage_bytes : (ab + 15) / 16 * 16;
+    P.bars_off = use_ts ? P.e_off + kEStages * P.e_stage_bytes : (ab + 15) / 16 * 16;
     smem_bytes = P.bars_off + kBarsBytes + 1024;
     ts = use_ts;
   }
