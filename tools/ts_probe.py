@@ -26,6 +26,8 @@ CASES = [
     dict(b=1, cin=64, cout=32, h=128, tr=1, rgb=0, skip=0, out=1, mod=0),
     dict(b=2, cin=256, cout=128, h=32, tr=1, rgb=0, skip=0, out=1, mod=0),
     dict(b=2, cin=128, cout=128, h=64, tr=0, rgb=0, skip=0, out=1, mod=1),
+    dict(b=3, cin=512, cout=256, h=20, tr=1, rgb=0, skip=0, out=1, mod=0),
+    dict(b=2, cin=512, cout=512, h=8, tr=1, rgb=0, skip=0, out=1, mod=0),
 ]
 
 
