@@ -174,14 +174,23 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
   const int c0 = c_t + g * 8;
   const int ox0 = ox_t + xb * kBlurPx;
   const int oy0 = oy_t + rg * kBlurRows;
-  float bias[8], nsc[8];
+  // per-channel constants as fp32 pairs: all arithmetic below is packed fp32x2 (FFMA2/FMUL2/FADD2), which
+  // halves the instruction count of this otherwise issue-bound kernel
+  uint64_t bias2[4], nsc2[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    bias[e] = (P.bias ? __ldg(P.bias + c0 + e) : 0.f) * gain;
-    nsc[e] = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + e) : 1.f;
+  for (int e = 0; e < 4; ++e) {
+    const float b0 = (P.bias ? __ldg(P.bias + c0 + 2 * e) : 0.f) * gain, b1 = (P.bias ? __ldg(P.bias + c0 + 2 * e + 1) : 0.f) * gain;
+    bias2[e] = pack2(b0, b1);
+    const float n0 = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + 2 * e) : 1.f;
+    const float n1 = P.next_scale ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + 2 * e + 1) : 1.f;
+    nsc2[e] = pack2(n0, n1);
   }
-  const float fv0 = P.fv[0] * gain, fv1 = P.fv[1] * gain, fv2 = P.fv[2] * gain, fv3 = P.fv[3] * gain;
-  const float fh0 = P.fh[0], fh1 = P.fh[1], fh2 = P.fh[2], fh3 = P.fh[3];
+  const uint64_t fv0 = pack2(P.fv[0] * gain, P.fv[0] * gain), fv1 = pack2(P.fv[1] * gain, P.fv[1] * gain);
+  const uint64_t fv2 = pack2(P.fv[2] * gain, P.fv[2] * gain), fv3 = pack2(P.fv[3] * gain, P.fv[3] * gain);
+  const uint64_t fh0 = pack2(P.fh[0], P.fh[0]), fh1 = pack2(P.fh[1], P.fh[1]);
+  const uint64_t fh2 = pack2(P.fh[2], P.fh[2]), fh3 = pack2(P.fh[3], P.fh[3]);
+  const float slope = lrelu ? 0.2f : 1.f;
+  const uint64_t slope2 = pack2(slope, slope);
   const bool has_noise = P.noise != nullptr;
   // output pointers of this thread's first row; advanced by one image row per output row
   const int64_t o_first = (((int64_t)b * P.H + oy0) * P.W + ox0) * P.C + c0;
@@ -198,25 +207,30 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
     while (!mbar_try_wait(&bar, 0))
       if (++spin > (1u << 26)) __trap();  // a lost TMA completion becomes a launch failure, not a hang
   }
-  const uint8_t* col = smem + ((size_t)(rg * kBlurRows) * sw + xb * kBlurPx) * pix_bytes + g * 16;
-  const int row_bytes = sw * pix_bytes;
+  const uint32_t col = smem_u32(smem) + (uint32_t)(((rg * kBlurRows) * sw + xb * kBlurPx) * pix_bytes + g * 16);
+  const uint32_t row_bytes = (uint32_t)(sw * pix_bytes);
 
-  float win[4][kBlurPx][8];
+  uint64_t win[4][kBlurPx][4];   // ring of the last four horizontally filtered rows (compile-time slots)
 #pragma unroll
   for (int t = 0; t < kBlurRows + 3; ++t) {
     const int u = t & 3;
-    float f[kBlurPx + 3][8];
+    uint64_t f[kBlurPx + 3][4];
 #pragma unroll
     for (int k = 0; k < kBlurPx + 3; ++k) {
-      bf16x8 v;
-      *reinterpret_cast<uint4*>(&v) = *reinterpret_cast<const uint4*>(col + t * row_bytes + k * pix_bytes);
-      unpack8(v, f[k]);
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                   : "r"(col + (uint32_t)t * row_bytes + (uint32_t)(k * pix_bytes)));
+      // bf16 pair -> fp32 pair: low element = w << 16, high element = w & 0xffff0000
+      f[k][0] = pack2u(w0 << 16, w0 & 0xffff0000u);
+      f[k][1] = pack2u(w1 << 16, w1 & 0xffff0000u);
+      f[k][2] = pack2u(w2 << 16, w2 & 0xffff0000u);
+      f[k][3] = pack2u(w3 << 16, w3 & 0xffff0000u);
     }
 #pragma unroll
     for (int px = 0; px < kBlurPx; ++px)
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        win[u][px][e] = fmaf(fh3, f[px + 3][e], fmaf(fh2, f[px + 2][e], fmaf(fh1, f[px + 1][e], fh0 * f[px][e])));
+      for (int e = 0; e < 4; ++e)
+        win[u][px][e] = fma2(fh3, f[px + 3][e], fma2(fh2, f[px + 2][e], fma2(fh1, f[px + 1][e], mul2(fh0, f[px][e]))));
     if (t >= 3) {
       const int r = t - 3;
       if (r < rows_ok) {
@@ -224,22 +238,30 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
         for (int px = 0; px < kBlurPx; ++px) {
           if (px_ok[px]) {
             const float nz = has_noise ? s_noise[rg * kBlurRows + r][xb * kBlurPx + px] : 0.f;
-            float v[8];
+            const uint64_t nz2 = pack2(nz, nz);
+            uint32_t po[4], pm[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 4; ++e) {
               // rows t-3 .. t live in slots (u+1)&3, (u+2)&3, (u+3)&3, u
-              const float a = fmaf(fv3, win[u][px][e],
-                                   fmaf(fv2, win[(u + 3) & 3][px][e],
-                                        fmaf(fv1, win[(u + 2) & 3][px][e],
-                                             fmaf(fv0, win[(u + 1) & 3][px][e], bias[e] + nz))));
-              v[e] = lrelu ? fmaxf(a, 0.2f * a) : a;
+              const uint64_t a = fma2(fv3, win[u][px][e],
+                                      fma2(fv2, win[(u + 3) & 3][px][e],
+                                           fma2(fv1, win[(u + 2) & 3][px][e],
+                                                fma2(fv0, win[(u + 1) & 3][px][e], add2(bias2[e], nz2)))));
+              const uint64_t a_s = mul2(a, slope2);
+              float x0, x1, y0, y1;
+              unpack2(a, x0, x1);
+              unpack2(a_s, y0, y1);
+              x0 = fmaxf(x0, y0);
+              x1 = fmaxf(x1, y1);
+              if (o_ptr) po[e] = cvt_bf16x2(x0, x1);
+              if (m_ptr) {
+                float m0, m1;
+                unpack2(mul2(pack2(x0, x1), nsc2[e]), m0, m1);
+                pm[e] = cvt_bf16x2(m0, m1);
+              }
             }
-            if (o_ptr) st8(o_ptr + px * P.C, pack8(v));
-            if (m_ptr) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= nsc[e];
-              st8(m_ptr + px * P.C, pack8(v));
-            }
+            if (o_ptr) *reinterpret_cast<uint4*>(o_ptr + px * P.C) = make_uint4(po[0], po[1], po[2], po[3]);
+            if (m_ptr) *reinterpret_cast<uint4*>(m_ptr + px * P.C) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
           }
         }
       }
