@@ -85,6 +85,21 @@ int64_t w2e_bias_act_bwd_workspace(int64_t outer, int C, int64_t inner);
 int w2e_style_demod(const float* style, const float* wsq, float* demod, int B, int Cin, int Cout,
                     void* stream);
 
+/* ---- all modulations / all demodulations of one Generator.forward in one launch each -------
+ * (EqualLinear of every ModulatedConv2d, models/stylegan2/model.py:130-159 via :238; demod :242).
+ * The host concatenates the per-layer tensors once:  w_all [sumCin, D] = modulation.weight*scale,
+ * b_all [sumCin] = modulation.bias*lr_mul, wsq_all = the per-conv wsq[Cout_l, Cin_l] back to back.
+ * block_layer[blk] names the layer of every 32-channel block (mod) / 8-channel block (demod);
+ * meta4 holds per layer {latent row, first channel, Cin, -} (mod) or {s offset, Cin, Cout, wsq offset}
+ * (demod); d_off[l] = first demod channel of layer l.  Results are per-layer contiguous blocks:
+ * s_all[B*first + b*Cin + c], d_all[B*d_off + b*Cout + o].  latent is [B, rows, D] with the given
+ * element strides.                                                                              */
+int w2e_style_mod_all(const float* latent, int64_t stride_b, int64_t stride_row, const float* w_all,
+                      const float* b_all, const int* block_layer, const int* meta4, float* s_all, int B,
+                      int D, int nblocks, void* stream);
+int w2e_style_demod_all(const float* s_all, const float* wsq_all, const int* block_layer, const int* meta4,
+                        const int* d_off, float* d_all, int B, int nblocks, void* stream);
+
 /* ---- modulated convolution, exact fp32 engine (models/stylegan2/model.py:249-274) ----------
  * Direct convolution on CUDA cores, fp32 FMA, NCHW.  One engine serves forward and dgrad:
  *   y[b,o,oy,ox] = out_scale[b,o] * sum_{c,t} in_scale[b,c] * x[b,c, j*in_stride+dy_t, i*in_stride+dx_t]

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "w2e_bias_act_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _L, _F, _F, _I, _P]),
     "w2e_bias_act_bwd_workspace": (_L, [_L, _I, _L]),
     "w2e_style_demod": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "w2e_style_mod_all": (_I, [_P, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "w2e_style_demod_all": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "w2e_conv_engine_f32": (_I, [_P] * 7 + [_I, _P] + [_I] * 13 + [_P, _I, _I, _I, _P]),
     "w2e_rowdot_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _P]),
     "w2e_torgb_fwd": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),

@@ -79,6 +79,96 @@ class SynthesisEngine:
             self._err.zero_()
             raise RuntimeError("where2edit_b200: a tcgen05 pipeline wait timed out (libw2e modconv_tc)")
 
+
+    # ------------------------------------------------------------------ styles / demodulation plan
+    def _style_plan(self, layers, dev):
+        """Concatenated modulation weights / wsq tables of every styled layer plus the device-side
+        block->layer maps of w2e_style_mod_all / w2e_style_demod_all; rebuilt when a weight changes."""
+        key = [str(dev)]
+        for module, _ in layers:
+            conv = module.conv
+            key += [conv.weight.data_ptr(), conv.weight._version, conv.modulation.weight.data_ptr(),
+                    conv.modulation.weight._version, conv.modulation.bias._version]
+        key = tuple(key)
+        plan = getattr(self, "_plan", None)
+        if plan is not None and plan["key"] == key:
+            return plan
+        rows = self.gen.latent_rows(False)
+        w_all, b_all, meta_mod, blk_mod = [], [], [], []
+        wsq_all, meta_dem, d_off, blk_dem = [], [], [], []
+        choff = coff = wsq_off = 0
+        seg = []   # per layer: (channel offset, Cin, demod index or None)
+        for li, ((module, kind), row) in enumerate(zip(layers, rows)):
+            conv = module.conv
+            mod = conv.modulation
+            cin = conv.in_channel
+            if cin % 32:
+                raise RuntimeError(f"where2edit_b200 bf16 engine: in_channel {cin} is not a multiple of 32")
+            w_all.append(mod.weight.detach().to(dev, torch.float32) * mod.scale)
+            b_all.append(mod.bias.detach().to(dev, torch.float32) * mod.lr_mul)
+            meta_mod.append([row, choff, cin, 0])
+            blk_mod += [li] * (cin // 32)
+            di = None
+            if kind != "rgb":
+                pw = self._tc_weight(conv)
+                cout = conv.out_channel
+                if cout % 8:
+                    raise RuntimeError(f"where2edit_b200 bf16 engine: out_channel {cout} is not a multiple of 8")
+                di = len(meta_dem)
+                wsq_all.append(pw.wsq.reshape(-1))
+                meta_dem.append([choff, cin, cout, wsq_off])
+                d_off.append(coff)
+                blk_dem += [di] * (cout // 8)
+                wsq_off += cin * cout
+                coff += cout
+            seg.append((choff, cin, di))
+            choff += cin
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        self._plan = {
+            "key": key, "seg": seg, "sum_c": choff, "sum_o": coff, "d_off": d_off, "cout": [m[2] for m in meta_dem],
+            "w_all": torch.cat(w_all).contiguous(), "b_all": torch.cat(b_all).contiguous(),
+            "wsq_all": torch.cat(wsq_all).contiguous(), "meta_mod": i32(meta_mod), "blk_mod": i32(blk_mod),
+            "meta_dem": i32(meta_dem), "blk_dem": i32(blk_dem), "d_off_dev": i32(d_off),
+            "style_dim": w_all[0].shape[1],
+        }
+        return self._plan
+
+    def _styles_and_demods(self, layers, rows, latent, stylespace, batch, dev):
+        plan = self._style_plan(layers, dev)
+        lib = N.load()
+        if stylespace:
+            parts = []
+            for (choff, cin, _), row in zip(plan["seg"], rows):
+                s = latent[row]
+                if s.numel() != batch * cin:
+                    raise ValueError(f"stylespace entry {row} has {tuple(s.shape)}, expected [{batch},1,{cin},1,1]")
+                parts.append(s.detach().reshape(-1).to(torch.float32))
+            s_all = torch.cat(parts).contiguous()
+        else:
+            lat = latent.detach().to(torch.float32).contiguous()
+            if lat.ndim != 3 or lat.shape[2] != plan["style_dim"]:
+                raise ValueError(f"W+ latent must be [B, n_latent, {plan['style_dim']}], got {tuple(lat.shape)}")
+            s_all = torch.empty(batch * plan["sum_c"], device=dev, dtype=torch.float32)
+            N.note(kind="style", tag="all modulations")
+            N.check(lib.w2e_style_mod_all(N.ptr(lat), lat.stride(0), lat.stride(1), N.ptr(plan["w_all"]),
+                                          N.ptr(plan["b_all"]), N.ptr(plan["blk_mod"]), N.ptr(plan["meta_mod"]),
+                                          N.ptr(s_all), batch, plan["style_dim"], plan["blk_mod"].numel(),
+                                          N.stream_ptr()), "style_mod_all")
+        d_all = torch.empty(batch * plan["sum_o"], device=dev, dtype=torch.float32)
+        N.note(kind="style", tag="all demodulations")
+        N.check(lib.w2e_style_demod_all(N.ptr(s_all), N.ptr(plan["wsq_all"]), N.ptr(plan["blk_dem"]),
+                                        N.ptr(plan["meta_dem"]), N.ptr(plan["d_off_dev"]), N.ptr(d_all), batch,
+                                        plan["blk_dem"].numel(), N.stream_ptr()), "style_demod_all")
+        styles, demods = [], []
+        for choff, cin, di in plan["seg"]:
+            styles.append(s_all[batch * choff:batch * (choff + cin)].view(batch, cin))
+            if di is None:
+                demods.append(None)
+            else:
+                o, c = plan["d_off"][di], plan["cout"][di]
+                demods.append(d_all[batch * o:batch * (o + c)].view(batch, c))
+        return styles, demods
+
     # ------------------------------------------------------------------ kernel launches
     def _conv(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, taps, in_hw, out_hw, grid_hw,
               out_stride, py, px, act, out=None):
@@ -219,16 +309,8 @@ class SynthesisEngine:
         dev = gen.input.input.device
         N.require_cuda(latent[0] if stylespace else latent)
 
-        # styles and demodulation coefficients of all layers up front (tiny fp32 work)
-        styles, demods = [], []
-        for (module, kind), row in zip(layers, rows):
-            s = module.conv.styles(pick(row), stylespace).to(torch.float32).contiguous()
-            styles.append(s)
-            if kind == "rgb":
-                demods.append(None)
-            else:
-                pw = self._tc_weight(module.conv)
-                demods.append(K.demod_coefficients(s, pw.wsq))
+        # styles and demodulation coefficients of ALL layers up front, in two launches (style_plan.cu)
+        styles, demods = self._styles_and_demods(layers, rows, latent, stylespace, batch, dev)
 
         def consumer_style(idx):
             """style of the next 3x3 conv after layer idx (None after the last one)."""
