@@ -200,6 +200,11 @@ void w2e_modconv_tc2_knobs(int max_ctas);
 /* epilogue selection of w2e_modconv_tc2[_rgb]: 1 (default) = shared-memory-staged TMA-store epilogue
  * whenever the shape is eligible, 0 = always the direct-store epilogue (A/B tests). */
 void w2e_modconv_tc2_epilogue(int ts_mode);
+/* debugging aid: when non-null, CTA 0 of every following w2e_modconv_tc2 launch with the staged
+ * epilogue writes clock64 stamps of its first 64 tiles into timeline[64][8] (device memory):
+ * producer {inputs slot free, A tile issued}, MMA issuer {accumulator free, A tile landed, MMAs
+ * issued}, epilogue {inputs landed, accumulator ready, tile done}.  See tools/tc2_timeline.py.   */
+void w2e_modconv_tc2_debug(void* timeline);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],

@@ -40,9 +40,11 @@
 namespace w2e {
 
 constexpr int kT2Threads = 320;    // TMA warp, MMA warp, 8 epilogue warps
-constexpr int kT2ThreadsTS = 576;  // TS flavour: two groups of 8 epilogue warps (one per accumulator buffer)
+constexpr int kT2ThreadsTS = 608;  // TS flavour: 2 x 8 epilogue warps (one group per accumulator buffer), two producer
+                                   // warps (A/B tiles; epilogue inputs), one MMA-issuing warp
+constexpr int kT2ThreadsTS2 = 640; // TS flavour with resident weights: plus a second MMA-issuing warp
 constexpr int kT2EpiThreads = 256;
-constexpr int kT2MaxA = 8, kT2MaxB = 16, kT2MaxAcc = 2;
+constexpr int kT2MaxA = 8, kT2MaxB = 16, kT2MaxAcc = 4;
 constexpr int kEStages = 4;   // epilogue-input ring (TS flavour): deep enough not to throttle the A-tile prefetch
 constexpr int kTileW = 8, kSubTileH = 16;  // one M=128 sub-tile = 16 rows x 8 pixels
 
@@ -55,6 +57,7 @@ struct Tc2Params {
   __nv_bfloat16* out;       // [B,OH,OW,Cout] or null
   __nv_bfloat16* out_mod;   // [B,OH,OW,Cout] or null
   int* error_flag;
+  long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
   const float* rgb_w;       // [3,Cout] 1x1 weight * 1/sqrt(Cout)
   const float* rgb_style;   // [B,Cout]
@@ -91,6 +94,7 @@ struct Tc2Bars {
   uint64_t acc_full[kT2MaxAcc], acc_empty[kT2MaxAcc];
   uint64_t w_full;
   uint64_t e_full[kEStages], e_empty[kEStages];
+  uint64_t mma_turn[2];   // issue token of the two MMA-issuing warps (they must alternate, not interleave)
   uint32_t tmem_slot;
   int abort_flag;
   // per-tile epilogue constants, double-buffered by tile parity: scale (demod*gain), shift (bias*gain), next style
@@ -166,11 +170,11 @@ struct Ring {
 };
 
 template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
-__global__ void __launch_bounds__(TS ? kT2ThreadsTS : kT2Threads, 1)
+__global__ void __launch_bounds__(TS ? (WRES ? kT2ThreadsTS2 : kT2ThreadsTS) : kT2Threads, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ Tc2Params P, const __grid_constant__ Tc2Maps M) {
   constexpr int NG = TR ? 4 : 1;
-  static_assert(!RGB || (!TR && MT == 2), "fused ToRGB needs the plain conv with two sub-tiles");
+  static_assert(!RGB || (!TR && (MT == 2 || (TS && MT == 4))), "fused ToRGB needs the plain conv with 2 (or 4) sub-tiles");
   constexpr int kRowBytes = KSTEPS * 32;  // BK * 2 bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   constexpr int kBK = KSTEPS * 16;
   extern __shared__ uint8_t smem_raw[];
@@ -188,7 +192,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   // arbiter favours the highest warp id of a scheduler, and a starved MMA issuer stalls everyone
   // (measured: with the issuer as warp 1 it got an issue slot every ~9 cycles next to busy epilogue warps).
   constexpr int kEpiWarps = TS ? 16 : 8;
-  constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  constexpr int kProducerWarp = kEpiWarps, kEProducerWarp = kEpiWarps + 1, kMmaWarp = kEpiWarps + (TS ? 2 : 1);
+  // TS flavour with resident weights: TWO MMA-issuing warps take alternate tiles.  tcgen05.mma issue
+  // blocks at the pipe's execution rate (shallow queue), so a single issuer leaves the tensor pipe idle
+  // for its whole per-tile bookkeeping (barrier waits, fences, commits: ~800 cycles measured against
+  // ~1600 cycles of MMAs per tile of the 32-channel layer); with two issuers one's bookkeeping hides
+  // behind the other's MMAs.  Accumulator buffers and A stages are consumed in tile order by both.
+  constexpr int kMmaWarps = (TS && WRES) ? 2 : 1;
   const int tiles_xy = P.tiles_x * P.tiles_y;
   const int tiles_per_n = tiles_xy * P.B;
 
@@ -205,6 +215,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t epi_arrivals = (TS && P.nbuf == 1) ? 2 * kT2EpiThreads : kT2EpiThreads;
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], epi_arrivals); }
       mbar_init(&bars->w_full, 1);
+      mbar_init(&bars->mma_turn[0], 1);
+      mbar_init(&bars->mma_turn[1], 1);
       for (int s = 0; s < kEStages; ++s) { mbar_init(&bars->e_full[s], 1); mbar_init(&bars->e_empty[s], epi_arrivals); }
       fence_mbar_init();
     }
@@ -225,39 +237,25 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int t = 0; t < 9; ++t)
             tma_load_3d(b_base + (size_t)(kc * 9 + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * kBK, 0, t);
       }
-      Ring ar, br, er;
+      Ring ar, br;
       bool ok = true;
       TileWalk wk;
       wk.init(blockIdx.x, gridDim.x, P);
       for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
         const int b = wk.b;
         const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW, co0 = wk.tn * P.bn;
-        if (TS) {
-          // epilogue inputs of this tile: its coordinates, the noise patch and (fused ToRGB) the skip-image
-          // patch of each sub-tile
-          ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
-          if (!ok) break;
-          uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
-          *reinterpret_cast<int4*>(eb + P.e_info_off) = make_int4(b, j0, i0, wk.tn);
-          mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);   // release: orders the info store
-          if (P.noise) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
-          if (RGB && P.rgb_skip) {
-#pragma unroll
-            for (int m = 0; m < MT; ++m)
-              tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
-                          ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
-          }
-          er.advance(kEStages);
-        }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
           if (!ok) break;
+          if (TS && P.dbg && blockIdx.x == 0 && kc == 0 && tile / (int)gridDim.x < 64) P.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
           mbar_arrive_expect_tx(&bars->a_full[ar.idx], (uint32_t)P.a_box_bytes);
           tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
                       j0 - 1, b);
           ar.advance(P.a_stages);
           if (!WRES) {
+            const bool edge_y = TR && j0 >= P.grid_h - 1, edge_x = TR && i0 >= P.grid_w - 1;   // see the MMA issuer
             for (int t = 0; t < 9; ++t) {
+              if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
@@ -268,8 +266,38 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // -------------------------------------------------------------------- MMA issuer
+  } else if (TS && warp == kEProducerWarp) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ epilogue-input producer
+      // Its own warp: a single thread issuing every TMA of a tile took ~2200 cycles per tile (measured),
+      // more than the MMAs of the 32-channel layers.  Per tile: the tile coordinates, the noise patch and
+      // (fused ToRGB) the skip-image patch of each sub-tile.
+      Ring er;
+      bool ok = true;
+      TileWalk wk;
+      wk.init(blockIdx.x, gridDim.x, P);
+      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
+        const int b = wk.b;
+        const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW;
+        ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
+        if (!ok) break;
+        if (P.dbg && blockIdx.x == 0 && tile / (int)gridDim.x < 64) P.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
+        uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
+        *reinterpret_cast<int4*>(eb + P.e_info_off) = make_int4(b, j0, i0, wk.tn);
+        mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);   // release: orders the info store
+        if (P.noise) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
+        if (RGB && P.rgb_skip) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
+                        ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
+        }
+        er.advance(kEStages);
+      }
+    }
+  } else if (warp >= kMmaWarp) {
+    // -------------------------------------------------------------------- MMA issuer(s)
+    const int mw = warp - kMmaWarp;   // issuer index: tiles mw, mw + kMmaWarps, ... of this CTA's sequence
     // The whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform
     // registers); only tcgen05.mma / tcgen05.commit are issued, by one elected lane.
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
@@ -284,70 +312,115 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     bool ok = true;
     if (WRES) {
       ok = mbar_wait_warp(&bars->w_full, 0, abort_flag);
-      tc_fence_after();
+      // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none)
     }
-    for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
+    // Two issuers only when each accumulator buffer and each A stage is always consumed by the SAME issuer
+    // (even buffer count, stage count a multiple of 2 * kchunks): an issuer that saw only every other phase
+    // of an mbarrier could mistake an old completion for the one it waits for.
+    const int nmw = (kMmaWarps == 2 && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
+    const int tile_step = nmw * (int)gridDim.x;
+    const int tile0 = mw < nmw ? (int)blockIdx.x + mw * (int)gridDim.x : P.ntiles;
+    if (mw == 1) {   // the second issuer starts one tile into the rings
+      for (int i = 0; i < kchunks; ++i) ar.advance(P.a_stages);
+      cr.advance(P.nbuf);
+    }
+    TileWalk wk;
+    wk.init(tile0 < P.ntiles ? tile0 : 0, tile_step, P);
+    uint32_t turn = 0;   // tiles issued by this warp so far (parity of its token waits)
+    for (int tile = tile0; tile < P.ntiles && ok; tile += tile_step, wk.next(P), ++turn) {
+      // Transposed conv: the class grids are (h+1) x (w+1), so the last tile row / column holds only
+      // the positions j == h / i == w, which see nothing but zero padding through every tap except
+      // ky == 2 / kx == 2: the other taps (and the second sub-tile) of such EDGE tiles are skipped.
+      // Their untouched accumulators belong to classes whose rows/columns are clipped by the stores.
+      const bool edge_y = TR && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
+      const bool edge_x = TR && wk.tx * kTileW >= P.grid_w - 1;
       ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
       if (!ok) break;
       tc_fence_after();
+      const bool dbg_on = TS && P.dbg && blockIdx.x == 0 && tile / (int)gridDim.x < 64 && lane == 0;
+      if (dbg_on) P.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
       uint32_t dcol[NG * MT];   // TMEM column of every accumulator of this tile
       dcol[0] = tmem_base + cr.idx * (uint32_t)(NG * MT) * bn;
 #pragma unroll
       for (int i = 1; i < NG * MT; ++i) dcol[i] = dcol[i - 1] + bn;
+      uint32_t started = 0;     // accumulators that already received their first (overwriting) MMA
       for (int kc = 0; kc < kchunks && ok; ++kc) {
         ok = mbar_wait_warp(&bars->a_full[ar.idx], ar.phase, abort_flag);
         if (!ok) break;
-        tc_fence_after();
+        // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none, and it was measured to drain the MMA queue)
         const uint32_t a_lo = a_lo0 + ar.idx * a_stage16;
-        const uint32_t first = (kc == 0) ? 0u : 1u;  // 0 => the first MMA of an accumulator overwrites it
+        if (nmw == 2 && kc == 0) {
+          // issue token: the other issuer's MMAs of the previous tile are all queued.  Without it the two
+          // warps interleave their MMAs, finish together and do their bookkeeping at the same time (measured).
+          ok = mbar_wait_warp(&bars->mma_turn[mw], mw == 0 ? (turn & 1u) ^ 1u : (turn & 1u), abort_flag);
+          if (!ok) break;
+        }
+        if (dbg_on && kc == 0) P.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
         if (WRES) {
           uint32_t b_lo = b_lo0 + (uint32_t)(kc * 9) * b_block16;
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
+              if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2))) {
 #pragma unroll
-              for (int m = 0; m < MT; ++m) {
-                constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
-                const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+                for (int m = 0; m < MT; ++m) {
+                  if (m == 1 && edge_y) continue;
+                  constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                  const int ai = tap_group<TR>(t) * MT + m;
+                  const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+                  const uint32_t first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
+                  started |= 1u << ai;
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_lohi(dcol[tap_group<TR>(t) * MT + m], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
-                                 (tap_first<TR>(t) && k == 0) ? first : 1u);
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                }
               }
               b_lo += b_block16;
             }
             umma_commit(&bars->a_empty[ar.idx]);
           }
-          __syncwarp();
+          started = __reduce_or_sync(0xffffffffu, started);   // the elected lane's view, warp-uniform again
         } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
+            if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
             ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
             if (!ok) break;
-            tc_fence_after();
+            // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none, and it was measured to drain the MMA queue)
             const uint32_t b_lo = b_lo0 + br.idx * b_block16;
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
+                if (m == 1 && edge_y) continue;
                 constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                const int ai = tap_group<TR>(t) * MT + m;
                 const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+                const uint32_t first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
+                started |= 1u << ai;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_lohi(dcol[tap_group<TR>(t) * MT + m], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
-                                 (tap_first<TR>(t) && k == 0) ? first : 1u);
+                  umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
               }
               umma_commit(&bars->b_empty[br.idx]);
               if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
             }
-            __syncwarp();
+            started = __reduce_or_sync(0xffffffffu, started);
             br.advance(P.b_stages);
           }
         }
         ar.advance(P.a_stages);
       }
-      if (ok && elect_one()) umma_commit(&bars->acc_full[cr.idx]);
+      if (ok && elect_one()) {
+        umma_commit(&bars->acc_full[cr.idx]);
+        if (nmw == 2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
+      }
       __syncwarp();
+      if (dbg_on) P.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
       cr.advance(P.nbuf);
+      if (nmw == 2) {   // skip the other issuer's tile in both rings
+        for (int i = 0; i < kchunks; ++i) ar.advance(P.a_stages);
+        cr.advance(P.nbuf);
+      }
     }
 
   } else if constexpr (TS) {
@@ -390,14 +463,17 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t e_base = smem_u32(smem + P.e_off);
       const int bar_group = 1 + group * 3, bar_half = 2 + group * 3 + half;
       const int stride = split ? (int)gridDim.x : 2 * (int)gridDim.x;
-      const uint32_t ci = split ? 0u : (uint32_t)group;   // accumulator buffer of this group's tiles
       const int unit0 = RGB ? 0 : (split ? group * 2 + half : half), unit_step = RGB ? 1 : (split ? 4 : 2);
-      const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + ci * (uint32_t)(NACC * P.bn);
+      const uint32_t nbuf_mask = (uint32_t)P.nbuf - 1u, nbuf_shift = P.nbuf == 4 ? 2u : (P.nbuf == 2 ? 1u : 0u);
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
       // skip-upsample polyphase taps of this thread's pixel (parity of (sy, sx): tile origins are even)
       const float cy0 = (sy & 1) ? P.kf[1] : P.kf[0], cy1 = (sy & 1) ? P.kf[3] : P.kf[2];
       const float cx0 = (sx & 1) ? P.kf[1] : P.kf[0], cx1 = (sx & 1) ? P.kf[3] : P.kf[2];
+      // fused ToRGB: a thread finishes NP = MT/2 pixels per tile (row r of sub-tiles half*NP .. half*NP+NP-1) and
+      // shares every per-channel constant it reads from shared memory between them
+      constexpr int NP = RGB ? MT / 2 : 1;
       const uint32_t skip_off = (uint32_t)P.e_noise_bytes +
-                                (uint32_t)(half * kSkipBoxBytes + (((sy + 1) >> 1) * kSkipBoxW + ((sx + 1) >> 1) + 3) * 4);
+                                (uint32_t)(half * NP * kSkipBoxBytes + (((sy + 1) >> 1) * kSkipBoxW + ((sx + 1) >> 1) + 3) * 4);
       const uint32_t noise_off = (uint32_t)((sy * kTileW + sx) * 4);
       float rgbb[3] = {0.f, 0.f, 0.f};
       if (RGB && P.rgb_bias) {
@@ -413,6 +489,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t seq = split ? k : 2u * k + (uint32_t)group;   // position in the CTA's tile sequence
         const uint32_t es = seq % (uint32_t)kEStages;
         if (ok) ok = mbar_wait(&bars->e_full[es], (seq / (uint32_t)kEStages) & 1u, abort_flag);
+        const bool dbg_on = P.dbg && blockIdx.x == 0 && seq < 64 && (gt & 255) == 0;
+        if (dbg_on) P.dbg[seq * 8 + 5] = clock64();
         const uint32_t eb = e_base + es * (uint32_t)P.e_stage_bytes;
         int b, j0, i0, tn;
         lds_4i(eb + (uint32_t)P.e_info_off, b, j0, i0, tn);
@@ -441,8 +519,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         float nzm[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) nzm[m] = 0.f;
-        uint64_t racc[3] = {0ull, 0ull, 0ull};
-        float rgb_init[3] = {rgbb[0], rgbb[1], rgbb[2]};
+        uint64_t racc[NP][3];
+        float rgb_init[NP][3];
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+          for (int o = 0; o < 3; ++o) { racc[p][o] = 0ull; rgb_init[p][o] = rgbb[o]; }
         if (has_noise) {
 #pragma unroll
           for (int m = 0; m < MT; ++m) nzm[m] = nw * lds_f32(eb + noise_off + (uint32_t)(m * kSubTileH * kTileW * 4));
@@ -451,38 +533,53 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // upfirdn2d(skip, up=2, pad=(2,1)) = a 2x2-tap polyphase filter on rows ya, ya+1 / columns xa, xa+1.
           // The box starts one row and FOUR columns before the sub-tile's first source pixel: the innermost
           // start coordinate of a TMA box must be 16-byte aligned (x0 - 1 faults with an illegal instruction).
-          const uint32_t sb = eb + skip_off;
           constexpr int kPlane = 10 * kSkipBoxW * 4, kRow = kSkipBoxW * 4;
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            const float t00 = lds_f32(sb + o * kPlane), t01 = lds_f32(sb + o * kPlane + 4);
-            const float t10 = lds_f32(sb + o * kPlane + kRow), t11 = lds_f32(sb + o * kPlane + kRow + 4);
-            rgb_init[o] += cy0 * fmaf(cx1, t01, cx0 * t00) + cy1 * fmaf(cx1, t11, cx0 * t10);
+          for (int p = 0; p < NP; ++p) {
+            const uint32_t sb = eb + skip_off + (uint32_t)(p * kSkipBoxBytes);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float t00 = lds_f32(sb + o * kPlane), t01 = lds_f32(sb + o * kPlane + 4);
+              const float t10 = lds_f32(sb + o * kPlane + kRow), t11 = lds_f32(sb + o * kPlane + kRow + 4);
+              rgb_init[p][o] += cy0 * fmaf(cx1, t01, cx0 * t00) + cy1 * fmaf(cx1, t11, cx0 * t10);
+            }
           }
         }
         mbar_arrive(&bars->e_empty[es]);
 
-        if (ok) ok = mbar_wait(&bars->acc_full[ci], k & 1u, abort_flag);
+        // accumulator buffer of this tile: with 4 buffers a group alternates between two of them, so the MMAs
+        // of its next tile run while it still drains this one
+        const uint32_t ci = seq & nbuf_mask;
+        const uint32_t t_tile = t_lane + ci * (uint32_t)(NACC * P.bn);
+        if (ok) ok = mbar_wait(&bars->acc_full[ci], (seq >> nbuf_shift) & 1u, abort_flag);
         tc_fence_after();
+        if (dbg_on) P.dbg[seq * 8 + 6] = clock64();
         const int nunits = RGB ? chunks : NACC * chunks;
         bool released = false;
         auto run_units = [&](auto out_tag, auto mod_tag) {
           constexpr bool OUT = decltype(out_tag)::value, MOD = decltype(mod_tag)::value;
           for (int ui = unit0; ui < nunits; ui += unit_step) {
-            const int acc = RGB ? half : ui / chunks;
+            const int acc = RGB ? half * NP : ui / chunks;     // (first) accumulator of this unit
             const int chunk = RGB ? ui : ui - acc * chunks;
             const int m = acc % MT;
             const uint32_t t_addr = t_tile + (uint32_t)(acc * P.bn + chunk * UC);
-            float nzv = nzm[0];
-            if (MT == 2 && m == 1) nzv = nzm[MT - 1];
-            const uint64_t nz2 = pack2(nzv, nzv);
+            uint64_t nz2[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              float nzv = nzm[0];
+#pragma unroll
+              for (int mm = 1; mm < MT; ++mm)
+                if (m + p == mm) nzv = nzm[mm];
+              nz2[p] = pack2(nzv, nzv);
+            }
             const uint32_t slot_o =
                 stage0 + (uint32_t)(((OUT && MOD) ? 0 : (int)(un & (uint32_t)(P.ts_slots - 1))) * P.ts_unit_bytes);
             const uint32_t slot_m = OUT ? stage0 + (uint32_t)P.ts_unit_bytes : slot_o;
             const bool last_unit = ui + unit_step >= nunits;
             for (int c16 = 0; c16 < UC; c16 += 16) {
-              uint32_t v[16];
-              tmem_ld16(t_addr + (uint32_t)c16, v);
+              uint32_t v[NP][16];
+#pragma unroll
+              for (int p = 0; p < NP; ++p) tmem_ld16(t_addr + (uint32_t)(p * P.bn + c16), v[p]);
               tmem_ld_wait();
               if (last_unit && c16 + 16 >= UC) {   // this thread's last TMEM read of the tile: hand the buffer back
                 tc_fence_before();
@@ -490,47 +587,50 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 released = true;
               }
               const uint32_t ca = sc_a + (uint32_t)((chunk * UC + c16) * 4);
-              uint32_t po[OUT ? 8 : 1], pm[MOD ? 8 : 1];
+              uint32_t po[OUT ? 8 : 1], pm[MOD ? 8 : 1];   // staged outputs: pixel 0 only (NP == 1 whenever OUT || MOD)
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                uint64_t a01, a23, f01, f23;
+                uint64_t a01, a23, b01 = 0, b23 = 0, w01[3], w23[3];
                 lds_2x2(ca + e * 16, a01, a23);
-                if (TR) {
-                  f01 = mul2(pack2u(v[4 * e], v[4 * e + 1]), a01);
-                  f23 = mul2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23);
-                } else {
-                  uint64_t b01, b23;
-                  lds_2x2(ca + 512 + e * 16, b01, b23);
-                  f01 = add2(fma2(pack2u(v[4 * e], v[4 * e + 1]), a01, b01), nz2);
-                  f23 = add2(fma2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23, b23), nz2);
-                  const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
-                  float x0, x1, x2, x3, y0, y1, y2, y3;
-                  unpack2(f01, x0, x1); unpack2(f23, x2, x3);
-                  unpack2(g01, y0, y1); unpack2(g23, y2, y3);
-                  f01 = pack2(fmaxf(x0, y0), fmaxf(x1, y1));
-                  f23 = pack2(fmaxf(x2, y2), fmaxf(x3, y3));
-                }
+                if (!TR) lds_2x2(ca + 512 + e * 16, b01, b23);
                 if (RGB) {
 #pragma unroll
-                  for (int o = 0; o < 3; ++o) {
-                    uint64_t w01, w23;
-                    lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01, w23);
-                    racc[o] = fma2(f23, w23, fma2(f01, w01, racc[o]));
+                  for (int o = 0; o < 3; ++o) lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01[o], w23[o]);
+                }
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                  uint64_t f01, f23;
+                  if (TR) {
+                    f01 = mul2(pack2u(v[p][4 * e], v[p][4 * e + 1]), a01);
+                    f23 = mul2(pack2u(v[p][4 * e + 2], v[p][4 * e + 3]), a23);
+                  } else {
+                    f01 = add2(fma2(pack2u(v[p][4 * e], v[p][4 * e + 1]), a01, b01), nz2[p]);
+                    f23 = add2(fma2(pack2u(v[p][4 * e + 2], v[p][4 * e + 3]), a23, b23), nz2[p]);
+                    const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
+                    float x0, x1, x2, x3, y0, y1, y2, y3;
+                    unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                    unpack2(g01, y0, y1); unpack2(g23, y2, y3);
+                    f01 = pack2(fmaxf(x0, y0), fmaxf(x1, y1));
+                    f23 = pack2(fmaxf(x2, y2), fmaxf(x3, y3));
                   }
-                }
-                if (OUT) {
-                  float x0, x1, x2, x3;
-                  unpack2(f01, x0, x1); unpack2(f23, x2, x3);
-                  po[2 * e] = cvt_bf16x2(x0, x1);
-                  po[2 * e + 1] = cvt_bf16x2(x2, x3);
-                }
-                if (MOD) {
-                  uint64_t n01, n23;
-                  lds_2x2(ca + 1024 + e * 16, n01, n23);
-                  float x0, x1, x2, x3;
-                  unpack2(mul2(f01, n01), x0, x1); unpack2(mul2(f23, n23), x2, x3);
-                  pm[2 * e] = cvt_bf16x2(x0, x1);
-                  pm[2 * e + 1] = cvt_bf16x2(x2, x3);
+                  if (RGB) {
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) racc[p][o] = fma2(f23, w23[o], fma2(f01, w01[o], racc[p][o]));
+                  }
+                  if (OUT && p == 0) {
+                    float x0, x1, x2, x3;
+                    unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                    po[2 * e] = cvt_bf16x2(x0, x1);
+                    po[2 * e + 1] = cvt_bf16x2(x2, x3);
+                  }
+                  if (MOD && p == 0) {
+                    uint64_t n01, n23;
+                    lds_2x2(ca + 1024 + e * 16, n01, n23);
+                    float x0, x1, x2, x3;
+                    unpack2(mul2(f01, n01), x0, x1); unpack2(mul2(f23, n23), x2, x3);
+                    pm[2 * e] = cvt_bf16x2(x0, x1);
+                    pm[2 * e + 1] = cvt_bf16x2(x2, x3);
+                  }
                 }
               }
               if (OUT || MOD) {
@@ -581,18 +681,22 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mbar_arrive(&bars->acc_empty[ci]);
         }
         if (RGB) {
-          const int oy = j0 + half * kSubTileH + sy, ox = i0 + sx;
-          if (oy < P.OH && ox < P.OW && ok) {
-            float* dst = P.rgb + ((int64_t)b * 3 * P.OH + oy) * P.OW + ox;
-            const int64_t plane = (int64_t)P.OH * P.OW;
+          const int64_t plane = (int64_t)P.OH * P.OW;
 #pragma unroll
-            for (int o = 0; o < 3; ++o) {
-              float lo, hi;
-              unpack2(racc[o], lo, hi);
-              dst[o * plane] = rgb_init[o] + (lo + hi);
+          for (int p = 0; p < NP; ++p) {
+            const int oy = j0 + (half * NP + p) * kSubTileH + sy, ox = i0 + sx;
+            if (oy < P.OH && ox < P.OW && ok) {
+              float* dst = P.rgb + ((int64_t)b * 3 * P.OH + oy) * P.OW + ox;
+#pragma unroll
+              for (int o = 0; o < 3; ++o) {
+                float lo, hi;
+                unpack2(racc[p][o], lo, hi);
+                dst[o * plane] = rgb_init[p][o] + (lo + hi);
+              }
             }
           }
         }
+        if (dbg_on) P.dbg[seq * 8 + 7] = clock64();
       }
       if (leader) bulk_wait_all();
     }
@@ -828,7 +932,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
     configured = true;
   }
   int per_sm = 1;
-  constexpr int kThreads = TS ? kT2ThreadsTS : kT2Threads;
+  constexpr int kThreads = TS ? (WRES ? kT2ThreadsTS2 : kT2ThreadsTS) : kT2Threads;
   W2E_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem_bytes));
   if (per_sm * P.tmem_cols > 512) per_sm = 512 / P.tmem_cols;
   if (per_sm > 2) per_sm = 2;
@@ -844,6 +948,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
 // debug / tuning knobs (tests flip them to validate the shifted-descriptor scheme on hardware)
 static int g_max_ctas = 0;
 static int g_ts_mode = 1;   // 0 = never use the TS epilogue, 1 = whenever eligible
+static long long* g_dbg = nullptr;
 
 }  // namespace w2e
 
@@ -851,6 +956,7 @@ using namespace w2e;
 
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
+extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -859,7 +965,7 @@ struct RgbArgs {
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
                    const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
                    int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
-                   const RgbArgs* rgb, void* stream) {
+                   const RgbArgs* rgb, void* stream, bool allow_mt4 = true) {
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
   W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
   W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
@@ -872,6 +978,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   memset(&P, 0, sizeof(P));
   P.out_scale = out_scale; P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.next_scale = next_scale;
   P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod; P.error_flag = error_flag;
+  P.dbg = g_dbg;
   P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
   P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
   if (rgb) {
@@ -894,15 +1001,23 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.bk = (Cin % 64 == 0) ? 64 : 32;
   const int row_bytes = P.bk * 2;
   P.mt = (P.grid_h > kSubTileH) ? 2 : 1;
+  // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
+  const bool mt4 = allow_mt4 && g_ts_mode != 0 && rgb && !out && !out_mod && Cin == 32 && Cout == 32 && in_h >= 64;
+  if (mt4) P.mt = 4;
   const int bn_max = transposed ? 128 : 256;
   P.bn = 16;
   for (int cand : {256, 128, 64, 32, 16})
     if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
   if (P.ng * P.mt * P.bn > 512) P.mt = 1;
-  P.nbuf = (P.ng * P.mt * P.bn * 2 <= 512) ? 2 : 1;
-  int cols = P.ng * P.mt * P.bn * P.nbuf;
-  P.tmem_cols = 32;
-  while (P.tmem_cols < cols) P.tmem_cols <<= 1;
+  const int acc_cols = P.ng * P.mt * P.bn;
+  const int nbuf_plain = (acc_cols * 2 <= 512) ? 2 : 1;
+  const int nbuf_ts = (acc_cols * 4 <= 512) ? 4 : nbuf_plain;   // TS flavour: two buffers per epilogue group
+  auto set_nbuf = [&](int n) {
+    P.nbuf = n;
+    P.tmem_cols = 32;
+    while (P.tmem_cols < acc_cols * n) P.tmem_cols <<= 1;
+  };
+  set_nbuf(nbuf_plain);
   P.box_rows = kSubTileH * P.mt + 2;
   P.a_box_bytes = P.box_rows * P.pitch * row_bytes;
   P.a_stage_bytes = (P.a_box_bytes + 1023) / 1024 * 1024;
@@ -917,8 +1032,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
 
   // TS epilogue eligibility (see the header): staging units of <= 64 channels, TMA-able strides
   const int n_out = (out ? 1 : 0) + (out_mod ? 1 : 0);
-  bool ts = g_ts_mode != 0 && (transposed || P.mt == 2) && P.bn >= 32 && P.bn <= 128;
-  if (rgb && P.nbuf != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
+  bool ts = g_ts_mode != 0 && (transposed || P.mt >= 2) && P.bn >= 32 && P.bn <= 128;
+  if (rgb && nbuf_plain != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
   if (transposed) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
   if (noise) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
   if (rgb && rgb->skip) ts = ts && ((P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
@@ -945,8 +1060,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       if (n_out > P.ts_slots) continue;
       P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
       P.use_e = 1;
-      P.e_noise_bytes = 1024;
-      P.e_info_off = 1024 + ((rgb && rgb->skip) ? 2 * kSkipBoxBytes : 0);
+      P.e_noise_bytes = P.mt == 4 ? 2048 : 1024;
+      P.e_info_off = P.e_noise_bytes + ((rgb && rgb->skip) ? P.mt * kSkipBoxBytes : 0);
       P.e_stage_bytes = P.e_info_off + 128;
       P.e_bytes = (noise ? kTileW * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * kSkipBoxW * 4 : 0);
       ts_bytes = n_out ? 2 * 2 * P.ts_slots * P.ts_unit_bytes : 0;
@@ -961,6 +1076,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     if (P.wres) {
       if (use_ts) P.a_stages = kT2MaxA;   // epilogue-bound layers: a deep A ring hides the DRAM latency of the tile loads
       while (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit && P.a_stages > 2) --P.a_stages;
+      // two MMA issuers (kernel: kMmaWarps) need a stage count that is a multiple of 2 * kchunks
+      if (use_ts && P.a_stages > 2 * kchunks) P.a_stages -= P.a_stages % (2 * kchunks);
       if (P.a_stages * P.a_stage_bytes + w_bytes + ts_bytes > smem_limit) continue;
       P.b_stages = 1;
       b_bytes = w_bytes;
@@ -968,7 +1085,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       const int avail = smem_limit - P.a_stages * P.a_stage_bytes - ts_bytes;
       P.b_stages = avail / P.b_block_bytes;
       if (P.b_stages > kT2MaxB) P.b_stages = kT2MaxB;
-      if (P.b_stages < (use_ts ? 6 : 2)) continue;
+      if (P.b_stages < (use_ts ? 4 : 2)) continue;
       b_bytes = P.b_stages * P.b_block_bytes;
     }
     const int ab = P.a_stages * P.a_stage_bytes + b_bytes;
@@ -977,8 +1094,12 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     P.bars_off = use_ts ? P.e_off + kEStages * P.e_stage_bytes : (ab + 15) / 16 * 16;
     smem_bytes = P.bars_off + kBarsBytes + 1024;
     ts = use_ts;
+    set_nbuf(use_ts ? nbuf_ts : nbuf_plain);
   }
   W2E_CHECK_ARG(smem_bytes > 0, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
+  if (P.mt == 4 && !ts)   // the direct-store epilogue has no 4-sub-tile variant: plan again with 256-pixel tiles
+    return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
+                   in_h, in_w, transposed, act, rgb, stream, false);
   W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
@@ -1041,7 +1162,12 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int ks = P.bk / 16;
   if (rgb) {
-    W2E_CHECK_ARG(P.mt == 2 && P.tiles_n == 1, "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
+    W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && P.tiles_n == 1, "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt,
+                  P.tiles_n);
+    if (P.mt == 4) {
+      if (P.wres) return launch_tc2<false, 4, 2, true, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
+      return launch_tc2<false, 4, 2, false, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
+    }
 #define W2E_TC2_RGB(KS_, WR_) \
   if (ks == KS_ && (P.wres != 0) == WR_) { \
     if (ts) return launch_tc2<false, 2, KS_, WR_, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st); \

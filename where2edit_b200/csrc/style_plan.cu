@@ -10,23 +10,41 @@
 
 namespace w2e {
 
-// meta[l] = {latent row, first concatenated channel, Cin}
+// meta[l] = {latent row, first concatenated channel, Cin}.  One block = 32 channels x kModB samples:
+// the latent rows of the samples are staged in shared memory and every weight row is read once per
+// kModB samples (the weights, 18 MB at 1024^2, are the only real traffic of this kernel).
+constexpr int kModB = 8;
 __global__ void __launch_bounds__(256)
 style_mod_all_kernel(const float* __restrict__ latent, int64_t stride_b, int64_t stride_row, const float* __restrict__ w_all,
                      const float* __restrict__ b_all, const int* __restrict__ block_layer, const int4* __restrict__ meta,
                      float* __restrict__ s_all, int B, int D) {
-  const int blk = blockIdx.x, b = blockIdx.y;
+  extern __shared__ float lat_s[];   // [kModB][D]
+  const int blk = blockIdx.x, b0 = blockIdx.y * kModB;
   const int4 m = __ldg(meta + __ldg(block_layer + blk));   // x = latent row, y = channel offset, z = Cin
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* lat = latent + (int64_t)b * stride_b + (int64_t)m.x * stride_row;
+  for (int e = threadIdx.x; e < kModB * D; e += blockDim.x) {
+    const int bb = e / D, i = e - bb * D;
+    lat_s[e] = (b0 + bb < B) ? __ldg(latent + (int64_t)(b0 + bb) * stride_b + (int64_t)m.x * stride_row + i) : 0.f;
+  }
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gc = blk * 32 + warp * 4 + j;     // concatenated channel
     const float* w = w_all + (int64_t)gc * D;
-    float acc = 0.f;
-    for (int i = lane; i < D; i += 32) acc = fmaf(__ldg(w + i), __ldg(lat + i), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) s_all[(int64_t)B * m.y + (int64_t)b * m.z + (gc - m.y)] = acc + __ldg(b_all + gc);
+    float acc[kModB];
+#pragma unroll
+    for (int bb = 0; bb < kModB; ++bb) acc[bb] = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float wv = __ldg(w + i);
+#pragma unroll
+      for (int bb = 0; bb < kModB; ++bb) acc[bb] = fmaf(wv, lat_s[bb * D + i], acc[bb]);
+    }
+    const float bias = __ldg(b_all + gc);
+#pragma unroll
+    for (int bb = 0; bb < kModB; ++bb) {
+      const float v = warp_sum(acc[bb]);
+      if (lane == 0 && b0 + bb < B) s_all[(int64_t)B * m.y + (int64_t)(b0 + bb) * m.z + (gc - m.y)] = v + bias;
+    }
   }
 }
 
@@ -59,9 +77,10 @@ extern "C" int w2e_style_mod_all(const float* latent, int64_t stride_b, int64_t 
                                  const float* b_all, const int* block_layer, const int* meta4, float* s_all, int B, int D,
                                  int nblocks, void* stream) {
   W2E_CHECK_ARG(latent && w_all && b_all && block_layer && meta4 && s_all, "style_mod_all: null pointer");
-  W2E_CHECK_ARG(B >= 0 && B <= 65535 && D > 0 && nblocks >= 0, "style_mod_all: bad shape");
+  W2E_CHECK_ARG(B >= 0 && D > 0 && D <= 1024 && nblocks >= 0, "style_mod_all: bad shape (style_dim <= 1024)");
   if (B == 0 || nblocks == 0) return W2E_OK;
-  style_mod_all_kernel<<<dim3((unsigned)nblocks, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+  style_mod_all_kernel<<<dim3((unsigned)nblocks, (unsigned)ceil_div(B, kModB)), 256, (size_t)kModB * D * sizeof(float),
+                         (cudaStream_t)stream>>>(
       latent, stride_b, stride_row, w_all, b_all, block_layer, reinterpret_cast<const int4*>(meta4), s_all, B, D);
   W2E_LAUNCH_OK();
   return W2E_OK;
