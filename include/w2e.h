@@ -205,6 +205,9 @@ void w2e_modconv_tc2_epilogue(int ts_mode);
  * producer {inputs slot free, A tile issued}, MMA issuer {accumulator free, A tile landed, MMAs
  * issued}, epilogue {inputs landed, accumulator ready, tile done}.  See tools/tc2_timeline.py.   */
 void w2e_modconv_tc2_debug(void* timeline);
+/* A/B switches for measurements: bit 0 = no edge-tile tap masking (transposed conv), bit 1 = a single
+ * MMA-issuing warp.  Results are identical for every setting.                                    */
+void w2e_modconv_tc2_flags(int flags);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],

@@ -1,0 +1,59 @@
+"""A/B timing of the 1024^2 generator's modconv launches under w2e_modconv_tc2 knob settings, all in
+ONE process on one GPU (box-to-box variance is several percent, so only same-run ratios count).
+    python tools/ab_layers.py [batch]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import where2edit_b200 as w2e  # noqa: E402
+from where2edit_b200 import _native as N  # noqa: E402
+
+
+def main():
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    gen = w2e.Generator(1024, 512, 8, channel_multiplier=2, precision="bf16").to(dev).eval()
+    w = torch.randn(batch, gen.n_latent, 512, device=dev)
+    lib = N.load()
+    settings = [("default", 1, 0), ("no-edge-mask", 1, 1), ("one-issuer", 1, 2), ("direct-store epilogue", 0, 0)]
+    results = {}
+    for name, ts, flags in settings:
+        lib.w2e_modconv_tc2_epilogue(ts)
+        lib.w2e_modconv_tc2_flags(flags)
+        with torch.no_grad():
+            for _ in range(2):
+                gen([w], input_is_latent=True, randomize_noise=False)
+            torch.cuda.synchronize()
+            acc = {}
+            for rep in range(3):
+                N.STATS.trace = []
+                gen([w], input_is_latent=True, randomize_noise=False)
+                torch.cuda.synchronize()
+                for call, note, e0, e1 in N.STATS.trace:
+                    tag = (note or {}).get("tag") or call
+                    acc.setdefault(tag, []).append(e0.elapsed_time(e1))
+                N.STATS.trace = None
+        results[name] = {k: min(v) for k, v in acc.items()}
+    lib.w2e_modconv_tc2_epilogue(1)
+    lib.w2e_modconv_tc2_flags(0)
+    base = results["default"]
+    names = [n for n, _, _ in settings]
+    print(f"{'launch':30s} " + " ".join(f"{n:>22s}" for n in names))
+    tot = {n: 0.0 for n in names}
+    for tag, t in base.items():
+        if t < 0.03:
+            continue
+        row = f"{tag:30s} "
+        for n in names:
+            v = results[n].get(tag, float('nan'))
+            tot[n] += v
+            row += f"{v:22.3f} "
+        print(row)
+    print(f"{'sum':30s} " + " ".join(f"{tot[n]:22.3f}" for n in names))
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ struct Tc2Params {
   __nv_bfloat16* out;       // [B,OH,OW,Cout] or null
   __nv_bfloat16* out_mod;   // [B,OH,OW,Cout] or null
   int* error_flag;
+  int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
   const float* rgb_w;       // [3,Cout] 1x1 weight * 1/sqrt(Cout)
@@ -253,7 +254,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                       j0 - 1, b);
           ar.advance(P.a_stages);
           if (!WRES) {
-            const bool edge_y = TR && j0 >= P.grid_h - 1, edge_x = TR && i0 >= P.grid_w - 1;   // see the MMA issuer
+            const bool edge_y = TR && !(P.flags & 1) && j0 >= P.grid_h - 1;   // see the MMA issuer
+            const bool edge_x = TR && !(P.flags & 1) && i0 >= P.grid_w - 1;
             for (int t = 0; t < 9; ++t) {
               if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
@@ -310,6 +312,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t bn = (uint32_t)P.bn;
     Ring ar, br, cr;
     bool ok = true;
+    // warp-uniform issue: every lane runs the loops (descriptors stay in uniform registers, per-tile state stays
+    // consistent across lanes); only the elected lane executes tcgen05.mma / tcgen05.commit
+    const bool leader = elect_one();
     if (WRES) {
       ok = mbar_wait_warp(&bars->w_full, 0, abort_flag);
       // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none)
@@ -317,7 +322,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // Two issuers only when each accumulator buffer and each A stage is always consumed by the SAME issuer
     // (even buffer count, stage count a multiple of 2 * kchunks): an issuer that saw only every other phase
     // of an mbarrier could mistake an old completion for the one it waits for.
-    const int nmw = (kMmaWarps == 2 && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
+    const int nmw = (kMmaWarps == 2 && !(P.flags & 2) && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
     const int tile_step = nmw * (int)gridDim.x;
     const int tile0 = mw < nmw ? (int)blockIdx.x + mw * (int)gridDim.x : P.ntiles;
     if (mw == 1) {   // the second issuer starts one tile into the rings
@@ -332,8 +337,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // the positions j == h / i == w, which see nothing but zero padding through every tap except
       // ky == 2 / kx == 2: the other taps (and the second sub-tile) of such EDGE tiles are skipped.
       // Their untouched accumulators belong to classes whose rows/columns are clipped by the stores.
-      const bool edge_y = TR && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
-      const bool edge_x = TR && wk.tx * kTileW >= P.grid_w - 1;
+      const bool edge_y = TR && !(P.flags & 1) && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
+      const bool edge_x = TR && !(P.flags & 1) && wk.tx * kTileW >= P.grid_w - 1;
       ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
       if (!ok) break;
       tc_fence_after();
@@ -358,59 +363,69 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (dbg_on && kc == 0) P.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
         if (WRES) {
           uint32_t b_lo = b_lo0 + (uint32_t)(kc * 9) * b_block16;
-          if (elect_one()) {
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2))) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                  if (m == 1 && edge_y) continue;
-                  constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
-                  const int ai = tap_group<TR>(t) * MT + m;
-                  const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
-                  const uint32_t first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
-                  started |= 1u << ai;
-#pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
-                }
-              }
-              b_lo += b_block16;
-            }
-            umma_commit(&bars->a_empty[ar.idx]);
-          }
-          started = __reduce_or_sync(0xffffffffu, started);   // the elected lane's view, warp-uniform again
-        } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
-            ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
-            if (!ok) break;
-            // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none, and it was measured to drain the MMA queue)
-            const uint32_t b_lo = b_lo0 + br.idx * b_block16;
-            if (elect_one()) {
+            if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2))) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
                 if (m == 1 && edge_y) continue;
                 constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
                 const int ai = tap_group<TR>(t) * MT + m;
                 const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
-                const uint32_t first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
+                uint32_t first = 1u;
+                if (TR) {
+                  first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
+                  started |= 1u << ai;
+                } else if (t == 0) {
+                  first = kc == 0 ? 0u : 1u;
+                }
+                if (leader) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                }
+              }
+            }
+            b_lo += b_block16;
+          }
+          if (leader) umma_commit(&bars->a_empty[ar.idx]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
+            ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
+            if (!ok) break;
+            // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none)
+            const uint32_t b_lo = b_lo0 + br.idx * b_block16;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              if (m == 1 && edge_y) continue;
+              constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+              const int ai = tap_group<TR>(t) * MT + m;
+              const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+              uint32_t first = 1u;
+              if (TR) {
+                first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
                 started |= 1u << ai;
+              } else if (t == 0) {
+                first = kc == 0 ? 0u : 1u;
+              }
+              if (leader) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
                   umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
               }
+            }
+            if (leader) {
               umma_commit(&bars->b_empty[br.idx]);
               if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
             }
-            started = __reduce_or_sync(0xffffffffu, started);
             br.advance(P.b_stages);
           }
         }
         ar.advance(P.a_stages);
       }
-      if (ok && elect_one()) {
+      if (ok && leader) {
         umma_commit(&bars->acc_full[cr.idx]);
         if (nmw == 2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
       }
@@ -949,6 +964,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
 static int g_max_ctas = 0;
 static int g_ts_mode = 1;   // 0 = never use the TS epilogue, 1 = whenever eligible
 static long long* g_dbg = nullptr;
+static int g_flags = 0;
 
 }  // namespace w2e
 
@@ -957,6 +973,7 @@ using namespace w2e;
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
 extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
+extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags; }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -979,6 +996,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.out_scale = out_scale; P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.next_scale = next_scale;
   P.out = (__nv_bfloat16*)out; P.out_mod = (__nv_bfloat16*)out_mod; P.error_flag = error_flag;
   P.dbg = g_dbg;
+  P.flags = g_flags;
   P.noise_per_sample = (noise && noise_batch != 1) ? 1 : 0;
   P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
   if (rgb) {
