@@ -214,11 +214,14 @@ def test_bf16_batch_invariance():
     assert torch.equal(full, singles)
 
 
-@pytest.mark.parametrize("b,cin,cout,h,with_skip,want_out", [
-    (2, 64, 64, 32, True, True), (1, 32, 32, 40, False, False), (2, 128, 256, 24, True, False),
-    (1, 64, 32, 72, True, True),
+@pytest.mark.parametrize("b,cin,cout,h,with_skip,want_out,want_mod", [
+    (2, 64, 64, 32, True, True, True), (1, 32, 32, 40, False, False, True), (2, 128, 256, 24, True, False, True),
+    (1, 64, 32, 72, True, True, True),
+    (2, 32, 32, 136, True, False, False),   # RGB-only last layer: 512-pixel tiles, two pixels per epilogue thread
+    (1, 64, 64, 64, True, False, True),     # one staging slot per epilogue half
+    (3, 128, 128, 48, True, False, True),   # weight ring + staged epilogue, 64-channel units
 ])
-def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, want_out):
+def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, want_out, want_mod):
     """StyledConv + ToRGB in one launch (w2e_modconv_tc2_rgb) vs the oracle's two modules"""
     layer = _Layer(cin, cout, False, 51)
     rgbm = w2e.ToRGB(cout, 16)
@@ -238,8 +241,8 @@ def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, w
     d = K.demod_coefficients(s.to(DEV), pw.wsq)
     xs = eng._to_nhwc(x.to(DEV), s.to(DEV).contiguous(), b)
     out, out_mod, rgb = eng._conv2_rgb(xs, pw, d, noise.to(DEV), m.noise.weight.detach(), m.activate.bias.detach(),
-                                       nxt.to(DEV).contiguous(), want_out, True, rgbm, s_rgb.to(DEV).contiguous(),
-                                       skip.to(DEV) if skip is not None else None)
+                                       nxt.to(DEV).contiguous() if want_mod else None, want_out, want_mod, rgbm,
+                                       s_rgb.to(DEV).contiguous(), skip.to(DEV) if skip is not None else None)
     eng.assert_ok()
     ref, _ = orc.modulated_conv2d_ref(x.double(), s.double().reshape(b, 1, cin, 1, 1), layer.weight.double(), None,
                                       None, True, False, None, input_is_stylespace=True)
@@ -250,8 +253,67 @@ def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, w
     ref_rgb, _ = orc._to_rgb(sd, "p", ref, s_rgb.double().reshape(b, 1, cout, 1, 1),
                              skip.double() if skip is not None else None, True)
     assert norm_err(rgb.cpu(), ref_rgb) <= 1e-2
-    assert norm_err(eng._to_nchw(out_mod).cpu(), ref * nxt.double().reshape(b, cout, 1, 1)) <= 1e-2
+    if want_mod:
+        assert norm_err(eng._to_nchw(out_mod).cpu(), ref * nxt.double().reshape(b, cout, 1, 1)) <= 1e-2
+    else:
+        assert out_mod is None
     if want_out:
         assert norm_err(eng._to_nchw(out).cpu(), ref) <= 1e-2
     else:
         assert out is None
+
+
+@pytest.mark.parametrize("b,cin,cout,h,up", [(2, 64, 32, 40, True), (1, 128, 64, 24, True), (2, 256, 128, 20, True),
+                                             (2, 64, 64, 48, False)])
+def test_staged_and_direct_epilogues_agree_bitwise(eng, b, cin, cout, h, up):
+    """the TMA-store epilogue (two MMA issuers, edge-tile tap masking, unit split) and the direct-store
+    epilogue are two schedules of the same arithmetic: results must be bit-identical"""
+    layer = _Layer(cin, cout, up, 71)
+    x = synth.make_tensor((b, cin, h, h), 72)
+    s = 1 + 0.3 * synth.make_tensor((b, cin), 73)
+    noise = synth.make_tensor((1, 1, 2 * h if up else h, 2 * h if up else h), 74)
+    nxt = 1 + 0.3 * synth.make_tensor((b, cout), 75)
+    lib = N.load()
+    outs = []
+    try:
+        for ts_mode, flags in [(1, 0), (0, 0), (1, 1), (1, 2), (1, 3)]:
+            lib.w2e_modconv_tc2_epilogue(ts_mode)
+            lib.w2e_modconv_tc2_flags(flags)
+            outs.append(run_layer(eng, layer, x, s, noise, nxt))
+    finally:
+        lib.w2e_modconv_tc2_epilogue(1)
+        lib.w2e_modconv_tc2_flags(0)
+    for got, got_mod in outs[1:]:
+        assert torch.equal(got, outs[0][0])
+        assert torch.equal(got_mod, outs[0][1])
+
+
+def test_style_plan_matches_per_layer_modules():
+    """w2e_style_mod_all / w2e_style_demod_all (two launches for all 26 styled layers) against the per-layer
+    EqualLinear modulation and demodulation of the module path"""
+    sd = synth.make_state_dict(64, seed=5, perturbed=True)
+    gen = w2e.Generator(64, 512, 8, precision="bf16")
+    gen.load_state_dict(sd)
+    gen = gen.to(DEV).eval()
+    eng_ = gen._engine if getattr(gen, "_engine", None) is not None else E.SynthesisEngine(gen)
+    wplus = synth.make_wplus(5, gen.n_latent, seed=6).to(DEV)
+    layers = gen.styled_layers()
+    rows = gen.latent_rows(False)
+    with torch.no_grad():
+        styles, demods = eng_._styles_and_demods(layers, rows, wplus, False, 5, torch.device(DEV))
+        for (module, kind), row, s, d in zip(layers, rows, styles, demods):
+            ref = module.conv.styles(wplus[:, row], False).double()
+            assert max_abs(s.cpu().double(), ref.cpu()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+            if kind == "rgb":
+                assert d is None
+            else:
+                pw = module.conv.packed()
+                dref = torch.rsqrt((ref * ref) @ pw.wsq.double().t() + 1e-8)
+                assert max_abs(d.cpu().double(), dref.cpu()) <= 1e-5 * float(dref.abs().max())
+        # stylespace entry: the concatenated styles go through the same demodulation launch
+        ss = [s.reshape(5, 1, -1, 1, 1) for s in styles]
+        styles2, demods2 = eng_._styles_and_demods(layers, gen.latent_rows(True), ss, True, 5, torch.device(DEV))
+        for a, b_ in zip(styles, styles2):
+            assert torch.equal(a, b_)
+        for a, b_ in zip(demods, demods2):
+            assert (a is None and b_ is None) or torch.equal(a, b_)
