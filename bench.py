@@ -203,7 +203,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images of the CPU-baseline sample (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="images of the CPU-baseline sample (0 = skip)")
     ap.add_argument("--layers-out", default=None, help="write the per-launch trace of one step to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -195,6 +195,17 @@ int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, c
                         int Cin, int Cout, int in_h, int in_w, int act, const float* rgb_w,
                         const float* rgb_style, const float* rgb_bias, const float* rgb_skip,
                         const float* host_taps1d, float* rgb, void* stream);
+/* Fused up-convolution + Blur + NoiseInjection + FusedLeakyReLU (models/stylegan2/model.py:249-260,
+ * 279-290; op/fused_act.py:23-39): the transposed x2 modulated convolution of w2e_modconv_tc2 whose
+ * (2h+1)^2 pre-blur result stays in shared memory and is filtered by the separable 4x4 FIR host_taps[16]
+ * (upfirdn2d, pad (1,1)) inside the same kernel.  out / out_mod: [B, 2h, 2w, Cout] bf16 channels-last (either
+ * may be null), noise: [noise_batch, 2h*2w] fp32 or null.  Returns W2E_ERR_UNSUPPORTED (and launches
+ * nothing) for shapes the fused kernel does not cover (Cout > 64, fewer than 17 input rows, a
+ * non-separable kernel): the caller then runs w2e_modconv_tc2 + w2e_blur_act_nhwc.                 */
+int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale, const float* host_taps,
+                           const float* bias, const float* noise, const float* noise_w, int noise_batch,
+                           const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
+                           int Cin, int Cout, int in_h, int in_w, int act, void* stream);
 /* tuning knob of w2e_modconv_tc2: cap on the number of persistent CTAs (0 = one or two per SM). */
 void w2e_modconv_tc2_knobs(int max_ctas);
 /* epilogue selection of w2e_modconv_tc2[_rgb]: 1 (default) = shared-memory-staged TMA-store epilogue

@@ -317,3 +317,36 @@ def test_style_plan_matches_per_layer_modules():
             assert torch.equal(a, b_)
         for a, b_ in zip(demods, demods2):
             assert (a is None and b_ is None) or torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,want_out", [(2, 64, 32, 40, True), (1, 128, 64, 24, False), (1, 64, 32, 72, False),
+                                                   (3, 32, 32, 18, True), (1, 128, 64, 66, True)])
+def test_fused_upconv_blur_matches_oracle(eng, b, cin, cout, h, want_out):
+    """w2e_modconv_tc2_upblur: conv_transpose x2 + demod + 4x4 blur + noise + bias + lrelu in one launch,
+    against the oracle and against the two-kernel path (which rounds the pre-blur tensor to bf16 as well)"""
+    layer = _Layer(cin, cout, True, 81)
+    x = synth.make_tensor((b, cin, h, h), 82)
+    s = 1 + 0.3 * synth.make_tensor((b, cin), 83)
+    noise = synth.make_tensor((1, 1, 2 * h, 2 * h), 84)
+    nxt = 1 + 0.3 * synth.make_tensor((b, cout), 85)
+    m = layer.m
+    pw = eng._tc_weight(m.conv)
+    d = K.demod_coefficients(s.to(DEV), pw.wsq)
+    xs = eng._to_nhwc(x.to(DEV), s.to(DEV).contiguous(), b)
+    fused = eng._upblur(xs, pw, d, m.conv.blur.kernel, m.conv.blur.pad, m.activate.bias.detach(), noise.to(DEV),
+                        m.noise.weight.detach(), nxt.to(DEV).contiguous(), want_out, True)
+    eng.assert_ok()
+    assert fused is not None
+    out, out_mod = fused
+    blur = synth.blur_kernel_2d(gain=4.0)
+    ref, _ = orc.modulated_conv2d_ref(x.double(), s.double().reshape(b, 1, cin, 1, 1), layer.weight.double(), None,
+                                      None, True, True, blur.double(), input_is_stylespace=True)
+    ref = orc.fused_leaky_relu_ref(ref + 0.3 * noise.double(), m.activate.bias.detach().cpu().double())
+    assert tuple(out_mod.shape) == (b, 2 * h, 2 * h, cout)
+    assert norm_err(eng._to_nchw(out_mod).cpu(), ref * nxt.double().reshape(b, cout, 1, 1)) <= 1e-2
+    if want_out:
+        assert norm_err(eng._to_nchw(out).cpu(), ref) <= 1e-2
+    else:
+        assert out is None
+    two, two_mod = run_layer(eng, layer, x, s, noise, nxt)
+    assert norm_err(eng._to_nchw(out_mod).cpu(), two_mod) <= 1e-2

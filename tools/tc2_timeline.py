@@ -1,7 +1,8 @@
 """Timeline of CTA 0 of one w2e_modconv_tc2[_rgb] launch (clock64 stamps written by the kernel's
 three roles, see include/w2e.h: w2e_modconv_tc2_debug).  Prints per tile, relative to the first
 stamp: producer {inputs slot free, A issued}, MMA {acc free, A landed, issued}, epilogue {inputs,
-acc ready, done}.    python tools/tc2_timeline.py [cin cout h batch rgb(0/1) tr(0/1)]"""
+acc ready, done}; with tr=2 (fused up-conv + blur) the P columns hold {pre-blur tile written, FIR of chunk 0 done}.
+    python tools/tc2_timeline.py [cin cout h batch rgb(0/1) tr(0/1/2)]"""
 import os
 import sys
 
@@ -31,6 +32,9 @@ def main():
     nxt = (1 + 0.3 * torch.randn(b, cout, device=dev)).contiguous()
 
     def run():
+        if tr == 2:   # fused up-convolution + blur
+            return eng._upblur(xs, pw, d, m.conv.blur.kernel, m.conv.blur.pad, m.activate.bias.detach(),
+                               torch.randn(1, 1, 2 * h, 2 * h, device=dev), m.noise.weight.detach(), nxt, False, True)
         if tr:
             return eng._conv2(xs, pw, d, None, None, None, None, True, False, True, N.ACT_NONE)
         if rgb:

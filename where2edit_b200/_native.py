@@ -43,6 +43,7 @@ PROTOTYPES = {
     "w2e_modconv_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 12 + [_P, _I, _I, _I, _P]),
     "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P]),
     "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 7),
+    "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P]),
     "w2e_modconv_tc2_knobs": (None, [_I]),
     "w2e_modconv_tc2_epilogue": (None, [_I]),
     "w2e_modconv_tc2_debug": (None, [_P]),
@@ -150,6 +151,9 @@ def load():
 def last_error():
     msg = load().w2e_last_error_string()
     return msg.decode("utf-8", "replace") if msg else ""
+
+
+ERR_UNSUPPORTED = 3
 
 
 def check(code, what):

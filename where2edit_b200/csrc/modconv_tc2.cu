@@ -57,6 +57,11 @@ struct Tc2Params {
   __nv_bfloat16* out;       // [B,OH,OW,Cout] or null
   __nv_bfloat16* out_mod;   // [B,OH,OW,Cout] or null
   int* error_flag;
+  // fused up-convolution + Blur (w2e_modconv_tc2_upblur): out/out_mod/noise/bias/next_scale then describe the
+  // FINAL [B, OH2, OW2, Cout] activation; fbv/fbh = flipped vertical/horizontal taps of the separable 4x4 FIR
+  int fb, OH2, OW2;
+  float fbv[4], fbh[4];
+  int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
@@ -163,6 +168,8 @@ __device__ __forceinline__ constexpr bool tap_first(int t) {  // first tap (in i
   return TR ? (t == 0 || t == 1 || t == 3 || t == 4) : (t == 0);
 }
 
+__device__ __forceinline__ uint32_t e_base_fb(uint8_t* smem, const Tc2Params& P) { return smem_u32(smem + P.e_off); }
+
 struct Ring {
   uint32_t idx = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t n) {
@@ -213,7 +220,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
       for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
       // TS flavour with a single accumulator buffer: both epilogue groups drain every tile (unit-split mode)
-      const uint32_t epi_arrivals = (TS && P.nbuf == 1) ? 2 * kT2EpiThreads : kT2EpiThreads;
+      const uint32_t epi_arrivals = (TS && (P.nbuf == 1 || P.fb)) ? 2 * kT2EpiThreads : kT2EpiThreads;
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], epi_arrivals); }
       mbar_init(&bars->w_full, 1);
       mbar_init(&bars->mma_turn[0], 1);
@@ -244,7 +251,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       wk.init(blockIdx.x, gridDim.x, P);
       for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
         const int b = wk.b;
-        const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW, co0 = wk.tn * P.bn;
+        const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o, co0 = wk.tn * P.bn;
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
           if (!ok) break;
@@ -254,8 +261,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                       j0 - 1, b);
           ar.advance(P.a_stages);
           if (!WRES) {
-            const bool edge_y = TR && !(P.flags & 1) && j0 >= P.grid_h - 1;   // see the MMA issuer
-            const bool edge_x = TR && !(P.flags & 1) && i0 >= P.grid_w - 1;
+            const bool edge_y = TR && !(P.flags & 1) && !P.fb && j0 >= P.grid_h - 1;   // see the MMA issuer
+            const bool edge_x = TR && !(P.flags & 1) && !P.fb && i0 >= P.grid_w - 1;
             for (int t = 0; t < 9; ++t) {
               if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
@@ -280,14 +287,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       wk.init(blockIdx.x, gridDim.x, P);
       for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
         const int b = wk.b;
-        const int j0 = wk.ty * (kSubTileH * MT), i0 = wk.tx * kTileW;
+        const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o;
         ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
         if (!ok) break;
         if (P.dbg && blockIdx.x == 0 && tile / (int)gridDim.x < 64) P.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
         uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
         *reinterpret_cast<int4*>(eb + P.e_info_off) = make_int4(b, j0, i0, wk.tn);
         mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);   // release: orders the info store
-        if (P.noise) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
+        if (P.noise && !P.fb) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
         if (RGB && P.rgb_skip) {
 #pragma unroll
           for (int m = 0; m < MT; ++m)
@@ -337,8 +344,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // the positions j == h / i == w, which see nothing but zero padding through every tap except
       // ky == 2 / kx == 2: the other taps (and the second sub-tile) of such EDGE tiles are skipped.
       // Their untouched accumulators belong to classes whose rows/columns are clipped by the stores.
-      const bool edge_y = TR && !(P.flags & 1) && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
-      const bool edge_x = TR && !(P.flags & 1) && wk.tx * kTileW >= P.grid_w - 1;
+      const bool edge_y = TR && !(P.flags & 1) && !P.fb && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
+      const bool edge_x = TR && !(P.flags & 1) && !P.fb && wk.tx * kTileW >= P.grid_w - 1;
       ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
       if (!ok) break;
       tc_fence_after();
@@ -454,6 +461,183 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int half = (ew >> 2) & 1;
     const int q = warp & 3;
     const int gt = (int)threadIdx.x - group * kT2EpiThreads;   // 0..255 inside the group
+    if constexpr (TR) {
+      if (P.fb) {
+        // -------------------------------------------------------------- fused up-convolution + Blur epilogue
+        // (model.py:249-260 + 279-290 + fused_act: conv_transpose2d -> demod -> upfirdn2d(4x4, pad (1,1)) -> + noise
+        // -> + bias -> leaky-ReLU*sqrt2 -> next layer's style.)  The (2h+1)^2 pre-blur tensor never reaches HBM:
+        // the tile's 64 x 16 pre-blur pixels (32 x 8 input positions x 4 parity classes) are written, demodulated,
+        // as bf16 into a swizzled shared-memory tile [64][16][32 channels]; then all 16 epilogue warps run the
+        // separable FIR over it (register ring of horizontally filtered rows, packed fp32x2 math) and store the
+        // 60 x 12 output pixels the tile fully covers.  Tiles therefore step by 30 x 6 input positions (the
+        // MMA recomputes the 2 x 2 halo: x1.42 MMA work for 8 GB less HBM traffic per 1024^2 batch-32 step).
+        const int t = (int)threadIdx.x;          // 0..511
+        const int q = warp & 3, quad = warp >> 2;
+        const int r = q * 32 + lane, sy = r >> 3, sx = r & 7;
+        const bool lrelu = P.act == W2E_ACT_LRELU;
+        const float gain = lrelu ? 1.41421356237309515f : 1.f;
+        const float slope = lrelu ? 0.2f : 1.f;
+        const uint64_t slope2 = pack2(slope, slope);
+        const float nw = P.noise ? __ldg(P.noise_w) * gain : 0.f;
+        const uint32_t z_base = smem_u32(smem + P.ts_off);
+        const uint32_t nbuf_mask = (uint32_t)P.nbuf - 1u, nbuf_shift = P.nbuf == 4 ? 2u : (P.nbuf == 2 ? 1u : 0u);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        // FIR role: 8 channels (cg) of output column fx, six consecutive output rows (segment seg)
+        const int cg = t & 3, fx = (t >> 2) % 12, seg = t / 48;
+        const bool fir_on = t < 480;
+        const uint64_t fv0 = pack2(P.fbv[0] * gain, P.fbv[0] * gain), fv1 = pack2(P.fbv[1] * gain, P.fbv[1] * gain);
+        const uint64_t fv2 = pack2(P.fbv[2] * gain, P.fbv[2] * gain), fv3 = pack2(P.fbv[3] * gain, P.fbv[3] * gain);
+        const uint64_t fh0 = pack2(P.fbh[0], P.fbh[0]), fh1 = pack2(P.fbh[1], P.fbh[1]);
+        const uint64_t fh2 = pack2(P.fbh[2], P.fbh[2]), fh3 = pack2(P.fbh[3], P.fbh[3]);
+        auto zaddr = [&](int zr, int zc, int ck) -> uint32_t {   // 16-byte chunk ck (8 channels) of pre-blur pixel (zr, zc)
+          return z_base + (uint32_t)(zr * 1024 + ((zc ^ ((zc >> 3) & 1)) * 64) + ((ck ^ ((zc >> 1) & 3)) * 16));
+        };
+        uint32_t gen = 0;
+        int prev_b = -1, prev_tn = -1;
+        bool ok = true;
+        uint32_t k = 0;
+        for (int tile = (int)blockIdx.x; tile < P.ntiles; tile += (int)gridDim.x, ++k) {
+          const uint32_t es = k % (uint32_t)kEStages;
+          if (ok) ok = mbar_wait(&bars->e_full[es], (k / (uint32_t)kEStages) & 1u, abort_flag);
+          int b, j0, i0, tn;
+          lds_4i(e_base_fb(smem, P) + es * (uint32_t)P.e_stage_bytes + (uint32_t)P.e_info_off, b, j0, i0, tn);
+          mbar_arrive(&bars->e_empty[es]);
+          const bool dbg_on = P.dbg && blockIdx.x == 0 && k < 64 && t == 0;
+          if (dbg_on) P.dbg[k * 8 + 5] = clock64();
+          if (b != prev_b || tn != prev_tn) {
+            prev_b = b; prev_tn = tn;
+            gen ^= 1u;
+            if (t < P.bn) {
+              float* cst = bars->ts_consts(0, (int)gen);
+              const int c = tn * P.bn + t, bc = b * P.Cout + c;
+              cst[t] = P.out_scale ? __ldg(P.out_scale + bc) : 1.f;
+              cst[128 + t] = (P.bias ? __ldg(P.bias + c) : 0.f) * gain;
+              cst[256 + t] = P.next_scale ? __ldg(P.next_scale + bc) : 1.f;
+            }
+            named_bar_sync(7, 2 * kT2EpiThreads);
+          }
+          const uint32_t sc_a = smem_u32(bars->ts_consts(0, (int)gen));
+          const uint32_t ci = k & nbuf_mask;
+          const uint32_t t_tile = t_lane + ci * (uint32_t)(NG * MT * P.bn);
+          if (ok) ok = mbar_wait(&bars->acc_full[ci], (k >> nbuf_shift) & 1u, abort_flag);
+          tc_fence_after();
+          if (dbg_on) P.dbg[k * 8 + 6] = clock64();
+          const int Y0 = 2 * (j0 + 1), X0 = 2 * (i0 + 1);   // first output pixel of the tile
+          const int nchunks = P.bn >> 5;
+          for (int chunk = 0; chunk < nchunks; ++chunk) {
+            // ---- phase 1: accumulators -> demodulated bf16 pre-blur tile
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int acc = quad + 4 * u;              // = class * MT + m (MT == 2)
+              const int g = acc >> 1, m = acc & 1;
+              const int zr = 2 * (m * kSubTileH + sy) + (g >> 1), zc = 2 * sx + (g & 1);
+#pragma unroll
+              for (int c16 = 0; c16 < 32; c16 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_tile + (uint32_t)(acc * P.bn + chunk * 32 + c16), v);
+                tmem_ld_wait();
+                if (chunk == nchunks - 1 && u == 1 && c16 == 16) {
+                  tc_fence_before();
+                  mbar_arrive(&bars->acc_empty[ci]);
+                }
+                const uint32_t ca = sc_a + (uint32_t)((chunk * 32 + c16) * 4);
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint64_t a01, a23;
+                  lds_2x2(ca + e * 16, a01, a23);
+                  float x0, x1, x2, x3;
+                  unpack2(mul2(pack2u(v[4 * e], v[4 * e + 1]), a01), x0, x1);
+                  unpack2(mul2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23), x2, x3);
+                  pk[2 * e] = cvt_bf16x2(x0, x1);
+                  pk[2 * e + 1] = cvt_bf16x2(x2, x3);
+                }
+                sts_128(zaddr(zr, zc, c16 >> 3), pk[0], pk[1], pk[2], pk[3]);
+                sts_128(zaddr(zr, zc, (c16 >> 3) + 1), pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+            named_bar_sync(7, 2 * kT2EpiThreads);
+            if (dbg_on && chunk == 0) P.dbg[k * 8 + 0] = clock64();   // (overwrites the producer's stamp: FB timeline)
+            // ---- phase 2: separable 4x4 FIR + noise + bias + activation + next style
+            if (fir_on) {
+              const int c0 = tn * P.bn + chunk * 32 + cg * 8;
+              uint64_t bias2[4], nsc2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(bias2[e]) : "r"(sc_a + (uint32_t)((128 + chunk * 32 + cg * 8 + 2 * e) * 4)));
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(nsc2[e]) : "r"(sc_a + (uint32_t)((256 + chunk * 32 + cg * 8 + 2 * e) * 4)));
+              }
+              const int Xg = X0 + fx;
+              const bool x_ok = Xg < P.OW2;
+              // the six noise values of this thread's outputs, all in flight before the filter loop
+              float nzv[6];
+#pragma unroll
+              for (int rr = 0; rr < 6; ++rr) {
+                const int Y = Y0 + 6 * seg + rr;
+                nzv[rr] = (P.noise && x_ok && Y < P.OH2)
+                    ? __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.OH2 * P.OW2 : 0) + (int64_t)Y * P.OW2 + Xg) : 0.f;
+              }
+              uint32_t zcol[4];   // swizzled column/chunk part of the four window columns
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) zcol[kk] = zaddr(6 * seg + 1, fx + 1 + kk, cg);
+              uint64_t win[4][4];
+#pragma unroll
+              for (int lr = 0; lr < 9; ++lr) {
+                const int u4 = lr & 3;
+                uint64_t f[4][4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  uint32_t w0, w1, w2, w3;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                               : "r"(zcol[kk] + (uint32_t)(lr * 1024)));
+                  f[kk][0] = pack2u(w0 << 16, w0 & 0xffff0000u);
+                  f[kk][1] = pack2u(w1 << 16, w1 & 0xffff0000u);
+                  f[kk][2] = pack2u(w2 << 16, w2 & 0xffff0000u);
+                  f[kk][3] = pack2u(w3 << 16, w3 & 0xffff0000u);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  win[u4][e] = fma2(fh3, f[3][e], fma2(fh2, f[2][e], fma2(fh1, f[1][e], mul2(fh0, f[0][e]))));
+                if (lr >= 3) {
+                  const int Y = Y0 + 6 * seg + lr - 3;
+                  if (x_ok && Y < P.OH2 && ok) {
+                    const float nz = nw * nzv[lr - 3];
+                    const uint64_t nz2 = pack2(nz, nz);
+                    uint32_t po[4], pm[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const uint64_t a = fma2(fv3, win[u4][e],
+                                              fma2(fv2, win[(u4 + 3) & 3][e],
+                                                   fma2(fv1, win[(u4 + 2) & 3][e],
+                                                        fma2(fv0, win[(u4 + 1) & 3][e], add2(bias2[e], nz2)))));
+                      const uint64_t a_s = mul2(a, slope2);
+                      float x0, x1, y0, y1;
+                      unpack2(a, x0, x1);
+                      unpack2(a_s, y0, y1);
+                      x0 = fmaxf(x0, y0);
+                      x1 = fmaxf(x1, y1);
+                      if (P.out) po[e] = cvt_bf16x2(x0, x1);
+                      if (P.out_mod) {
+                        float m0, m1;
+                        unpack2(mul2(pack2(x0, x1), nsc2[e]), m0, m1);
+                        pm[e] = cvt_bf16x2(m0, m1);
+                      }
+                    }
+                    const int64_t o = (((int64_t)b * P.OH2 + Y) * P.OW2 + Xg) * P.Cout + c0;
+                    if (P.out) *reinterpret_cast<uint4*>(P.out + o) = make_uint4(po[0], po[1], po[2], po[3]);
+                    if (P.out_mod) *reinterpret_cast<uint4*>(P.out_mod + o) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+                  }
+                }
+              }
+            }
+            named_bar_sync(7, 2 * kT2EpiThreads);   // the tile may be overwritten
+            if (dbg_on && chunk == 0) P.dbg[k * 8 + 1] = clock64();
+          }
+          if (dbg_on) P.dbg[k * 8 + 7] = clock64();
+        }
+      }
+    }
+    if (!(TR && P.fb))
     {
       const bool split = P.nbuf == 1;   // one accumulator buffer: the two groups share every tile and split its units
       const int r = q * 32 + lane;
@@ -979,10 +1163,14 @@ struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
 };
 
+struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped taps)
+  float fv[4], fh[4];
+};
+
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
                    const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
                    int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
-                   const RgbArgs* rgb, void* stream, bool allow_mt4 = true) {
+                   const RgbArgs* rgb, void* stream, bool allow_mt4 = true, const FbArgs* fb = nullptr) {
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
   W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
   W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
@@ -1042,6 +1230,17 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.b_block_bytes = P.bn * row_bytes;
   P.tiles_x = ceil_div(P.grid_w, kTileW);
   P.tiles_y = ceil_div(P.grid_h, kSubTileH * P.mt);
+  P.tile_dy = kSubTileH * P.mt; P.tile_dx = kTileW; P.tile_o = 0;
+  if (fb) {
+    // 64 x 16 pre-blur pixels per tile, of which the 60 x 12 outputs with a complete 4x4 window are kept
+    if (!(transposed && P.mt == 2 && acc_cols <= 512 && P.bn % 32 == 0 && g_ts_mode != 0))
+      return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shape not supported by the fused kernel");
+    P.fb = 1; P.OH2 = 2 * in_h; P.OW2 = 2 * in_w;
+    for (int i = 0; i < 4; ++i) { P.fbv[i] = fb->fv[i]; P.fbh[i] = fb->fh[i]; }
+    P.tile_dy = 30; P.tile_dx = 6; P.tile_o = -1;
+    P.tiles_x = ceil_div(P.OW2, 12);
+    P.tiles_y = ceil_div(P.OH2, 60);
+  }
   P.tiles_n = Cout / P.bn;
   const int64_t ntiles = (int64_t)P.tiles_x * P.tiles_y * P.tiles_n * B;
   W2E_CHECK_ARG(ntiles < (1ll << 31), "modconv_tc2: too many tiles");
@@ -1052,8 +1251,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   const int n_out = (out ? 1 : 0) + (out_mod ? 1 : 0);
   bool ts = g_ts_mode != 0 && (transposed || P.mt >= 2) && P.bn >= 32 && P.bn <= 128;
   if (rgb && nbuf_plain != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
-  if (transposed) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
-  if (noise) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
+  if (transposed && !fb) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
+  if (noise && !fb) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
   if (rgb && rgb->skip) ts = ts && ((P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
   if (out) ts = ts && (((uintptr_t)out & 15) == 0);
   if (out_mod) ts = ts && (((uintptr_t)out_mod & 15) == 0);
@@ -1075,14 +1274,15 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       P.ts_unit_ch = P.bn < cands[ci].unit_ch ? P.bn : cands[ci].unit_ch;
       if (ci >= 2 && P.bn <= 32) continue;   // same unit as candidates 0/1
       P.ts_slots = cands[ci].slots;
-      if (n_out > P.ts_slots) continue;
+      if (!fb && n_out > P.ts_slots) continue;
       P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
       P.use_e = 1;
       P.e_noise_bytes = P.mt == 4 ? 2048 : 1024;
       P.e_info_off = P.e_noise_bytes + ((rgb && rgb->skip) ? P.mt * kSkipBoxBytes : 0);
       P.e_stage_bytes = P.e_info_off + 128;
       P.e_bytes = (noise ? kTileW * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * kSkipBoxW * 4 : 0);
-      ts_bytes = n_out ? 2 * 2 * P.ts_slots * P.ts_unit_bytes : 0;
+      ts_bytes = fb ? 64 * 1024 : (n_out ? 2 * 2 * P.ts_slots * P.ts_unit_bytes : 0);
+      if (fb) { P.e_bytes = 0; P.e_info_off = 0; P.e_stage_bytes = 128; }
       extra = 1024 /*alignment of the staging area*/ + kEStages * P.e_stage_bytes;
     } else {
       P.ts_unit_ch = P.ts_unit_bytes = P.ts_slots = P.use_e = P.e_stage_bytes = P.e_bytes = 0;
@@ -1137,7 +1337,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   }
   Tc2Maps M;
   memset(&M, 0, sizeof(M));
-  if (ts) {
+  if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
+  if (ts && !fb) {
     if (noise) {
       const uint64_t dims[3] = {(uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)noise_batch};
       const uint64_t strides[2] = {(uint64_t)P.OW * 4, (uint64_t)P.OH * P.OW * 4};
@@ -1232,4 +1433,30 @@ extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* o
   const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb};
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
                  in_h, in_w, 0, act, &a, stream);
+}
+
+
+extern "C" int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale, const float* host_taps,
+                                      const float* bias, const float* noise, const float* noise_w, int noise_batch,
+                                      const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
+                                      int Cin, int Cout, int in_h, int in_w, int act, void* stream) {
+  W2E_CHECK_ARG(host_taps, "modconv_tc2_upblur: null taps");
+  // separable factorisation of the 4x4 kernel (rank-1 check as in w2e_blur_act_nhwc)
+  int bi = 0, bj = 0;
+  float best = 0.f;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (fabsf(host_taps[i * 4 + j]) > best) best = fabsf(host_taps[i * 4 + j]), bi = i, bj = j;
+  W2E_CHECK_ARG(best > 0.f, "modconv_tc2_upblur: zero kernel");
+  float kv[4], kh[4];
+  for (int i = 0; i < 4; ++i) kv[i] = host_taps[i * 4 + bj];
+  for (int j = 0; j < 4; ++j) kh[j] = host_taps[bi * 4 + j] / host_taps[bi * 4 + bj];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (fabsf(host_taps[i * 4 + j] - kv[i] * kh[j]) > 1e-6f * best)
+        return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: the 4x4 kernel is not separable");
+  FbArgs fb;
+  for (int i = 0; i < 4; ++i) { fb.fv[i] = kv[3 - i]; fb.fh[i] = kh[3 - i]; }
+  return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
+                 in_h, in_w, 1, act, nullptr, stream, false, &fb);
 }

@@ -56,6 +56,10 @@ class SynthesisEngine:
         self.v1 = os.environ.get("W2E_TC_V1", "0") == "1"
         # W2E_FUSE_RGB=0 keeps ToRGB as its own kernel (w2e_torgb_nhwc) instead of the conv epilogue
         self.fuse_rgb = os.environ.get("W2E_FUSE_RGB", "1") == "1"
+        # W2E_FUSE_UPBLUR=1 runs the up-convolution and its Blur as ONE kernel where w2e_modconv_tc2_upblur covers
+        # the shape.  Off by default: parity-green, but its CUDA-core FIR phase is not yet faster than the
+        # HBM round trip it removes.
+        self.fuse_upblur = os.environ.get("W2E_FUSE_UPBLUR", "0") == "1"
         if not N.load().w2e_modconv_tc_supported():
             raise RuntimeError("where2edit_b200: precision='bf16' needs an sm_100 (B200) device and a driver with "
                                "cuTensorMapEncodeTiled; there is no fallback -- use precision='fp32'")
@@ -231,6 +235,30 @@ class SynthesisEngine:
             N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb), N.stream_ptr()), "modconv_tc2_rgb")
         return out, out_mod, rgb
 
+    def _upblur(self, xs, pw, d, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod):
+        """Up-convolution + Blur + noise + bias + lrelu in ONE launch (w2e_modconv_tc2_upblur); returns None
+        when the fused kernel does not cover the shape (the caller then runs the two-kernel path)."""
+        b, h, w, _ = xs.shape
+        taps = kernel_taps(blur_kernel)
+        if len(taps) != 16 or tuple(pad) != (1, 1) or pw.cout > 64 or h <= 16:
+            return None
+        dev = xs.device
+        out = torch.empty((b, 2 * h, 2 * w, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
+        out_mod = torch.empty((b, 2 * h, 2 * w, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
+        nb = 0 if noise is None else noise.shape[0]
+        # 2 x 2 halo recomputed per tile: the MMA does 64*16/(60*12) = 1.42x the algorithmic work
+        N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"up+blur {pw.cin}->{pw.cout}@{h}x{w}",
+               bytes=2.0 * b * (h * w * pw.cin + 4 * h * w * pw.cout * (int(want_out) + int(want_mod))))
+        rc = N.load().w2e_modconv_tc2_upblur(
+            N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.host_floats(taps), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
+            N.ptr(next_scale), N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w,
+            N.ACT_LRELU, N.stream_ptr())
+        if rc == N.ERR_UNSUPPORTED:
+            N.STATS.note = None
+            return None
+        N.check(rc, "modconv_tc2_upblur")
+        return out, out_mod
+
     def _blur(self, z, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod, out_hw):
         b, ih, iw, c = z.shape
         dev = z.device
@@ -376,11 +404,18 @@ class SynthesisEngine:
                     for (py, px), taps in _TAPS_UP.items():
                         self._conv(xs, pw, demods[idx], None, None, None, None, True, False, taps, (h, w), (zh, zw),
                                    (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
-                else:
-                    z, _ = self._conv2(xs, pw, demods[idx], None, None, None, None, True, False, True, N.ACT_NONE)
+                fused = None
+                if not self.v1 and self.fuse_upblur:
+                    fused = self._upblur(xs, pw, demods[idx], conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt,
+                                         need_out, need_mod)
                 hw = (2 * h, 2 * w)
-                act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, need_out,
-                                          need_mod, hw)
+                if fused is not None:
+                    act, xs_next = fused
+                else:
+                    if not self.v1:
+                        z, _ = self._conv2(xs, pw, demods[idx], None, None, None, None, True, False, True, N.ACT_NONE)
+                    act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, need_out,
+                                              need_mod, hw)
             if blend_here:
                 carry = True
                 act, xs_next = self._blend(act, feature_map[layer - 1], attention_map, nxt, nxt is not None)
