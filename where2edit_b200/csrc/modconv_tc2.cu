@@ -62,6 +62,7 @@ struct Tc2Params {
   int fb, OH2, OW2;
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
+  int cluster;              // 1 = launched as 2-CTA clusters with multicast weight blocks
   int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
@@ -91,6 +92,7 @@ struct Tc2Params {
 struct alignas(64) Tc2Maps {
   CUtensorMap noise;   // fp32 {OW, OH, noise_batch}, box {8, 16*MT, 1}
   CUtensorMap skip;    // fp32 {OW/2, OH/2, B*3}, box {12, 10, 3}
+  CUtensorMap bh;      // cluster mode: weight map with a half-block box {BK, bn/2, 1}
   CUtensorMap st[4];   // bf16 stores, box {unit_ch, 8, 16, 1}: plain [0] = out, [1] = out_mod; transposed [g] = class g of out
 };
 
@@ -196,6 +198,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   volatile int* abort_flag = &bars->abort_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 2-CTA cluster mode (weight-ring kernels): the two CTAs of a cluster work on the SAME tile position of two
+  // consecutive samples, so they consume identical weight blocks: each loads half of every block and TMA-
+  // multicasts it to both (half the L2->SM weight traffic).  P.B / P.ntiles then count sample PAIRS.
+  const int cl = P.cluster;
+  const uint32_t crank = cl ? cluster_ctarank() : 0u;
+  const int cta_slot = (int)blockIdx.x >> cl, cta_slots = (int)gridDim.x >> cl;
   // Warp roles: the epilogue warps come FIRST and the TMA producer / MMA issuer LAST: the SM's warp
   // arbiter favours the highest warp id of a scheduler, and a starved MMA issuer stalls everyone
   // (measured: with the issuer as warp 1 it got an issue slot every ~9 cycles next to busy epilogue warps).
@@ -218,7 +226,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
-      for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
+      for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], cl ? 2 : 1); }
       // TS flavour with a single accumulator buffer: both epilogue groups drain every tile (unit-split mode)
       const uint32_t epi_arrivals = (TS && (P.nbuf == 1 || P.fb)) ? 2 * kT2EpiThreads : kT2EpiThreads;
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], epi_arrivals); }
@@ -233,6 +241,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (cl) cluster_sync();   // the peer's mbarriers are initialised before any multicast / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
 
@@ -248,9 +257,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       Ring ar, br;
       bool ok = true;
       TileWalk wk;
-      wk.init(blockIdx.x, gridDim.x, P);
-      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
-        const int b = wk.b;
+      wk.init(cta_slot, cta_slots, P);
+      for (int tile = cta_slot; tile < P.ntiles && ok; tile += cta_slots, wk.next(P)) {
+        const int b = (wk.b << cl) + (int)crank;
         const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o, co0 = wk.tn * P.bn;
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
@@ -268,7 +277,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
-              tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
+              if (cl)   // my half of the block, delivered to both CTAs of the cluster (each signals its own b_full)
+                tma_load_3d_mc(b_base + (size_t)br.idx * P.b_block_bytes + (size_t)crank * (P.b_block_bytes >> 1), &M.bh,
+                               &bars->b_full[br.idx], kc * kBK, co0 + (int)crank * (P.bn >> 1), t, (uint16_t)3);
+              else
+                tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
               br.advance(P.b_stages);
             }
           }
@@ -284,9 +297,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       Ring er;
       bool ok = true;
       TileWalk wk;
-      wk.init(blockIdx.x, gridDim.x, P);
-      for (int tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, wk.next(P)) {
-        const int b = wk.b;
+      wk.init(cta_slot, cta_slots, P);
+      for (int tile = cta_slot; tile < P.ntiles && ok; tile += cta_slots, wk.next(P)) {
+        const int b = (wk.b << cl) + (int)crank;
         const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o;
         ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
         if (!ok) break;
@@ -330,8 +343,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // (even buffer count, stage count a multiple of 2 * kchunks): an issuer that saw only every other phase
     // of an mbarrier could mistake an old completion for the one it waits for.
     const int nmw = (kMmaWarps == 2 && !(P.flags & 2) && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
-    const int tile_step = nmw * (int)gridDim.x;
-    const int tile0 = mw < nmw ? (int)blockIdx.x + mw * (int)gridDim.x : P.ntiles;
+    const int tile_step = nmw * cta_slots;
+    const int tile0 = mw < nmw ? cta_slot + mw * cta_slots : P.ntiles;
     if (mw == 1) {   // the second issuer starts one tile into the rings
       for (int i = 0; i < kchunks; ++i) ar.advance(P.a_stages);
       cr.advance(P.nbuf);
@@ -424,7 +437,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               }
             }
             if (leader) {
-              umma_commit(&bars->b_empty[br.idx]);
+              if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)3);   // the slot is free once BOTH CTAs consumed it
+              else umma_commit(&bars->b_empty[br.idx]);
               if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
             }
             br.advance(P.b_stages);
@@ -496,7 +510,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int prev_b = -1, prev_tn = -1;
         bool ok = true;
         uint32_t k = 0;
-        for (int tile = (int)blockIdx.x; tile < P.ntiles; tile += (int)gridDim.x, ++k) {
+        for (int tile = cta_slot; tile < P.ntiles; tile += cta_slots, ++k) {
           const uint32_t es = k % (uint32_t)kEStages;
           if (ok) ok = mbar_wait(&bars->e_full[es], (k / (uint32_t)kEStages) & 1u, abort_flag);
           int b, j0, i0, tn;
@@ -661,7 +675,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t swz = (UC == 64) ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
       const uint32_t e_base = smem_u32(smem + P.e_off);
       const int bar_group = 1 + group * 3, bar_half = 2 + group * 3 + half;
-      const int stride = split ? (int)gridDim.x : 2 * (int)gridDim.x;
+      const int stride = split ? cta_slots : 2 * cta_slots;
       const int unit0 = RGB ? 0 : (split ? group * 2 + half : half), unit_step = RGB ? 1 : (split ? 4 : 2);
       const uint32_t nbuf_mask = (uint32_t)P.nbuf - 1u, nbuf_shift = P.nbuf == 4 ? 2u : (P.nbuf == 2 ? 1u : 0u);
       const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -684,7 +698,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int prev_b = -1, prev_tn = -1;
       bool ok = true;
       uint32_t k = 0;
-      for (int tile = (int)blockIdx.x + (split ? 0 : group * (int)gridDim.x); tile < P.ntiles; tile += stride, ++k) {
+      for (int tile = cta_slot + (split ? 0 : group * cta_slots); tile < P.ntiles; tile += stride, ++k) {
         const uint32_t seq = split ? k : 2u * k + (uint32_t)group;   // position in the CTA's tile sequence
         const uint32_t es = seq % (uint32_t)kEStages;
         if (ok) ok = mbar_wait(&bars->e_full[es], (seq / (uint32_t)kEStages) & 1u, abort_flag);
@@ -936,8 +950,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       Pre t;
       const int tn = tile / tiles_per_n;
       int rem = tile - tn * tiles_per_n;
-      t.b = rem / tiles_xy;
+      t.b = rem / tiles_xy;   // (pair-local sample index in cluster mode, mapped below)
       rem -= t.b * tiles_xy;
+      t.b = (t.b << cl) + (int)crank;
       const int ty = rem / P.tiles_x, tx = rem - ty * P.tiles_x;
       t.j0 = ty * (kSubTileH * MT); t.i0 = tx * kTileW; t.co0 = tn * P.bn;
       t.scale = 1.f; t.shift = 0.f; t.next = 0.f; t.rgbs = 0.f; t.rgbw[0] = t.rgbw[1] = t.rgbw[2] = 0.f;
@@ -995,10 +1010,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     Ring cr;
     uint32_t parity = 0;
     bool ok = true;
-    int tile = blockIdx.x;
+    int tile = cta_slot;
     Pre cur;
     if (tile < P.ntiles) cur = prefetch(tile);
-    for (; tile < P.ntiles; tile += gridDim.x) {
+    for (; tile < P.ntiles; tile += cta_slots) {
       // publish this tile's per-channel constants (double-buffered by tile parity: the single named
       // barrier per tile also orders the reuse of the other buffer)
       const int cb = parity;
@@ -1014,7 +1029,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kT2EpiThreads) : "memory");
       const Pre me = cur;
-      if (tile + (int)gridDim.x < P.ntiles) cur = prefetch(tile + gridDim.x);  // in flight during this tile
+      if (tile + cta_slots < P.ntiles) cur = prefetch(tile + cta_slots);  // in flight during this tile
       if (ok) ok = mbar_wait(&bars->acc_full[cr.idx], cr.phase, abort_flag);
       tc_fence_after();
       const float* sc = bars->ep_scale[cb];
@@ -1114,6 +1129,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (cl) cluster_sync();   // no CTA exits while its peer may still multicast into it
   if (threadIdx.x == 0 && bars->abort_flag && P.error_flag) *P.error_flag = 1;
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -1138,6 +1154,26 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
   if (per_sm < 1) per_sm = 1;
   int ctas = sm_count() * per_sm;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  if (P.cluster) {
+    // 2-CTA clusters (one CTA per SM of a TPC); P.ntiles counts tile PAIRS
+    ctas = sm_count() & ~1;
+    if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas & ~1;
+    if (ctas > 2 * P.ntiles) ctas = 2 * P.ntiles;
+    if (ctas < 2) ctas = 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3((unsigned)kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    W2E_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, P, M));
+    return W2E_OK;
+  }
   if (ctas > P.ntiles) ctas = P.ntiles;
   kern<<<ctas, kThreads, smem_bytes, s>>>(ma, mb, P, M);
   W2E_LAUNCH_OK();
@@ -1149,6 +1185,10 @@ static int g_max_ctas = 0;
 static int g_ts_mode = 1;   // 0 = never use the TS epilogue, 1 = whenever eligible
 static long long* g_dbg = nullptr;
 static int g_flags = 0;
+// 1 = 2-CTA clusters with multicast weight blocks for the weight-ring kernels.  Off by default: bit-identical
+// results but no gain measured -- the L2 already merges the unicast requests of a few CTAs, and what binds the
+// weight ring is the SM's TMA ingest, which multicast does not reduce.
+static int g_cluster_mode = 0;
 
 }  // namespace w2e
 
@@ -1157,7 +1197,7 @@ using namespace w2e;
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
 extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
-extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags; }
+extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 11; g_cluster_mode = (flags & 4) ? 1 : 0; }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -1210,7 +1250,11 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
   const bool mt4 = allow_mt4 && g_ts_mode != 0 && rgb && !out && !out_mod && Cin == 32 && Cout == 32 && in_h >= 64;
   if (mt4) P.mt = 4;
-  const int bn_max = transposed ? 128 : 256;
+  // Transposed conv: 4 parity classes x MT sub-tiles x bn columns must fit 512 TMEM columns.  Measured (B=32):
+  // (MT 1, bn 128) beats (MT 2, bn 64) on every >=128-channel up-layer (0.48 vs 0.59 ms at 512->256@64^2) although
+  // its 16 KB weight blocks feed only 4 MMAs each and the ring is then bound by the SM's TMA ingest (~42 B/clk:
+  // 385 cycles per block against 256 cycles of MMAs) -- bn 64 serialises MMA and epilogue on one accumulator set.
+  const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : 256;
   P.bn = 16;
   for (int cand : {256, 128, 64, 32, 16})
     if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
@@ -1337,6 +1381,17 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   }
   Tc2Maps M;
   memset(&M, 0, sizeof(M));
+  // 2-CTA clusters: the pair works on the same tile of two consecutive samples and shares every weight block
+  if (g_cluster_mode && !P.wres && !fb && B % 2 == 0 && P.bn >= 32 && sm_count() >= 2) {
+    P.cluster = 1;
+    P.B = B / 2;
+    P.ntiles = P.ntiles / 2;
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)(P.bn / 2), 1u};
+    int rc = make_bf16_map(&M.bh, w, 3, dims, strides, box, row_bytes);
+    if (rc) return rc;
+  }
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
   if (ts && !fb) {
     if (noise) {
