@@ -218,7 +218,8 @@ void w2e_modconv_tc2_epilogue(int ts_mode);
 void w2e_modconv_tc2_debug(void* timeline);
 /* A/B switches for measurements: bit 0 = no edge-tile tap masking (transposed conv), bit 1 = a single
  * MMA-issuing warp, bit 2 = 2-CTA clusters with TMA-multicast weight blocks (off by default: no gain
- * measured), bit 3 = 64-column tiles for the transposed conv.  Results are identical for every setting. */
+ * measured), bit 3 = 64-column tiles for the transposed conv,
+ * bit 4 = 256-pixel tiles for the 32-channel transposed conv.  Results are identical for every setting. */
 void w2e_modconv_tc2_flags(int flags);
 
 /* ---- layout transforms ----------------------------------------------------------------------

@@ -276,7 +276,7 @@ def test_staged_and_direct_epilogues_agree_bitwise(eng, b, cin, cout, h, up):
     lib = N.load()
     outs = []
     try:
-        for ts_mode, flags in [(1, 0), (0, 0), (1, 1), (1, 2), (1, 3), (1, 4), (0, 4), (1, 8)]:
+        for ts_mode, flags in [(1, 0), (0, 0), (1, 1), (1, 2), (1, 3), (1, 4), (0, 4), (1, 8), (1, 16)]:
             lib.w2e_modconv_tc2_epilogue(ts_mode)
             lib.w2e_modconv_tc2_flags(flags)
             outs.append(run_layer(eng, layer, x, s, noise, nxt))

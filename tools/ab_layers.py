@@ -18,7 +18,7 @@ def main():
     gen = w2e.Generator(1024, 512, 8, channel_multiplier=2, precision="bf16").to(dev).eval()
     w = torch.randn(batch, gen.n_latent, 512, device=dev)
     lib = N.load()
-    settings = [("default", 1, 0), ("clusters+multicast", 1, 4), ("up: bn 64", 1, 8), ("no-edge-mask", 1, 1)]
+    settings = [("default", 1, 0), ("clusters+multicast", 1, 4), ("up 32ch: 256-px tiles", 1, 16), ("no-edge-mask", 1, 1)]
     results = {}
     for name, ts, flags in settings:
         lib.w2e_modconv_tc2_epilogue(ts)

@@ -1197,7 +1197,7 @@ using namespace w2e;
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
 extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
-extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 11; g_cluster_mode = (flags & 4) ? 1 : 0; }
+extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 27; g_cluster_mode = (flags & 4) ? 1 : 0; }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -1259,6 +1259,10 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   for (int cand : {256, 128, 64, 32, 16})
     if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
   if (P.ng * P.mt * P.bn > 512) P.mt = 1;
+  // 32-channel transposed layer: 128-pixel tiles leave room for FOUR accumulator sets, so each epilogue group's
+  // MMAs of the next tile overlap its drain of the current one (0.64 -> 0.57 ms at 64->32@512^2, the HBM floor is
+  // 0.49).  Not for 64 channels: its weights are not resident and smaller tiles make the ring ingest-bound.
+  if (transposed && P.bn <= 32 && !fb && !(g_flags & 16)) P.mt = 1;
   const int acc_cols = P.ng * P.mt * P.bn;
   const int nbuf_plain = (acc_cols * 2 <= 512) ? 2 : 1;
   const int nbuf_ts = (acc_cols * 4 <= 512) ? 4 : nbuf_plain;   // TS flavour: two buffers per epilogue group
