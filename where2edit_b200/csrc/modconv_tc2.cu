@@ -729,9 +729,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t sc_a = smem_u32(bars->ts_consts(group, (int)gen));
 
         // epilogue inputs staged by the producer's TMA boxes
-        float nzm[MT];
+        // noise of this thread's pixel(s): fused ToRGB -> sub-tiles half*NP + p; otherwise one value per sub-tile
+        constexpr int NZ = RGB ? NP : (MT < 2 ? 1 : 2);
+        float nzm[NZ];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) nzm[m] = 0.f;
+        for (int m = 0; m < NZ; ++m) nzm[m] = 0.f;
         uint64_t racc[NP][3];
         float rgb_init[NP][3];
 #pragma unroll
@@ -740,7 +742,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int o = 0; o < 3; ++o) { racc[p][o] = 0ull; rgb_init[p][o] = rgbb[o]; }
         if (has_noise) {
 #pragma unroll
-          for (int m = 0; m < MT; ++m) nzm[m] = nw * lds_f32(eb + noise_off + (uint32_t)(m * kSubTileH * kTileW * 4));
+          for (int m = 0; m < NZ; ++m)
+            nzm[m] = nw * lds_f32(eb + noise_off + (uint32_t)(((RGB ? half * NP : 0) + m) * kSubTileH * kTileW * 4));
         }
         if (has_skip) {
           // upfirdn2d(skip, up=2, pad=(2,1)) = a 2x2-tap polyphase filter on rows ya, ya+1 / columns xa, xa+1.
@@ -779,10 +782,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             uint64_t nz2[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-              float nzv = nzm[0];
-#pragma unroll
-              for (int mm = 1; mm < MT; ++mm)
-                if (m + p == mm) nzv = nzm[mm];
+              const float nzv = RGB ? nzm[p] : ((NZ == 2 && m == 1) ? nzm[NZ - 1] : nzm[0]);
               nz2[p] = pack2(nzv, nzv);
             }
             const uint32_t slot_o =
