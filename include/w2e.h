@@ -221,6 +221,9 @@ void w2e_modconv_tc2_debug(void* timeline);
  * measured), bit 3 = 64-column tiles for the transposed conv,
  * bit 4 = 256-pixel tiles for the 32-channel transposed conv.  Results are identical for every setting. */
 void w2e_modconv_tc2_flags(int flags);
+/* weight-ring kernels as clusters of 2^log2_size CTAs (0 = none, up to 3 = 8 CTAs) that work on the same
+ * tile of consecutive samples and TMA-multicast every weight block (each CTA loads 1/size of it).   */
+void w2e_modconv_tc2_cluster(int log2_size);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],

@@ -18,11 +18,12 @@ def main():
     gen = w2e.Generator(1024, 512, 8, channel_multiplier=2, precision="bf16").to(dev).eval()
     w = torch.randn(batch, gen.n_latent, 512, device=dev)
     lib = N.load()
-    settings = [("default", 1, 0), ("clusters+multicast", 1, 4), ("up 32ch: 256-px tiles", 1, 16), ("no-edge-mask", 1, 1)]
+    settings = [("default", 1, 0, 0), ("clusters of 4", 1, 0, 2), ("clusters of 8", 1, 0, 3), ("one MMA issuer", 1, 2, 0)]
     results = {}
-    for name, ts, flags in settings:
+    for name, ts, flags, clus in settings:
         lib.w2e_modconv_tc2_epilogue(ts)
         lib.w2e_modconv_tc2_flags(flags)
+        lib.w2e_modconv_tc2_cluster(clus)
         with torch.no_grad():
             for _ in range(2):
                 gen([w], input_is_latent=True, randomize_noise=False)
@@ -39,8 +40,9 @@ def main():
         results[name] = {k: min(v) for k, v in acc.items()}
     lib.w2e_modconv_tc2_epilogue(1)
     lib.w2e_modconv_tc2_flags(0)
+    lib.w2e_modconv_tc2_cluster(0)
     base = results["default"]
-    names = [n for n, _, _ in settings]
+    names = [n for n, _, _, _ in settings]
     print(f"{'launch':30s} " + " ".join(f"{n:>22s}" for n in names))
     tot = {n: 0.0 for n in names}
     for tag, t in base.items():

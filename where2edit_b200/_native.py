@@ -48,6 +48,7 @@ PROTOTYPES = {
     "w2e_modconv_tc2_epilogue": (None, [_I]),
     "w2e_modconv_tc2_debug": (None, [_P]),
     "w2e_modconv_tc2_flags": (None, [_I]),
+    "w2e_modconv_tc2_cluster": (None, [_I]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),
     "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 9 + [_P]),
@@ -57,7 +58,7 @@ PROTOTYPES = {
 
 # entry points that enqueue no kernel (host queries)
 _HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace",
-              "w2e_modconv_tc_supported", "w2e_modconv_tc2_knobs", "w2e_modconv_tc2_epilogue", "w2e_modconv_tc2_debug", "w2e_modconv_tc2_flags"}
+              "w2e_modconv_tc_supported", "w2e_modconv_tc2_knobs", "w2e_modconv_tc2_epilogue", "w2e_modconv_tc2_debug", "w2e_modconv_tc2_flags", "w2e_modconv_tc2_cluster"}
 
 
 class Stats:

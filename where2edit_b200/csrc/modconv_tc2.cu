@@ -40,9 +40,8 @@
 namespace w2e {
 
 constexpr int kT2Threads = 320;    // TMA warp, MMA warp, 8 epilogue warps
-constexpr int kT2ThreadsTS = 608;  // TS flavour: 2 x 8 epilogue warps (one group per accumulator buffer), two producer
-                                   // warps (A/B tiles; epilogue inputs), one MMA-issuing warp
-constexpr int kT2ThreadsTS2 = 640; // TS flavour with resident weights: plus a second MMA-issuing warp
+constexpr int kT2ThreadsTS = 640;  // TS flavour: 2 x 8 epilogue warps (one group per accumulator buffer) + 4 service warps
+constexpr int kT2ThreadsTS2 = 640; // (see the warp-role table in the kernel)
 constexpr int kT2EpiThreads = 256;
 constexpr int kT2MaxA = 8, kT2MaxB = 16, kT2MaxAcc = 4;
 constexpr int kEStages = 4;   // epilogue-input ring (TS flavour): deep enough not to throttle the A-tile prefetch
@@ -62,7 +61,7 @@ struct Tc2Params {
   int fb, OH2, OW2;
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
-  int cluster;              // 1 = launched as 2-CTA clusters with multicast weight blocks
+  int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
   int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
@@ -208,13 +207,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   // arbiter favours the highest warp id of a scheduler, and a starved MMA issuer stalls everyone
   // (measured: with the issuer as warp 1 it got an issue slot every ~9 cycles next to busy epilogue warps).
   constexpr int kEpiWarps = TS ? 16 : 8;
-  constexpr int kProducerWarp = kEpiWarps, kEProducerWarp = kEpiWarps + 1, kMmaWarp = kEpiWarps + (TS ? 2 : 1);
+  // TS flavour, 20 warps: resident weights -> [16 epilogue][A producer][epilogue-input producer][2 MMA issuers];
+  // weight ring -> [16 epilogue][A + epilogue-input producer][weight-ring producer][2 MMA issuers]
+  constexpr int kProducerWarp = kEpiWarps, kEProducerWarp = kEpiWarps + 1, kBProducerWarp = kEpiWarps + 1;
+  constexpr int kMmaWarp = kEpiWarps + (TS ? 2 : 1);
   // TS flavour with resident weights: TWO MMA-issuing warps take alternate tiles.  tcgen05.mma issue
   // blocks at the pipe's execution rate (shallow queue), so a single issuer leaves the tensor pipe idle
   // for its whole per-tile bookkeeping (barrier waits, fences, commits: ~800 cycles measured against
   // ~1600 cycles of MMAs per tile of the 32-channel layer); with two issuers one's bookkeeping hides
   // behind the other's MMAs.  Accumulator buffers and A stages are consumed in tile order by both.
-  constexpr int kMmaWarps = (TS && WRES) ? 2 : 1;
+  constexpr int kMmaWarps = TS ? 2 : 1;   // resident weights: alternate TILES; weight ring: alternate weight BLOCKS
   const int tiles_xy = P.tiles_x * P.tiles_y;
   const int tiles_per_n = tiles_xy * P.B;
 
@@ -226,7 +228,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
-      for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], cl ? 2 : 1); }
+      for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1u << cl); }
       // TS flavour with a single accumulator buffer: both epilogue groups drain every tile (unit-split mode)
       const uint32_t epi_arrivals = (TS && (P.nbuf == 1 || P.fb)) ? 2 * kT2EpiThreads : kT2EpiThreads;
       for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], epi_arrivals); }
@@ -254,13 +256,29 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int t = 0; t < 9; ++t)
             tma_load_3d(b_base + (size_t)(kc * 9 + t) * P.b_block_bytes, &map_b, &bars->w_full, kc * kBK, 0, t);
       }
-      Ring ar, br;
+      Ring ar, br, er;
       bool ok = true;
       TileWalk wk;
       wk.init(cta_slot, cta_slots, P);
       for (int tile = cta_slot; tile < P.ntiles && ok; tile += cta_slots, wk.next(P)) {
         const int b = (wk.b << cl) + (int)crank;
         const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o, co0 = wk.tn * P.bn;
+        if (TS && !WRES) {
+          // weight-ring kernels: this warp also produces the epilogue inputs (tile coordinates, noise, skip patches)
+          ok = mbar_wait(&bars->e_empty[er.idx], er.phase ^ 1u, abort_flag);
+          if (!ok) break;
+          uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
+          *reinterpret_cast<int4*>(eb + P.e_info_off) = make_int4(b, j0, i0, wk.tn);
+          mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);   // release: orders the info store
+          if (P.noise && !P.fb) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
+          if (RGB && P.rgb_skip) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
+                          ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
+          }
+          er.advance(kEStages);
+        }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           ok = mbar_wait(&bars->a_empty[ar.idx], ar.phase ^ 1u, abort_flag);
           if (!ok) break;
@@ -269,26 +287,56 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
                       j0 - 1, b);
           ar.advance(P.a_stages);
-          if (!WRES) {
-            const bool edge_y = TR && !(P.flags & 1) && !P.fb && j0 >= P.grid_h - 1;   // see the MMA issuer
-            const bool edge_x = TR && !(P.flags & 1) && !P.fb && i0 >= P.grid_w - 1;
+          if (!WRES && !TS) {
+            const bool edge_y = TR && !(P.flags & 1) && j0 >= P.grid_h - 1;   // see the MMA issuer
+            const bool edge_x = TR && !(P.flags & 1) && i0 >= P.grid_w - 1;
             for (int t = 0; t < 9; ++t) {
               if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
-              if (cl)   // my half of the block, delivered to both CTAs of the cluster (each signals its own b_full)
-                tma_load_3d_mc(b_base + (size_t)br.idx * P.b_block_bytes + (size_t)crank * (P.b_block_bytes >> 1), &M.bh,
-                               &bars->b_full[br.idx], kc * kBK, co0 + (int)crank * (P.bn >> 1), t, (uint16_t)3);
-              else
-                tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
+              tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
               br.advance(P.b_stages);
             }
           }
         }
       }
     }
-  } else if (TS && warp == kEProducerWarp) {
+  } else if (TS && !WRES && warp == kBProducerWarp) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ weight-ring producer (TS flavour)
+      // its own warp, so that the A tiles / epilogue inputs and the weight blocks are issued concurrently
+      const int pj = 0;
+      Ring br;
+      bool ok = true;
+      uint32_t nblk = 0;
+      TileWalk wk;
+      wk.init(cta_slot, cta_slots, P);
+      for (int tile = cta_slot; tile < P.ntiles && ok; tile += cta_slots, wk.next(P)) {
+        const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o, co0 = wk.tn * P.bn;
+        const bool edge_y = TR && !(P.flags & 1) && !P.fb && j0 >= P.grid_h - 1;   // see the MMA issuer
+        const bool edge_x = TR && !(P.flags & 1) && !P.fb && i0 >= P.grid_w - 1;
+        for (int kc = 0; kc < kchunks && ok; ++kc) {
+          for (int t = 0; t < 9; ++t) {
+            if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
+            if (pj == 0) {
+              ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
+              if (!ok) break;
+              mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
+              if (cl)   // my share of the block, delivered to every CTA of the cluster (each signals its own b_full)
+                tma_load_3d_mc(b_base + (size_t)br.idx * P.b_block_bytes + (size_t)crank * (P.b_block_bytes >> cl), &M.bh,
+                               &bars->b_full[br.idx], kc * kBK, co0 + (int)crank * (P.bn >> cl), t,
+                               (uint16_t)((1u << (1 << cl)) - 1u));
+              else
+                tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &map_b, &bars->b_full[br.idx], kc * kBK, co0, t);
+            }
+            ++nblk;
+            br.advance(P.b_stages);
+          }
+        }
+      }
+    }
+  } else if (TS && WRES && warp == kEProducerWarp) {
     if (lane == 0) {
       // ------------------------------------------------------------------ epilogue-input producer
       // Its own warp: a single thread issuing every TMA of a tile took ~2200 cycles per tile (measured),
@@ -342,10 +390,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // Two issuers only when each accumulator buffer and each A stage is always consumed by the SAME issuer
     // (even buffer count, stage count a multiple of 2 * kchunks): an issuer that saw only every other phase
     // of an mbarrier could mistake an old completion for the one it waits for.
-    const int nmw = (kMmaWarps == 2 && !(P.flags & 2) && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
+    const int nmw = (WRES && kMmaWarps == 2 && !(P.flags & 2) && P.nbuf >= 2 && P.a_stages % (2 * kchunks) == 0) ? 2 : 1;
+    // Weight-ring kernels: both issuers walk every tile and take alternate weight BLOCKS (one tap of one K
+    // chunk), again ordered by the issue token.  The per-block bookkeeping of a single issuer (b_full wait,
+    // commits, ring arithmetic: ~400 cycles next to 16 busy epilogue warps) exceeded the 256...384 cycles of MMAs
+    // a block feeds (measured: 94 cycles per MMA instead of 48 at 128->64@256^2).
+    const bool blk2 = !WRES && kMmaWarps == 2 && !(P.flags & 2);
     const int tile_step = nmw * cta_slots;
-    const int tile0 = mw < nmw ? cta_slot + mw * cta_slots : P.ntiles;
-    if (mw == 1) {   // the second issuer starts one tile into the rings
+    const int tile0 = (mw < nmw || blk2) ? cta_slot + (blk2 ? 0 : mw * cta_slots) : P.ntiles;
+    uint32_t nblk = 0, myblk = 0;   // weight blocks seen / issued by this warp (block-alternating mode)
+    if (mw == 1 && !blk2) {   // the second issuer starts one tile into the rings
       for (int i = 0; i < kchunks; ++i) ar.advance(P.a_stages);
       cr.advance(P.nbuf);
     }
@@ -413,8 +467,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
-            ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
-            if (!ok) break;
+            const bool mine = !blk2 || (int)(nblk & 1u) == mw;
+            ++nblk;
+            if (mine) {
+              ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
+              if (ok && blk2) ok = mbar_wait_warp(&bars->mma_turn[mw], mw == 0 ? (myblk & 1u) ^ 1u : (myblk & 1u), abort_flag);
+              if (!ok) break;
+              ++myblk;
+            }
             // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none)
             const uint32_t b_lo = b_lo0 + br.idx * b_block16;
 #pragma unroll
@@ -430,23 +490,26 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               } else if (t == 0) {
                 first = kc == 0 ? 0u : 1u;
               }
-              if (leader) {
+              if (leader && mine) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
                   umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
               }
             }
-            if (leader) {
-              if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)3);   // the slot is free once BOTH CTAs consumed it
+            if (leader && mine) {
+              // (the pipe executes in issue order: a commit also covers the other issuer's earlier MMAs)
+              if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)((1u << (1 << cl)) - 1u));   // free once ALL CTAs consumed it
               else umma_commit(&bars->b_empty[br.idx]);
               if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
+              if (t == 8 && kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);   // last block of the tile
+              if (blk2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
             }
             br.advance(P.b_stages);
           }
         }
         ar.advance(P.a_stages);
       }
-      if (ok && leader) {
+      if (ok && leader && WRES) {
         umma_commit(&bars->acc_full[cr.idx]);
         if (nmw == 2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
       }
@@ -1155,22 +1218,27 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
   int ctas = sm_count() * per_sm;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (P.cluster) {
-    // 2-CTA clusters (one CTA per SM of a TPC); P.ntiles counts tile PAIRS
-    ctas = sm_count() & ~1;
-    if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas & ~1;
-    if (ctas > 2 * P.ntiles) ctas = 2 * P.ntiles;
-    if (ctas < 2) ctas = 2;
+    // clusters of 2^P.cluster CTAs (one per SM); P.ntiles counts tile GROUPS (same tile of consecutive samples)
+    const int csize = 1 << P.cluster;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)ctas);
     cfg.blockDim = dim3((unsigned)kThreads);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = (unsigned)csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(sm_count() / csize * csize));
+    static int max_clusters[4] = {0, 0, 0, 0};   // per cluster size (this kernel instantiation, this smem plan class)
+    int nclusters = 0;
+    W2E_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+    (void)max_clusters;
+    if (nclusters < 1) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2: no %d-CTA cluster fits", csize);
+    if (max_ctas > 0 && nclusters * csize > max_ctas) nclusters = max_ctas / csize > 0 ? max_ctas / csize : 1;
+    if (nclusters > P.ntiles) nclusters = P.ntiles;
+    cfg.gridDim = dim3((unsigned)(nclusters * csize));
     W2E_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, P, M));
     return W2E_OK;
   }
@@ -1197,7 +1265,8 @@ using namespace w2e;
 extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
 extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
 extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
-extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 27; g_cluster_mode = (flags & 4) ? 1 : 0; }
+extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 59; g_cluster_mode = (flags & 4) ? 1 : 0; }
+extern "C" void w2e_modconv_tc2_cluster(int log2_size) { g_cluster_mode = log2_size < 0 ? 0 : (log2_size > 3 ? 3 : log2_size); }
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
@@ -1386,13 +1455,15 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   Tc2Maps M;
   memset(&M, 0, sizeof(M));
   // 2-CTA clusters: the pair works on the same tile of two consecutive samples and shares every weight block
-  if (g_cluster_mode && !P.wres && !fb && B % 2 == 0 && P.bn >= 32 && sm_count() >= 2) {
-    P.cluster = 1;
-    P.B = B / 2;
-    P.ntiles = P.ntiles / 2;
+  int clog = g_cluster_mode;
+  while (clog > 0 && (B % (1 << clog) != 0 || (P.bn >> clog) < 8)) --clog;
+  if (clog > 0 && !P.wres && !fb && sm_count() >= (1 << clog)) {
+    P.cluster = clog;
+    P.B = B >> clog;
+    P.ntiles = P.ntiles >> clog;
     const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
     const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-    const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)(P.bn / 2), 1u};
+    const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)(P.bn >> clog), 1u};
     int rc = make_bf16_map(&M.bh, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
