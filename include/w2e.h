@@ -188,7 +188,7 @@ int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const
  * is produced without re-reading the activation; out and out_mod may then both be NULL.
  * rgb_w: float [3,Cout] pre-scaled by 1/sqrt(Cout); rgb_skip: float [B,3,in_h/2,in_w/2] or NULL;
  * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: float [B,3,in_h,in_w].
- * Needs Cout <= 256 and in_h > 16.                                                             */
+ * Needs Cout <= 512 (the rgb image must be zero-initialised when Cout > 256: two channel blocks add into it) and in_h > 16.                                                             */
 int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
                         const float* noise, const float* noise_w, int noise_batch,
                         const float* next_scale, void* out, void* out_mod, int* error_flag, int B,

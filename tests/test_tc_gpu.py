@@ -220,6 +220,7 @@ def test_bf16_batch_invariance():
     (2, 32, 32, 136, True, False, False),   # RGB-only last layer: 512-pixel tiles, two pixels per epilogue thread
     (1, 64, 64, 64, True, False, True),     # one staging slot per epilogue half
     (3, 128, 128, 48, True, False, True),   # weight ring + staged epilogue, 64-channel units
+    (2, 512, 512, 24, True, True, True),    # two channel blocks adding their partial ToRGB sums
 ])
 def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, want_out, want_mod):
     """StyledConv + ToRGB in one launch (w2e_modconv_tc2_rgb) vs the oracle's two modules"""

@@ -1027,7 +1027,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (RGB) {
           t.rgbs = __ldg(P.rgb_style + bc);
 #pragma unroll
-          for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + et);
+          for (int o = 0; o < 3; ++o) t.rgbw[o] = __ldg(P.rgb_w + o * P.Cout + t.co0 + et);
         }
       }
 #pragma unroll
@@ -1109,6 +1109,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int o = 0; o < 3; ++o)
           rgb_acc[o] = me.rgbb[o] + cy0 * fmaf(cx1, me.tap[o][1], cx0 * me.tap[o][0]) +
                        cy1 * fmaf(cx1, me.tap[o][3], cx0 * me.tap[o][2]);
+        // several channel blocks (Cout > 256): every block adds its partial sum to the zero-initialised image, the
+        // first one also bias + skip.  Two addends commute, so the result does not depend on the arrival order.
+        if (me.co0 != 0) rgb_acc[0] = rgb_acc[1] = rgb_acc[2] = 0.f;
       }
 #pragma unroll
       for (int gmi = 0; gmi < NPIX; ++gmi) {
@@ -1180,7 +1183,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         if (RGB && valid) {
 #pragma unroll
-          for (int o = 0; o < 3; ++o) P.rgb[(((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox] = rgb_acc[o];
+          for (int o = 0; o < 3; ++o) {
+            float* dst = P.rgb + (((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox;
+            if (P.tiles_n > 1) atomicAdd(dst, rgb_acc[o]);
+            else *dst = rgb_acc[o];
+          }
         }
       }
       // accumulator buffer drained: hand it back to the MMA warp
@@ -1298,8 +1305,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.B = B; P.Cin = Cin; P.Cout = Cout; P.act = act;
   if (rgb) {
     W2E_CHECK_ARG(rgb->w && rgb->style && rgb->rgb, "modconv_tc2_rgb: null pointer");
-    W2E_CHECK_ARG(!transposed && Cout <= 256 && in_h > kSubTileH,
-                  "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 256 and more than %d rows", kSubTileH);
+    W2E_CHECK_ARG(!transposed && Cout <= 512 && in_h > kSubTileH,
+                  "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 512 and more than %d rows", kSubTileH);
     W2E_CHECK_ARG(rgb->skip == nullptr || (rgb->host_taps1d && in_h % 2 == 0 && in_w % 2 == 0),
                   "modconv_tc2_rgb: skip needs taps and even H, W");
     P.rgb_w = rgb->w; P.rgb_style = rgb->style; P.rgb_bias = rgb->bias; P.rgb_skip = rgb->skip; P.rgb = rgb->rgb;
@@ -1511,8 +1518,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int ks = P.bk / 16;
   if (rgb) {
-    W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && P.tiles_n == 1, "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt,
-                  P.tiles_n);
+    W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && (P.tiles_n == 1 || (P.tiles_n == 2 && !ts)),
+                  "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
     if (P.mt == 4) {
       if (P.wres) return launch_tc2<false, 4, 2, true, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
       return launch_tc2<false, 4, 2, false, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);

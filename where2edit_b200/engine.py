@@ -216,7 +216,8 @@ class SynthesisEngine:
         dev = xs.device
         out = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
         out_mod = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
-        rgb = torch.empty((b, 3, h, w), device=dev, dtype=torch.float32)
+        # Cout > 256 runs as two channel blocks that ADD their partial ToRGB sums: the image starts at zero
+        rgb = (torch.zeros if pw.cout > 256 else torch.empty)((b, 3, h, w), device=dev, dtype=torch.float32)
         rpw = rgb_module.conv.packed()
         taps1d = None
         if skip is not None:
@@ -383,7 +384,7 @@ class SynthesisEngine:
             next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
             need_out = next_is_rgb or want_features or blend_here
             need_mod = nxt is not None and not blend_here
-            fuse = (kind == "conv" and next_is_rgb and not self.v1 and self.fuse_rgb and pw.cout <= 256
+            fuse = (kind == "conv" and next_is_rgb and not self.v1 and self.fuse_rgb and pw.cout <= 512
                     and hw[0] > 16 and not (attention_layer and attention_layer in (layer, layer + 1)))
             if fuse:
                 act, xs_next, fused_rgb = self._conv2_rgb(xs, pw, demods[idx], nz, noise_w, bias, nxt,
