@@ -20,6 +20,9 @@ import sys
 from contextlib import redirect_stdout
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# where the summaries go: profiles/ here; on the GPU box W2E_PROFILES_OUT=gpurun_out/profiles (the .ncu-rep files are
+# too big to travel back, so the summaries are made there and only the text is copied)
+OUT = os.environ.get("W2E_PROFILES_OUT") or os.path.join(ROOT, "profiles")
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_hot  # noqa: E402
 import ncu_summary  # noqa: E402
@@ -40,7 +43,7 @@ def launches(rnd):
         lines = [l for l in fh if l.startswith('"')]
     for r in csv.DictReader(lines):
         rows.append((int(r["ID"]), r["Kernel Name"], r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3))
-    with open(os.path.join(ROOT, "profiles", f"{rnd}_launches.csv"), "w") as fh:
+    with open(os.path.join(OUT, f"{rnd}_launches.csv"), "w") as fh:
         fh.write("id,kernel,grid,block,time_us\n")
         for i, k, g, b, t in rows:
             fh.write(f'{i},"{short(k)}","{g}","{b}",{t:.2f}\n')
@@ -61,13 +64,13 @@ def launches(rnd):
                "| kernel | launches | time (us) | share |", "|---|---|---|---|"]
         for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             md.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / total:.1f}% |")
-    with open(os.path.join(ROOT, "profiles", f"{rnd}_launches.md"), "w") as fh:
+    with open(os.path.join(OUT, f"{rnd}_launches.md"), "w") as fh:
         fh.write("\n".join(md) + "\n")
 
 
 def full_reports(rnd):
     traffic = {}
-    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{rnd}_*.ncu-rep"))):
+    for rep in sorted(glob.glob(os.path.join(os.environ.get("W2E_NCU_REP_DIR") or os.path.join(ROOT, "gpurun_out"), f"{rnd}_*.ncu-rep"))):
         name = os.path.basename(rep)[:-8]
         buf = io.StringIO()
         with redirect_stdout(buf):
@@ -75,7 +78,7 @@ def full_reports(rnd):
             ncu_summary.main(rep)
             print()
             ncu_hot.main(rep, 14)
-        with open(os.path.join(ROOT, "profiles", f"{name}.ncu.txt"), "w") as fh:
+        with open(os.path.join(OUT, f"{name}.ncu.txt"), "w") as fh:
             fh.write(buf.getvalue())
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
@@ -100,12 +103,12 @@ def full_reports(rnd):
                         "dram_write_bytes": wr, "duration_us_under_ncu": dur_us})
         traffic[name] = per
     if traffic:
-        with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w") as fh:
+        with open(os.path.join(OUT, f"{rnd}_traffic.json"), "w") as fh:
             json.dump(traffic, fh, indent=1)
 
 
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    os.makedirs(OUT, exist_ok=True)
     launches(rnd)
     full_reports(rnd)
