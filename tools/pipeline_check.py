@@ -56,7 +56,6 @@ def main():
     del img0, img1
     torch.cuda.empty_cache()
 
-    gen.set_precision("fp32")
     wb = torch.randn(bb, gen.n_latent, 512, device=dev, requires_grad=True)
     gimg = torch.randn(bb, 3, 1024, 1024, device=dev) / (3 * 1024 * 1024)
 
@@ -66,11 +65,18 @@ def main():
         img.backward(gimg)
         return wb.grad
 
-    ms = timed(fwd_bwd, 2)
-    g = fwd_bwd()
-    print(json.dumps({"pipeline": "forward + backward to W+ (fp32 kernels, autograd)", "batch": bb, "ms": round(ms, 2),
-                      "images_per_s": round(bb / ms * 1e3, 2), "grad_finite": bool(torch.isfinite(g).all()),
-                      "grad_abs_mean": float(g.abs().mean())}))
+    grads = {}
+    for prec, what in (("fp32", "fp32 kernels"), ("bf16", "3x3 convolutions and their dgrad on the tensor cores")):
+        gen.set_precision(prec)
+        ms = timed(fwd_bwd, 2)
+        g = fwd_bwd()
+        grads[prec] = g.detach().double().flatten()
+        print(json.dumps({"pipeline": f"forward + backward to W+ (autograd, {what})", "batch": bb, "ms": round(ms, 2),
+                          "images_per_s": round(bb / ms * 1e3, 2), "grad_finite": bool(torch.isfinite(g).all()),
+                          "grad_abs_mean": float(g.abs().mean())}))
+    a, b = grads["bf16"], grads["fp32"]
+    print(json.dumps({"bf16 vs fp32 gradient": {"cosine": float(torch.dot(a, b) / (a.norm() * b.norm())),
+                                               "rel_l2": float((a - b).norm() / b.norm())}}))
 
 
 if __name__ == "__main__":

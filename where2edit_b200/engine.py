@@ -68,8 +68,7 @@ class SynthesisEngine:
     def _tc_weight(self, conv):
         """bf16 [k*k][Cout][Cin] with the equalised-lr scale folded in (model.py:216-217)."""
         pw = conv.packed()
-        if pw.tc is None:
-            pw.tc = pw.dgr.to(torch.bfloat16).contiguous()
+        pw.tc_fwd()
         return pw
 
     def error_flag(self, device):

@@ -30,6 +30,20 @@ class PackedWeight:
         self.wsq = w.pow(2).sum((2, 3)).contiguous()
         self.rgb = w.reshape(cout, cin).contiguous() if k == 1 else None
         self.tc = None  # bf16 tensor-core layout, filled lazily by the engine
+        self._tc_dgrad = None
+
+    def tc_fwd(self):
+        """bf16 [k*k][Cout][Cin] (equalised-lr scale folded in): operand of the tcgen05 forward convolution."""
+        if self.tc is None:
+            self.tc = self.dgr.to(torch.bfloat16).contiguous()
+        return self.tc
+
+    def tc_dgrad(self):
+        """bf16 [k*k][Cin][Cout] with the taps flipped: the dgrad of a same-padded 3x3 convolution is the same
+        convolution kernel run on the upstream gradient with input/output channels swapped."""
+        if self._tc_dgrad is None:
+            self._tc_dgrad = self.fwd.flip(0).to(torch.bfloat16).contiguous()
+        return self._tc_dgrad
 
 
 def demod_coefficients(s, wsq):
@@ -106,6 +120,73 @@ def conv_dgrad(gy, d, pw, k, upsample, in_hw):
     return gxs
 
 
+# --------------------------------------------------------------------------------------------
+# tensor-core (bf16 operands, fp32 accumulate) variants of the two convolutions of the autograd path.
+# Used when the generator's precision is "bf16" and gradients are required (CLIP/ID-loss latent edits,
+# attention/run_attention.py:1419): the forward and the dgrad of every 3x3 ModulatedConv2d run on the
+# tcgen05 kernel (csrc/modconv_tc2.cu) between two layout passes; everything else of the backward
+# (activation, blur, ToRGB, style reductions) stays on the fp32 kernels.
+# --------------------------------------------------------------------------------------------
+TC_AUTOGRAD = False   # set by Generator._forward_modules for the duration of a bf16-precision autograd forward
+_TC_ERR = {}
+
+
+def _tc_error_flag(dev):
+    f = _TC_ERR.get(dev)
+    if f is None:
+        f = _TC_ERR[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return f
+
+
+def tc_assert_ok():
+    """Synchronising check of the pipeline-timeout flag of the tensor-core kernels used by autograd."""
+    for f in _TC_ERR.values():
+        if int(f.item()) != 0:
+            f.zero_()
+            raise RuntimeError("where2edit_b200: a tcgen05 pipeline wait timed out (libw2e modconv_tc2, autograd path)")
+
+
+def _nhwc_mod(x, scale):
+    """fp32 NCHW -> bf16 NHWC, times scale[b, c] (None = 1)."""
+    b, c, h, w = x.shape
+    y = torch.empty((b, h, w, c), device=x.device, dtype=torch.bfloat16)
+    N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(scale), N.ptr(y), b, b, c, h * w, N.stream_ptr()),
+            "nchw_to_nhwc_mod")
+    return y
+
+
+def _nchw_f32(x):
+    b, h, w, c = x.shape
+    y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.stream_ptr()), "nhwc_to_nchw_f32")
+    return y
+
+
+def tc_supported(cin, cout, k):
+    return k == 3 and cin % 32 == 0 and cout % 16 == 0 and bool(N.load().w2e_modconv_tc_supported())
+
+
+def _tc_conv(xs, w, out_scale, cin, cout, transposed):
+    b, h, wd, _ = xs.shape
+    oh, ow = (2 * h + 1, 2 * wd + 1) if transposed else (h, wd)
+    y = torch.empty((b, oh, ow, cout), device=xs.device, dtype=torch.bfloat16)
+    N.check(N.load().w2e_modconv_tc2(
+        N.ptr(xs), N.ptr(w), N.ptr(out_scale), None, None, None, 0, None, N.ptr(y), None,
+        N.ptr(_tc_error_flag(xs.device)), b, cin, cout, h, wd, int(transposed), N.ACT_NONE, N.stream_ptr()),
+        "modconv_tc2")
+    return y
+
+
+def conv_forward_tc(x, s, d, pw, upsample):
+    """conv_forward on the tensor cores: y = d * conv(bf16(x*s), bf16(W)), fp32 accumulate, bf16 result."""
+    return _nchw_f32(_tc_conv(_nhwc_mod(x, s), pw.tc_fwd(), d, pw.cin, pw.cout, upsample))
+
+
+def conv_dgrad_tc(gy, d, pw):
+    """conv_dgrad of the plain (same-padded) 3x3 convolution on the tensor cores."""
+    return _nchw_f32(_tc_conv(_nhwc_mod(gy, d), pw.tc_dgrad(), None, pw.cout, pw.cin, False))
+
+
 def _rowdot(a, b, scale=None, want_prod=False):
     rows = a.shape[0] * a.shape[1]
     inner = a[0, 0].numel()
@@ -119,16 +200,18 @@ def _rowdot(a, b, scale=None, want_prod=False):
 class _ModConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, s, d, pw, k, upsample):
-        y = conv_forward(x, s, d, pw, k, upsample)
+        tc = TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k)
+        y = conv_forward_tc(x, s, d, pw, upsample) if tc else conv_forward(x, s, d, pw, k, upsample)
         ctx.save_for_backward(x, s, d if d is not None else x.new_zeros(0), y)
-        ctx.cfg = (pw, k, upsample, d is not None)
+        # dgrad on the tensor cores: plain conv only (the dgrad of the transposed conv is a stride-2 convolution)
+        ctx.cfg = (pw, k, upsample, d is not None, tc and not upsample and tc_supported(pw.cout, pw.cin, k))
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, s, d, y = ctx.saved_tensors
-        pw, k, upsample, has_d = ctx.cfg
+        pw, k, upsample, has_d, tc_dgrad = ctx.cfg
         gy = gy.contiguous()
         d_or_none = d if has_d else None
         gx = gs = gd = None
@@ -136,7 +219,10 @@ class _ModConv(torch.autograd.Function):
             dot, _ = _rowdot(gy, y)                 # sum_p gy*y = d * sum_p gy*z
             gd = dot / d
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            gxs = conv_dgrad(gy, d_or_none, pw, k, upsample, (x.shape[2], x.shape[3]))
+            if tc_dgrad:
+                gxs = conv_dgrad_tc(gy, d_or_none, pw)
+            else:
+                gxs = conv_dgrad(gy, d_or_none, pw, k, upsample, (x.shape[2], x.shape[3]))
             gs, gx = _rowdot(gxs, x, scale=s.contiguous(), want_prod=True)   # gs = sum_p gxs*x ; gx = gxs*s
         return gx, gs, gd, None, None, None
 
@@ -149,6 +235,8 @@ def modulated_conv2d(x, s, d, pw, k, upsample):
         d = d.contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or s.requires_grad or (d is not None and d.requires_grad)):
         return _ModConv.apply(x, s, d, pw, k, upsample)
+    if TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k):
+        return conv_forward_tc(x, s, d, pw, upsample)
     return conv_forward(x, s, d, pw, k, upsample)
 
 

@@ -401,8 +401,15 @@ class Generator(nn.Module):
                 attention_layer=attention_layer if blending else 0, attention_map=attention_map,
                 feature_map=feature_map)
         else:
-            image, style_vector, captured = self._forward_modules(
-                latent, input_is_stylespace, noise, attention_layer if blending else 0, attention_map, feature_map)
+            # precision "bf16" under autograd: the 3x3 convolutions (forward and dgrad) run on the tensor cores,
+            # the rest of the differentiable path on the fp32 kernels (functional.TC_AUTOGRAD)
+            prev = K.TC_AUTOGRAD
+            K.TC_AUTOGRAD = self.precision == "bf16"
+            try:
+                image, style_vector, captured = self._forward_modules(
+                    latent, input_is_stylespace, noise, attention_layer if blending else 0, attention_map, feature_map)
+            finally:
+                K.TC_AUTOGRAD = prev
 
         if return_latents:
             return image, latent, style_vector
