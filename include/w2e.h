@@ -232,6 +232,14 @@ int w2e_nchw_to_nhwc_mod(const float* x, const float* style, void* y, int B, int
                          int64_t HW, void* stream);
 /* x bf16 [B,HW,C] -> y fp32 [B,C,HW]  (feature capture, attention_model.py:542-543).          */
 int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, void* stream);
+/* Pieces of the tensor-core dgrad of the transposed x2 convolution (autograd of model.py:249-259): the
+ * output-parity class (py, px) of a fp32 NCHW gradient [B,C,H,W] as bf16 channels-last
+ * y[b,j,i,c] = x[b,c,2j+py,2i+px]*scale[b,c] ([B,(H-py+1)/2,(W-px+1)/2,C]); and the sum of the four
+ * per-class convolution results y_pq [B,h+1-p,w+1-q,C] over their common h x w region as fp32 NCHW.   */
+int w2e_nchw_class_to_nhwc_mod(const float* x, const float* scale, void* y, int B, int C, int H, int W, int py,
+                               int px, void* stream);
+int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10, const void* y11, float* out,
+                              int B, int C, int h, int w, void* stream);
 
 /* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
  * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->

@@ -98,6 +98,76 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
   }
 }
 
+// Output-parity class (py, px) of a fp32 NCHW tensor x [B, C, H, W] as bf16 NHWC [B, hc, wc, C], times scale[b, c]:
+// y[b, j, i, c] = x[b, c, 2j+py, 2i+px] * scale[b, c].  (The dgrad of the transposed x2 convolution consumes the
+// upstream gradient class by class.)
+__global__ void __launch_bounds__(256)
+nchw_class_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ scale, __nv_bfloat16* __restrict__ y,
+                              int C, int H, int W, int hc, int wc, int py, int px) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t HWc = (int64_t)hc * wc;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HWc) {
+      const int j = (int)(p / wc), i = (int)(p - (int64_t)j * wc);
+      v = __ldg(x + (((int64_t)b * C + c) * H + (2 * j + py)) * W + (2 * i + px));
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    if (p < HWc && c < C) {
+      float v = tile[tx][r];
+      if (scale) v *= __ldg(scale + (int64_t)b * C + c);
+      y[((int64_t)b * HWc + p) * C + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// out[b, c, j, i] = sum over the four class results y_pq [B, h+1-p, w+1-q, C] (bf16 NHWC) at (j, i), fp32 NCHW [B, C, h, w]
+__global__ void __launch_bounds__(256)
+nhwc_sum4_to_nchw_kernel(const __nv_bfloat16* __restrict__ y00, const __nv_bfloat16* __restrict__ y01,
+                         const __nv_bfloat16* __restrict__ y10, const __nv_bfloat16* __restrict__ y11,
+                         float* __restrict__ out, int C, int h, int w) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t HW = (int64_t)h * w;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t p = p0 + r;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const int j = (int)(p / w), i = (int)(p - (int64_t)j * w);
+      v = __bfloat162float(y00[(((int64_t)b * (h + 1) + j) * (w + 1) + i) * C + c]) +
+          __bfloat162float(y01[(((int64_t)b * (h + 1) + j) * w + i) * C + c]) +
+          __bfloat162float(y10[(((int64_t)b * h + j) * (w + 1) + i) * C + c]) +
+          __bfloat162float(y11[(((int64_t)b * h + j) * w + i) * C + c]);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t p = p0 + tx;
+    if (c < C && p < HW) out[((int64_t)b * C + c) * HW + p] = tile[tx][r];
+  }
+}
+
 // ------------------------------------------------------------------------------ blur + noise + bias + act
 // One thread = 8 channels of kBlurPx adjacent output columns, walking down kBlurRows output rows.
 // Per input row it loads kBlurPx+3 pixels (128-bit each), filters them horizontally in registers
@@ -417,6 +487,31 @@ extern "C" int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64
   if (B == 0) return W2E_OK;
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
   nhwc_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_nchw_class_to_nhwc_mod(const float* x, const float* scale, void* y, int B, int C, int H, int W, int py,
+                                          int px, void* stream) {
+  W2E_CHECK_ARG(x && y, "nchw_class_to_nhwc_mod: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && (py == 0 || py == 1) && (px == 0 || px == 1) && B <= 65535,
+                "nchw_class_to_nhwc_mod: bad shape");
+  const int hc = (H - py + 1) / 2, wc = (W - px + 1) / 2;
+  if (B == 0 || hc == 0 || wc == 0) return W2E_OK;
+  dim3 grid((unsigned)ceil_div64((int64_t)hc * wc, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+  nchw_class_to_nhwc_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, (__nv_bfloat16*)y, C, H, W, hc, wc, py, px);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10, const void* y11, float* out,
+                                         int B, int C, int h, int w, void* stream) {
+  W2E_CHECK_ARG(y00 && y01 && y10 && y11 && out, "nhwc_sum4_to_nchw_f32: null pointer");
+  W2E_CHECK_ARG(B >= 0 && C > 0 && h > 0 && w > 0 && B <= 65535, "nhwc_sum4_to_nchw_f32: bad shape");
+  if (B == 0) return W2E_OK;
+  dim3 grid((unsigned)ceil_div64((int64_t)h * w, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+  nhwc_sum4_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y00, (const __nv_bfloat16*)y01, (const __nv_bfloat16*)y10, (const __nv_bfloat16*)y11, out, C, h, w);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

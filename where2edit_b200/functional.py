@@ -45,6 +45,24 @@ class PackedWeight:
             self._tc_dgrad = self.fwd.flip(0).to(torch.bfloat16).contiguous()
         return self._tc_dgrad
 
+    def tc_dgrad_up(self):
+        """{(py, px): bf16 [9][Cin][Cout]} -- dgrad of the transposed (x2) convolution as four plain convolutions,
+        one per output-parity class of the upstream gradient: class (py, px) holds gz[2j+py, 2i+px] and contributes
+        gx[j, i] += gz_class[j+a, i+b] . W[ky, kx]^T with (a, ky) in {(0,0), (1,2)} for py = 0 and {(0,1)} for
+        py = 1 (same for b, kx, px).  Offset (+a, +b) is tap (a+1, b+1) of the 3x3 kernel; the other taps are zero."""
+        if getattr(self, "_tc_dgrad_up", None) is None:
+            axis = {0: [(0, 0), (1, 2)], 1: [(0, 1)]}
+            out = {}
+            for py in (0, 1):
+                for px in (0, 1):
+                    w = torch.zeros_like(self.fwd)
+                    for a, ky in axis[py]:
+                        for b, kx in axis[px]:
+                            w[(a + 1) * 3 + (b + 1)] = self.fwd[ky * 3 + kx]
+                    out[(py, px)] = w.to(torch.bfloat16).contiguous()
+            self._tc_dgrad_up = out
+        return self._tc_dgrad_up
+
 
 def demod_coefficients(s, wsq):
     """d[b,o] = rsqrt(sum_i s[b,i]^2 * wsq[o,i] + 1e-8) (model.py:242).  Uses libw2e's kernel when no
@@ -182,9 +200,27 @@ def conv_forward_tc(x, s, d, pw, upsample):
     return _nchw_f32(_tc_conv(_nhwc_mod(x, s), pw.tc_fwd(), d, pw.cin, pw.cout, upsample))
 
 
-def conv_dgrad_tc(gy, d, pw):
-    """conv_dgrad of the plain (same-padded) 3x3 convolution on the tensor cores."""
-    return _nchw_f32(_tc_conv(_nhwc_mod(gy, d), pw.tc_dgrad(), None, pw.cout, pw.cin, False))
+def conv_dgrad_tc(gy, d, pw, upsample=False, in_hw=None):
+    """conv_dgrad on the tensor cores.  Plain (same-padded) 3x3 convolution: one launch with flipped taps.
+    Transposed x2 convolution: its dgrad is a stride-2 convolution of the (2h+1)^2 upstream gradient, run as four
+    plain convolutions over the gradient's output-parity classes (PackedWeight.tc_dgrad_up) and summed."""
+    if not upsample:
+        return _nchw_f32(_tc_conv(_nhwc_mod(gy, d), pw.tc_dgrad(), None, pw.cout, pw.cin, False))
+    h, w = in_hw
+    b, cout, zh, zw = gy.shape
+    lib = N.load()
+    ys = []
+    for py in (0, 1):
+        for px in (0, 1):
+            hc, wc = (zh - py + 1) // 2, (zw - px + 1) // 2
+            g_c = torch.empty((b, hc, wc, cout), device=gy.device, dtype=torch.bfloat16)
+            N.check(lib.w2e_nchw_class_to_nhwc_mod(N.ptr(gy), N.ptr(d), N.ptr(g_c), b, cout, zh, zw, py, px,
+                                                   N.stream_ptr()), "nchw_class_to_nhwc_mod")
+            ys.append(_tc_conv(g_c, pw.tc_dgrad_up()[(py, px)], None, pw.cout, pw.cin, False))
+    gxs = torch.empty((b, pw.cin, h, w), device=gy.device, dtype=torch.float32)
+    N.check(lib.w2e_nhwc_sum4_to_nchw_f32(N.ptr(ys[0]), N.ptr(ys[1]), N.ptr(ys[2]), N.ptr(ys[3]), N.ptr(gxs), b, pw.cin,
+                                          h, w, N.stream_ptr()), "nhwc_sum4_to_nchw_f32")
+    return gxs
 
 
 def _rowdot(a, b, scale=None, want_prod=False):
@@ -203,8 +239,7 @@ class _ModConv(torch.autograd.Function):
         tc = TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k)
         y = conv_forward_tc(x, s, d, pw, upsample) if tc else conv_forward(x, s, d, pw, k, upsample)
         ctx.save_for_backward(x, s, d if d is not None else x.new_zeros(0), y)
-        # dgrad on the tensor cores: plain conv only (the dgrad of the transposed conv is a stride-2 convolution)
-        ctx.cfg = (pw, k, upsample, d is not None, tc and not upsample and tc_supported(pw.cout, pw.cin, k))
+        ctx.cfg = (pw, k, upsample, d is not None, tc and tc_supported(pw.cout, pw.cin, k))
         return y
 
     @staticmethod
@@ -220,7 +255,7 @@ class _ModConv(torch.autograd.Function):
             gd = dot / d
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if tc_dgrad:
-                gxs = conv_dgrad_tc(gy, d_or_none, pw)
+                gxs = conv_dgrad_tc(gy, d_or_none, pw, upsample, (x.shape[2], x.shape[3]))
             else:
                 gxs = conv_dgrad(gy, d_or_none, pw, k, upsample, (x.shape[2], x.shape[3]))
             gs, gx = _rowdot(gxs, x, scale=s.contiguous(), want_prod=True)   # gs = sum_p gxs*x ; gx = gxs*s
