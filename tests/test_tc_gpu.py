@@ -351,3 +351,23 @@ def test_fused_upconv_blur_matches_oracle(eng, b, cin, cout, h, want_out):
         assert out is None
     two, two_mod = run_layer(eng, layer, x, s, noise, nxt)
     assert norm_err(eng._to_nchw(out_mod).cpu(), two_mod) <= 1e-2
+
+
+@pytest.mark.parametrize("b,cin,cout,h,up", [(2, 64, 32, 20, False), (1, 128, 64, 17, True), (2, 32, 32, 36, True),
+                                             (1, 512, 256, 8, True)])
+def test_tensor_core_dgrad_matches_fp32_engine(b, cin, cout, h, up):
+    """autograd path of precision='bf16': conv_dgrad_tc (flipped-tap kernel / four parity-class convolutions for the
+    transposed conv) against the exact fp32 conv engine on the same upstream gradient"""
+    m = w2e.StyledConv(cin, cout, 3, 16, upsample=up)
+    with torch.no_grad():
+        m.conv.weight.copy_(synth.make_tensor((1, cout, cin, 3, 3), 91))
+    m = m.to(DEV)
+    pw = m.conv.packed()
+    zh = 2 * h + 1 if up else h
+    gy = synth.make_tensor((b, cout, zh, zh), 92).to(DEV)
+    d = (1 + 0.3 * synth.make_tensor((b, cout), 93)).to(DEV).contiguous()
+    ref = K.conv_dgrad(gy, d, pw, 3, up, (h, h))
+    got = K.conv_dgrad_tc(gy, d, pw, up, (h, h))
+    K.tc_assert_ok()
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert norm_err(got.cpu(), ref.cpu()) <= 1e-2
