@@ -122,6 +122,12 @@ int w2e_conv_engine_f32(const float* x, const float* w, const float* in_scale,
  * prod[r,p] = a[r,p] * scale[r] (scale may be NULL = 1).                                     */
 int w2e_rowdot_f32(const float* a, const float* b, const float* scale, float* prod, float* dot,
                    int64_t rows, int64_t inner, void* stream);
+/* The same reduction with each row split into nseg fixed segments (long rows of the high-resolution layers);
+ * partial [rows, nseg] is caller-provided workspace, w2e_rowdot_segments() the recommended nseg.  Deterministic:
+ * the partial sums are combined in segment order.  inner % 4 == 0, rows <= 65535, 16-byte aligned operands.  */
+int64_t w2e_rowdot_segments(int64_t rows, int64_t inner);
+int w2e_rowdot_seg_f32(const float* a, const float* b, const float* scale, float* prod, float* dot,
+                       float* partial, int64_t rows, int64_t inner, int nseg, void* stream);
 
 /* ---- ToRGB  (models/stylegan2/model.py:353-362) -------------------------------------------
  * rgb[b,o,p] = sum_c x[b,c,p]*style[b,c]*w[o,c] + bias[o] + upfirdn2d(skip, k4*4, up=2, pad=(2,1))

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "w2e_style_demod_all": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "w2e_conv_engine_f32": (_I, [_P] * 7 + [_I, _P] + [_I] * 13 + [_P, _I, _I, _I, _P]),
     "w2e_rowdot_f32": (_I, [_P, _P, _P, _P, _P, _L, _L, _P]),
+    "w2e_rowdot_segments": (_L, [_L, _L]),
+    "w2e_rowdot_seg_f32": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
     "w2e_torgb_fwd": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),
     "w2e_torgb_bwd": (_I, [_P] * 6 + [_I, _I, _I, _I, _P]),
     "w2e_mask_blend_fwd": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_I, _P]),
@@ -59,7 +61,7 @@ PROTOTYPES = {
 }
 
 # entry points that enqueue no kernel (host queries)
-_HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace",
+_HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace", "w2e_rowdot_segments",
               "w2e_modconv_tc_supported", "w2e_modconv_tc2_knobs", "w2e_modconv_tc2_epilogue", "w2e_modconv_tc2_debug", "w2e_modconv_tc2_flags", "w2e_modconv_tc2_cluster"}
 
 

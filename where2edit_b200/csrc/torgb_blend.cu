@@ -161,6 +161,40 @@ rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, const fl
   if (threadIdx.x == 0 && dot) dot[r] = acc;
 }
 
+// Same reduction with every row split into nseg segments (grid = nseg x rows): long rows of the >= 256^2 layers
+// would otherwise run on as few blocks as there are (sample, channel) rows.  Deterministic: fixed segments, the
+// partial sums are combined in segment order by rowdot_finish_kernel.
+__global__ void __launch_bounds__(256)
+rowdot_seg_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ scale,
+                  float* __restrict__ prod, float* __restrict__ partial, int64_t inner, int64_t seg_len, int nseg) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.y;
+  const int sg = blockIdx.x;
+  const int64_t p0 = (int64_t)sg * seg_len, p1 = min(inner, p0 + seg_len);
+  const float* ar = a + r * inner;
+  const float* br = b + r * inner;
+  const float s = scale ? __ldg(scale + r) : 1.f;
+  float acc = 0.f;
+  // seg_len and inner are multiples of 4 and the rows 16-byte aligned (checked by the launcher)
+  for (int64_t p = p0 + (int64_t)threadIdx.x * 4; p < p1; p += (int64_t)blockDim.x * 4) {
+    const float4 av = *reinterpret_cast<const float4*>(ar + p);
+    const float4 bv = *reinterpret_cast<const float4*>(br + p);
+    acc = fmaf(av.x, bv.x, acc); acc = fmaf(av.y, bv.y, acc); acc = fmaf(av.z, bv.z, acc); acc = fmaf(av.w, bv.w, acc);
+    if (prod) *reinterpret_cast<float4*>(prod + r * inner + p) = make_float4(av.x * s, av.y * s, av.z * s, av.w * s);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[r * nseg + sg] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+rowdot_finish_kernel(const float* __restrict__ partial, float* __restrict__ dot, int64_t rows, int nseg) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int sg = 0; sg < nseg; ++sg) acc += partial[r * nseg + sg];
+  dot[r] = acc;
+}
+
 // one warp per (b, o): demod = rsqrt(sum_i style^2 * wsq + 1e-8)   (models/stylegan2/model.py:242)
 __global__ void __launch_bounds__(256)
 style_demod_kernel(const float* __restrict__ style, const float* __restrict__ wsq, float* __restrict__ demod, int B,
@@ -260,6 +294,32 @@ extern "C" int w2e_rowdot_f32(const float* a, const float* b, const float* scale
   W2E_CHECK_ARG(rows >= 0 && inner > 0 && rows < (1ll << 31), "rowdot: bad shape");
   if (rows == 0) return W2E_OK;
   rowdot_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(a, b, scale, prod, dot, inner);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int64_t w2e_rowdot_segments(int64_t rows, int64_t inner) {
+  // enough blocks to fill the machine (~8 per SM), at least 8192 elements per segment, at most 64 segments
+  if (rows <= 0 || inner <= 0 || inner % 4 != 0) return 1;
+  int64_t want = ceil_div64((int64_t)sm_count() * 8, rows);
+  int64_t cap = inner / 8192;
+  if (want > cap) want = cap;
+  if (want > 64) want = 64;
+  return want < 1 ? 1 : want;
+}
+
+extern "C" int w2e_rowdot_seg_f32(const float* a, const float* b, const float* scale, float* prod, float* dot,
+                                  float* partial, int64_t rows, int64_t inner, int nseg, void* stream) {
+  W2E_CHECK_ARG(a && b && dot && partial, "rowdot_seg: null pointer");
+  W2E_CHECK_ARG(rows >= 0 && rows <= 65535 && inner > 0 && inner % 4 == 0 && nseg >= 1 && nseg <= 64,
+                "rowdot_seg: bad shape (inner must be a multiple of 4, rows <= 65535)");
+  W2E_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)prod) & 15) == 0, "rowdot_seg: operands must be 16-byte aligned");
+  if (rows == 0) return W2E_OK;
+  int64_t seg_len = ceil_div64(ceil_div64(inner, nseg), 4) * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  rowdot_seg_kernel<<<dim3((unsigned)nseg, (unsigned)rows), 256, 0, st>>>(a, b, scale, prod, partial, inner, seg_len, nseg);
+  W2E_LAUNCH_OK();
+  rowdot_finish_kernel<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(partial, dot, rows, nseg);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

@@ -228,8 +228,15 @@ def _rowdot(a, b, scale=None, want_prod=False):
     inner = a[0, 0].numel()
     dot = torch.empty((a.shape[0], a.shape[1]), device=a.device, dtype=torch.float32)
     prod = torch.empty_like(a) if want_prod else None
-    N.check(N.load().w2e_rowdot_f32(N.ptr(a), N.ptr(b), N.ptr(scale), N.ptr(prod), N.ptr(dot), rows, inner,
-                                    N.stream_ptr()), "rowdot")
+    lib = N.load()
+    nseg = int(lib.w2e_rowdot_segments(rows, inner)) if rows <= 65535 else 1
+    if nseg > 1:   # long rows: segmented, deterministic two-pass reduction
+        partial = torch.empty((rows, nseg), device=a.device, dtype=torch.float32)
+        N.check(lib.w2e_rowdot_seg_f32(N.ptr(a), N.ptr(b), N.ptr(scale), N.ptr(prod), N.ptr(dot), N.ptr(partial), rows,
+                                       inner, nseg, N.stream_ptr()), "rowdot_seg")
+    else:
+        N.check(lib.w2e_rowdot_f32(N.ptr(a), N.ptr(b), N.ptr(scale), N.ptr(prod), N.ptr(dot), rows, inner,
+                                   N.stream_ptr()), "rowdot")
     return dot, prod
 
 
