@@ -142,6 +142,10 @@ int w2e_torgb_fwd(const void* x, const float* w, const float* style, const float
  * upfirdn2d_bwd of g; the bias gradient a plain reduction -- both done by the caller.)      */
 int w2e_torgb_bwd(const float* g, const float* x, const float* w, const float* style, float* gx,
                   float* gstyle, int B, int Cin, int H, int W, void* stream);
+/* the same with every (sample, channel) plane split into nseg fixed segments (w2e_rowdot_segments(B*Cin, H*W));
+ * partial [B*Cin, nseg] is caller-provided workspace; H*W % 4 == 0, 16-byte aligned operands.                */
+int w2e_torgb_bwd_seg(const float* g, const float* x, const float* w, const float* style, float* gx,
+                      float* gstyle, float* partial, int B, int Cin, int H, int W, int nseg, void* stream);
 
 /* ---- region-mask blend  (attention/attention_model.py:548-549 and siblings) ---------------
  * out = m*edited + (1-m)*orig, m = mask[b,0,floor(y*mh/H),floor(x*mw/W)] (F.interpolate

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "w2e_rowdot_seg_f32": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _P]),
     "w2e_torgb_fwd": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),
     "w2e_torgb_bwd": (_I, [_P] * 6 + [_I, _I, _I, _I, _P]),
+    "w2e_torgb_bwd_seg": (_I, [_P] * 7 + [_I, _I, _I, _I, _I, _P]),
     "w2e_mask_blend_fwd": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_I, _P]),
     "w2e_mask_blend_bwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
     "w2e_modconv_tc_supported": (_I, []),

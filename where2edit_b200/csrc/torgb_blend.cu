@@ -87,6 +87,38 @@ torgb_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const
   if (threadIdx.x == 0) gstyle[(int64_t)b * Cin + c] = acc;
 }
 
+// the same with every (c, b) plane split into nseg fixed segments (grid = nseg x Cin x B); the partial sums of
+// gstyle are combined in segment order by rowdot_finish_kernel (deterministic)
+__global__ void __launch_bounds__(256)
+torgb_bwd_seg_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ style, float* __restrict__ gx, float* __restrict__ partial, int Cin,
+                     int64_t HW, int64_t seg_len, int nseg) {
+  __shared__ float red[32];
+  const int sg = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+  const float w0 = __ldg(w + c), w1 = __ldg(w + Cin + c), w2 = __ldg(w + 2 * Cin + c);
+  const float s = __ldg(style + (int64_t)b * Cin + c);
+  const float* gp = g + (int64_t)b * 3 * HW;
+  const float* xp = x + ((int64_t)b * Cin + c) * HW;
+  float* gxp = gx + ((int64_t)b * Cin + c) * HW;
+  const int64_t p0 = (int64_t)sg * seg_len, p1 = min(HW, p0 + seg_len);
+  float acc = 0.f;
+  for (int64_t p = p0 + (int64_t)threadIdx.x * 4; p < p1; p += (int64_t)blockDim.x * 4) {
+    const float4 g0 = *reinterpret_cast<const float4*>(gp + p);
+    const float4 g1 = *reinterpret_cast<const float4*>(gp + HW + p);
+    const float4 g2 = *reinterpret_cast<const float4*>(gp + 2 * HW + p);
+    const float4 xv = *reinterpret_cast<const float4*>(xp + p);
+    float4 t;
+    t.x = fmaf(g0.x, w0, fmaf(g1.x, w1, g2.x * w2));
+    t.y = fmaf(g0.y, w0, fmaf(g1.y, w1, g2.y * w2));
+    t.z = fmaf(g0.z, w0, fmaf(g1.z, w1, g2.z * w2));
+    t.w = fmaf(g0.w, w0, fmaf(g1.w, w1, g2.w * w2));
+    *reinterpret_cast<float4*>(gxp + p) = make_float4(t.x * s, t.y * s, t.z * s, t.w * s);
+    acc = fmaf(t.x, xv.x, acc); acc = fmaf(t.y, xv.y, acc); acc = fmaf(t.z, xv.z, acc); acc = fmaf(t.w, xv.w, acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[((int64_t)b * Cin + c) * nseg + sg] = acc;
+}
+
 // ------------------------------------------------------------------------------------------ blend
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -245,6 +277,25 @@ extern "C" int w2e_torgb_bwd(const float* g, const float* x, const float* w, con
   W2E_CHECK_ARG(B >= 0 && Cin > 0 && H > 0 && W > 0 && B <= 65535, "torgb_bwd: bad shape");
   if (B == 0) return W2E_OK;
   torgb_bwd_kernel<<<dim3(Cin, B), 256, 0, (cudaStream_t)stream>>>(g, x, w, style, gx, gstyle, Cin, (int64_t)H * W);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_torgb_bwd_seg(const float* g, const float* x, const float* w, const float* style, float* gx,
+                                 float* gstyle, float* partial, int B, int Cin, int H, int W, int nseg, void* stream) {
+  W2E_CHECK_ARG(g && x && w && style && gx && gstyle && partial, "torgb_bwd_seg: null pointer");
+  const int64_t HW = (int64_t)H * W;
+  W2E_CHECK_ARG(B >= 0 && Cin > 0 && Cin <= 65535 && H > 0 && W > 0 && B <= 65535 && HW % 4 == 0 && nseg >= 1 && nseg <= 64,
+                "torgb_bwd_seg: bad shape (H*W must be a multiple of 4)");
+  W2E_CHECK_ARG((((uintptr_t)g | (uintptr_t)x | (uintptr_t)gx) & 15) == 0, "torgb_bwd_seg: operands must be 16-byte aligned");
+  if (B == 0) return W2E_OK;
+  const int64_t seg_len = ceil_div64(ceil_div64(HW, nseg), 4) * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  torgb_bwd_seg_kernel<<<dim3((unsigned)nseg, (unsigned)Cin, (unsigned)B), 256, 0, st>>>(g, x, w, style, gx, partial, Cin, HW,
+                                                                                     seg_len, nseg);
+  W2E_LAUNCH_OK();
+  const int64_t rows = (int64_t)B * Cin;
+  rowdot_finish_kernel<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(partial, gstyle, rows, nseg);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

@@ -338,8 +338,15 @@ class _ToRGB(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             gx = torch.empty_like(x, dtype=torch.float32)
             gs = torch.empty((b, cin), device=x.device, dtype=torch.float32)
-            N.check(N.load().w2e_torgb_bwd(N.ptr(g), N.ptr(x), N.ptr(w_rgb), N.ptr(s), N.ptr(gx), N.ptr(gs), b, cin,
-                                           h, w, N.stream_ptr()), "torgb_bwd")
+            lib = N.load()
+            nseg = int(lib.w2e_rowdot_segments(b * cin, h * w)) if x.dtype == torch.float32 else 1
+            if nseg > 1:   # long planes: segmented, deterministic two-pass reduction of gstyle
+                partial = torch.empty((b * cin, nseg), device=x.device, dtype=torch.float32)
+                N.check(lib.w2e_torgb_bwd_seg(N.ptr(g), N.ptr(x), N.ptr(w_rgb), N.ptr(s), N.ptr(gx), N.ptr(gs), N.ptr(partial),
+                                              b, cin, h, w, nseg, N.stream_ptr()), "torgb_bwd_seg")
+            else:
+                N.check(lib.w2e_torgb_bwd(N.ptr(g), N.ptr(x), N.ptr(w_rgb), N.ptr(s), N.ptr(gx), N.ptr(gs), b, cin,
+                                          h, w, N.stream_ptr()), "torgb_bwd")
         if has_skip and ctx.needs_input_grad[2]:
             gskip = torch.empty((b, 3, h // 2, w // 2), device=x.device, dtype=torch.float32)
             N.check(N.load().w2e_upfirdn2d_bwd(N.ptr(g), N.ptr(gskip), N.host_floats(taps2d), b * 3, h // 2, w // 2,
