@@ -229,6 +229,13 @@ def main():
     from where2edit_b200 import _native as N
     from where2edit_b200 import parallel
     gen = make_generator(args.size, args.precision, dev)
+    # Multi-GPU: the persistent convolution kernels normally occupy every SM, so the NCCL all-gather kernels of
+    # the previous step could only run in the gaps between them; leaving a few SMs free lets the collective
+    # overlap the kernels (W2E_RESERVE_SMS; default 0: measured at 4 GPUs 14 649 / 14 362 / 13 335 images/s with 0 / 8 / 16 SMs reserved).
+    reserve = int(os.environ.get("W2E_RESERVE_SMS", "0"))
+    if reserve > 0:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        N.load().w2e_modconv_tc2_knobs(max(2, sms - reserve))
     B, K_, W_ = args.batch, args.steps, args.warmup
     peaks = measured_peaks()
 
