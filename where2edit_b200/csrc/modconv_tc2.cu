@@ -227,11 +227,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
+      // two block-alternating MMA issuers (weight-ring TS kernels): BOTH commit every A stage and every accumulator
+      // set, so no ordering between the two issuers' MMAs has to be assumed
+      const uint32_t n_issuers = (TS && !WRES && !(P.flags & 2)) ? 2u : 1u;
+      for (int s = 0; s < P.a_stages; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], n_issuers); }
       for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1u << cl); }
       // TS flavour with a single accumulator buffer: both epilogue groups drain every tile (unit-split mode)
       const uint32_t epi_arrivals = (TS && (P.nbuf == 1 || P.fb)) ? 2 * kT2EpiThreads : kT2EpiThreads;
-      for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], epi_arrivals); }
+      for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], n_issuers); mbar_init(&bars->acc_empty[s], epi_arrivals); }
       mbar_init(&bars->w_full, 1);
       mbar_init(&bars->mma_turn[0], 1);
       mbar_init(&bars->mma_turn[1], 1);
@@ -497,14 +500,19 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               }
             }
             if (leader && mine) {
-              // (the pipe executes in issue order: a commit also covers the other issuer's earlier MMAs)
               if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)((1u << (1 << cl)) - 1u));   // free once ALL CTAs consumed it
               else umma_commit(&bars->b_empty[br.idx]);
-              if (t == 8) umma_commit(&bars->a_empty[ar.idx]);
-              if (t == 8 && kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);   // last block of the tile
+              if (!blk2 && t == 8) {
+                umma_commit(&bars->a_empty[ar.idx]);
+                if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);   // last block of the tile
+              }
               if (blk2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
             }
             br.advance(P.b_stages);
+          }
+          if (blk2 && ok && leader) {   // this issuer's MMAs on the A stage (and, at the last chunk, on the tile) are queued
+            umma_commit(&bars->a_empty[ar.idx]);
+            if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
           }
         }
         ar.advance(P.a_stages);
