@@ -151,18 +151,19 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    import where2edit_b200 as w2e
-    gen = w2e.Generator(args.size, 512, 8, channel_multiplier=2)
-    sd = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    import math
+    from oracle import synth
+    sd = synth.make_state_dict(args.size, seed=0, channel_multiplier=2)   # nothing of the product package on this arm
+    n_latent = 2 * int(math.log2(args.size)) - 2
     g = torch.Generator().manual_seed(2)
     sample_batch = 1
     with torch.no_grad():
         for _ in range(args.warmup):
-            orc.generator_forward_ref(sd, [torch.randn(sample_batch, gen.n_latent, 512, generator=g)], args.size,
+            orc.generator_forward_ref(sd, [torch.randn(sample_batch, n_latent, 512, generator=g)], args.size,
                                       input_is_latent=True)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            orc.generator_forward_ref(sd, [torch.randn(sample_batch, gen.n_latent, 512, generator=g)], args.size,
+            orc.generator_forward_ref(sd, [torch.randn(sample_batch, n_latent, 512, generator=g)], args.size,
                                       input_is_latent=True)
         dt = time.perf_counter() - t0
     value = sample_batch * args.steps / dt
