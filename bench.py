@@ -28,12 +28,12 @@ UNIT = "images/s"
 MODCONV_GFLOP_PER_IMAGE = 148.13
 
 
-def workload_config(size, batch, precision, world):
+def workload_config(size, batch, precision, world, gather="NCCL all-gather"):
     return {"workload": f"StyleGAN2 FFHQ-{size} generator forward (random init, channel_multiplier 2), "
                         f"batch {batch} per GPU from W+ latents, fixed noise buffers, {precision} mode",
             "batch_per_gpu": batch, "global_batch": batch * world,
             "parallelism": f"batch sharded over {world} GPU(s)"
-                           + (", bf16 all-gather of images overlapped on a side stream" if world > 1 else ""),
+                           + (f", bf16 all-gather of images overlapped on a side stream ({gather})" if world > 1 else ""),
             "l2": "inputs larger than L2: every step streams multi-GB activations (no flush needed)"}
 
 
@@ -250,8 +250,21 @@ def main():
     host_w = [torch.randn(B, n_lat, 512, generator=g).pin_memory() for _ in range(2)]
     dev_w = [w.to(dev) for w in host_w]
     comm_stream = torch.cuda.Stream() if dist is not None else None
-    gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=torch.bfloat16) for _ in range(2)] \
-        if dist is not None else None
+    gathered = peer = None
+    gather_kind = "none"
+    if dist is not None:
+        # W2E_GATHER=p2p: copy-engine pushes into peer-mapped buffers (no SM use); default: NCCL all-gather
+        if os.environ.get("W2E_GATHER", "nccl") == "p2p":
+            try:
+                peer = parallel.PeerGather((B, 3, args.size, args.size), torch.bfloat16, dev, slots=2)
+                gather_kind = "copy-engine peer pushes (symmetric memory)"
+            except Exception as exc:   # no symmetric memory in this build / topology: the NCCL collective
+                if rank == 0:
+                    print(f"bench.py: PeerGather unavailable ({exc!r}); using NCCL", file=sys.stderr)
+        if peer is None:
+            gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=torch.bfloat16)
+                        for _ in range(2)]
+            gather_kind = "NCCL all-gather"
 
     def step(i, w, gather=True):
         """One pass of the hot path; at N>1 the images are all-gathered (bf16) on a side stream so the
@@ -262,7 +275,10 @@ def main():
             small = img.to(torch.bfloat16)
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
-                parallel.gather_images(small, out=gathered[i % 2])
+                if peer is not None:
+                    peer.push(small, i % 2)
+                else:
+                    parallel.gather_images(small, out=gathered[i % 2])
             small.record_stream(comm_stream)
         return img
 
@@ -282,6 +298,9 @@ def main():
     for i in range(K_):
         step(i, dev_w[i % 2])
     if comm_stream is not None:
+        if peer is not None:
+            with torch.cuda.stream(comm_stream):
+                peer.barrier()   # every rank's pushes have landed
         torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
     barrier()
@@ -378,7 +397,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
             "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args.size, B, args.precision, world),
+            "config": workload_config(args.size, B, args.precision, world, gather_kind),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

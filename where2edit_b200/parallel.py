@@ -50,3 +50,42 @@ def gather_images(local, total=None, group=None, out=None):
     dist.all_gather_into_tensor(buf, padded, group=group)
     parts = [buf[r * biggest: r * biggest + (e - b)] for r, (b, e) in enumerate(sizes)]
     return torch.cat(parts, 0)
+
+
+class PeerGather:
+    """All-gather of equal per-rank shards by COPY-ENGINE pushes into peer-mapped (symmetric-memory) buffers
+    over NVLink: no SM is used, so the transfer overlaps the persistent convolution kernels, which occupy
+    every SM (the NCCL all-gather kernels can only run in the gaps between them).
+
+        pg = PeerGather(shard.shape, shard.dtype, device)          # once (collective)
+        pg.push(shard, slot)                                       # every step, on any stream
+        pg.barrier(); full = pg.result(slot)                       # before reading / before a slot is reused
+
+    `slots` independent buffers let step i+1 be pushed while step i is still being read."""
+
+    def __init__(self, shard_shape, dtype, device, group=None, slots=2):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.shape = (slots, self.world) + tuple(shard_shape)
+        try:
+            symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:   # newer builds enable it implicitly
+            pass
+        self.buf = symm.empty(self.shape, dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.peers = [self.handle.get_buffer(r, self.shape, dtype) for r in range(self.world)]
+
+    def push(self, local, slot):
+        """Copy this rank's shard into slot `slot` of every rank's buffer (current stream, asynchronous)."""
+        for r in range(self.world):
+            self.peers[(self.rank + r) % self.world][slot, self.rank].copy_(local, non_blocking=True)
+
+    def barrier(self):
+        """All pushes issued before it (on every rank, in stream order) have landed when it returns on the stream."""
+        self.handle.barrier()
+
+    def result(self, slot):
+        """[world * shard, ...] in rank order (valid after barrier())."""
+        return self.buf[slot].flatten(0, 1)
