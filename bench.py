@@ -253,8 +253,9 @@ def main():
     gathered = peer = None
     gather_kind = "none"
     if dist is not None:
-        # W2E_GATHER=p2p: copy-engine pushes into peer-mapped buffers (no SM use); default: NCCL all-gather
-        if os.environ.get("W2E_GATHER", "nccl") == "p2p":
+        # default: copy-engine pushes into peer-mapped buffers (no SM use; 29 054 vs 26 855 images/s at 8 GPUs);
+        # W2E_GATHER=nccl: the NCCL all-gather
+        if os.environ.get("W2E_GATHER", "p2p") == "p2p":
             try:
                 peer = parallel.PeerGather((B, 3, args.size, args.size), torch.bfloat16, dev, slots=2)
                 gather_kind = "copy-engine peer pushes (symmetric memory)"

@@ -1,5 +1,8 @@
 """End-to-end GPU parity of Generator.forward (fp32 mode) against the reference goldens and the
 oracle: images, captured features, styles, blends, z/truncation/mixing paths, gradients."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -195,3 +198,20 @@ def test_batch_invariance_and_ragged_batch():
     assert torch.equal(full_ss, singles)
     ref, _ = orc.generator_forward_ref(sd, [wplus.cpu()], 16, input_is_latent=True)
     assert max_abs(full.cpu(), ref) <= TOL
+
+
+@pytest.mark.gpu
+def test_peer_gather_matches_nccl_all_gather():
+    """parallel.PeerGather (copy-engine pushes into symmetric-memory buffers) returns what the NCCL all-gather
+    returns; one rank per visible GPU (world size 1 on a single-GPU box still maps, pushes and barriers)."""
+    import socket
+    import subprocess
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = min(torch.cuda.device_count(), 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "PeerGather OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -69,10 +69,6 @@ class PeerGather:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.shape = (slots, self.world) + tuple(shard_shape)
-        try:
-            symm.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:   # newer builds enable it implicitly
-            pass
         self.buf = symm.empty(self.shape, dtype=dtype, device=device)
         self.handle = symm.rendezvous(self.buf, self.group)
         self.peers = [self.handle.get_buffer(r, self.shape, dtype) for r in range(self.world)]
