@@ -270,6 +270,30 @@ int w2e_blend_nhwc(const void* edited, const void* orig, const float* mask, cons
                    void* out, void* out_mod, int B, int C, int H, int W, int mh, int mw,
                    void* stream);
 
+/* ---- region-mask construction of the cluster-style mapper -------
+ * The step just before the blended Generator.forward: attention/run_attention.py:775-794 (cluster
+ * assignment) and :852-884 (per-cluster mean attention, losses, threshold, gaussian blur).
+ *
+ * w2e_cluster_assign: feature f32 NCHW [B,C,h,h]; centres f32 [K, C + 2*pos_channels] (feature
+ *   channels, then pos_channels copies of the x position, then of the y position, positions =
+ *   i*2/(h-1)-1); ids int64 [B,S,S] = b*K + argmin_k squared distance (utils.py:244-263), nearest-
+ *   resized from h to S.  low_ws: int32 workspace [B,h,h].
+ * w2e_region_mask_fwd: each f32 [B,S,S] (the sigmoid attention), ids as above; host_taps25 = the
+ *   5x5 blur kernel (HOST pointer, row-major).  Writes final_map [B,S,S] (the attention_map, add the
+ *   channel axis in the caller), same [B,S,S] (per-cluster means painted back), stats [B,K,2]
+ *   (mean, count), losses[2] = {loss_reg, loss_tv}; parts_ws: f32 workspace [B,2].  Pixels whose id
+ *   lies outside [b*K, (b+1)*K) keep the value 1 (the reference's torch.ones initialisation).
+ * w2e_region_mask_bwd: g_each = d/d each of <final_map, g_final> + g_losses[0]*loss_reg +
+ *   g_losses[1]*loss_tv (g_final and g_losses are device pointers and may be null = zero).      */
+int w2e_cluster_assign(const float* feature, const float* centres, int* low_ws, int64_t* ids, int B, int C,
+                       int h, int K, int pos_channels, int S, void* stream);
+int w2e_region_mask_fwd(const float* each, const int64_t* ids, const float* host_taps25, float* final_map,
+                        float* same, float* stats, float* parts_ws, float* losses, int B, int S, int K,
+                        float threshold, float margin, void* stream);
+int w2e_region_mask_bwd(const float* g_final, const float* g_losses, const float* each, const int64_t* ids,
+                        const float* same, const float* stats, const float* host_taps25, float* g_each, int B,
+                        int S, int K, float margin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

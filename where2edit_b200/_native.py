@@ -59,6 +59,9 @@ PROTOTYPES = {
     "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 9 + [_P]),
     "w2e_torgb_nhwc": (_I, [_P] * 7 + [_I, _I, _I, _I, _P]),
     "w2e_blend_nhwc": (_I, [_P] * 6 + [_I] * 6 + [_P]),
+    "w2e_cluster_assign": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P]),
+    "w2e_region_mask_fwd": (_I, [_P] * 8 + [_I, _I, _I, _F, _F, _P]),
+    "w2e_region_mask_bwd": (_I, [_P] * 8 + [_I, _I, _I, _F, _P]),
 }
 
 # entry points that enqueue no kernel (host queries)
