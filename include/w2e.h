@@ -294,6 +294,16 @@ int w2e_region_mask_bwd(const float* g_final, const float* g_losses, const float
                         const float* same, const float* stats, const float* host_taps25, float* g_each, int B,
                         int S, int K, float margin, void* stream);
 
+/* ---- CLIP / VGG pre-resample ------------------------------------
+ * y = AvgPool2d(pool)(Upsample(scale_factor=up, mode="nearest")(x))  (criteria/clip_loss.py:10-14,
+ * criteria/perceptual_loss.py:12-17; up = 7, pool = stylegan_size/32 -> 224x224) without the
+ * upsampled intermediate.  x f32 [planes,H,W] -> y f32 [planes, H*up/pool, W*up/pool] (floor);
+ * bwd: gy -> gx, the exact adjoint.                                                             */
+int w2e_box_resample_fwd(const float* x, float* y, int64_t planes, int H, int W, int up, int pool,
+                         void* stream);
+int w2e_box_resample_bwd(const float* gy, float* gx, int64_t planes, int H, int W, int up, int pool,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

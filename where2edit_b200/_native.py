@@ -62,6 +62,8 @@ PROTOTYPES = {
     "w2e_cluster_assign": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P]),
     "w2e_region_mask_fwd": (_I, [_P] * 8 + [_I, _I, _I, _F, _F, _P]),
     "w2e_region_mask_bwd": (_I, [_P] * 8 + [_I, _I, _I, _F, _P]),
+    "w2e_box_resample_fwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _P]),
+    "w2e_box_resample_bwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _P]),
 }
 
 # entry points that enqueue no kernel (host queries)

@@ -1,0 +1,114 @@
+// CLIP / VGG pre-resample: AvgPool2d(P)(Upsample(scale_factor=U, nearest)(image)),
+// criteria/clip_loss.py:10-14, criteria/perceptual_loss.py:12-17, called on every generated image right after
+// Generator.forward (attention/run_attention.py:1163,1259).  The reference materialises the upsampled
+// [B,3,U*H,U*W] tensor (617 MB fp32 per 1024^2 image at U=7) to produce 224x224; composed, every output pixel is
+// a small weighted box of source pixels with integer weights
+//     w(o, j) = |[U*j, U*j+U-1]  intersect  [P*o, P*o+P-1]|          (rows and columns separately),
+// so one pass reads the image once and writes the 224x224 result; the backward is the transposed gather.
+#include "common.cuh"
+
+namespace w2e {
+
+// overlap of upsampled rows [U*j, U*j+U-1] with the pooling window [P*o, P*o+P-1]
+__device__ __forceinline__ int box_weight(int j, int o, int U, int P) {
+  return min(U * j + U - 1, P * o + P - 1) - max(U * j, P * o) + 1;
+}
+
+__global__ void __launch_bounds__(256)
+box_resample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int H, int W, int OH, int OW,
+                        int U, int P) {
+  const float denom = (float)P * (float)P;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW), oy = (int)((i / OW) % OH);
+    const int64_t n = i / ((int64_t)OW * OH);
+    const float* xp = x + n * H * W;
+    const int j0 = (P * oy) / U, j1 = (P * oy + P - 1) / U;
+    const int i0 = (P * ox) / U, i1 = (P * ox + P - 1) / U;
+    float acc = 0.f;
+    for (int j = j0; j <= j1; ++j) {
+      const float wy = (float)box_weight(j, oy, U, P);
+      float row = 0.f;
+      for (int c = i0; c <= i1; ++c) row = fmaf((float)box_weight(c, ox, U, P), __ldg(xp + (int64_t)j * W + c), row);
+      acc = fmaf(wy, row, acc);
+    }
+    y[i] = __fdiv_rn(acc, denom);
+  }
+}
+
+// gx[n, j, c] = (1/P^2) * sum_{oy, ox} w(oy, j) * w(ox, c) * gy[n, oy, ox]; upsampled rows beyond OH*P (AvgPool's floor)
+// receive nothing.  One thread writes 4 consecutive source columns (16-byte stores when W % 4 == 0).
+__global__ void __launch_bounds__(256)
+box_resample_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total4, int H, int W, int W4, int OH,
+                        int OW, int U, int P, int vec) {
+  const float inv = 1.f / ((float)P * (float)P);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % W4), j = (int)((i / W4) % H);
+    const int64_t n = i / ((int64_t)W4 * H);
+    const float* gp = gy + n * OH * OW;
+    const int oy0 = (U * j) / P, oy1 = min((U * j + U - 1) / P, OH - 1);
+    float out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c4 * 4 + e;
+      float acc = 0.f;
+      if (c < W) {
+        const int ox0 = (U * c) / P, ox1 = min((U * c + U - 1) / P, OW - 1);
+        for (int oy = oy0; oy <= oy1; ++oy) {
+          const float wy = (float)box_weight(j, oy, U, P);
+          float row = 0.f;
+          for (int ox = ox0; ox <= ox1; ++ox) row = fmaf((float)box_weight(c, ox, U, P), __ldg(gp + (int64_t)oy * OW + ox), row);
+          acc = fmaf(wy, row, acc);
+        }
+      }
+      out[e] = acc * inv;
+    }
+    float* dst = gx + (n * H + j) * W + c4 * 4;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c4 * 4 + e < W) dst[e] = out[e];
+    }
+  }
+}
+
+static int resample_dims(int H, int W, int U, int P, int* OH, int* OW) {
+  *OH = (int)(((int64_t)H * U) / P);
+  *OW = (int)(((int64_t)W * U) / P);
+  return *OH > 0 && *OW > 0;
+}
+
+}  // namespace w2e
+
+using namespace w2e;
+
+extern "C" int w2e_box_resample_fwd(const float* x, float* y, int64_t planes, int H, int W, int up, int pool, void* stream) {
+  W2E_CHECK_ARG(x && y, "box_resample_fwd: null pointer");
+  W2E_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && up >= 1 && pool >= 1 && (int64_t)H * up < (1 << 30) && (int64_t)W * up < (1 << 30),
+                "box_resample_fwd: bad shape");
+  int OH, OW;
+  W2E_CHECK_ARG(resample_dims(H, W, up, pool, &OH, &OW), "box_resample_fwd: pooling window larger than the upsampled image");
+  const int64_t total = planes * OH * OW;
+  if (total == 0) return W2E_OK;
+  box_resample_fwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      x, y, total, H, W, OH, OW, up, pool);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_box_resample_bwd(const float* gy, float* gx, int64_t planes, int H, int W, int up, int pool, void* stream) {
+  W2E_CHECK_ARG(gy && gx, "box_resample_bwd: null pointer");
+  W2E_CHECK_ARG(planes >= 0 && H > 0 && W > 0 && up >= 1 && pool >= 1 && (int64_t)H * up < (1 << 30) && (int64_t)W * up < (1 << 30),
+                "box_resample_bwd: bad shape");
+  int OH, OW;
+  W2E_CHECK_ARG(resample_dims(H, W, up, pool, &OH, &OW), "box_resample_bwd: pooling window larger than the upsampled image");
+  const int W4 = ceil_div(W, 4);
+  const int64_t total4 = planes * H * W4;
+  if (total4 == 0) return W2E_OK;
+  const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
+  box_resample_bwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total4, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      gy, gx, total4, H, W, W4, OH, OW, up, pool, vec);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
