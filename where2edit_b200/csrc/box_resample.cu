@@ -73,6 +73,94 @@ box_resample_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, in
   }
 }
 
+// ---- row kernels: the fast path (fully coalesced global traffic) ---------------------------------------------
+// Forward: one CTA per (plane, output row).  The <= ceil(P/U)+1 source rows of the window are read with 16-byte
+// loads (all issued before the first use) and reduced vertically into a shared-memory row; OW threads then
+// take the horizontal boxes from shared memory.
+constexpr int kRowChunk = 8;   // source rows in flight per thread
+
+__global__ void __launch_bounds__(256)
+box_resample_fwd_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int OH, int OW, int U, int P) {
+  extern __shared__ float vs[];   // [W] vertically reduced row
+  const int oy = blockIdx.x % OH;
+  const int64_t n = blockIdx.x / OH;
+  const int j0 = (P * oy) / U, j1 = (P * oy + P - 1) / U;
+  const float* xp = x + n * H * W;
+  const int W4 = W >> 2;
+  for (int c4 = threadIdx.x; c4 < W4; c4 += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = j0; jb <= j1; jb += kRowChunk) {
+      float4 v[kRowChunk];
+#pragma unroll
+      for (int r = 0; r < kRowChunk; ++r)
+        if (jb + r <= j1) v[r] = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)(jb + r) * W) + c4);
+#pragma unroll
+      for (int r = 0; r < kRowChunk; ++r)
+        if (jb + r <= j1) {
+          const float wy = (float)box_weight(jb + r, oy, U, P);
+          acc.x = fmaf(wy, v[r].x, acc.x);
+          acc.y = fmaf(wy, v[r].y, acc.y);
+          acc.z = fmaf(wy, v[r].z, acc.z);
+          acc.w = fmaf(wy, v[r].w, acc.w);
+        }
+    }
+    *reinterpret_cast<float4*>(vs + 4 * c4) = acc;
+  }
+  __syncthreads();
+  const float denom = (float)P * (float)P;
+  float* yp = y + (n * OH + oy) * OW;
+  for (int ox = threadIdx.x; ox < OW; ox += 256) {
+    const int i0 = (P * ox) / U, i1 = (P * ox + P - 1) / U;
+    float acc = 0.f;
+    for (int c = i0; c <= i1; ++c) acc = fmaf((float)box_weight(c, ox, U, P), vs[c], acc);
+    yp[ox] = __fdiv_rn(acc, denom);
+  }
+}
+
+// Backward: one CTA per (plane, group of kBwdRows source rows).  The window range of every source column is
+// tabulated once per CTA; per source row the <= 2 contributing gradient rows are reduced into shared memory,
+// then every thread writes 4 consecutive source columns with one 16-byte store.
+constexpr int kBwdRows = 16;
+
+__global__ void __launch_bounds__(256)
+box_resample_bwd_rows_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W, int OH, int OW, int U, int P) {
+  extern __shared__ float bs[];            // g_row[OW] then short2 tab[W]
+  float* g_row = bs;
+  short2* tab = reinterpret_cast<short2*>(bs + OW);
+  const int groups = (H + kBwdRows - 1) / kBwdRows;
+  const int jg = blockIdx.x % groups;
+  const int64_t n = blockIdx.x / groups;
+  const float* gp = gy + n * OH * OW;
+  for (int c = threadIdx.x; c < W; c += 256)
+    tab[c] = make_short2((short)((U * c) / P), (short)min((U * c + U - 1) / P, OW - 1));
+  const float inv = 1.f / ((float)P * (float)P);
+  const int W4 = W >> 2;
+  const int j_end = min(H, (jg + 1) * kBwdRows);
+  for (int j = jg * kBwdRows; j < j_end; ++j) {
+    const int oy0 = (U * j) / P, oy1 = min((U * j + U - 1) / P, OH - 1);
+    __syncthreads();                       // tab ready / previous row consumed
+    for (int ox = threadIdx.x; ox < OW; ox += 256) {
+      float s = 0.f;
+      for (int oy = oy0; oy <= oy1; ++oy) s = fmaf((float)box_weight(j, oy, U, P), __ldg(gp + (int64_t)oy * OW + ox), s);
+      g_row[ox] = s * inv;
+    }
+    __syncthreads();
+    float* dst = gx + (n * H + j) * W;
+    for (int c4 = threadIdx.x; c4 < W4; c4 += 256) {
+      float out[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = 4 * c4 + e;
+        const short2 t = tab[c];
+        float acc = 0.f;
+        for (int ox = t.x; ox <= t.y; ++ox) acc = fmaf((float)box_weight(c, ox, U, P), g_row[ox], acc);
+        out[e] = acc;
+      }
+      *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+  }
+}
+
 static int resample_dims(int H, int W, int U, int P, int* OH, int* OW) {
   *OH = (int)(((int64_t)H * U) / P);
   *OW = (int)(((int64_t)W * U) / P);
@@ -91,8 +179,14 @@ extern "C" int w2e_box_resample_fwd(const float* x, float* y, int64_t planes, in
   W2E_CHECK_ARG(resample_dims(H, W, up, pool, &OH, &OW), "box_resample_fwd: pooling window larger than the upsampled image");
   const int64_t total = planes * OH * OW;
   if (total == 0) return W2E_OK;
-  box_resample_fwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      x, y, total, H, W, OH, OW, up, pool);
+  const bool rows_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && W <= 8192 && planes * OH < (1ll << 31);
+  if (rows_ok) {   // coalesced row kernel (every configuration of the reference)
+    box_resample_fwd_rows_kernel<<<(unsigned)(planes * OH), 256, (size_t)W * sizeof(float), (cudaStream_t)stream>>>(
+        x, y, H, W, OH, OW, up, pool);
+  } else {         // any shape / alignment
+    box_resample_fwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        x, y, total, H, W, OH, OW, up, pool);
+  }
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
@@ -107,8 +201,14 @@ extern "C" int w2e_box_resample_bwd(const float* gy, float* gx, int64_t planes, 
   const int64_t total4 = planes * H * W4;
   if (total4 == 0) return W2E_OK;
   const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
-  box_resample_bwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total4, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      gy, gx, total4, H, W, W4, OH, OW, up, pool, vec);
+  const int64_t groups = ceil_div(H, kBwdRows);
+  if (vec && OW + W <= 12288 && planes * groups < (1ll << 31)) {
+    box_resample_bwd_rows_kernel<<<(unsigned)(planes * groups), 256, (size_t)(OW + W) * sizeof(float), (cudaStream_t)stream>>>(
+        gy, gx, H, W, OH, OW, up, pool);
+  } else {
+    box_resample_bwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total4, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        gy, gx, total4, H, W, W4, OH, OW, up, pool, vec);
+  }
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

@@ -16,16 +16,20 @@
 namespace w2e {
 
 // ------------------------------------------------------------------------------------------ cluster assignment
-// Sums of squared differences are accumulated in fp64 from fp32 (a-b)^2 terms (the reference's fp32 terms, summed
-// without the order-dependent rounding of an fp32 reduction), rounded to fp32 and compared with first-index ties.
-constexpr int kAssignKC = 8;        // clusters per pass (fp64 accumulators in registers)
+// Squared differences are fp32 (the reference's terms); they are summed in fp32 over groups of kAssignGroup
+// channels and the group sums are accumulated in fp64, so the total carries less rounding error than one fp32
+// ulp of the result -- any fp32 reduction order the reference's `.sum(-1)` may use lands within that.  The fp32
+// rounding of the total is compared with first-index ties.
+constexpr int kAssignKC = 8;        // clusters per pass (accumulators in registers)
 constexpr int kAssignThreads = 128;
+constexpr int kAssignGroup = 16;    // channels per fp32 partial sum
 
 __global__ void __launch_bounds__(kAssignThreads)
 cluster_assign_kernel(const float* __restrict__ feature, const float* __restrict__ centres, int* __restrict__ low,
                       int C, int h, int K, int pc) {
-  extern __shared__ float ctr_s[];   // [kAssignKC][D]
+  extern __shared__ __align__(16) float ctr_s[];   // [kAssignKC][Dp], Dp = D rounded up to 4 (16-byte rows)
   const int D = C + 2 * pc;
+  const int Dp = (D + 3) & ~3;
   const int b = blockIdx.y;
   const int hw = h * h;
   const int p = blockIdx.x * kAssignThreads + threadIdx.x;
@@ -35,43 +39,66 @@ cluster_assign_kernel(const float* __restrict__ feature, const float* __restrict
   const float xpos = __fdiv_rn((float)x * 2.f, (float)(h - 1)) - 1.f;
   const float ypos = __fdiv_rn((float)y * 2.f, (float)(h - 1)) - 1.f;
   const float* f = feature + (int64_t)b * C * hw + (live ? p : 0);
+  const int C4 = C & ~3;
   float best = 0.f;
   int best_k = -1;
   for (int k0 = 0; k0 < K; k0 += kAssignKC) {
     const int kc = min(kAssignKC, K - k0);
     __syncthreads();
-    for (int e = threadIdx.x; e < kc * D; e += kAssignThreads) ctr_s[e] = __ldg(centres + (int64_t)k0 * D + e);
+    for (int e = threadIdx.x; e < kAssignKC * Dp; e += kAssignThreads) {
+      const int k = e / Dp, m = e - k * Dp;
+      ctr_s[e] = (k < kc && m < D) ? __ldg(centres + (int64_t)(k0 + k) * D + m) : 0.f;   // unused clusters: zeros
+    }
     __syncthreads();
+    if (!live) continue;
     double acc[kAssignKC];
+    float part[kAssignKC];
 #pragma unroll
-    for (int k = 0; k < kAssignKC; ++k) acc[k] = 0.0;
-    if (live) {
-      for (int c = 0; c < C; ++c) {
-        const float v = __ldg(f + (int64_t)c * hw);
-#pragma unroll
-        for (int k = 0; k < kAssignKC; ++k) {
-          if (k < kc) {
-            const float d = v - ctr_s[k * D + c];
-            acc[k] += (double)(d * d);
-          }
-        }
-      }
-      for (int j = 0; j < 2 * pc; ++j) {
-        const float v = j < pc ? xpos : ypos;
-#pragma unroll
-        for (int k = 0; k < kAssignKC; ++k) {
-          if (k < kc) {
-            const float d = v - ctr_s[k * D + C + j];
-            acc[k] += (double)(d * d);
-          }
-        }
-      }
+    for (int k = 0; k < kAssignKC; ++k) { acc[k] = 0.0; part[k] = 0.f; }
+    for (int c = 0; c < C4; c += 4) {
+      const float v0 = __ldg(f + (int64_t)c * hw), v1 = __ldg(f + (int64_t)(c + 1) * hw);
+      const float v2 = __ldg(f + (int64_t)(c + 2) * hw), v3 = __ldg(f + (int64_t)(c + 3) * hw);
 #pragma unroll
       for (int k = 0; k < kAssignKC; ++k) {
-        if (k < kc) {
-          const float dist = (float)acc[k];
-          if (best_k < 0 || dist < best) { best = dist; best_k = k0 + k; }
-        }
+        const float4 q = *reinterpret_cast<const float4*>(ctr_s + k * Dp + c);
+        const float d0 = v0 - q.x, d1 = v1 - q.y, d2 = v2 - q.z, d3 = v3 - q.w;
+        part[k] = fmaf(d0, d0, part[k]);
+        part[k] = fmaf(d1, d1, part[k]);
+        part[k] = fmaf(d2, d2, part[k]);
+        part[k] = fmaf(d3, d3, part[k]);
+      }
+      if (((c + 4) & (kAssignGroup - 1)) == 0) {
+#pragma unroll
+        for (int k = 0; k < kAssignKC; ++k) { acc[k] += (double)part[k]; part[k] = 0.f; }
+      }
+    }
+    for (int c = C4; c < C; ++c) {   // channel tail (C % 4)
+      const float v = __ldg(f + (int64_t)c * hw);
+#pragma unroll
+      for (int k = 0; k < kAssignKC; ++k) {
+        const float d = v - ctr_s[k * Dp + c];
+        part[k] = fmaf(d, d, part[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kAssignKC; ++k) { acc[k] += (double)part[k]; part[k] = 0.f; }
+    for (int j = 0; j < 2 * pc; ++j) {
+      const float v = j < pc ? xpos : ypos;
+#pragma unroll
+      for (int k = 0; k < kAssignKC; ++k) {
+        const float d = v - ctr_s[k * Dp + C + j];
+        part[k] = fmaf(d, d, part[k]);
+      }
+      if (((j + 1) & (kAssignGroup - 1)) == 0) {
+#pragma unroll
+        for (int k = 0; k < kAssignKC; ++k) { acc[k] += (double)part[k]; part[k] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kAssignKC; ++k) {
+      if (k < kc) {
+        const float dist = (float)(acc[k] + (double)part[k]);
+        if (best_k < 0 || dist < best) { best = dist; best_k = k0 + k; }
       }
     }
   }
@@ -260,7 +287,7 @@ extern "C" int w2e_cluster_assign(const float* feature, const float* centres, in
                 "cluster_assign: bad shape (h >= 2, clusters > 0)");
   if (B == 0) return W2E_OK;
   const int D = C + 2 * pos_channels;
-  const size_t smem = (size_t)kAssignKC * D * sizeof(float);
+  const size_t smem = (size_t)kAssignKC * ((D + 3) & ~3) * sizeof(float);
   W2E_CHECK_ARG(smem <= 200 * 1024, "cluster_assign: feature dimension too large for the shared-memory centre tile");
   static bool configured = false;
   if (!configured) {
