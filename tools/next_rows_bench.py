@@ -67,7 +67,22 @@ def main():
         e.grad = None
         f, _, r, tv = region.region_attention(e, ids, k)
         ((f * head).sum() + r.sum() + tv).backward()
-    out["region_attention_fwd_bwd"] = {"ms": gpu_ms(fwd_bwd, args.iters)}
+    out["region_attention_fwd_bwd"] = {"ms": gpu_ms(fwd_bwd, args.iters), "note": "through autograd (host-bound)"}
+    # the backward kernel alone, through the C ABI
+    from where2edit_b200 import _native as N
+    f_, same_, _, _ = region.region_attention(each, ids, k)
+    stats_ = torch.empty(b, k, 2, device=dev)
+    parts_ = torch.empty(b, 2, device=dev)
+    losses_ = torch.empty(2, device=dev)
+    lib = N.load()
+    taps = region._taps()
+    lib.w2e_region_mask_fwd(N.ptr(each), N.ptr(ids), taps, N.ptr(f_), N.ptr(same_), N.ptr(stats_), N.ptr(parts_),
+                            N.ptr(losses_), b, h, k, 0.8, 0.7, N.stream_ptr())
+    g_each = torch.empty_like(each)
+    g_l = torch.ones(2, device=dev)
+    out["region_mask_bwd_kernel"] = {"ms": gpu_ms(lambda: lib.w2e_region_mask_bwd(
+        N.ptr(head), N.ptr(g_l), N.ptr(each), N.ptr(ids), N.ptr(same_), N.ptr(stats_), taps, N.ptr(g_each), b, h, k, 0.7,
+        N.stream_ptr()), args.iters)}
 
     # the reference's formulation on the same GPU (utils.py:244-263, run_attention.py:775-794, 852-884)
     import torchvision
@@ -126,6 +141,11 @@ def main():
     ms2 = gpu_ms(rs_bwd, args.iters)
     out["clip_resample_fwd_bwd"] = {"ms": ms2, "algorithmic_bytes": 2 * byts, "gbs": 2 * byts / ms2 / 1e6,
                                     "frac_hbm": 2 * byts / ms2 / 1e6 / peak}
+    gx = torch.empty(bb, 3, 1024, 1024, device=dev)
+    ms3 = gpu_ms(lambda: lib.w2e_box_resample_bwd(N.ptr(gy), N.ptr(gx), bb * 3, 1024, 1024, 7, 32, N.stream_ptr()), args.iters)
+    out["clip_resample_bwd_kernel"] = {"ms": ms3, "algorithmic_bytes": byts, "gbs": byts / ms3 / 1e6,
+                                       "frac_hbm": byts / ms3 / 1e6 / peak}
+    out["clip_resample_fwd_bwd"]["note"] = "through autograd (host-bound)"
     small = img[:4].detach()
     f = torch.nn.functional
     out["clip_resample_fwd"]["torch_formulation_ms_per_32"] = 8 * gpu_ms(
