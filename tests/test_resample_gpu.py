@@ -36,7 +36,8 @@ def test_clip_resample_matches_reference_golden(golden_resample, name):
 
 
 @pytest.mark.parametrize("shape,scale,pool", [((1, 1, 5, 7), 7, 3), ((2, 3, 16, 16), 3, 8), ((1, 2, 9, 9), 1, 2),
-                                              ((1, 1, 4, 4), 9, 2), ((0, 3, 8, 8), 7, 2), ((1, 1, 3, 50), 2, 6)])
+                                              ((1, 1, 4, 4), 9, 2), ((0, 3, 8, 8), 7, 2), ((1, 1, 3, 50), 2, 6), ((1, 2, 12, 20), 7, 9),
+                                              ((1, 3, 256, 256), 7, 8)])
 def test_clip_resample_matches_oracle(shape, scale, pool):
     """Windows wider and narrower than a source pixel, scale 1 (pure pooling), ragged remainders, empty batch."""
     rng = np.random.default_rng(sum(shape) + scale)

@@ -117,46 +117,47 @@ box_resample_fwd_rows_kernel(const float* __restrict__ x, float* __restrict__ y,
   }
 }
 
-// Backward: one CTA per (plane, group of kBwdRows source rows).  The window range of every source column is
-// tabulated once per CTA; per source row the <= 2 contributing gradient rows are reduced into shared memory,
-// then every thread writes 4 consecutive source columns with one 16-byte store.
+// Backward (U <= P: a source pixel's U upsampled copies span at most two pooling windows per axis): one CTA per
+// (plane, group of kBwdRows source rows); a thread owns 4 consecutive source columns, whose two window indices
+// and weights are computed once, then walks the rows: <= 2 x 2 gradient values per element straight from L1/L2
+// (the gradient image is 19 MB), one 16-byte store per row.  No shared memory, no barriers.
 constexpr int kBwdRows = 16;
 
 __global__ void __launch_bounds__(256)
 box_resample_bwd_rows_kernel(const float* __restrict__ gy, float* __restrict__ gx, int H, int W, int OH, int OW, int U, int P) {
-  extern __shared__ float bs[];            // g_row[OW] then short2 tab[W]
-  float* g_row = bs;
-  short2* tab = reinterpret_cast<short2*>(bs + OW);
   const int groups = (H + kBwdRows - 1) / kBwdRows;
   const int jg = blockIdx.x % groups;
   const int64_t n = blockIdx.x / groups;
   const float* gp = gy + n * OH * OW;
-  for (int c = threadIdx.x; c < W; c += 256)
-    tab[c] = make_short2((short)((U * c) / P), (short)min((U * c + U - 1) / P, OW - 1));
   const float inv = 1.f / ((float)P * (float)P);
   const int W4 = W >> 2;
   const int j_end = min(H, (jg + 1) * kBwdRows);
-  for (int j = jg * kBwdRows; j < j_end; ++j) {
-    const int oy0 = (U * j) / P, oy1 = min((U * j + U - 1) / P, OH - 1);
-    __syncthreads();                       // tab ready / previous row consumed
-    for (int ox = threadIdx.x; ox < OW; ox += 256) {
-      float s = 0.f;
-      for (int oy = oy0; oy <= oy1; ++oy) s = fmaf((float)box_weight(j, oy, U, P), __ldg(gp + (int64_t)oy * OW + ox), s);
-      g_row[ox] = s * inv;
+  for (int c4 = threadIdx.x; c4 < W4; c4 += 256) {
+    int xa[4], xb[4];
+    float wa[4], wb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * c4 + e;
+      const int o0 = (U * c) / P, o1 = (U * c + U - 1) / P;
+      wa[e] = o0 < OW ? (float)box_weight(c, o0, U, P) * inv : 0.f;
+      wb[e] = (o1 != o0 && o1 < OW) ? (float)box_weight(c, o1, U, P) * inv : 0.f;
+      xa[e] = min(o0, OW - 1);
+      xb[e] = min(o1, OW - 1);
     }
-    __syncthreads();
-    float* dst = gx + (n * H + j) * W;
-    for (int c4 = threadIdx.x; c4 < W4; c4 += 256) {
+    for (int j = jg * kBwdRows; j < j_end; ++j) {
+      const int o0 = (U * j) / P, o1 = (U * j + U - 1) / P;
+      const float wy0 = o0 < OH ? (float)box_weight(j, o0, U, P) : 0.f;
+      const float wy1 = (o1 != o0 && o1 < OH) ? (float)box_weight(j, o1, U, P) : 0.f;
+      const float* g0 = gp + (int64_t)min(o0, OH - 1) * OW;
       float out[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = 4 * c4 + e;
-        const short2 t = tab[c];
-        float acc = 0.f;
-        for (int ox = t.x; ox <= t.y; ++ox) acc = fmaf((float)box_weight(c, ox, U, P), g_row[ox], acc);
-        out[e] = acc;
+      for (int e = 0; e < 4; ++e) out[e] = wy0 * fmaf(wa[e], __ldg(g0 + xa[e]), wb[e] * __ldg(g0 + xb[e]));
+      if (wy1 != 0.f) {   // uniform over the CTA: this source row straddles two pooling windows
+        const float* g1 = gp + (int64_t)o1 * OW;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = fmaf(wy1, fmaf(wa[e], __ldg(g1 + xa[e]), wb[e] * __ldg(g1 + xb[e])), out[e]);
       }
-      *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(out[0], out[1], out[2], out[3]);
+      *reinterpret_cast<float4*>(gx + (n * H + j) * W + 4 * c4) = make_float4(out[0], out[1], out[2], out[3]);
     }
   }
 }
@@ -202,9 +203,8 @@ extern "C" int w2e_box_resample_bwd(const float* gy, float* gx, int64_t planes, 
   if (total4 == 0) return W2E_OK;
   const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
   const int64_t groups = ceil_div(H, kBwdRows);
-  if (vec && OW + W <= 12288 && planes * groups < (1ll << 31)) {
-    box_resample_bwd_rows_kernel<<<(unsigned)(planes * groups), 256, (size_t)(OW + W) * sizeof(float), (cudaStream_t)stream>>>(
-        gy, gx, H, W, OH, OW, up, pool);
+  if (vec && up <= pool && planes * groups < (1ll << 31)) {
+    box_resample_bwd_rows_kernel<<<(unsigned)(planes * groups), 256, 0, (cudaStream_t)stream>>>(gy, gx, H, W, OH, OW, up, pool);
   } else {
     box_resample_bwd_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total4, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
         gy, gx, total4, H, W, W4, OH, OW, up, pool, vec);
