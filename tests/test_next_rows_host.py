@@ -1,0 +1,67 @@
+"""Host-side logic of the SURVEY.md section 8f rows that needs no GPU: blur taps, module hyper-parameters,
+state-dict layout, and the loud failure on CPU tensors (there is no CPU path)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import mapper_oracle as mo  # noqa: E402
+from oracle import region_oracle as ro  # noqa: E402
+from where2edit_b200 import mappers, region, resample  # noqa: E402
+
+
+def test_gaussian_taps_equal_torchvision_and_oracle():
+    taps = np.array(region.gaussian_taps(), np.float32).reshape(5, 5)
+    assert np.array_equal(taps, ro.gaussian_kernel2d())
+    tvf = pytest.importorskip("torchvision.transforms._functional_tensor")
+    k2 = tvf._get_gaussian_kernel2d([5, 5], [1.1, 1.1], dtype=torch.float32, device=torch.device("cpu"))
+    np.testing.assert_allclose(taps, k2.numpy(), rtol=0, atol=1e-8)
+
+
+def test_gaussian_blur_oracle_matches_torchvision():
+    tv = pytest.importorskip("torchvision.transforms.functional")
+    x = torch.rand(2, 1, 9, 9)
+    ref = tv.gaussian_blur(x, 5).numpy()[:, 0]
+    np.testing.assert_allclose(ro.gaussian_blur(x.numpy()[:, 0]), ref, rtol=0, atol=1e-6)
+
+
+def test_no_cpu_path_for_the_next_rows():
+    each, ids = torch.rand(1, 8, 8), torch.zeros(1, 8, 8, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        region.region_attention(each, ids, 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        region.assign_clusters(torch.randn(1, 16, 4, 4), torch.randn(2, 18), 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        resample.clip_resample(torch.randn(1, 3, 32, 32), 7, 1)
+
+
+def test_clip_resample_module_mirrors_cliploss_hyperparameters():
+    m = resample.ClipResample(1024)
+    assert (m.scale_factor, m.kernel_size) == (7, 32)          # criteria/clip_loss.py:10-11
+    assert resample.ClipResample(256).kernel_size == 8
+
+
+def test_levels_mapper_state_dict_layout():
+    opts = types.SimpleNamespace(no_coarse_mapper=False, no_medium_mapper=False, no_fine_mapper=False)
+    sd = mappers.LevelsMapper(opts).state_dict()
+    want = mo.mapper_state()
+    assert sorted(sd) == sorted(want) and all(tuple(sd[k].shape) == want[k].shape for k in want)
+    opts.no_medium_mapper = True
+    assert not any(k.startswith("medium_mapping") for k in mappers.LevelsMapper(opts).state_dict())
+    ref_root = os.environ.get("W2E_REFERENCE", "/root/reference")
+    if os.path.isdir(ref_root):     # build container only: the reference's own class has the same keys
+        sys.path.insert(0, ref_root)
+        try:
+            from mapper.latent_mappers import LevelsMapper as RefLevels
+        finally:
+            sys.path.remove(ref_root)
+        opts.no_medium_mapper = False
+        ref_sd = RefLevels(opts).state_dict()
+        assert sorted(ref_sd) == sorted(sd) and all(ref_sd[k].shape == sd[k].shape for k in sd)
