@@ -34,6 +34,10 @@ def main():
         head = torch.randn_like(y)
         (y * head).sum().backward()
         out[f"{name}/y"], out[f"{name}/head"], out[f"{name}/gx"] = y.detach().numpy(), head.numpy(), xi.grad.numpy()
+        if name == "all":   # the mapper is what the edit loop trains: pin its parameter gradients (subsampled)
+            for pn, p in m.named_parameters():
+                out[f"{name}/grad/{pn}"] = p.grad.reshape(-1)[::997].numpy().copy()
+                out[f"{name}/gradsum/{pn}"] = np.array([p.grad.double().sum().item(), p.grad.double().abs().sum().item()])
         print(name, tuple(y.shape), float(y.abs().max()), float(xi.grad.abs().max()))
     path = os.path.join(ROOT, "tests", "golden", "mapper.npz")
     np.savez_compressed(path, **out)

@@ -37,6 +37,14 @@ def test_levels_mapper_matches_reference_golden(name, no_fine):
     (y * torch.from_numpy(g[f"{name}/head"]).to(DEV)).sum().backward()
     gs = np.abs(g[f"{name}/gx"]).max()
     np.testing.assert_allclose(x.grad.cpu().numpy() / gs, g[f"{name}/gx"] / gs, rtol=0, atol=2e-5)
+    if name == "all":   # parameter gradients (the mapper is trained by the edit loop): subsample + sums
+        for pn, p in m.named_parameters():
+            want = g[f"{name}/grad/{pn}"]
+            got = p.grad.reshape(-1)[::997].cpu().numpy()
+            sc = max(float(np.abs(want).max()), 1e-12)
+            np.testing.assert_allclose(got / sc, want / sc, rtol=0, atol=5e-5, err_msg=pn)
+            sums = g[f"{name}/gradsum/{pn}"]
+            assert abs(float(p.grad.double().abs().sum()) - sums[1]) <= 1e-4 * sums[1], pn
 
 
 def test_levels_mapper_matches_oracle_on_a_ragged_batch():
