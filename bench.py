@@ -393,6 +393,19 @@ def main():
                "sample": f"{args.cpu_sample} images of the same {args.size}^2 generator forward in one batch "
                          f"({dt:.1f} s), fp32 torch CPU ops via the oracle port, after a 1-image warm-up"}
 
+    # ---------------- the callers either side of the path, outside the timed region
+    next_rows = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and os.environ.get("W2E_BENCH_NEXT_ROWS", "1") == "1":
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("next_rows_bench", os.path.join(ROOT, "tools", "next_rows_bench.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            torch.cuda.empty_cache()
+            next_rows = mod.measure(iters=10)
+        except Exception as exc:   # auxiliary numbers must never cost the headline line
+            next_rows = {"error": repr(exc)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
@@ -406,6 +419,7 @@ def main():
             "modconv_tflops_per_step_algorithmic": MODCONV_GFLOP_PER_IMAGE * B / 1e3 if args.size == 1024 else None,
             "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in kinds.items()},
             "cpu_baseline": cpu,
+            "next_rows": next_rows,
         }
         print(json.dumps(line))
     if dist is not None:

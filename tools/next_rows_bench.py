@@ -39,11 +39,10 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=20)
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+def measure(iters=20):
+    """All timings as one dict (also called by bench.py, outside its timed region)."""
+    args = argparse.Namespace(iters=iters)
+    dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(0)
     peak, peak_src = hbm_peak()
     out = {"hbm_peak_gbs": peak, "peak_source": peak_src}
@@ -162,7 +161,13 @@ def main():
     t0 = time.time()
     rso.clip_resample(x1, 7, 32)
     out["clip_resample_fwd"]["cpu_oracle_ms_per_32"] = (time.time() - t0) * 1e3 * 32
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    print(json.dumps(measure(ap.parse_args().iters)))
 
 
 if __name__ == "__main__":
