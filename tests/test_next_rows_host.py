@@ -65,3 +65,25 @@ def test_levels_mapper_state_dict_layout():
         opts.no_medium_mapper = False
         ref_sd = RefLevels(opts).state_dict()
         assert sorted(ref_sd) == sorted(sd) and all(ref_sd[k].shape == sd[k].shape for k in sd)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Argument validation happens before any CUDA call: null pointers / bad shapes return an error code and
+    set w2e_last_error_string (no kernel is enqueued, so this runs on a CPU-only box)."""
+    from where2edit_b200 import _native as N
+    lib = N.load()
+    one = 0x1000   # any non-null address: validation fails on the shapes before it could be dereferenced
+    cases = [
+        (lib.w2e_box_resample_fwd(None, None, 1, 8, 8, 7, 2, None), "box_resample_fwd"),
+        (lib.w2e_box_resample_fwd(one, one, 1, 8, 8, 0, 2, None), "box_resample_fwd"),       # scale 0
+        (lib.w2e_box_resample_bwd(one, one, 1, 2, 2, 1, 9, None), "box_resample_bwd"),       # window larger than the image
+        (lib.w2e_cluster_assign(None, None, None, None, 1, 16, 4, 2, 1, 4, None), "cluster_assign"),
+        (lib.w2e_cluster_assign(one, one, one, one, 1, 16, 1, 2, 1, 4, None), "cluster_assign"),   # h = 1
+        (lib.w2e_region_mask_fwd(None, None, None, None, None, None, None, None, 1, 8, 2, 0.8, 0.7, None), "region_mask_fwd"),
+        (lib.w2e_region_mask_fwd(one, one, one, one, one, one, one, one, 1, 2, 2, 0.8, 0.7, None), "region_mask_fwd"),  # S < 3
+        (lib.w2e_region_mask_bwd(None, None, None, None, None, None, None, None, 1, 8, 2, 0.7, None), "region_mask_bwd"),
+    ]
+    for code, what in cases:
+        assert code != 0, what
+    assert "region_mask_bwd" in N.last_error()
+    assert lib.w2e_box_resample_fwd(one, one, 0, 8, 8, 7, 2, None) == 0      # empty batch: nothing to do, no launch
