@@ -24,6 +24,7 @@ to activations, styles / W+ latents and the attention mask, not to generator wei
 """
 import math
 import random
+import warnings
 
 import torch
 from torch import nn
@@ -153,6 +154,8 @@ class ModulatedConv2d(nn.Module):
     """models/stylegan2/model.py:179-276.  forward(input, style, input_is_stylespace=False) ->
     (out [B,Cout,H',W'], style [B,1,Cin,1,1])."""
 
+    _warned = False
+
     def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
                  downsample=False, blur_kernel=[1, 3, 3, 1]):
         super().__init__()
@@ -202,6 +205,13 @@ class ModulatedConv2d(nn.Module):
             raise NotImplementedError(
                 "ModulatedConv2d(downsample=True) is never reached by the synthesis path (only the "
                 "discriminator-era code uses it) and is out of scope of where2edit_b200")
+        if self.training and self.weight.requires_grad and torch.is_grad_enabled() and not ModulatedConv2d._warned:
+            ModulatedConv2d._warned = True   # once per process
+            warnings.warn(
+                "where2edit_b200.ModulatedConv2d does not compute gradients for its convolution weight (every "
+                "caller of the synthesis path keeps the generator frozen / in eval mode): this module is in "
+                "training mode with a trainable weight, whose .grad will stay None. Gradients to the input, the "
+                "style and the modulation layer are computed.", RuntimeWarning, stacklevel=2)
         batch = input.shape[0]
         s = self.styles(style, input_is_stylespace)
         pw = self.packed()
