@@ -13,6 +13,16 @@ from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d, upfirdn2d_native
 __version__ = "0.1.0"
 
 
+def enable_weight_gradients(module, enabled=True):
+    """Turn the (opt-in) convolution-weight gradient on for every ModulatedConv2d under `module` -- for networks
+    that TRAIN StyledConv weights (ToRGB runs a fused kernel and is not covered), e.g. the cluster-style mapper's attention heads
+    (attention/run_attention.py:725-735).  The generator stays frozen in every caller and does not need it."""
+    for m in module.modules():
+        if isinstance(m, ModulatedConv2d):
+            m.weight_grad = bool(enabled)
+    return module
+
+
 def install_as_reference():
     """Make `from models.stylegan2.op import upfirdn2d`, `from models.stylegan2.model import Generator`,
     `from attention_model import Generator` and `from attention.attention_model import ...` resolve to
@@ -48,4 +58,5 @@ def install_as_reference():
 
 __all__ = ["Generator", "ModulatedConv2d", "StyledConv", "ToRGB", "EqualLinear", "EqualConv2d", "PixelNorm",
            "Blur", "Upsample", "Downsample", "NoiseInjection", "ConstantInput", "ScaledLeakyReLU", "make_kernel",
-           "FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "upfirdn2d_native", "install_as_reference"]
+           "FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "upfirdn2d_native", "install_as_reference",
+           "enable_weight_gradients"]

@@ -283,6 +283,67 @@ def modulated_conv2d(x, s, d, pw, k, upsample):
 
 
 # --------------------------------------------------------------------------------------------
+# convolution-weight gradient (opt-in: trainable ModulatedConv2d outside the frozen generator)
+# --------------------------------------------------------------------------------------------
+def modconv_weight_grad(x, s, d, y, gy, weight, scale, k, upsample):
+    """dL/dweight [1,Cout,Cin,k,k] of  y = modulated_conv2d(x, s, d, weight)  (models/stylegan2/model.py:240-274)
+    for gy = dL/dy, y being the convolution output BEFORE the up path's Blur.  With W~ = scale * weight:
+
+        y[b,o] = d[b,o] * conv(x[b] * s[b], W~)[o],      d[b,o] = rsqrt(sum_{c,t} (W~[o,c,t] s[b,c])^2 + eps)
+
+      direct term   conv-weight-gradient of (x*s) against (gy*d), summed over the batch: ONE library
+                    (cuDNN) weight-gradient call -- the reference's per-sample [B*Cout,Cin,k,k] weights never exist;
+                    for the transposed x2 convolution the roles of input and output swap (stride-2 correlation of
+                    gy with x*s);
+      demod term    dL/dd[b,o] = sum_p gy*y / d   and   dd/dW~ = -d^3 s^2 W~   ->   -W~ * ((dL/dd * d^3)^T @ s^2).
+
+    Plain torch ops (library GEMM / convolution): used only for modules whose weight is being trained -- the
+    cluster-style mapper's 1x1 StyledConv attention heads (attention/run_attention.py:725-735); the synthesis
+    path keeps the generator frozen and never calls it."""
+    cout, cin = weight.shape[1], weight.shape[2]
+    dt = torch.float64 if x.dtype == torch.float64 else torch.float32   # fp32 on the GPU path; fp64 for the CPU check
+    w = weight[0].to(dt) * scale
+    s = s.to(dt)
+    xm = x.to(dt) * s[:, :, None, None]
+    gy = gy.to(dt)
+    gyd = gy if d is None else gy * d[:, :, None, None]
+    if upsample:
+        gw = torch.nn.grad.conv2d_weight(gyd, (cin, cout, k, k), xm, stride=2).transpose(0, 1)
+    else:
+        gw = torch.nn.grad.conv2d_weight(xm, (cout, cin, k, k), gyd, padding=k // 2)
+    if d is not None:
+        gd = (gy * y).sum((2, 3)) / d
+        gw = gw - w * ((gd * d.pow(3)).t() @ s.square())[:, :, None, None]
+    return (gw * scale).unsqueeze(0).to(weight.dtype)
+
+
+class _WeightGradTap(torch.autograd.Function):
+    """Identity on the convolution output that hands `modconv_weight_grad` to autograd as the gradient of
+    `weight` (the convolution kernels themselves take the weight as a packed, detached constant)."""
+
+    @staticmethod
+    def forward(ctx, y, weight, x, s, d, scale, k, upsample):
+        ctx.save_for_backward(y, weight, x, s, d if d is not None else y.new_zeros(0))
+        ctx.cfg = (scale, k, upsample, d is not None)
+        return y.view_as(y)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        y, weight, x, s, d = ctx.saved_tensors
+        scale, k, upsample, has_d = ctx.cfg
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = modconv_weight_grad(x, s, d if has_d else None, y, gy.contiguous(), weight, scale, k, upsample)
+        return gy, gw, None, None, None, None, None, None
+
+
+def weight_grad_tap(y, weight, x, s, d, scale, k, upsample):
+    return _WeightGradTap.apply(y, weight, x.detach(), s.detach(), None if d is None else d.detach(), float(scale),
+                                int(k), bool(upsample))
+
+
+# --------------------------------------------------------------------------------------------
 # noise + bias + activation
 # --------------------------------------------------------------------------------------------
 def noise_bias_act(x, bias, noise, noise_w, slope, scale):

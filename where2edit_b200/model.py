@@ -160,6 +160,7 @@ class ModulatedConv2d(nn.Module):
                  downsample=False, blur_kernel=[1, 3, 3, 1]):
         super().__init__()
         self.eps = 1e-8
+        self.weight_grad = False   # opt-in gradient for self.weight (see forward)
         self.kernel_size = kernel_size
         self.in_channel = in_channel
         self.out_channel = out_channel
@@ -205,18 +206,23 @@ class ModulatedConv2d(nn.Module):
             raise NotImplementedError(
                 "ModulatedConv2d(downsample=True) is never reached by the synthesis path (only the "
                 "discriminator-era code uses it) and is out of scope of where2edit_b200")
-        if self.training and self.weight.requires_grad and torch.is_grad_enabled() and not ModulatedConv2d._warned:
+        want_wgrad = self.weight_grad and self.weight.requires_grad and torch.is_grad_enabled()
+        if (self.training and self.weight.requires_grad and torch.is_grad_enabled() and not self.weight_grad
+                and not ModulatedConv2d._warned):
             ModulatedConv2d._warned = True   # once per process
             warnings.warn(
                 "where2edit_b200.ModulatedConv2d does not compute gradients for its convolution weight (every "
                 "caller of the synthesis path keeps the generator frozen / in eval mode): this module is in "
-                "training mode with a trainable weight, whose .grad will stay None. Gradients to the input, the "
-                "style and the modulation layer are computed.", RuntimeWarning, stacklevel=2)
+                "training mode with a trainable weight, whose .grad will stay None (set `module.weight_grad = True` "
+                "or call where2edit_b200.enable_weight_gradients(model) to have it computed). Gradients to the "
+                "input, the style and the modulation layer are always computed.", RuntimeWarning, stacklevel=2)
         batch = input.shape[0]
         s = self.styles(style, input_is_stylespace)
         pw = self.packed()
         d = K.demod_coefficients(s, pw.wsq) if self.demodulate else None
         out = K.modulated_conv2d(input, s, d, pw, self.kernel_size, self.upsample)
+        if want_wgrad:   # opt-in: trainable convolution weight (library weight-gradient, functional.modconv_weight_grad)
+            out = K.weight_grad_tap(out, self.weight, input, s, d, self.scale, self.kernel_size, self.upsample)
         if self.upsample:
             out = self.blur(out)
         return out, s.reshape(batch, 1, self.in_channel, 1, 1)
@@ -261,6 +267,10 @@ class StyledConv(nn.Module):
 
     def forward(self, input, style, noise=None, input_is_stylespace=False):
         out, style = self.conv(input, style, input_is_stylespace=input_is_stylespace)
+        if self.conv.weight_grad and torch.is_grad_enabled():
+            # trainable StyledConv (opt-in): module-by-module like model.py:337-339, so that noise.weight and
+            # activate.bias receive gradients too (the fused epilogue treats them as constants)
+            return self.activate(self.noise(out, noise=noise)), style
         if noise is None:  # model.py:286-288: fresh per-sample noise
             noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
         out = K.noise_bias_act(out, self.activate.bias, noise, self.noise.weight,
