@@ -42,7 +42,7 @@ def test_trainable_styled_conv_parameter_gradients(cin, cout, k, upsample, style
     (out_o * head).sum().backward()
 
     out, _ = m(x.to(DEV), style.to(DEV), noise=noise.to(DEV), input_is_stylespace=stylespace)
-    c = float(out_o.abs().max())
+    c = float(out_o.detach().abs().max())
     assert float((out.detach().cpu() - out_o.detach()).abs().max()) <= 1e-4 * max(c, 1.0)
     (out * head.to(DEV)).sum().backward()
     checked = 0
