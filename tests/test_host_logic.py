@@ -4,6 +4,7 @@ logic agrees with the oracle.  No GPU compute here."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -136,3 +137,23 @@ def test_shared_weight_identity_against_oracle():
         if up:
             y = orc.upfirdn2d_ref(y, blur, pad=(1, 1))
         assert (y - ref).abs().max().item() < 1e-12
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: one JSON line with the
+    contract's keys, impl = reference, the oracle port as cpu_baseline and an e2e block repeating the value."""
+    import json
+    import subprocess
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "32", "--batch", "2",
+                        "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["unit"] == "images/s" and j["value"] > 0 and j["warmup"] >= 3
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and "model" not in j["config"]
