@@ -341,6 +341,176 @@ blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_con
   }
 }
 
+// ---- blur v2 (opt-in: W2E_BLUR_V2=1; NOT yet measured on hardware) -----------------------------------------
+// ncu on the 1024^2 launch of blur_act_nhwc_kernel: issue-bound (69 % issue utilisation, DRAM 59 %), ~2 500
+// instructions per thread of which ~40 % are integer / predicate overhead: shared-memory addresses built from
+// the run-time tile shape, per-store edge predicates, null checks of the two outputs.  v2 keeps the tile, the
+// thread mapping and the arithmetic order of v1 (so results are bit-identical) and makes the channel tile and
+// the output set template parameters (shared-memory offsets become immediates) with a predicate-free body for
+// tiles that lie fully inside the image.
+template <int CT, bool HAS_OUT, bool HAS_MOD, bool INTERIOR>
+__device__ __forceinline__ void blur_v2_body(const uint8_t* __restrict__ tile, const float* __restrict__ nz_row,
+                                             bool has_noise, const uint64_t (&bias2)[4], const uint64_t (&nsc2)[4],
+                                             const uint64_t (&fv)[4], const uint64_t (&fh)[4], uint64_t slope2,
+                                             __nv_bfloat16* o_ptr, __nv_bfloat16* m_ptr, int64_t row_stride, int chan_stride,
+                                             int rows_ok, bool px_ok0, bool px_ok1) {
+  constexpr int TX = 1024 / CT, SW = TX + 3, PIX = CT * 2, ROW = SW * PIX;
+  uint64_t win[4][kBlurPx][4];
+#pragma unroll
+  for (int t = 0; t < kBlurRows + 3; ++t) {
+    const int u = t & 3;
+    uint64_t f[kBlurPx + 3][4];
+#pragma unroll
+    for (int k = 0; k < kBlurPx + 3; ++k) {
+      const uint4 w = *reinterpret_cast<const uint4*>(tile + t * ROW + k * PIX);
+      f[k][0] = pack2u(w.x << 16, w.x & 0xffff0000u);
+      f[k][1] = pack2u(w.y << 16, w.y & 0xffff0000u);
+      f[k][2] = pack2u(w.z << 16, w.z & 0xffff0000u);
+      f[k][3] = pack2u(w.w << 16, w.w & 0xffff0000u);
+    }
+#pragma unroll
+    for (int px = 0; px < kBlurPx; ++px)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        win[u][px][e] = fma2(fh[3], f[px + 3][e], fma2(fh[2], f[px + 2][e], fma2(fh[1], f[px + 1][e], mul2(fh[0], f[px][e]))));
+    if (t >= 3) {
+      const int r = t - 3;
+      if (INTERIOR || r < rows_ok) {
+#pragma unroll
+        for (int px = 0; px < kBlurPx; ++px) {
+          if (INTERIOR || (px == 0 ? px_ok0 : px_ok1)) {
+            const float nz = has_noise ? nz_row[r * 128 + px] : 0.f;
+            const uint64_t nz2 = pack2(nz, nz);
+            uint32_t po[4], pm[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint64_t a = fma2(fv[3], win[u][px][e],
+                                      fma2(fv[2], win[(u + 3) & 3][px][e],
+                                           fma2(fv[1], win[(u + 2) & 3][px][e],
+                                                fma2(fv[0], win[(u + 1) & 3][px][e], add2(bias2[e], nz2)))));
+              const uint64_t a_s = mul2(a, slope2);
+              float x0, x1, y0, y1;
+              unpack2(a, x0, x1);
+              unpack2(a_s, y0, y1);
+              x0 = fmaxf(x0, y0);
+              x1 = fmaxf(x1, y1);
+              if (HAS_OUT) po[e] = cvt_bf16x2(x0, x1);
+              if (HAS_MOD) {
+                float m0, m1;
+                unpack2(mul2(pack2(x0, x1), nsc2[e]), m0, m1);
+                pm[e] = cvt_bf16x2(m0, m1);
+              }
+            }
+            if (HAS_OUT) *reinterpret_cast<uint4*>(o_ptr + r * row_stride + px * chan_stride) = make_uint4(po[0], po[1], po[2], po[3]);
+            if (HAS_MOD) *reinterpret_cast<uint4*>(m_ptr + r * row_stride + px * chan_stride) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int CT, bool HAS_OUT, bool HAS_MOD>
+__global__ void __launch_bounds__(128, 4)
+blur_act_nhwc_v2_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ BlurParams P,
+                        const __grid_constant__ BlurTile T) {
+  constexpr int TX = 1024 / CT, SW = TX + 3, PIX = CT * 2, CG = CT / 8, XB = TX / kBlurPx;
+  static_assert(CG * XB * kBlurRG == 128, "128 threads = 2 row groups x column pairs x channel groups");
+  extern __shared__ __align__(128) uint8_t blur_v2_smem[];
+  __shared__ uint64_t bar;
+  __shared__ float s_noise[kBlurTY][128];
+  const int tid = threadIdx.x;
+  int tile = blockIdx.x;
+  const int tcx = tile % T.tiles_c; tile /= T.tiles_c;
+  const int tx_i = tile % T.tiles_x; tile /= T.tiles_x;
+  const int ty_i = tile % T.tiles_y;
+  const int b = tile / T.tiles_y;
+  const int ox_t = tx_i * TX, oy_t = ty_i * kBlurTY, c_t = tcx * CT;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&bar, (uint32_t)((kBlurTY + 3) * SW * PIX));
+    tma_load_4d(blur_v2_smem, &map_z, &bar, c_t, ox_t - P.px0, oy_t - P.py0, b);
+  }
+  const bool lrelu = P.act == W2E_ACT_LRELU;
+  const float gain = lrelu ? 1.41421356237309515f : 1.f;
+  if (P.noise) {
+    const float nw = __ldg(P.noise_w) * gain;
+    const float* noise = P.noise + (P.noise_per_sample ? (int64_t)b * P.H * P.W : 0);
+    for (int e = tid; e < kBlurTY * TX; e += 128) {
+      const int yy = e / TX, xx = e % TX;
+      const int oy = oy_t + yy, ox = ox_t + xx;
+      s_noise[yy][xx] = (oy < P.H && ox < P.W) ? nw * __ldg(noise + (int64_t)oy * P.W + ox) : 0.f;
+    }
+  }
+  const int g = tid % CG;
+  const int xb = (tid / CG) % XB;
+  const int rg = tid / (CG * XB);
+  const int c0 = c_t + g * 8;
+  const int ox0 = ox_t + xb * kBlurPx;
+  const int oy0 = oy_t + rg * kBlurRows;
+  uint64_t bias2[4], nsc2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float b0 = (P.bias ? __ldg(P.bias + c0 + 2 * e) : 0.f) * gain, b1 = (P.bias ? __ldg(P.bias + c0 + 2 * e + 1) : 0.f) * gain;
+    bias2[e] = pack2(b0, b1);
+    const float n0 = HAS_MOD ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + 2 * e) : 1.f;
+    const float n1 = HAS_MOD ? __ldg(P.next_scale + (int64_t)b * P.C + c0 + 2 * e + 1) : 1.f;
+    nsc2[e] = pack2(n0, n1);
+  }
+  uint64_t fv[4], fh[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    fv[i] = pack2(P.fv[i] * gain, P.fv[i] * gain);
+    fh[i] = pack2(P.fh[i], P.fh[i]);
+  }
+  const float slope = lrelu ? 0.2f : 1.f;
+  const uint64_t slope2 = pack2(slope, slope);
+  const int64_t o_first = (((int64_t)b * P.H + oy0) * P.W + ox0) * P.C + c0;
+  __nv_bfloat16* o_ptr = HAS_OUT ? P.out + o_first : nullptr;
+  __nv_bfloat16* m_ptr = HAS_MOD ? P.out_mod + o_first : nullptr;
+  const int64_t row_stride = (int64_t)P.W * P.C;
+  const int rows_ok = min(kBlurRows, P.H - oy0);
+  const bool px_ok0 = ox0 < P.W, px_ok1 = ox0 + 1 < P.W;
+  const bool interior = (oy_t + kBlurTY <= P.H) && (ox_t + TX <= P.W);   // uniform over the CTA
+  __syncthreads();
+  {
+    uint32_t spin = 0;
+    while (!mbar_try_wait(&bar, 0))
+      if (++spin > (1u << 26)) __trap();
+  }
+  const uint8_t* tile_ptr = blur_v2_smem + ((rg * kBlurRows) * SW + xb * kBlurPx) * PIX + g * 16;
+  const float* nz_row = &s_noise[rg * kBlurRows][xb * kBlurPx];
+  const bool has_noise = P.noise != nullptr;
+  if (interior)
+    blur_v2_body<CT, HAS_OUT, HAS_MOD, true>(tile_ptr, nz_row, has_noise, bias2, nsc2, fv, fh, slope2, o_ptr, m_ptr, row_stride,
+                                             P.C, rows_ok, px_ok0, px_ok1);
+  else
+    blur_v2_body<CT, HAS_OUT, HAS_MOD, false>(tile_ptr, nz_row, has_noise, bias2, nsc2, fv, fh, slope2, o_ptr, m_ptr, row_stride,
+                                              P.C, rows_ok, px_ok0, px_ok1);
+}
+
+template <int CT>
+static int launch_blur_v2(const CUtensorMap& mz, const BlurParams& P, const BlurTile& T, int64_t blocks, int smem_bytes,
+                          cudaStream_t stream) {
+#define W2E_BLUR_V2_CASE(O, M)                                                                                        \
+  {                                                                                                                    \
+    static bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                 \
+      W2E_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_v2_kernel<CT, O, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       100 * 1024));                                                                   \
+      configured = true;                                                                                               \
+    }                                                                                                                  \
+    blur_act_nhwc_v2_kernel<CT, O, M><<<(unsigned)blocks, 128, smem_bytes, stream>>>(mz, P, T);                        \
+  }
+  if (P.out && P.out_mod) W2E_BLUR_V2_CASE(true, true)
+  else if (P.out) W2E_BLUR_V2_CASE(true, false)
+  else W2E_BLUR_V2_CASE(false, true)
+#undef W2E_BLUR_V2_CASE
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
 // ------------------------------------------------------------------------------ ToRGB (NHWC in, NCHW out)
 // LP lanes share one pixel (8 channels per lane per step); a warp covers 32/LP pixels per step.
 template <int LP>
@@ -565,6 +735,12 @@ extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const fl
     if (rc) return rc;
   }
   const int smem_bytes = (kBlurTY + 3) * (T.tx + 3) * T.ct * 2 + 128;
+  static const bool use_v2 = [] { const char* e = getenv("W2E_BLUR_V2"); return e && e[0] == '1'; }();
+  if (use_v2 && T.ct >= 32) {   // opt-in A/B variant (bit-identical results); default: the measured kernel below
+    if (T.ct == 32) return launch_blur_v2<32>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
+    if (T.ct == 64) return launch_blur_v2<64>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
+    return launch_blur_v2<128>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
+  }
   static bool configured = false;
   if (!configured) {
     W2E_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
