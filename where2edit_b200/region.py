@@ -3,7 +3,8 @@
 
 The reference has no function for it: the code is inline in
 `FullSpaceMapperFEATClusterLinStyle_Net.forward` / `FullSpaceMapperFEATClusterLin_Net.forward`
-(attention/run_attention.py:775-794 and :852-884, same lines at :508-527 / :556-587).  The two calls below
+(attention/run_attention.py:775-794 and :852-884; the older ...ClusterLin_Net has the same assignment without
+the resize at :508-527 and the same mask block with margin 0.8, training mode only, at :560-587).  The two calls below
 replace those two blocks (INTEGRATION.md section 6 shows the edit):
 
     choice_cluster = assign_clusters(feature_map[self.cluster_layer - 1], self.initial_state, size, self.clusters)
