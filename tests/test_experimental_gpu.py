@@ -43,3 +43,44 @@ def test_blur_v2_is_bit_identical_to_the_default_kernel(tmp_path, size, batch):
         assert p.returncode == 0, p.stderr[-2000:]
         outs.append(torch.load(path))
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["same_res", "upsampled"])
+def test_cluster_style_mapper_matches_reference_golden(name):
+    """mappers.ClusterStyleMapper (the reference's cluster-style mapper on this package's modules and region
+    kernels) end to end against tests/golden/cluster_mapper.npz; gated because it has not run on hardware yet."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import where2edit_b200 as w2e
+    from oracle import cluster_mapper_oracle as cmo
+    from oracle import synth
+    from where2edit_b200 import mappers
+    dev = "cuda:0"
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cluster_mapper.npz"))
+    size, clusters, cluster_layer, attention_layer = (int(v) for v in g[f"{name}/cfg"])
+    gen = w2e.Generator(32, 512, 8, channel_multiplier=2)
+    gen.load_state_dict(synth.make_state_dict(32, seed=0, perturbed=True), strict=True)
+    gen = gen.to(dev).eval()
+    with torch.no_grad():
+        _, _, styles, feats = gen([synth.make_wplus(2, gen.n_latent, seed=2).to(dev)], input_is_latent=True,
+                                  randomize_noise=False, return_features=True)
+        feats = list(feats) + [gen.input.input.repeat(2, 1, 1, 1)]
+    m = mappers.ClusterStyleMapper(gen.n_latent, 1024, 512, attention_layer=attention_layer, cluster_layer=cluster_layer,
+                                   clusters=clusters, cluster_dim=576)
+    with torch.no_grad():
+        for key, p in m.named_parameters():
+            if key != "initial_bias":
+                p.copy_(cmo.seeded_value(key, tuple(p.shape)))
+        m.initial_bias.fill_(float(g[f"{name}/bias"]))
+    m = m.to(dev).eval()
+    m.store_clusters(torch.from_numpy(g[f"{name}/centres"]).to(dev))
+    text = torch.from_numpy(g[f"{name}/text"]).to(dev)
+    x = [torch.cat([text.unsqueeze(1), s[:, :, :, 0, 0]], dim=-1) for s in styles]
+    with torch.no_grad():
+        out, final, (loss_delta, loss_reg, loss_tv) = m(x, feats, size)
+    got = torch.stack([s[:, 0, :, 0, 0] for s in out]).cpu().numpy()
+    want = g[f"{name}/styles_out"]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-4 * np.abs(want).max())
+    np.testing.assert_allclose(final.cpu().numpy(), g[f"{name}/final"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose([float(loss_delta), float(loss_reg), float(loss_tv)], g[f"{name}/losses"], rtol=1e-3)

@@ -87,3 +87,17 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
         assert code != 0, what
     assert "region_mask_bwd" in N.last_error()
     assert lib.w2e_box_resample_fwd(one, one, 0, 8, 8, 7, 2, None) == 0      # empty batch: nothing to do, no launch
+
+
+def test_cluster_style_mapper_state_dict_equals_the_reference_layout():
+    """Keys and shapes of mappers.ClusterStyleMapper == those of the reference class as recorded by
+    oracle/make_cluster_mapper_golden.py (so reference checkpoints load with strict=True)."""
+    import json
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cluster_mapper.npz"))
+    for name in ("same_res", "upsampled"):
+        size, clusters, cluster_layer, attention_layer = (int(v) for v in g[f"{name}/cfg"])
+        m = mappers.ClusterStyleMapper(8, 1024, 512, attention_layer=attention_layer, cluster_layer=cluster_layer,
+                                       clusters=clusters, cluster_dim=576)
+        assert {k: list(v.shape) for k, v in m.state_dict().items()} == json.loads(str(g[f"{name}/keys"]))
+        with pytest.raises(ValueError):
+            m.store_clusters(torch.zeros(clusters + 1, 576))

@@ -63,4 +63,94 @@ class LevelsMapper(nn.Module):
         return torch.cat([x_coarse, x_medium, x_fine], dim=1)
 
 
-__all__ = ["Mapper", "SingleMapper", "LevelsMapper"]
+class _TextCA(nn.Module):
+    """Parameter container of the reference's CA_NET (utils.py:199-223): the cluster-style mapper constructs one
+    per mapped layer (run_attention.py:717) but never calls it; kept so that its checkpoints load strictly."""
+
+    def __init__(self, t_dim, c_dim):
+        super().__init__()
+        self.fc = nn.Linear(t_dim, c_dim * 4, bias=True)
+
+
+class ClusterStyleMapper(nn.Module):
+    """`FullSpaceMapperFEATClusterLinStyle_Net` (attention/run_attention.py:703-893) on this package's modules:
+    per-layer style mappers conditioned on the text feature, 1x1 `StyledConv` attention heads over the captured
+    generator features (stylespace inputs from `attention_textca_*`), and the region-mask block through
+    `region.assign_clusters` / `region.region_attention` instead of the inline code at :775-794 / :852-884.
+    Same constructor arguments, attribute / state-dict names and return value
+    `(styles, final_attention_map, [loss_delta, loss_reg, loss_tv])`.
+
+    Status: composition of GPU-verified parts; its end-to-end parity test against the reference golden
+    (tests/test_experimental_gpu.py) has not run on hardware yet.  Call
+    `where2edit_b200.enable_weight_gradients(mapper)` before training it."""
+
+    LAYER_NUM = (0, 2, 3, 5, 6, 8, 9, 11, 12, 14, 15, 17, 18, 20, 21, 23, 24)
+    STYLE_LAYERS = (0, 2, 2, 3, 5, 5, 6, 8, 8, 9, 11, 11, 12, 14, 14, 15, 17, 17, 18, 20, 20, 21, 23, 23, 24, 26, 26)
+
+    def __init__(self, layers, in_dim=512, latent_dim=512, attention_layer=11, cluster_layer=11, channel_multiplier=1,
+                 clusters=10, cluster_dim=512):
+        super().__init__()
+        from .model import StyledConv
+        cm = channel_multiplier
+        dim = [512] * 12 + [256 * cm] * 3 + [128 * cm] * 3 + [64 * cm] * 3 + [32 * cm] * 3 + [16 * cm] * 3
+        self.dim = dim
+        self.mapper_layer = self.STYLE_LAYERS[attention_layer]
+        for c in range(layers + int((layers - 2) * 0.5)):
+            if c < self.mapper_layer:
+                setattr(self, f"mapper_{c}", EqualLinear(dim[c], dim[c], bias_init=1))
+                setattr(self, f"mapper_textca_{c}", _TextCA(latent_dim, latent_dim))
+                hidden = (latent_dim + 512) // 2
+                setattr(self, f"mapper_text_{c}", nn.Sequential(
+                    EqualLinear(latent_dim, hidden, lr_mul=1, activation="fused_lrelu"),
+                    EqualLinear(hidden, 512, lr_mul=1, activation="fused_lrelu")))
+                setattr(self, f"mapper_all_{c}", EqualLinear(dim[c] + 512, dim[c], bias_init=1))
+            if c in self.LAYER_NUM:
+                setattr(self, f"attention_textca_{c}", EqualLinear(latent_dim, dim[c + 1], bias_init=1))
+                setattr(self, f"attention_{c}", StyledConv(dim[c + 1], 32, 1, dim[c + 1]))
+        self.attention_textca_first = EqualLinear(latent_dim, dim[0], bias_init=1)
+        self.attention_first = StyledConv(dim[0], 32, 1, dim[0])
+        self.attention_textca_last = EqualLinear(latent_dim, 32 * layers, bias_init=1)
+        self.attention_last = StyledConv(32 * layers, 1, 1, 32 * layers)
+        self.initial_bias = nn.Parameter(torch.full((1,), 5.0))
+        self.latent_dim = latent_dim
+        self.register_buffer("initial_state", torch.randn(clusters, cluster_dim))
+        self.cluster_layer = cluster_layer
+        self.clusters = clusters
+
+    def store_clusters(self, initial_state):
+        if tuple(initial_state.shape) != tuple(self.initial_state.shape):
+            raise ValueError(f"cluster centres must be {tuple(self.initial_state.shape)}, got {tuple(initial_state.shape)}")
+        self.initial_state = initial_state.to(self.initial_bias.device)
+
+    def _attend(self, name, feature, text, size):
+        style = getattr(self, f"attention_textca_{name}")(text)
+        res, _ = getattr(self, f"attention_{name}")(feature, style.view(style.shape[0], 1, -1, 1, 1), input_is_stylespace=True)
+        return res if size is None else torch.nn.functional.interpolate(res, size)
+
+    def forward(self, x, feature_map, size, attention_text=None):
+        from . import region
+        batch = x[0].shape[0]
+        x_text = x[0][:, 0, :self.latent_dim]
+        if attention_text is None:
+            attention_text = x_text
+        choice_cluster = region.assign_clusters(feature_map[self.cluster_layer - 1], self.initial_state, size, self.clusters)
+        maps = [self._attend("first", feature_map[-1], attention_text, size)]
+        styles, loss_delta = [], 0
+        for c in range(len(x)):
+            x_c = x[c][:, :, self.latent_dim:]
+            if c < self.mapper_layer:
+                text_hidden = getattr(self, f"mapper_text_{c}")(x_text).unsqueeze(1)
+                mixed = getattr(self, f"mapper_all_{c}")(torch.cat([getattr(self, f"mapper_{c}")(x_c), text_hidden], dim=-1))
+                x_new = x_c + 0.1 * (mixed - x_c)
+                loss_delta = loss_delta + torch.mean(torch.norm(x_new - x_c, dim=-1)) / float(self.mapper_layer)
+                x_c = x_new
+            styles.append(x_c.unsqueeze(3).unsqueeze(3))
+            if c in self.LAYER_NUM:
+                maps.append(self._attend(c, feature_map[c], attention_text, size))
+        logits = self._attend("last", torch.cat(maps, dim=1), attention_text, None)
+        each = torch.sigmoid(logits + self.initial_bias).view(batch, size, size)
+        final_map, _, loss_reg, loss_tv = region.region_attention(each, choice_cluster, self.clusters)
+        return styles, final_map, [loss_delta, loss_reg, loss_tv]
+
+
+__all__ = ["Mapper", "SingleMapper", "LevelsMapper", "ClusterStyleMapper"]
