@@ -52,3 +52,44 @@ def test_shard_then_gather_equals_single_process(tmp_path, total):
     mp.spawn(_worker, args=(world, port, total, str(tmp_path)), nprocs=world, join=True)
     a, b = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
     assert torch.equal(a, b) and a.shape[0] == total
+
+
+def _mb_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for total, mb in [(0, 4), (1, 4), (5, 2), (8, 3), (7, 100)]:
+            latents = torch.arange(total * 6, dtype=torch.float32).reshape(total, 2, 3)
+            calls = []
+
+            def generate(chunk):      # per-sample "synthesis" stand-in producing [n, 3, 2, 2] images
+                calls.append(chunk.shape[0])
+                return (chunk.sum((1, 2)).reshape(-1, 1, 1, 1) + torch.arange(12.).reshape(1, 3, 2, 2)) * 0.5
+
+            full = parallel.synthesize_sharded(generate, latents, micro_batch=mb)
+            b, e = parallel.shard_bounds(total, rank, world)
+            assert calls == [min(mb, e - i) for i in range(b, e, mb)], (total, mb, calls)
+            calls.clear()
+            want = generate(latents) if total else torch.zeros(0)
+            assert full.shape[0] == total and (total == 0 or torch.equal(full, want)), (rank, total, mb)
+            mine = parallel.synthesize_sharded(generate, latents, micro_batch=mb, gather=False)
+            assert mine.shape[0] == e - b and (e == b or torch.equal(mine, want[b:e]))
+        torch.save(torch.ones(1), os.path.join(result_dir, f"ok{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_micro_batched_sharded_synthesis_equals_single_process(tmp_path):
+    """Config 5's host logic: contiguous shards, micro-batches, ragged totals, an empty shard, final all-gather."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mp.spawn(_mb_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok0.pt").exists() and (tmp_path / "ok1.pt").exists()
+
+
+def test_micro_batched_synthesis_without_process_group():
+    latents = torch.randn(5, 4)
+    out = parallel.synthesize_sharded(lambda w: w * 2, latents, micro_batch=2)
+    assert torch.equal(out, latents * 2)
+    with pytest.raises(ValueError):
+        parallel.synthesize_sharded(lambda w: w, latents, micro_batch=0)

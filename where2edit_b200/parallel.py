@@ -52,6 +52,35 @@ def gather_images(local, total=None, group=None, out=None):
     return torch.cat(parts, 0)
 
 
+def synthesize_sharded(generate, latents, micro_batch=32, gather=True, group=None):
+    """a global latent batch [B_total, ...] (the same tensor on every rank) is split
+    contiguously by rank; each rank runs `generate(chunk) -> images` on micro-batches of at most `micro_batch`
+    latents (a 1024^2 forward holds ~0.45 GB of activations per image, so the micro-batch bounds memory, not
+    the batch) and concatenates the results in order.  `gather=True` returns the whole batch on every rank
+    (one all-gather; ragged totals and empty shards are handled), otherwise this rank's shard.
+    Because every kernel of the path is batch-invariant, the result equals `generate(latents)` on one GPU."""
+    if micro_batch < 1:
+        raise ValueError("micro_batch must be positive")
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    total = latents.shape[0]
+    b, e = shard_bounds(total, rank, world)
+    chunks = [generate(latents[i:min(i + micro_batch, e)]) for i in range(b, e, micro_batch)]
+    local = torch.cat(chunks, 0) if len(chunks) > 1 else (chunks[0] if chunks else None)
+    if world == 1 or not gather:
+        return local if local is not None else latents.new_zeros((0,))
+    if total == 0:
+        return latents.new_zeros((0,))
+    if total < world:   # some rank has nothing to run: it learns the image shape / dtype from its peers
+        metas = [None] * world
+        dist.all_gather_object(metas, None if local is None else (tuple(local.shape[1:]), local.dtype), group=group)
+        shape, dtype = next(m for m in metas if m is not None)
+        if local is None:
+            local = torch.zeros((0,) + shape, dtype=dtype, device=latents.device)
+    return gather_images(local, total=total, group=group)
+
+
 class PeerGather:
     """All-gather of equal per-rank shards by COPY-ENGINE pushes into peer-mapped (symmetric-memory) buffers
     over NVLink: no SM is used, so the transfer overlaps the persistent convolution kernels, which occupy
