@@ -1,0 +1,185 @@
+"""Parity AT THE CONFIGURATIONS THE METRIC IS QUOTED ON (BASELINE.json configs 1-4), against the reference and
+the oracle -- not against this package's own fp32 path:
+
+  * tests/golden/fullsize.npz holds outputs of the UNMODIFIED reference at 256^2 (batch 4) and 1024^2
+    (channel_multiplier 2): a regular sub-grid of every image, whole-image statistics, the LevelsMapper-edited
+    W+, and the reference's fp32 AND fp64 autograd gradients (oracle/make_fullsize_golden.py);
+  * the live CPU oracle (pinned to the same vectors by tests/test_fullsize_oracle.py) gives the FULL image.
+
+Tolerances are the north star's: fp32 mode <= 1e-4 max-abs; bf16 mode <= 2e-2 max-abs and >= 45 dB PSNR after
+dividing both images by c = max|reference| (random-init images are not in [-1,1]).
+Gradients: fp32 no further from the reference's fp64 gradient than twice the reference's own fp32 run; bf16
+(bf16 operands and bf16-stored convolution results) cosine >= 0.99 and relative L2 error <= 0.12 against fp64."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import where2edit_b200 as w2e
+from conftest import GOLDEN, max_abs, psnr_db
+from oracle import make_fullsize_golden as mfg
+from oracle import mapper_oracle as mo
+from oracle import stylegan2_oracle as orc
+from oracle import synth
+from where2edit_b200 import mappers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(os.path.join(GOLDEN, "fullsize.npz")))
+
+
+def build(size, precision="fp32"):
+    sd = synth.make_state_dict(size, seed=0, perturbed=True, channel_multiplier=2)
+    gen = w2e.Generator(size, 512, 8, channel_multiplier=2, precision=precision)
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.to(DEV).eval()
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    return gen, sd
+
+
+@pytest.fixture(scope="module")
+def g1024():
+    return build(1024)
+
+
+def check_image(img, ref_full, grid, stats, precision):
+    """img (GPU) against the oracle's full image and the reference's sub-grid / statistics."""
+    img = img.float().cpu()
+    c = float(np.abs(stats[..., 2]).max())                    # max|reference image|
+    assert abs(float(ref_full.abs().max()) - c) <= 1e-4       # the oracle and the reference agree on it
+    g = torch.from_numpy(grid)
+    assert max_abs(mfg.grid(ref_full), g) <= 2e-5             # oracle == reference on the sub-grid
+    if precision == "fp32":
+        assert max_abs(img, ref_full) <= TOL32
+        assert max_abs(mfg.grid(img), g) <= TOL32
+        np.testing.assert_allclose(mfg.image_stats(img)[..., 1], stats[..., 1], rtol=1e-5)
+    else:
+        assert max_abs(img / c, ref_full / c) <= 2e-2
+        assert psnr_db(img / c, ref_full / c, peak=2.0) >= 45.0
+        assert max_abs(mfg.grid(img) / c, g / c) <= 2e-2
+        np.testing.assert_allclose(mfg.image_stats(img)[..., 1], stats[..., 1], rtol=5e-3)
+        assert not torch.equal(img, ref_full)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg1_generator256_batch4(golden, precision):
+    """BASELINE config 1: Generator(256, 512, 8), batch 4 from random W+."""
+    gen, sd = build(256, precision)
+    wplus = synth.make_wplus(4, gen.n_latent, seed=2)
+    ref, _ = orc.generator_forward_ref(sd, [wplus], 256, input_is_latent=True)
+    with torch.no_grad():
+        img, _ = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False)
+    gen.assert_ok()
+    check_image(img, ref, golden["cfg1/grid"], golden["cfg1/stats"], precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg2_ffhq1024_forward(g1024, golden, precision):
+    """BASELINE config 2: FFHQ-1024 generator (channel_multiplier 2) from W+, fixed noise buffers; batch 2 here
+    (the kernels are batch-invariant: tests/test_fullsize_gpu.py), checked against the oracle's full images."""
+    gen, sd = g1024
+    wplus = synth.make_wplus(2, gen.n_latent, seed=2)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref, _, _, ref_feats = orc.generator_forward_ref(sd, [wplus], 1024, input_is_latent=True, return_features=True)
+    gen.set_precision(precision)
+    try:
+        with torch.no_grad():
+            img, _, _, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+        gen.assert_ok()
+    finally:
+        gen.set_precision("fp32")
+    check_image(img, ref, golden["cfg2/grid"], golden["cfg2/stats"], precision)
+    # captured features (consumers: run_attention.py:1108-1110, clustering_feature.py:373): every one of the 26
+    assert len(feats) == 26
+    for i, (f, r) in enumerate(zip(feats, ref_feats)):
+        c = float(r.abs().max())
+        tol = 1e-4 * max(c, 1.0) if precision == "fp32" else 3e-2 * c
+        assert max_abs(f.float().cpu(), r) <= tol, (i, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg3_levels_mapper_edit_with_region_blend(g1024, golden, precision):
+    """BASELINE config 3: w_hat = w + 0.1 * LevelsMapper(w) (mapper/scripts/inference.py:98) -> styles of w_hat ->
+    forward blended at layer 13 through a 64^2 mask into the captured features of w (utils_demo.py:156)."""
+    gen, sd = g1024
+    wplus = synth.make_wplus(2, gen.n_latent, seed=2)
+    opts = types.SimpleNamespace(no_coarse_mapper=False, no_medium_mapper=False, no_fine_mapper=False)
+    mapper = mappers.LevelsMapper(opts)
+    mapper.load_state_dict({k: torch.from_numpy(v) for k, v in mo.mapper_state().items()}, strict=True)
+    mapper = mapper.to(DEV).eval()
+    mask = synth.make_mask(2, 64, seed=3)
+    with torch.no_grad():
+        w_hat = wplus.to(DEV) + 0.1 * mapper(wplus.to(DEV))
+    want = golden["cfg3/w_hat"]
+    assert max_abs(w_hat.cpu(), want) <= 1e-5 * float(np.abs(want).max())
+    # the oracle's version of the whole edit, from the reference's w_hat
+    w_ref = torch.from_numpy(want)
+    _, _, _, ref_feats = orc.generator_forward_ref(sd, [wplus], 1024, input_is_latent=True, return_features=True)
+    _, _, ref_styles = orc.generator_forward_ref(sd, [w_ref], 1024, input_is_latent=True, return_latents=True)
+    ref, _, _, _ = orc.generator_forward_ref(sd, [ref_styles], 1024, input_is_stylespace=True, return_features=True,
+                                             attention_layer=13, attention_map=mask, feature_map=ref_feats)
+    gen.set_precision(precision)
+    try:
+        with torch.no_grad():
+            _, _, _, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+            _, _, styles_hat = gen([w_hat], input_is_latent=True, randomize_noise=False, return_latents=True)
+            img, _, _, _ = gen([styles_hat], input_is_stylespace=True, randomize_noise=False, return_features=True,
+                               attention_layer=13, attention_map=mask.to(DEV), feature_map=feats)
+        gen.assert_ok()
+    finally:
+        gen.set_precision("fp32")
+    for s, r in zip(styles_hat, ref_styles):
+        assert tuple(s.shape) == tuple(r.shape) and max_abs(s.cpu(), r) <= 1e-4 * max(1.0, float(r.abs().max()))
+    check_image(img, ref, golden["cfg3/grid"], golden["cfg3/stats"], precision)
+
+
+def _grad_check(ours, ref32, ref64, precision, tag):
+    ours, ref32, ref64 = (np.asarray(t, np.float64).reshape(-1) for t in (ours, ref32, ref64))
+    scale = float(np.abs(ref64).max())
+    if precision == "fp32":
+        err_ours, err_ref = float(np.abs(ours - ref64).max()), float(np.abs(ref32 - ref64).max())
+        assert err_ours <= 2 * err_ref + 1e-4 * scale, (tag, err_ours, err_ref, scale)
+    else:
+        cos = float(ours @ ref64 / (np.linalg.norm(ours) * np.linalg.norm(ref64)))
+        rel = float(np.linalg.norm(ours - ref64) / np.linalg.norm(ref64))
+        assert cos >= 0.99 and rel <= 0.12, (tag, cos, rel)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg4_gradients_at_1024_match_reference_fp64_autograd(g1024, golden, precision):
+    """BASELINE config 4 (CLIP-loss latent optimisation, run_attention.py:1419 / coach.py:91): dL/dW+ of the plain
+    forward and dL/d(styles, mask) of the layer-13-blended stylespace forward for the seeded upstream dL/dimage,
+    against the reference's own fp64 autograd at 1024^2."""
+    gen, sd = g1024
+    wplus = synth.make_wplus(2, gen.n_latent, seed=2)[:1]
+    up = mfg.upstream_grad((1, 3, 1024, 1024)).to(DEV)
+    mask1 = synth.make_mask(2, 64, seed=3)[:1]
+    with torch.no_grad():
+        _, _, styles, feats = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False, return_features=True)
+    edited = [s.cpu() * (1 + 0.05 * synth.make_tensor((2,) + tuple(s.shape[1:]), 500 + i)[:1])
+              for i, s in enumerate(styles)]
+    gen.set_precision(precision)
+    try:
+        wp = wplus.to(DEV).requires_grad_(True)
+        img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+        (img * up).sum().backward()
+        st = [s.to(DEV).requires_grad_(True) for s in edited]
+        mk = mask1.to(DEV).requires_grad_(True)
+        img, _, _, _ = gen([st], input_is_stylespace=True, randomize_noise=False, return_features=True,
+                           attention_layer=13, attention_map=mk, feature_map=feats)
+        (img * up).sum().backward()
+        gen.assert_ok()
+    finally:
+        gen.set_precision("fp32")
+    _grad_check(wp.grad.cpu(), golden["cfg4/grad_wplus_f32"], golden["cfg4/grad_wplus_f64"], precision, "wplus")
+    gs = np.concatenate([s.grad.reshape(-1).cpu().numpy() for s in st])
+    _grad_check(gs, golden["cfg4/grad_styles_f32"], golden["cfg4/grad_styles_f64"], precision, "styles")
+    _grad_check(mk.grad.cpu(), golden["cfg4/grad_mask_f32"], golden["cfg4/grad_mask_f64"], precision, "mask")

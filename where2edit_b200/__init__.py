@@ -35,11 +35,18 @@ def install_as_reference():
     from .op import upfirdn2d as _up
 
     def pkg(name):
+        """The reference's REAL package when it is importable (its other submodules -- models.facial_recognition,
+        models.encoders, models.psp, ... -- must keep resolving; only the stylegan2 leaves are overridden);
+        an empty stub package only when the reference tree is not on sys.path at all."""
+        import importlib
         m = sys.modules.get(name)
         if m is None:
-            m = types.ModuleType(name)
-            m.__path__ = []
-            sys.modules[name] = m
+            try:
+                m = importlib.import_module(name)
+            except ImportError:
+                m = types.ModuleType(name)
+                m.__path__ = []
+                sys.modules[name] = m
         return m
 
     pkg("models")

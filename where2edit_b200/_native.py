@@ -172,8 +172,57 @@ def check(code, what):
         raise RuntimeError(f"libw2e {what} failed (code {code}): {last_error()}")
 
 
-def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """torch's current stream ON `device` (a tensor's device); None = the current device."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class ErrorFlag:
+    """Device-side pipeline-timeout flag of the tcgen05 kernels (tc_ptx.cuh mbar_wait: a hung barrier wait sets
+    it instead of hanging the GPU) with a pinned host mirror, so that the PUBLIC path notices a failure without a
+    per-call synchronisation: `publish()` queues a 4-byte device->host copy behind the kernels of a call,
+    `poll()` (start of the next call / of a backward) raises once that copy has landed non-zero, `check()` is
+    the synchronising variant.  A raised failure resets the flag."""
+
+    def __init__(self, what):
+        self.what = what
+        self.dev = None
+        self.host = None
+        self.event = None
+
+    def tensor(self, device):
+        if self.dev is None or self.dev.device != device:
+            self.dev = torch.zeros(1, dtype=torch.int32, device=device)
+            self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.event = None
+        return self.dev
+
+    def publish(self):
+        if self.dev is None or torch.cuda.is_current_stream_capturing():
+            return
+        self.host.copy_(self.dev, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(self.dev.device))
+
+    def _raise_if_set(self):
+        if int(self.host[0]) != 0:
+            self.host.zero_()
+            self.dev.zero_()
+            self.event = None
+            raise RuntimeError(f"where2edit_b200: a tcgen05 pipeline wait timed out ({self.what}); the outputs of "
+                               "the calls since the last successful check are invalid")
+
+    def poll(self):
+        if self.event is not None and self.event.query():
+            self._raise_if_set()
+
+    def check(self):
+        if self.dev is None:
+            return
+        self.publish()   # a fresh copy behind everything queued so far
+        if self.event is not None:
+            self.event.synchronize()
+        self._raise_if_set()
 
 
 def ptr(t):

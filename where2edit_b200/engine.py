@@ -51,7 +51,7 @@ class SynthesisEngine:
     def __init__(self, gen):
         self.gen = gen
         self._w = {}
-        self._err = None
+        self._err = N.ErrorFlag("libw2e modconv_tc2, bf16 synthesis engine")
         # W2E_TC_V1=1 selects the first-generation kernel (one tile per CTA, 9 shifted TMA loads)
         self.v1 = os.environ.get("W2E_TC_V1", "0") == "1"
         # W2E_FUSE_RGB=0 keeps ToRGB as its own kernel (w2e_torgb_nhwc) instead of the conv epilogue
@@ -72,15 +72,12 @@ class SynthesisEngine:
         return pw
 
     def error_flag(self, device):
-        if self._err is None or self._err.device != device:
-            self._err = torch.zeros(1, dtype=torch.int32, device=device)
-        return self._err
+        return self._err.tensor(device)
 
     def assert_ok(self):
-        """Synchronising check of the pipeline-timeout flag of the tensor-core kernels."""
-        if self._err is not None and int(self._err.item()) != 0:
-            self._err.zero_()
-            raise RuntimeError("where2edit_b200: a tcgen05 pipeline wait timed out (libw2e modconv_tc)")
+        """Synchronising check of the pipeline-timeout flag of the tensor-core kernels (run() itself polls the
+        flag of the previous calls without synchronising, see _native.ErrorFlag)."""
+        self._err.check()
 
 
     # ------------------------------------------------------------------ styles / demodulation plan
@@ -329,6 +326,15 @@ class SynthesisEngine:
     @torch.no_grad()
     def run(self, latent, stylespace, noise, want_features=False, attention_layer=0, attention_map=None,
             feature_map=None):
+        """One forward.  Launches on the generator's device (made current for the call, so a model on cuda:1
+        works while cuda:0 is current); a pipeline timeout of an EARLIER call raises here (no synchronisation)."""
+        self._err.poll()
+        with torch.cuda.device(self.gen.input.input.device):
+            out = self._run(latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map)
+            self._err.publish()
+        return out
+
+    def _run(self, latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map):
         gen = self.gen
         layers = gen.styled_layers()
         rows = gen.latent_rows(stylespace)

@@ -152,16 +152,26 @@ _TC_ERR = {}
 def _tc_error_flag(dev):
     f = _TC_ERR.get(dev)
     if f is None:
-        f = _TC_ERR[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
-    return f
+        f = _TC_ERR[dev] = N.ErrorFlag("libw2e modconv_tc2, autograd path")
+    return f.tensor(dev)
+
+
+def tc_poll():
+    """Non-synchronising check (start of every bf16-precision autograd forward): raises if a tensor-core kernel
+    of an EARLIER forward/backward timed out."""
+    for f in _TC_ERR.values():
+        f.poll()
+
+
+def tc_publish():
+    for f in _TC_ERR.values():
+        f.publish()
 
 
 def tc_assert_ok():
     """Synchronising check of the pipeline-timeout flag of the tensor-core kernels used by autograd."""
     for f in _TC_ERR.values():
-        if int(f.item()) != 0:
-            f.zero_()
-            raise RuntimeError("where2edit_b200: a tcgen05 pipeline wait timed out (libw2e modconv_tc2, autograd path)")
+        f.check()
 
 
 def _nhwc_mod(x, scale):

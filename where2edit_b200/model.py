@@ -361,6 +361,13 @@ class Generator(nn.Module):
         self.precision = precision
         return self
 
+    def assert_ok(self):
+        """Synchronising check that no tensor-core kernel of this generator reported a pipeline timeout (the
+        forward itself polls the flag of earlier calls without synchronising and raises when one did)."""
+        if self._engine is not None:
+            self._engine.assert_ok()
+        K.tc_assert_ok()
+
     def styled_layers(self):
         """[(module, kind)] in execution order: kind in {'conv', 'up', 'rgb'} (26 entries at 1024)."""
         seq = [(self.conv1, "conv"), (self.to_rgb1, "rgb")]
@@ -426,8 +433,12 @@ class Generator(nn.Module):
             prev = K.TC_AUTOGRAD
             K.TC_AUTOGRAD = self.precision == "bf16"
             try:
+                if K.TC_AUTOGRAD:
+                    K.tc_poll()   # a pipeline timeout of an earlier forward / backward raises here (no sync)
                 image, style_vector, captured = self._forward_modules(
                     latent, input_is_stylespace, noise, attention_layer if blending else 0, attention_map, feature_map)
+                if K.TC_AUTOGRAD:
+                    K.tc_publish()
             finally:
                 K.TC_AUTOGRAD = prev
 
