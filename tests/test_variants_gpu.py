@@ -1,8 +1,5 @@
-"""A/B checks of kernel variants that are in the tree but NOT yet measured on hardware and therefore off by
-default.  Skipped unless W2E_TEST_EXPERIMENTAL=1 (run them first thing when a GPU is available):
-
-    W2E_TEST_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu
-"""
+"""A/B check of the second blur kernel (bit-identity with the first) and the whole cluster-style mapper
+against the reference golden.  Both run by default."""
 import os
 import subprocess
 import sys
@@ -10,8 +7,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("W2E_TEST_EXPERIMENTAL") != "1", reason="experimental variants: opt-in")]
+pytestmark = pytest.mark.gpu
 
 SCRIPT = r"""
 import sys, torch
@@ -31,8 +27,9 @@ torch.save(img.cpu(), out)
 
 @pytest.mark.parametrize("size,batch", [(256, 2), (1024, 1)])
 def test_blur_v2_is_bit_identical_to_the_default_kernel(tmp_path, size, batch):
-    """W2E_BLUR_V2=1 (templated channel tile, predicate-free interior body; csrc/nhwc_ops.cu) must reproduce the
-    default blur kernel bit for bit through the whole bf16 engine (channel tiles 128 / 64 / 32, edge tiles)."""
+    """The two blur kernels of csrc/nhwc_ops.cu (W2E_BLUR_V2=0: run-time tile shape; W2E_BLUR_V2=1: templated
+    channel tile with a predicate-free interior body) must agree bit for bit through the whole bf16 engine
+    (channel tiles 128 / 64 / 32, edge tiles)."""
     import torch
     outs = []
     for flag in ("0", "1"):
@@ -48,7 +45,7 @@ def test_blur_v2_is_bit_identical_to_the_default_kernel(tmp_path, size, batch):
 @pytest.mark.parametrize("name", ["same_res", "upsampled"])
 def test_cluster_style_mapper_matches_reference_golden(name):
     """mappers.ClusterStyleMapper (the reference's cluster-style mapper on this package's modules and region
-    kernels) end to end against tests/golden/cluster_mapper.npz; gated because it has not run on hardware yet."""
+    kernels) end to end against tests/golden/cluster_mapper.npz (written by the unmodified reference class)."""
     import numpy as np
     import torch
     sys.path.insert(0, ROOT)
@@ -84,3 +81,32 @@ def test_cluster_style_mapper_matches_reference_golden(name):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-4 * np.abs(want).max())
     np.testing.assert_allclose(final.cpu().numpy(), g[f"{name}/final"], rtol=0, atol=1e-4)
     np.testing.assert_allclose([float(loss_delta), float(loss_reg), float(loss_tv)], g[f"{name}/losses"], rtol=1e-3)
+
+
+def test_cluster_style_mapper_trains_every_parameter():
+    """Every parameter the reference trains (mapper linears, text branches, the 1x1 StyledConv attention heads'
+    weight / modulation / noise weight / activation bias, run_attention.py:725-735) receives a gradient after
+    one backward through styles, attention map and losses; the unused CA_NET containers (:717) do not."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import where2edit_b200 as w2e
+    from oracle import synth
+    from where2edit_b200 import mappers
+    dev = "cuda:0"
+    gen = w2e.Generator(32, 512, 8, channel_multiplier=2)
+    gen.load_state_dict(synth.make_state_dict(32, seed=0, perturbed=True), strict=True)
+    gen = gen.to(dev).eval()
+    with torch.no_grad():
+        _, _, styles, feats = gen([synth.make_wplus(2, gen.n_latent, seed=2).to(dev)], input_is_latent=True,
+                                  randomize_noise=False, return_features=True)
+        feats = list(feats) + [gen.input.input.repeat(2, 1, 1, 1)]
+    m = mappers.ClusterStyleMapper(gen.n_latent, 1024, 512, attention_layer=7, cluster_layer=7, clusters=4,
+                                   cluster_dim=feats[6].shape[1] + 64).to(dev).train()
+    text = torch.randn(2, 512, device=dev)
+    x = [torch.cat([text.unsqueeze(1), s[:, :, :, 0, 0]], dim=-1) for s in styles]
+    out, final, (loss_delta, loss_reg, loss_tv) = m(x, feats, 16)
+    loss = sum(s.square().mean() for s in out) + final.square().mean() + loss_delta + loss_reg + loss_tv
+    loss.backward()
+    missing = [n for n, p in m.named_parameters() if p.grad is None and not n.startswith("mapper_textca_")]
+    assert not missing, missing
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)

@@ -80,9 +80,9 @@ class ClusterStyleMapper(nn.Module):
     Same constructor arguments, attribute / state-dict names and return value
     `(styles, final_attention_map, [loss_delta, loss_reg, loss_tv])`.
 
-    Status: composition of GPU-verified parts; its end-to-end parity test against the reference golden
-    (tests/test_experimental_gpu.py) has not run on hardware yet.  Call
-    `where2edit_b200.enable_weight_gradients(mapper)` before training it."""
+    End-to-end parity against the reference class: tests/test_variants_gpu.py (golden written by the
+    unmodified reference).  The reference trains the attention heads, so their convolution-weight gradients are
+    switched on here (the frozen generator's stay off)."""
 
     LAYER_NUM = (0, 2, 3, 5, 6, 8, 9, 11, 12, 14, 15, 17, 18, 20, 21, 23, 24)
     STYLE_LAYERS = (0, 2, 2, 3, 5, 5, 6, 8, 8, 9, 11, 11, 12, 14, 14, 15, 17, 17, 18, 20, 20, 21, 23, 23, 24, 26, 26)
@@ -116,6 +116,10 @@ class ClusterStyleMapper(nn.Module):
         self.register_buffer("initial_state", torch.randn(clusters, cluster_dim))
         self.cluster_layer = cluster_layer
         self.clusters = clusters
+        from .model import ModulatedConv2d
+        for m in self.modules():   # trainable 1x1 StyledConv heads: weight, noise weight and bias all get gradients
+            if isinstance(m, ModulatedConv2d):
+                m.weight_grad = True
 
     def store_clusters(self, initial_state):
         if tuple(initial_state.shape) != tuple(self.initial_state.shape):

@@ -2,8 +2,12 @@
 
 Synthesis is embarrassingly parallel (each image depends only on its own latent, replicated weights and
 the shared fixed noise buffers, models/stylegan2/model.py:492-494), so ranks never exchange data on the
-path itself.  The only collective is the north-star's final all-gather of images / latents, the
-equivalent of the reference's GatherLayer (utils.py:114-131) for the no-grad case.
+path itself.  Collectives, as in the reference:
+  * the final all-gather of images / latents (`gather_images`, `PeerGather`), and its autograd form
+    `GatherLayer` / `gather_with_grad` (utils.py:114-131, used at attention/run_attention.py:1313-1314);
+  * for the optimisation loop, the all-reduce of the shared mapper's gradients (`GradBucketReducer`: what
+    DistributedDataParallel does for the mapper at run_attention.py:1022-1030), bucketed and issued on a side
+    stream while the generator backward is still producing the gradients of earlier layers.
 """
 import torch
 import torch.distributed as dist
@@ -81,16 +85,166 @@ def synthesize_sharded(generate, latents, micro_batch=32, gather=True, group=Non
     return gather_images(local, total=total, group=group)
 
 
+class GatherLayer(torch.autograd.Function):
+    """utils.py:114-131: all-gather with autograd.  forward returns one tensor per rank (a tuple, in rank order);
+    backward hands back ONLY the gradient of this rank's own slice (`grads[rank]`) -- the gradients that other
+    ranks' losses would send to this rank's features are dropped, exactly as in the reference, whose
+    DistributedDataParallel then averages the mapper gradients over ranks."""
+
+    @staticmethod
+    def forward(ctx, input, group=None):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        x = input.contiguous()
+        buf = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(buf.view(world * x.shape[0], *x.shape[1:]) if x.ndim else buf, x, group=group)
+        return tuple(buf.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return grads[dist.get_rank(ctx.group)].clone(), None
+
+
+def gather_with_grad(x, group=None):
+    """`torch.cat(GatherLayer.apply(x), dim=0)` (run_attention.py:1313-1314); identity without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    return torch.cat(GatherLayer.apply(x, group), dim=0)
+
+
+class GradBucketReducer:
+    """All-reduce (average) of a shared mapper's gradients over the ranks, overlapped with the backward that
+    produces them -- the job DistributedDataParallel(find_unused_parameters=True) does for the mapper in the
+    reference (run_attention.py:1022-1030); the generator is frozen and replicated, so nothing else is reduced.
+
+    All gradients live in ONE flat fp32 buffer (`p.grad` of every parameter is a view into it), cut into buckets
+    of about `bucket_bytes` in REVERSE parameter order: in the edit loop the styles of the last generator layers
+    receive their gradient first (the backward runs image -> ... -> 4x4), so their mapper branches finish first.
+    A post-accumulate-grad hook counts a bucket's parameters down; when the last one lands, the bucket is
+    all-reduced on a side stream (NCCL over NVLink) while the main stream keeps running the generator backward.
+    `finish()` reduces the buckets that never completed (parameters without a gradient this step contribute
+    zeros, as with find_unused_parameters=True), joins the side stream and divides by the world size.
+
+        reducer = GradBucketReducer(mapper.parameters())
+        for step in ...:
+            reducer.zero_grad()                # instead of optimizer.zero_grad(): keeps the views
+            loss.backward()                    # buckets are reduced as they fill
+            reducer.finish()
+            optimizer.step()
+    """
+
+    def __init__(self, params, group=None, bucket_bytes=25 << 20, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucketReducer: no trainable parameter")
+        self.group = group
+        self.average = average
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        dev = self.params[0].device
+        if any(p.device != dev for p in self.params):
+            raise ValueError("GradBucketReducer: parameters must live on one device")
+        order = list(reversed(self.params))
+        total = sum(p.numel() for p in order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buckets = []       # [begin, end) ranges of the flat buffer
+        self._bucket_of = {}
+        self._views = {}
+        off = begin = 0
+        count = 0
+        for p in order:
+            if p.dtype != torch.float32:
+                raise ValueError("GradBucketReducer: fp32 parameters only (the reference trains the mapper in fp32)")
+            self._views[p] = self.flat[off:off + p.numel()].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += p.numel()
+            count += 1
+            if (off - begin) * 4 >= bucket_bytes:
+                self.buckets.append((begin, off, count))
+                begin, count = off, 0
+        if count:
+            self.buckets.append((begin, off, count))
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._pending = []
+        self._works = []
+        self._launched = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.zero_grad()
+
+    def zero_grad(self):
+        self.flat.zero_()
+        for p in self.params:
+            p.grad = self._views[p]
+        self._pending = [c for (_, _, c) in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def _on_grad(self, p):
+        view = self._views[p]
+        if p.grad is not view and p.grad.data_ptr() != view.data_ptr():   # someone replaced .grad (set_to_none)
+            view.copy_(p.grad)
+            p.grad = view
+        b = self._bucket_of[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        if self.world == 1:
+            return
+        begin, end, _ = self.buckets[b]
+        chunk = self.flat[begin:end]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(chunk, group=self.group)
+        else:
+            self._works.append(dist.all_reduce(chunk, group=self.group, async_op=True))
+
+    def finish(self):
+        """Reduce what is still outstanding, wait for the collectives, average.  Returns the flat gradient."""
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
+        if self.average and self.world > 1:
+            self.flat.div_(self.world)
+        return self.flat
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def allreduce_mapper_grads(module_or_params, group=None, bucket_bytes=25 << 20):
+    """Convenience constructor: `reducer = allreduce_mapper_grads(mapper)`; see GradBucketReducer."""
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    return GradBucketReducer(params, group=group, bucket_bytes=bucket_bytes)
+
+
 class PeerGather:
     """All-gather of equal per-rank shards by COPY-ENGINE pushes into peer-mapped (symmetric-memory) buffers
     over NVLink: no SM is used, so the transfer overlaps the persistent convolution kernels, which occupy
     every SM (the NCCL all-gather kernels can only run in the gaps between them).
 
         pg = PeerGather(shard.shape, shard.dtype, device)          # once (collective)
-        pg.push(shard, slot)                                       # every step, on any stream
-        pg.barrier(); full = pg.result(slot)                       # before reading / before a slot is reused
+        pg.own(slot).copy_(image)                                  # producer writes its shard in place ...
+        pg.push(None, slot)                                        # ... and pushes it to the peers, every step
+        full = pg.result(slot)                                     # consumable on the same stream right after
 
-    `slots` independent buffers let step i+1 be pushed while step i is still being read."""
+    `push` is a complete per-step collective: a cross-rank barrier BEFORE the copies (every rank has stopped
+    reading this slot: a rank enters it only after its own reads, which precede the push in stream order) and one
+    AFTER them (every rank's shard has landed everywhere), both device-side on the pushing stream, so `result`
+    may be read as soon as `push` returns (in stream order).  `slots` independent buffers let step i+1 be pushed
+    while step i is still being read on another stream (make that stream's reads precede the next push of the
+    same slot, e.g. `push_stream.wait_stream(reader_stream)`)."""
 
     def __init__(self, shard_shape, dtype, device, group=None, slots=2):
         import torch.distributed._symmetric_memory as symm
@@ -102,10 +256,23 @@ class PeerGather:
         self.handle = symm.rendezvous(self.buf, self.group)
         self.peers = [self.handle.get_buffer(r, self.shape, dtype) for r in range(self.world)]
 
-    def push(self, local, slot):
-        """Copy this rank's shard into slot `slot` of every rank's buffer (current stream, asynchronous)."""
-        for r in range(self.world):
-            self.peers[(self.rank + r) % self.world][slot, self.rank].copy_(local, non_blocking=True)
+    def own(self, slot):
+        """This rank's shard inside its own buffer: the producer can write there directly (no self-copy)."""
+        return self.buf[slot, self.rank]
+
+    def push(self, local, slot, sync=True):
+        """Copy this rank's shard into slot `slot` of every rank's buffer (current stream, asynchronous).
+        `local=None`: the shard already sits in `own(slot)` and only the peers are written.  `sync=False` skips the
+        two barriers (an upper bound for measurements only: the result is then NOT consumable per step)."""
+        if sync:
+            self.handle.barrier(channel=slot)
+        if local is not None:
+            self.buf[slot, self.rank].copy_(local, non_blocking=True)
+        src = self.buf[slot, self.rank]
+        for r in range(1, self.world):
+            self.peers[(self.rank + r) % self.world][slot, self.rank].copy_(src, non_blocking=True)
+        if sync:
+            self.handle.barrier(channel=self.shape[0] + slot)
 
     def barrier(self):
         """All pushes issued before it (on every rank, in stream order) have landed when it returns on the stream."""
