@@ -28,12 +28,22 @@ UNIT = "images/s"
 MODCONV_GFLOP_PER_IMAGE = 148.13
 
 
-def workload_config(size, batch, precision, world, gather="NCCL all-gather"):
-    return {"workload": f"StyleGAN2 FFHQ-{size} generator forward (random init, channel_multiplier 2), "
-                        f"batch {batch} per GPU from W+ latents, fixed noise buffers, {precision} mode",
-            "batch_per_gpu": batch, "global_batch": batch * world,
-            "parallelism": f"batch sharded over {world} GPU(s)"
-                           + (f", bf16 all-gather of images overlapped on a side stream ({gather})" if world > 1 else ""),
+def workload_config(size, batch, precision, world, gather="NCCL all-gather", workload="synthesis", image_dtype="bf16"):
+    if workload == "train":
+        what = (f"CLIP-loss latent optimisation step (BASELINE config 4): LevelsMapper edit w + 0.1*mapper(w) -> "
+                f"StyleGAN2 FFHQ-{size} generator forward + backward to the mapper parameters through modconv / "
+                f"upfirdn2d / fused_act (random init, channel_multiplier 2), batch {batch} per GPU, seeded synthetic "
+                f"dL/dimage, {precision} mode")
+        par = (f"batch sharded over {world} GPU(s)"
+               + (", bucketed all-reduce of the shared mapper gradients overlapped with the backward (NCCL)" if world > 1 else ""))
+    else:
+        what = (f"StyleGAN2 FFHQ-{size} generator forward (random init, channel_multiplier 2), "
+                f"batch {batch} per GPU from W+ latents, fixed noise buffers, {precision} mode")
+        par = (f"batch sharded over {world} GPU(s)"
+               + (f", per-step all-gather of the {image_dtype} images ({batch} per GPU per step: steady state of config 5's "
+                  f"256 per GPU in micro-batches) overlapped on a side stream ({gather})" if world > 1 else ""))
+    return {"workload": what, "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": par,
+            "image_dtype": image_dtype if workload != "train" else "f32",
             "l2": "inputs larger than L2: every step streams multi-GB activations (no flush needed)"}
 
 
@@ -140,6 +150,46 @@ def cpu_forward_images_per_s(state_dict, size, n_latent, batch, threads):
     return batch / dt, dt
 
 
+def cpu_op_baselines(threads):
+    """BASELINE.md section 5 (a, b) and config 1 on the host cores, through the oracle port of the reference's
+    native ops (op/upfirdn2d.py:19-60, op/fused_act.py:23-39) and of its 256^2 generator: best of 3 each."""
+    from oracle import stylegan2_oracle as orc
+    from oracle import synth
+    torch.set_num_threads(threads)
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    out = {"cores": threads, "kind": "port"}
+    with torch.no_grad():
+        k4 = synth.blur_kernel_2d(gain=4.0)
+        x = torch.randn(4, 128, 257, 257)
+        dt = best(lambda: orc.upfirdn2d_native_ref(x, k4, 1, 1, 1, 1, 1, 1, 1, 1))
+        byts = 4 * 128 * (257 * 257 + 256 * 256) * 4
+        out["upfirdn2d_native_blur"] = {"shape": "[4,128,257,257] -> [4,128,256,256] fp32, pad (1,1)", "ms": dt * 1e3,
+                                        "gbs_algorithmic": byts / dt / 1e9}
+        xs = torch.randn(4, 3, 128, 128)
+        dt = best(lambda: orc.upfirdn2d_native_ref(xs, k4, 2, 2, 1, 1, 2, 1, 2, 1))
+        byts = 4 * 3 * (128 * 128 + 256 * 256) * 4
+        out["upfirdn2d_native_up2"] = {"shape": "[4,3,128,128] -> [4,3,256,256] fp32, up 2, pad (2,1)", "ms": dt * 1e3,
+                                       "gbs_algorithmic": byts / dt / 1e9}
+        y = torch.randn(4, 128, 256, 256)
+        b = torch.randn(128)
+        dt = best(lambda: orc.fused_leaky_relu_ref(y, b))
+        out["fused_leaky_relu"] = {"shape": "[4,128,256,256] fp32", "ms": dt * 1e3, "gbs_algorithmic": 2 * y.numel() * 4 / dt / 1e9}
+        sd = synth.make_state_dict(256, seed=0, channel_multiplier=2)
+        w = synth.make_wplus(4, 14, seed=2)
+        dt = best(lambda: orc.generator_forward_ref(sd, [w], 256, input_is_latent=True))
+        out["config1_generator256_batch4"] = {"ms": dt * 1e3, "images_per_s": 4 / dt}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (it ships no native
     code and its Python cannot travel to the GPU box, so the pinned oracle port is timed) on all
@@ -167,12 +217,16 @@ def run_reference(args):
                                       input_is_latent=True)
         dt = time.perf_counter() - t0
     value = sample_batch * args.steps / dt
-    sample = f"{sample_batch} image(s) of the {args.size}^2 generator per step, fp32, torch CPU ops, {threads} threads"
+    sample = (f"{sample_batch} image(s) of the {args.size}^2 generator per step (a bounded sample of the batch-{args.batch} "
+              f"workload; the CPU path's images/s does not grow with the batch), fp32, torch CPU ops through the oracle "
+              f"port of the reference (the reference is pure Python and does not travel to the GPU box), {threads} threads")
+    cfg = workload_config(args.size, args.batch, args.precision, 1)
+    cfg["sample_batch"] = sample_batch
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.size, args.batch, args.precision, 1),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -195,19 +249,230 @@ def summarise_trace(trace, peaks):
     return kinds, layers
 
 
+def gpu_ms(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def roofline_from_trace(trace, peaks, B, size, with_traffic):
+    kinds, layers = summarise_trace(trace, peaks)
+    traced_ms = sum(k["ms"] for k in kinds.values())
+    roofline = roofline_up = None
+    if "modconv" in kinds and kinds["modconv"]["ms"] > 0:
+        k = kinds["modconv"]
+        ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "modconv_tc2_kernel (all 3x3 modulated-conv launches of a step)",
+                    "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"],
+                    "traffic": ncu_traffic("modconv") if with_traffic else None,
+                    "peak_source": peaks["source"] + " bf16_tflops_sustained", "algorithmic_flops": k["flops"],
+                    "launches": k["launches"], "share_of_step": k["ms"] / traced_ms}
+    if "upfirdn2d" in kinds and kinds["upfirdn2d"]["ms"] > 0:
+        k = kinds["upfirdn2d"]
+        ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        roofline_up = {"bound": "hbm", "kernel": "blur_act_nhwc_kernel (all blur launches of a step)",
+                       "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                       "traffic": ncu_traffic("blur") if with_traffic else None,
+                       "algorithmic_bytes": k["bytes"], "peak_source": peaks["source"] + " hbm_gbs", "launches": k["launches"],
+                       "share_of_step": k["ms"] / traced_ms}
+    return roofline, roofline_up, kinds, layers
+
+
+def make_levels_mapper(dev):
+    """LevelsMapper of the StyleCLIP-style edit (mapper/latent_mappers.py:47-82), seeded like the parity tests."""
+    import types
+    from where2edit_b200 import mappers
+    torch.manual_seed(5)
+    opts = types.SimpleNamespace(no_coarse_mapper=False, no_medium_mapper=False, no_fine_mapper=False)
+    return mappers.LevelsMapper(opts).to(dev)
+
+
+def extra_pipelines(gen, dev, size, n_lat):
+    """Numbers the metric's name asks for but the headline workload does not contain (outside the timed region):
+    cfg3 = mapper edit + original forward with feature capture + blended edited forward (edited images/s);
+    cfg4 = forward + backward of the latent-optimisation step; the B=1 latency eager vs CUDA graph."""
+    import where2edit_b200 as w2e
+    out = {}
+    mapper = make_levels_mapper(dev).eval()
+    for p in mapper.parameters():
+        p.requires_grad_(False)
+    eb = 32
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(eb, n_lat, 512, generator=g).to(dev)
+    mask = torch.rand(eb, 1, 64, 64, generator=g).to(dev)
+
+    def edit():
+        with torch.no_grad():
+            _, _, _, feats = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
+            w_hat = w + 0.1 * mapper(w)
+            _, _, styles = gen([w_hat], input_is_latent=True, randomize_noise=False, return_latents=True)
+            img, _ = gen([styles], input_is_stylespace=True, randomize_noise=False, attention_layer=13,
+                         attention_map=mask, feature_map=feats)
+        return img
+    try:
+        ms = gpu_ms(edit, 3, warm=2)
+        out["edit_pipeline_cfg3"] = {
+            "what": "LevelsMapper edit + original forward with all 26 features captured (fp32 NCHW) + styles of the "
+                    "edited code + edited forward blended at layer 13 through a 64^2 mask, bf16 engine",
+            "batch": eb, "ms": ms, "edited_images_per_s": eb / ms * 1e3}
+    except Exception as exc:
+        out["edit_pipeline_cfg3"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
+    # CUDA graph: B = 1 latency
+    try:
+        w1 = w[:1].contiguous()
+        with torch.no_grad():
+            eager = gpu_ms(lambda: gen([w1], input_is_latent=True, randomize_noise=False), 20, warm=3)
+        fast = w2e.GraphedGenerator(gen, [w1], input_is_latent=True)
+        graphed = gpu_ms(lambda: fast([w1]), 20, warm=3)
+        out["latency_batch1"] = {"eager_ms": eager, "cuda_graph_ms": graphed}
+        del fast
+    except Exception as exc:
+        out["latency_batch1"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args, world, rank, dev, dist, peaks):
+    """--workload train (BASELINE config 4): one step = LevelsMapper edit of a W+ batch -> generator forward ->
+    seeded synthetic dL/dimage -> backward to the mapper parameters (+ at N > 1 the bucketed all-reduce of those
+    gradients, overlapped with the backward).  Same contract line; `value` with the latents resident, `e2e` with the
+    latents copied from pinned host memory and the loss read back every step."""
+    from where2edit_b200 import _native as N
+    from where2edit_b200 import parallel
+    gen = make_generator(args.size, args.precision, dev)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    mapper = make_levels_mapper(dev).train()
+    reducer = parallel.GradBucketReducer(mapper.parameters())
+    B, K_, W_ = args.batch, args.steps, args.warmup
+    g = torch.Generator().manual_seed(2 + rank)
+    host_w = [torch.randn(B, gen.n_latent, 512, generator=g).pin_memory() for _ in range(2)]
+    dev_w = [w.to(dev) for w in host_w]
+    gimg = (torch.randn(B, 3, args.size, args.size, generator=g) / (3 * args.size * args.size)).to(dev)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(w):
+        reducer.zero_grad()
+        w_hat = w + 0.1 * mapper(w)
+        img, _ = gen([w_hat], input_is_latent=True, randomize_noise=False)
+        loss = (img * gimg).sum()
+        loss.backward()
+        reducer.finish()
+        return loss
+
+    for i in range(W_):
+        step(dev_w[i % 2])
+    barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    N.STATS.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(K_):
+        step(dev_w[i % 2])
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    launches = N.STATS.total()
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    gen.assert_ok()
+    value = world * B * K_ / (total_ms / 1e3)
+
+    def e2e_step(i):
+        w = host_w[i % 2].to(dev, non_blocking=True)
+        loss = step(w)
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(K_):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K_ / (float(ms2.item()) / 1e3)
+
+    roofline = None
+    kinds = {}
+    fwd_ms = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        N.STATS.trace = []
+        reducer.world, saved_world = 1, reducer.world    # rank-0 only: no collective in the traced step
+        step(dev_w[0])
+        reducer.world = saved_world
+        torch.cuda.synchronize()
+        trace, N.STATS.trace = N.STATS.trace, None
+        roofline, _, kinds, layers = roofline_from_trace(trace, peaks, B, args.size, False)
+        if roofline is not None:
+            roofline["kernel"] = "modconv_tc2_kernel (forward and dgrad launches of one forward+backward step)"
+        if args.layers_out:
+            with open(args.layers_out, "w") as fh:
+                json.dump({"batch": B, "size": args.size, "workload": "train", "launches": layers, "kinds": kinds}, fh, indent=1)
+        with torch.no_grad():   # the forward alone (same precision, module path) for the fwd+bwd : fwd ratio
+            fwd_ms = gpu_ms(lambda: gen([dev_w[0]], input_is_latent=True, randomize_noise=False), 3, warm=1)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
+            "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args.size, B, args.precision, world, workload="train"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_w[0].numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "roofline": roofline,
+            "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in kinds.items()},
+            "forward_only_ms_same_path": fwd_ms,
+            "mapper_gradient_floats": int(reducer.flat.numel()), "gradient_buckets": len(reducer.buckets),
+            "cpu_baseline": None,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synthesis", choices=["synthesis", "train"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (32; 16 for --workload train)")
     ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--image-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="dtype of the images the last layer writes / the caller receives")
     ap.add_argument("--cpu-sample", type=int, default=12, help="images of the CPU-baseline sample (0 = skip)")
     ap.add_argument("--layers-out", default=None, help="write the per-launch trace of one step to this JSON file")
+    ap.add_argument("--verify", action="store_true", help="N > 1: check the gathered images slot by slot (default on)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.batch is None:
+        args.batch = 16 if args.workload == "train" else 32
 
     if args.impl == "reference":
         run_reference(args)
@@ -227,18 +492,27 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
+    peaks = measured_peaks()
+    if args.workload == "train":
+        run_train(args, world, rank, dev, dist, peaks)
+        return
+
     from where2edit_b200 import _native as N
     from where2edit_b200 import parallel
     gen = make_generator(args.size, args.precision, dev)
+    img_dtype = torch.bfloat16 if (args.image_dtype == "bf16" and args.precision == "bf16") else torch.float32
+    img_name = "bf16" if img_dtype == torch.bfloat16 else "f32"
+    gen.set_image_output(img_dtype)
     # Multi-GPU: the persistent convolution kernels normally occupy every SM, so the NCCL all-gather kernels of
     # the previous step could only run in the gaps between them; leaving a few SMs free lets the collective
     # overlap the kernels (W2E_RESERVE_SMS; default 0: measured at 4 GPUs 14 649 / 14 362 / 13 335 images/s with 0 / 8 / 16 SMs reserved).
     reserve = int(os.environ.get("W2E_RESERVE_SMS", "0"))
-    if reserve > 0:
+    if reserve > 0 and args.precision == "bf16":
+        from where2edit_b200 import engine as _engine
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        N.load().w2e_modconv_tc2_knobs(max(2, sms - reserve))
+        gen._engine = _engine.SynthesisEngine(gen)
+        gen._engine.tc2_cfg = N.tc2_config(max_ctas=max(2, sms - reserve))   # per-engine, per-call: no library global
     B, K_, W_ = args.batch, args.steps, args.warmup
-    peaks = measured_peaks()
 
     def barrier():
         if dist is not None:
@@ -252,35 +526,47 @@ def main():
     comm_stream = torch.cuda.Stream() if dist is not None else None
     gathered = peer = None
     gather_kind = "none"
+    SLOTS = 2
     if dist is not None:
-        # default: copy-engine pushes into peer-mapped buffers (no SM use; 29 054 vs 26 855 images/s at 8 GPUs);
-        # W2E_GATHER=nccl: the NCCL all-gather
+        # default: copy-engine pushes into peer-mapped buffers (no SM use), each step closed by two device-side
+        # cross-rank barriers so that every step's gathered batch is consumable; W2E_GATHER=nccl: the NCCL all-gather
         if os.environ.get("W2E_GATHER", "p2p") == "p2p":
             try:
-                peer = parallel.PeerGather((B, 3, args.size, args.size), torch.bfloat16, dev, slots=2)
-                gather_kind = "copy-engine peer pushes (symmetric memory)"
+                peer = parallel.PeerGather((B, 3, args.size, args.size), img_dtype, dev, slots=SLOTS)
+                gather_kind = "copy-engine peer pushes into symmetric memory, barrier before and after every step's pushes"
             except Exception as exc:   # no symmetric memory in this build / topology: the NCCL collective
                 if rank == 0:
                     print(f"bench.py: PeerGather unavailable ({exc!r}); using NCCL", file=sys.stderr)
         if peer is None:
-            gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=torch.bfloat16)
-                        for _ in range(2)]
+            gathered = [torch.empty((world * B, 3, args.size, args.size), device=dev, dtype=img_dtype)
+                        for _ in range(SLOTS)]
             gather_kind = "NCCL all-gather"
+    pushed = [None] * SLOTS   # event on the side stream after the pushes of the step that last used a slot
 
     def step(i, w, gather=True):
-        """One pass of the hot path; at N>1 the images are all-gathered (bf16) on a side stream so the
-        collective of step i overlaps the kernels of step i+1."""
+        """One pass of the hot path; at N>1 the images are all-gathered on a side stream so the collective of
+        step i overlaps the kernels of step i+1.  The last layer writes its image straight into this rank's shard of
+        the gather buffer, in the gathered dtype (no conversion pass, no self-copy)."""
+        slot = i % SLOTS
+        if peer is not None and gather:
+            # the compute stream must not overwrite the shard while step i-SLOTS is still being pushed from it
+            if pushed[slot] is not None:
+                torch.cuda.current_stream().wait_event(pushed[slot])
+            gen.set_image_output(img_dtype, peer.own(slot))
+        else:
+            gen.set_image_output(img_dtype)
         with torch.no_grad():
             img, _ = gen([w], input_is_latent=True, randomize_noise=False)
         if dist is not None and gather:
-            small = img.to(torch.bfloat16)
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
                 if peer is not None:
-                    peer.push(small, i % 2)
+                    peer.push(None, slot)
+                    pushed[slot] = torch.cuda.Event()
+                    pushed[slot].record(comm_stream)
                 else:
-                    parallel.gather_images(small, out=gathered[i % 2])
-            small.record_stream(comm_stream)
+                    parallel.gather_images(img, out=gathered[slot])
+            img.record_stream(comm_stream)
         return img
 
     # ---------------- device-resident throughput (`value`)
@@ -299,9 +585,6 @@ def main():
     for i in range(K_):
         step(i, dev_w[i % 2])
     if comm_stream is not None:
-        if peer is not None:
-            with torch.cuda.stream(comm_stream):
-                peer.barrier()   # every rank's pushes have landed
         torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
     barrier()
@@ -312,42 +595,76 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    if gen._engine is not None:
-        gen._engine.assert_ok()
+    gen.assert_ok()
     value = world * B * K_ / (total_ms / 1e3)
+
+    # ---------------- N > 1: the gathered batch of one more step, checked slot by slot against local recomputation
+    gather_ok = None
+    if dist is not None:
+        step(0, dev_w[0])
+        torch.cuda.current_stream().wait_stream(comm_stream)
+        torch.cuda.synchronize()
+        full = peer.result(0) if peer is not None else gathered[0]
+        ok = True
+        gen.set_image_output(img_dtype)
+        for q in range(world):   # every kernel is deterministic and batch-invariant: rank q's images can be recomputed here
+            gq = torch.Generator().manual_seed(2 + q)
+            wq = torch.randn(B, n_lat, 512, generator=gq).to(dev)
+            with torch.no_grad():
+                want, _ = gen([wq], input_is_latent=True, randomize_noise=False)
+            ok = ok and bool(torch.equal(full[q * B:(q + 1) * B], want))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+        barrier()
 
     # ---------------- end to end through the public API with host buffers (`e2e`)
     copy_stream = torch.cuda.Stream()
-    host_img = [torch.empty((B, 3, args.size, args.size), dtype=torch.float32).pin_memory() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step(i):
-        w = host_w[i % 2].to(dev, non_blocking=True)            # H2D of this step's latents (pinned)
-        img = step(i, w)
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        done[i % 2].synchronize()                               # host buffer i%2 free again
-        with torch.cuda.stream(copy_stream):
-            host_img[i % 2].copy_(img, non_blocking=True)       # D2H of the step's images
-            done[i % 2].record(copy_stream)
-        img.record_stream(copy_stream)
+    def measure_e2e(dtype, steps):
+        host_img = [torch.empty((B, 3, args.size, args.size), dtype=dtype).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        keep_dtype = dtype
 
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(K_):
-        e2e_step(i)
-    torch.cuda.current_stream().wait_stream(copy_stream)
-    if comm_stream is not None:
-        torch.cuda.current_stream().wait_stream(comm_stream)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K_ / (float(ms2.item()) / 1e3)
+        def e2e_step(i):
+            done[i % 2].synchronize()                               # host buffer (and gather shard) i%2 free again
+            w = host_w[i % 2].to(dev, non_blocking=True)            # H2D of this step's latents (pinned)
+            if dist is None or peer is None:
+                gen.set_image_output(keep_dtype)
+                with torch.no_grad():
+                    img, _ = gen([w], input_is_latent=True, randomize_noise=False)
+            else:
+                img = step(i, w)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                host_img[i % 2].copy_(img, non_blocking=True)       # D2H of the step's images
+                done[i % 2].record(copy_stream)
+            img.record_stream(copy_stream)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            e2e_step(i)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        if comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(comm_stream)
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        return world * B * steps / (float(ms2.item()) / 1e3), host_img[0].numel() * host_img[0].element_size()
+
+    e2e_value, d2h = measure_e2e(img_dtype, K_)
     h2d = host_w[0].numel() * 4
-    d2h = host_img[0].numel() * 4
+    e2e_f32 = None
+    if dist is None and img_dtype != torch.float32:
+        v32, d32 = measure_e2e(torch.float32, max(5, K_ // 3))
+        e2e_f32 = {"value": v32, "unit": UNIT, "d2h_bytes_per_step": d32,
+                   "note": "same, with fp32 images (the reference's output dtype) copied out: PCIe-bound"}
+    gen.set_image_output(img_dtype)
 
     # ---------------- per-kernel roofline from one traced step (CUDA events around every launch)
     roofline = roofline_up = None
@@ -359,25 +676,7 @@ def main():
         step(1, dev_w[1], gather=False)
         torch.cuda.synchronize()
         trace, N.STATS.trace = N.STATS.trace, None
-        kinds, layers = summarise_trace(trace, peaks)
-        traced_ms = sum(k["ms"] for k in kinds.values())
-        if "modconv" in kinds and kinds["modconv"]["ms"] > 0:
-            k = kinds["modconv"]
-            ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "modconv_tc2_kernel (all 3x3 modulated-conv launches of a step)",
-                        "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["bf16_tflops_sustained"],
-                        "traffic": ncu_traffic("modconv") if (B == 32 and args.size == 1024) else None,
-                        "peak_source": peaks["source"] + " bf16_tflops_sustained", "algorithmic_flops": k["flops"],
-                        "launches": k["launches"], "share_of_step": k["ms"] / traced_ms}
-        if "upfirdn2d" in kinds and kinds["upfirdn2d"]["ms"] > 0:
-            k = kinds["upfirdn2d"]
-            ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
-            roofline_up = {"bound": "hbm", "kernel": "blur_act_nhwc_kernel (all blur launches of a step)",
-                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                           "traffic": ncu_traffic("blur") if (B == 32 and args.size == 1024) else None,
-                           "algorithmic_bytes": k["bytes"], "peak_source": peaks["source"] + " hbm_gbs", "launches": k["launches"],
-                           "share_of_step": k["ms"] / traced_ms}
+        roofline, roofline_up, kinds, layers = roofline_from_trace(trace, peaks, B, args.size, B == 32 and args.size == 1024)
         if args.layers_out:
             with open(args.layers_out, "w") as fh:
                 json.dump({"batch": B, "size": args.size, "precision": args.precision, "launches": layers,
@@ -391,10 +690,20 @@ def main():
         v, dt = cpu_forward_images_per_s(sd, args.size, n_lat, args.cpu_sample, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.cpu_sample} images of the same {args.size}^2 generator forward in one batch "
-                         f"({dt:.1f} s), fp32 torch CPU ops via the oracle port, after a 1-image warm-up"}
+                         f"({dt:.1f} s), fp32 torch CPU ops via the oracle port of the reference (pure Python: it cannot "
+                         f"travel to the GPU box), after a 1-image warm-up",
+               "ops": cpu_op_baselines(threads)}
 
-    # ---------------- the callers either side of the path, outside the timed region
-    next_rows = None
+    # ---------------- configs 3 / 4 and the callers either side of the path, outside the timed region
+    extras = next_rows = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and args.size == 1024 \
+            and os.environ.get("W2E_BENCH_EXTRAS", "1") == "1":
+        gen.set_image_output(torch.float32)
+        try:
+            extras = extra_pipelines(gen, dev, args.size, n_lat)
+        except Exception as exc:
+            extras = {"error": repr(exc)[:300]}
+        gen.set_image_output(img_dtype)
     if rank == 0 and world == 1 and args.precision == "bf16" and os.environ.get("W2E_BENCH_NEXT_ROWS", "1") == "1":
         try:
             import importlib.util
@@ -411,14 +720,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
             "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args.size, B, args.precision, world, gather_kind),
+            "config": workload_config(args.size, B, args.precision, world, gather_kind, image_dtype=img_name),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "image_dtype": img_name},
+            "e2e_fp32_images": e2e_f32,
             "gpu_launches": launches,
+            "gather_ok": gather_ok,
             "roofline": roofline, "roofline_upfirdn2d": roofline_up,
             "modconv_tflops_per_step_algorithmic": MODCONV_GFLOP_PER_IMAGE * B / 1e3 if args.size == 1024 else None,
             "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in kinds.items()},
             "cpu_baseline": cpu,
+            "pipelines": extras,
             "next_rows": next_rows,
         }
         print(json.dumps(line))

@@ -161,50 +161,56 @@ int w2e_mask_blend_bwd(const float* g, const float* edited, const float* orig, c
 /* ==== bf16 tensor-core path: channels-last (NHWC) bf16 activations ==========================
  *
  * ---- modulated convolution on tcgen05 tensor cores (models/stylegan2/model.py:249-274) ------
- * Implicit GEMM, one launch per "class" of output pixels:
- *   acc[b,j,i,o] = sum_{t<ntaps} sum_c xs[b, j+dy_t, i+dx_t, c] * w[slot_t][o][c]     (fp32 accumulate)
+ * Persistent, warp-specialised implicit GEMM (haloed TMA input tile shared by all 9 taps, accumulators in
+ * TMEM, the four parity classes of the transposed convolution fused into one pass):
+ *   acc[b,y,x,o] = sum_{taps} sum_c xs[b, y+dy, x+dx, c] * w[tap][o][c]                 (fp32 accumulate)
  *   v = acc * out_scale[b,o]                                  (demodulation, model.py:242-243)
- *   act == W2E_ACT_LRELU:  v = lrelu(v + noise_w*noise[oy,ox] + bias[o], 0.2) * sqrt(2)
- *   out[b,oy,ox,o] = v ;  out_mod[b,oy,ox,o] = v * next_scale[b,o]
- * with (oy,ox) = (j*out_stride+py, i*out_stride+px), (j,i) on a grid_h x grid_w grid.
+ *   act == W2E_ACT_LRELU:  v = lrelu(v + noise_w*noise[y,x] + bias[o], 0.2) * sqrt(2)
+ *   out[b,y,x,o] = v ;  out_mod[b,y,x,o] = v * next_scale[b,o]
  *   xs:  bf16 [B,in_h,in_w,Cin]  -- the input ALREADY multiplied by this layer's style (its
  *        producer wrote it through out_mod/next_scale), so all samples share one weight tensor;
  *        reads outside the image are zero (= the convolution padding, done by TMA).
- *   w:   bf16 [nslots][Cout][Cin], pre-scaled by 1/sqrt(Cin*k*k) (model.py:216-217).
- *   host_taps: ntaps x {dy, dx, slot} ints.  Plain 3x3: 9 taps, out_stride 1.  Transposed x2
- *   (conv_transpose2d stride 2): four launches with 4/2/2/1 taps, out_stride 2, (py,px) the parity.
- *   out / out_mod: bf16 [B,out_h,out_w,Cout]; either may be NULL.  error_flag: device int set to 1
- *   if the kernel's pipeline timed out (never expected; turns a hang into a reportable error).
- * Requires Cin % 32 == 0, Cout % 16 == 0, 16-byte aligned tensors, an sm_100 device.          */
-int w2e_modconv_tc_supported(void);
-int w2e_modconv_tc(const void* xs, const void* w, const float* out_scale, const float* bias,
-                   const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
-                   void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
-                   int in_w, int out_h, int out_w, int grid_h, int grid_w, int out_stride, int py,
-                   int px, const int* host_taps, int ntaps, int nslots, int act, void* stream);
+ *   w:   bf16 [9][Cout][Cin], pre-scaled by 1/sqrt(Cin*k*k) (model.py:216-217).
+ *   transposed == 0: plain 3x3, padding 1: xs [B,in_h,in_w,Cin] -> out [B,in_h,in_w,Cout].
+ *   transposed == 1: conv_transpose2d stride 2: -> out [B,2*in_h+1,2*in_w+1,Cout] (the pre-blur tensor).
+ *   out / out_mod: bf16 channels-last; either may be NULL.  error_flag: device int set to 1 if the kernel's
+ *   pipeline timed out (never expected; turns a hang into a reportable error).
+ * Requires Cin % 32 == 0, Cout % 16 == 0, 16-byte aligned tensors, an sm_100 device.
+ *
+ * cfg (may be NULL = defaults) carries the PER-CALL tuning / A-B switches; the library keeps no mutable
+ * global tuning state.  Results are bit-identical for every setting.                           */
+typedef struct w2e_tc2_config {
+  int max_ctas;       /* cap on the number of persistent CTAs (0 = one per SM)                               */
+  int ts_mode;        /* 1 = shared-memory-staged TMA-store epilogue whenever eligible, 0 = direct stores    */
+  int flags;          /* bit 0 no edge-tile tap masking (transposed), bit 1 a single MMA-issuing warp,
+                         bit 3 64-column tiles for the transposed conv, bit 4 256-pixel tiles for the 32-channel
+                         transposed conv, bit 5 128-pixel tiles (two accumulator sets) for the 64-channel one   */
+  int cluster_log2;   /* weight-ring kernels as clusters of 2^n CTAs with TMA-multicast weight blocks (0..3)  */
+  void* timeline;     /* device long long[64][8] or NULL: clock64 stamps of CTA 0's first 64 tiles
+                         (tools/tc2_timeline.py)                                                              */
+} w2e_tc2_config;
 
-/* Persistent v2 of the kernel above (haloed input tile shared by all 9 taps, double-buffered TMEM
- * accumulators, the four parity classes of the transposed convolution fused into one pass).
- * transposed == 0: plain 3x3, padding 1: xs [B,in_h,in_w,Cin] -> out [B,in_h,in_w,Cout].
- * transposed == 1: conv_transpose2d stride 2: -> out [B,2*in_h+1,2*in_w+1,Cout] (the pre-blur tensor).
- * Same epilogue, operands and constraints as w2e_modconv_tc.                                  */
+int w2e_modconv_tc_supported(void);
 int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
                     const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
-                    int in_w, int transposed, int act, void* stream);
+                    int in_w, int transposed, int act, const w2e_tc2_config* cfg, void* stream);
 /* Plain 3x3 variant with the following ToRGB (models/stylegan2/model.py:353-362) fused into the
  * epilogue: every epilogue thread holds one pixel's full channel row, so
  *   rgb[b,o,y,x] = sum_c act[b,y,x,c]*rgb_style[b,c]*rgb_w[o,c] + rgb_bias[o] + upsample2(rgb_skip)[b,o,y,x]
  * is produced without re-reading the activation; out and out_mod may then both be NULL.
  * rgb_w: float [3,Cout] pre-scaled by 1/sqrt(Cout); rgb_skip: float [B,3,in_h/2,in_w/2] or NULL;
- * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: float [B,3,in_h,in_w].
- * Needs Cout <= 512 (the rgb image must be zero-initialised when Cout > 256: two channel blocks add into it) and in_h > 16.                                                             */
+ * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: [B,3,in_h,in_w] of rgb_dtype
+ * (W2E_F32 or W2E_BF16: the image in the dtype the caller wants, straight from the epilogue).
+ * Needs Cout <= 512 (the rgb image must be fp32 and zero-initialised when Cout > 256: two channel blocks add
+ * into it) and in_h > 16.                                                                        */
 int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
                         const float* noise, const float* noise_w, int noise_batch,
                         const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
                         int Cin, int Cout, int in_h, int in_w, int act, const float* rgb_w,
                         const float* rgb_style, const float* rgb_bias, const float* rgb_skip,
-                        const float* host_taps1d, float* rgb, void* stream);
+                        const float* host_taps1d, void* rgb, int rgb_dtype, const w2e_tc2_config* cfg,
+                        void* stream);
 /* Fused up-convolution + Blur + NoiseInjection + FusedLeakyReLU (models/stylegan2/model.py:249-260,
  * 279-290; op/fused_act.py:23-39): the transposed x2 modulated convolution of w2e_modconv_tc2 whose
  * (2h+1)^2 pre-blur result stays in shared memory and is filtered by the separable 4x4 FIR host_taps[16]
@@ -215,25 +221,8 @@ int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, c
 int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale, const float* host_taps,
                            const float* bias, const float* noise, const float* noise_w, int noise_batch,
                            const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
-                           int Cin, int Cout, int in_h, int in_w, int act, void* stream);
-/* tuning knob of w2e_modconv_tc2: cap on the number of persistent CTAs (0 = one or two per SM). */
-void w2e_modconv_tc2_knobs(int max_ctas);
-/* epilogue selection of w2e_modconv_tc2[_rgb]: 1 (default) = shared-memory-staged TMA-store epilogue
- * whenever the shape is eligible, 0 = always the direct-store epilogue (A/B tests). */
-void w2e_modconv_tc2_epilogue(int ts_mode);
-/* debugging aid: when non-null, CTA 0 of every following w2e_modconv_tc2 launch with the staged
- * epilogue writes clock64 stamps of its first 64 tiles into timeline[64][8] (device memory):
- * producer {inputs slot free, A tile issued}, MMA issuer {accumulator free, A tile landed, MMAs
- * issued}, epilogue {inputs landed, accumulator ready, tile done}.  See tools/tc2_timeline.py.   */
-void w2e_modconv_tc2_debug(void* timeline);
-/* A/B switches for measurements: bit 0 = no edge-tile tap masking (transposed conv), bit 1 = a single
- * MMA-issuing warp, bit 2 = 2-CTA clusters with TMA-multicast weight blocks (off by default: no gain
- * measured), bit 3 = 64-column tiles for the transposed conv,
- * bit 4 = 256-pixel tiles for the 32-channel transposed conv.  Results are identical for every setting. */
-void w2e_modconv_tc2_flags(int flags);
-/* weight-ring kernels as clusters of 2^log2_size CTAs (0 = none, up to 3 = 8 CTAs) that work on the same
- * tile of consecutive samples and TMA-multicast every weight block (each CTA loads 1/size of it).   */
-void w2e_modconv_tc2_cluster(int log2_size);
+                           int Cin, int Cout, int in_h, int in_w, int act, const w2e_tc2_config* cfg,
+                           void* stream);
 
 /* ---- layout transforms ----------------------------------------------------------------------
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],
@@ -253,11 +242,13 @@ int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10,
 
 /* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
  * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->
- * [B,out_h,out_w,C]; then the same epilogue as w2e_modconv_tc (no demodulation).              */
+ * [B,out_h,out_w,C]; then the same epilogue as w2e_modconv_tc2 (no demodulation).
+ * variant: 0 = kernel with a run-time tile shape, 1 = templated channel tile with a predicate-free interior
+ * body (C >= 32); both give bit-identical results.                                                */
 int w2e_blur_act_nhwc(const void* z, const float* host_taps, const float* bias, const float* noise,
                       const float* noise_w, int noise_batch, const float* next_scale, void* out,
                       void* out_mod, int B, int C, int in_h, int in_w, int py0, int px0, int out_h,
-                      int out_w, int act, void* stream);
+                      int out_w, int act, int variant, void* stream);
 
 /* ---- ToRGB, channels-last input (model.py:353-362): as w2e_torgb_fwd with x bf16 [B,H,W,C]. */
 int w2e_torgb_nhwc(const void* x, const float* w, const float* style, const float* bias,

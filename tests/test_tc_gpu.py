@@ -37,7 +37,7 @@ class _Layer:
         self.m = self.m.to(DEV)
 
 
-def run_layer(eng, layer, x, s, noise, nxt, act=True, version="v2"):
+def run_layer(eng, layer, x, s, noise, nxt, act=True):
     """x fp32 NCHW, s [B,Cin] -> (out NCHW fp32, out_mod NCHW fp32) through the bf16 kernels."""
     m = layer.m
     b, cin, h, w = x.shape
@@ -49,21 +49,10 @@ def run_layer(eng, layer, x, s, noise, nxt, act=True, version="v2"):
     bias = m.activate.bias.detach()
     nxt_d = nxt.to(DEV).contiguous() if nxt is not None else None
     if not m.conv.upsample:
-        if version == "v1":
-            out, out_mod = eng._conv(xs, pw, d, nz, nw, bias, nxt_d, True, nxt is not None, E._TAPS_PLAIN, (h, w),
-                                     (h, w), (h, w), 1, 0, 0, N.ACT_LRELU if act else N.ACT_NONE)
-        else:
-            out, out_mod = eng._conv2(xs, pw, d, nz, nw, bias, nxt_d, True, nxt is not None, False,
-                                      N.ACT_LRELU if act else N.ACT_NONE)
+        out, out_mod = eng._conv2(xs, pw, d, nz, nw, bias, nxt_d, True, nxt is not None, False,
+                                  N.ACT_LRELU if act else N.ACT_NONE)
     else:
-        zh, zw = 2 * h + 1, 2 * w + 1
-        if version == "v1":
-            z = torch.full((b, zh, zw, pw.cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-            for (py, px), taps in E._TAPS_UP.items():
-                eng._conv(xs, pw, d, None, None, None, None, True, False, taps, (h, w), (zh, zw),
-                          (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
-        else:
-            z, _ = eng._conv2(xs, pw, d, None, None, None, None, True, False, True, N.ACT_NONE)
+        z, _ = eng._conv2(xs, pw, d, None, None, None, None, True, False, True, N.ACT_NONE)
         out, out_mod = eng._blur(z, m.conv.blur.kernel, m.conv.blur.pad, bias, nz, nw, nxt_d, True, nxt is not None,
                                  (2 * h, 2 * w))
     eng.assert_ok()
@@ -76,7 +65,6 @@ def eng():
     return E.SynthesisEngine(gen)
 
 
-@pytest.mark.parametrize("version", ["v2", "v1"])
 @pytest.mark.parametrize("b,cin,cout,h,up", [
     (2, 64, 64, 16, False),     # BK 64, one pixel tile per image row block
     (1, 32, 32, 40, False),     # BK 32 (64-byte swizzle), ragged 40x40 grid
@@ -90,14 +78,14 @@ def eng():
     (1, 64, 32, 36, True),      # resident weights, ragged 37x37 class grid, two accumulator buffers
     (2, 32, 32, 72, False),     # many tiles per CTA slot: accumulator double-buffering wraps
 ])
-def test_styled_conv_tc_matches_oracle(eng, b, cin, cout, h, up, version):
+def test_styled_conv_tc_matches_oracle(eng, b, cin, cout, h, up):
     layer = _Layer(cin, cout, up, 31)
     x = synth.make_tensor((b, cin, h, h), 32)
     s = 1 + 0.3 * synth.make_tensor((b, cin), 33)
     oh = 2 * h if up else h
     noise = synth.make_tensor((1, 1, oh, oh), 34)
     nxt = 1 + 0.3 * synth.make_tensor((b, cout), 35)
-    got, got_mod = run_layer(eng, layer, x, s, noise, nxt, version=version)
+    got, got_mod = run_layer(eng, layer, x, s, noise, nxt)
     blur = synth.blur_kernel_2d(gain=4.0)
     ref, _ = orc.modulated_conv2d_ref(x.double(), s.double().reshape(b, 1, cin, 1, 1), layer.weight.double(), None,
                                       None, True, up, blur.double(), input_is_stylespace=True)
@@ -274,16 +262,15 @@ def test_staged_and_direct_epilogues_agree_bitwise(eng, b, cin, cout, h, up):
     s = 1 + 0.3 * synth.make_tensor((b, cin), 73)
     noise = synth.make_tensor((1, 1, 2 * h if up else h, 2 * h if up else h), 74)
     nxt = 1 + 0.3 * synth.make_tensor((b, cout), 75)
-    lib = N.load()
     outs = []
     try:
-        for ts_mode, flags in [(1, 0), (0, 0), (1, 1), (1, 2), (1, 3), (1, 4), (0, 4), (1, 8), (1, 16)]:
-            lib.w2e_modconv_tc2_epilogue(ts_mode)
-            lib.w2e_modconv_tc2_flags(flags)
+        # (ts_mode, flags, cluster_log2): the per-call w2e_tc2_config switches (include/w2e.h)
+        for ts_mode, flags, clus in [(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (1, 0, 1), (0, 0, 1), (1, 8, 0),
+                                     (1, 16, 0), (1, 32, 0)]:
+            eng.tc2_cfg = N.tc2_config(ts_mode=ts_mode, flags=flags, cluster_log2=clus)
             outs.append(run_layer(eng, layer, x, s, noise, nxt))
     finally:
-        lib.w2e_modconv_tc2_epilogue(1)
-        lib.w2e_modconv_tc2_flags(0)
+        eng.tc2_cfg = None
     for got, got_mod in outs[1:]:
         assert torch.equal(got, outs[0][0])
         assert torch.equal(got_mod, outs[0][1])

@@ -17,19 +17,24 @@ def main():
     torch.manual_seed(0)
     gen = w2e.Generator(1024, 512, 8, channel_multiplier=2, precision="bf16").to(dev).eval()
     w = torch.randn(batch, gen.n_latent, 512, device=dev)
-    lib = N.load()
-    settings = [("default", 1, 0, 0), ("clusters of 4", 1, 0, 2), ("clusters of 8", 1, 0, 3), ("one MMA issuer", 1, 2, 0)]
+    from where2edit_b200 import engine as E
+    gen._engine = E.SynthesisEngine(gen)
+    eng = gen._engine
+    # (name, ts_mode, flags, cluster_log2, blur variant): per-call switches, no library-global state
+    settings = [("default", 1, 0, 0, 0), ("blur v2", 1, 0, 0, 1), ("up 128->64: 128-px tiles", 1, 32, 0, 0),
+                ("one MMA issuer", 1, 2, 0, 0)]
+    if len(sys.argv) > 2:
+        settings = [("default", 1, 0, 0, 0)] + [(a, *[int(v) for v in a.split(",")]) for a in sys.argv[2:]]
     results = {}
-    for name, ts, flags, clus in settings:
-        lib.w2e_modconv_tc2_epilogue(ts)
-        lib.w2e_modconv_tc2_flags(flags)
-        lib.w2e_modconv_tc2_cluster(clus)
+    for name, ts, flags, clus, blur in settings:
+        eng.tc2_cfg = N.tc2_config(ts_mode=ts, flags=flags, cluster_log2=clus)
+        eng.blur_variant = blur
         with torch.no_grad():
             for _ in range(2):
                 gen([w], input_is_latent=True, randomize_noise=False)
             torch.cuda.synchronize()
             acc = {}
-            for rep in range(3):
+            for rep in range(5):
                 N.STATS.trace = []
                 gen([w], input_is_latent=True, randomize_noise=False)
                 torch.cuda.synchronize()
@@ -38,11 +43,9 @@ def main():
                     acc.setdefault(tag, []).append(e0.elapsed_time(e1))
                 N.STATS.trace = None
         results[name] = {k: min(v) for k, v in acc.items()}
-    lib.w2e_modconv_tc2_epilogue(1)
-    lib.w2e_modconv_tc2_flags(0)
-    lib.w2e_modconv_tc2_cluster(0)
+    eng.tc2_cfg = None
     base = results["default"]
-    names = [n for n, _, _, _ in settings]
+    names = [s_[0] for s_ in settings]
     print(f"{'launch':30s} " + " ".join(f"{n:>22s}" for n in names))
     tot = {n: 0.0 for n in names}
     for tag, t in base.items():

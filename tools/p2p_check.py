@@ -10,14 +10,17 @@ dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 shard = torch.full((4, 3, 64, 64), float(rank + 1), device=dev, dtype=torch.bfloat16) + torch.arange(64, device=dev).to(torch.bfloat16)
 pg = parallel.PeerGather(shard.shape, shard.dtype, dev)
 ref = parallel.gather_images(shard)
-for slot in (0, 1, 0):
-    pg.push(shard, slot); pg.barrier()
-    assert torch.equal(pg.result(slot), ref), "mismatch"
+for it, slot in enumerate((0, 1, 0, 1)):
+    if it < 2:
+        pg.push(shard * (it + 1), slot)                      # copy-in + pushes, closed by the per-step barriers
+    else:
+        pg.own(slot).copy_(shard * (it + 1)); pg.push(None, slot)   # producer wrote its shard in place
+    assert torch.equal(pg.result(slot), parallel.gather_images(shard * (it + 1))), "mismatch"   # consumable at once
 # timing at image size
 big = torch.randn(32, 3, 1024, 1024, device=dev).to(torch.bfloat16)
 pg2 = parallel.PeerGather(big.shape, big.dtype, dev)
 out = torch.empty((world * 32, 3, 1024, 1024), device=dev, dtype=torch.bfloat16)
-for name, fn in (("p2p", lambda: (pg2.push(big, 0), pg2.barrier())), ("nccl", lambda: parallel.gather_images(big, out=out))):
+for name, fn in (("p2p", lambda: pg2.push(big, 0)), ("nccl", lambda: parallel.gather_images(big, out=out))):
     for _ in range(3): fn()
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)

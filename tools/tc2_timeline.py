@@ -1,5 +1,5 @@
 """Timeline of CTA 0 of one w2e_modconv_tc2[_rgb] launch (clock64 stamps written by the kernel's
-three roles, see include/w2e.h: w2e_modconv_tc2_debug).  Prints per tile, relative to the first
+three roles, see include/w2e.h: w2e_tc2_config.timeline).  Prints per tile, relative to the first
 stamp: producer {inputs slot free, A issued}, MMA {acc free, A landed, issued}, epilogue {inputs,
 acc ready, done}; with tr=2 (fused up-conv + blur) the P columns hold {pre-blur tile written, FIR of chunk 0 done}.
     python tools/tc2_timeline.py [cin cout h batch rgb(0/1) tr(0/1/2)]"""
@@ -47,10 +47,10 @@ def main():
 
     run()
     torch.cuda.synchronize()
-    N.load().w2e_modconv_tc2_debug(N.ptr(buf))
+    eng.tc2_cfg = N.tc2_config(timeline=buf, flags=int(os.environ.get("W2E_TC2_FLAGS", "0")))
     run()
     torch.cuda.synchronize()
-    N.load().w2e_modconv_tc2_debug(None)
+    eng.tc2_cfg = None
     t = buf.cpu().reshape(64, 8)
     t0 = int(t[t > 0].min())
     print("tile |  P:slot  P:Aiss | M:accfree M:Aland M:issued | E:inputs E:accrdy E:done   (cycles since start)")

@@ -9,6 +9,7 @@ from . import _native
 from .model import (Blur, ConstantInput, Downsample, EqualConv2d, EqualLinear, Generator, ModulatedConv2d,
                     NoiseInjection, PixelNorm, ScaledLeakyReLU, StyledConv, ToRGB, Upsample, make_kernel)
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d, upfirdn2d_native
+from .graph import GraphedGenerator
 
 __version__ = "0.1.0"
 
@@ -66,4 +67,4 @@ def install_as_reference():
 __all__ = ["Generator", "ModulatedConv2d", "StyledConv", "ToRGB", "EqualLinear", "EqualConv2d", "PixelNorm",
            "Blur", "Upsample", "Downsample", "NoiseInjection", "ConstantInput", "ScaledLeakyReLU", "make_kernel",
            "FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "upfirdn2d_native", "install_as_reference",
-           "enable_weight_gradients"]
+           "enable_weight_gradients", "GraphedGenerator"]

@@ -43,20 +43,14 @@ PROTOTYPES = {
     "w2e_mask_blend_fwd": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_I, _P]),
     "w2e_mask_blend_bwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
     "w2e_modconv_tc_supported": (_I, []),
-    "w2e_modconv_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 12 + [_P, _I, _I, _I, _P]),
-    "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P]),
-    "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 7),
-    "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P]),
-    "w2e_modconv_tc2_knobs": (None, [_I]),
-    "w2e_modconv_tc2_epilogue": (None, [_I]),
-    "w2e_modconv_tc2_debug": (None, [_P]),
-    "w2e_modconv_tc2_flags": (None, [_I]),
-    "w2e_modconv_tc2_cluster": (None, [_I]),
+    "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
+    "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 6 + [_I, _P, _P]),
+    "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P, _P]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),
     "w2e_nchw_class_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "w2e_nhwc_sum4_to_nchw_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 9 + [_P]),
+    "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 10 + [_P]),
     "w2e_torgb_nhwc": (_I, [_P] * 7 + [_I, _I, _I, _I, _P]),
     "w2e_blend_nhwc": (_I, [_P] * 6 + [_I] * 6 + [_P]),
     "w2e_cluster_assign": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P]),
@@ -68,7 +62,23 @@ PROTOTYPES = {
 
 # entry points that enqueue no kernel (host queries)
 _HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace", "w2e_rowdot_segments",
-              "w2e_modconv_tc_supported", "w2e_modconv_tc2_knobs", "w2e_modconv_tc2_epilogue", "w2e_modconv_tc2_debug", "w2e_modconv_tc2_flags", "w2e_modconv_tc2_cluster"}
+              "w2e_modconv_tc_supported"}
+
+
+class Tc2Config(ctypes.Structure):
+    """include/w2e.h: w2e_tc2_config -- per-call tuning / A-B switches of the tcgen05 convolution (the library
+    keeps no global tuning state).  Pass `tc2_cfg(obj)` as the `cfg` argument; None = defaults."""
+    _fields_ = [("max_ctas", ctypes.c_int), ("ts_mode", ctypes.c_int), ("flags", ctypes.c_int),
+                ("cluster_log2", ctypes.c_int), ("timeline", ctypes.c_void_p)]
+
+
+def tc2_config(max_ctas=0, ts_mode=1, flags=0, cluster_log2=0, timeline=None):
+    return Tc2Config(int(max_ctas), int(ts_mode), int(flags), int(cluster_log2),
+                     None if timeline is None else timeline.data_ptr())
+
+
+def tc2_cfg(cfg):
+    return None if cfg is None else ctypes.byref(cfg)
 
 
 class Stats:
@@ -97,11 +107,14 @@ def note(**work):
         STATS.note = work
 
 
+_tls = threading.local()   # .device = ordinal of the CUDA tensors of the call being assembled (set by ptr())
+
+
 def _wrap(name, fn):
     if name in _HOST_ONLY:
         return fn
 
-    def call(*args):
+    def launch(*args):
         st = STATS
         st.launches[name] = st.launches.get(name, 0) + 1
         if st.trace is None:
@@ -114,6 +127,16 @@ def _wrap(name, fn):
         st.trace.append((name, st.note, e0, e1))
         st.note = None
         return rc
+
+    def call(*args):
+        # device guard: the kernels run on the device of their tensors (ptr() noted it while the arguments were
+        # built, stream_ptr() took that device's current stream), whichever device is current in the caller
+        dev = getattr(_tls, "device", None)
+        _tls.device = None
+        if dev is not None and dev != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return launch(*args)
+        return launch(*args)
 
     return call
 
@@ -138,8 +161,14 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB
-        if not os.path.exists(path) or (os.environ.get("W2E_REBUILD") == "1"):
-            path = _build.build(force=True)
+        stale = os.path.exists(path) and os.path.exists(_build.STAMP) and not _build.is_current()
+        if not os.path.exists(path) or stale or (os.environ.get("W2E_REBUILD") == "1"):
+            # a stale library would be called through mismatched prototypes: rebuild it, or refuse to load it
+            try:
+                path = _build.build(force=True)
+            except RuntimeError as e:
+                raise RuntimeError(f"where2edit_b200: {path} is missing or older than csrc/ and cannot be rebuilt "
+                                   f"here ({e}); run `python -m where2edit_b200.build`") from e
         try:
             lib = ctypes.CDLL(path)
         except OSError as e:  # fail loudly: there is no other implementation
@@ -173,7 +202,10 @@ def check(code, what):
 
 
 def stream_ptr(device=None):
-    """torch's current stream ON `device` (a tensor's device); None = the current device."""
+    """torch's current stream on the device of the tensors passed through ptr() for this call (else `device`,
+    else the current device)."""
+    if device is None:
+        device = getattr(_tls, "device", None)
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -213,6 +245,8 @@ class ErrorFlag:
                                "the calls since the last successful check are invalid")
 
     def poll(self):
+        if torch.cuda.is_current_stream_capturing():
+            return
         if self.event is not None and self.event.query():
             self._raise_if_set()
 
@@ -233,6 +267,7 @@ def ptr(t):
         raise RuntimeError("where2edit_b200 has no CPU path: tensor must live on a CUDA device")
     if not t.is_contiguous():
         raise RuntimeError("where2edit_b200: tensor must be contiguous")
+    _tls.device = t.device.index
     return ctypes.c_void_p(t.data_ptr())
 
 

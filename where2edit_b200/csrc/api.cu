@@ -19,17 +19,20 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;  // B200; do not cache a failed query
-  }
-  return cached;
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (dev < 0) return 148;  // B200; do not cache a failed query
+  if (dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev < 64) cached[dev] = n;
+  return n;
 }
 
 }  // namespace w2e

@@ -32,7 +32,15 @@ int set_error(int code, const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-int sm_count();  // cached, api.cu
+int sm_count();        // of the CURRENT device (cached per device ordinal), api.cu
+int current_device();  // cudaGetDevice; -1 if it fails
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember it per device ordinal
+struct PerDeviceOnce {
+  bool flag[64] = {};
+  bool done() const { const int d = current_device(); return d >= 0 && d < 64 && flag[d]; }
+  void mark() { const int d = current_device(); if (d >= 0 && d < 64) flag[d] = true; }
+};
 
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);

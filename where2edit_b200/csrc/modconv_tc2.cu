@@ -69,7 +69,8 @@ struct Tc2Params {
   const float* rgb_style;   // [B,Cout]
   const float* rgb_bias;    // [3] or null
   const float* rgb_skip;    // [B,3,OH/2,OW/2] fp32 NCHW or null
-  float* rgb;               // [B,3,OH,OW] fp32 NCHW
+  void* rgb;                // [B,3,OH,OW] NCHW, fp32 or (rgb_bf16) bf16: the image in the dtype the caller wants
+  int rgb_bf16;
   float kf[4];              // flipped 1-D taps of the skip upsample filter
   int noise_per_sample;
   int B, Cin, Cout, OH, OW;
@@ -970,12 +971,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int p = 0; p < NP; ++p) {
             const int oy = j0 + (half * NP + p) * kSubTileH + sy, ox = i0 + sx;
             if (oy < P.OH && ox < P.OW && ok) {
-              float* dst = P.rgb + ((int64_t)b * 3 * P.OH + oy) * P.OW + ox;
+              const int64_t di = ((int64_t)b * 3 * P.OH + oy) * P.OW + ox;
 #pragma unroll
               for (int o = 0; o < 3; ++o) {
                 float lo, hi;
                 unpack2(racc[p][o], lo, hi);
-                dst[o * plane] = rgb_init[p][o] + (lo + hi);
+                const float v = rgb_init[p][o] + (lo + hi);
+                if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di + o * plane] = __float2bfloat16_rn(v);
+                else reinterpret_cast<float*>(P.rgb)[di + o * plane] = v;
               }
             }
           }
@@ -1192,9 +1195,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (RGB && valid) {
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
-            float* dst = P.rgb + (((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox;
-            if (P.tiles_n > 1) atomicAdd(dst, rgb_acc[o]);
-            else *dst = rgb_acc[o];
+            const int64_t di = (((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox;
+            if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di] = __float2bfloat16_rn(rgb_acc[o]);   // (tiles_n == 1)
+            else if (P.tiles_n > 1) atomicAdd(reinterpret_cast<float*>(P.rgb) + di, rgb_acc[o]);
+            else reinterpret_cast<float*>(P.rgb)[di] = rgb_acc[o];
           }
         }
       }
@@ -1219,10 +1223,10 @@ template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, const Tc2Maps& M, int smem_bytes,
                       int max_ctas, cudaStream_t s) {
   auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB, TS>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
     W2E_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    configured.mark();
   }
   int per_sm = 1;
   constexpr int kThreads = TS ? (WRES ? kT2ThreadsTS2 : kT2ThreadsTS) : kT2Threads;
@@ -1263,28 +1267,12 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Par
   return W2E_OK;
 }
 
-// debug / tuning knobs (tests flip them to validate the shifted-descriptor scheme on hardware)
-static int g_max_ctas = 0;
-static int g_ts_mode = 1;   // 0 = never use the TS epilogue, 1 = whenever eligible
-static long long* g_dbg = nullptr;
-static int g_flags = 0;
-// 1 = 2-CTA clusters with multicast weight blocks for the weight-ring kernels.  Off by default: bit-identical
-// results but no gain measured -- the L2 already merges the unicast requests of a few CTAs, and what binds the
-// weight ring is the SM's TMA ingest, which multicast does not reduce.
-static int g_cluster_mode = 0;
-
 }  // namespace w2e
 
 using namespace w2e;
 
-extern "C" void w2e_modconv_tc2_knobs(int max_ctas) { g_max_ctas = max_ctas; }
-extern "C" void w2e_modconv_tc2_epilogue(int ts_mode) { g_ts_mode = ts_mode; }
-extern "C" void w2e_modconv_tc2_debug(void* timeline) { g_dbg = (long long*)timeline; }
-extern "C" void w2e_modconv_tc2_flags(int flags) { g_flags = flags & 59; g_cluster_mode = (flags & 4) ? 1 : 0; }
-extern "C" void w2e_modconv_tc2_cluster(int log2_size) { g_cluster_mode = log2_size < 0 ? 0 : (log2_size > 3 ? 3 : log2_size); }
-
 struct RgbArgs {
-  const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; float* rgb;
+  const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; void* rgb; int rgb_dtype;
 };
 
 struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped taps)
@@ -1294,7 +1282,14 @@ struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
                    const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
                    int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
-                   const RgbArgs* rgb, void* stream, bool allow_mt4 = true, const FbArgs* fb = nullptr) {
+                   const RgbArgs* rgb, const w2e_tc2_config* cfg, void* stream, bool allow_mt4 = true,
+                   const FbArgs* fb = nullptr) {
+  // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
+  const int g_max_ctas = cfg ? cfg->max_ctas : 0;
+  const int g_ts_mode = cfg ? cfg->ts_mode : 1;
+  const int g_flags = cfg ? (cfg->flags & 59) : 0;
+  const int g_cluster_mode = cfg ? (cfg->cluster_log2 < 0 ? 0 : (cfg->cluster_log2 > 3 ? 3 : cfg->cluster_log2)) : 0;
+  long long* const g_dbg = cfg ? (long long*)cfg->timeline : nullptr;
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
   W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
   W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
@@ -1317,7 +1312,10 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
                   "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 512 and more than %d rows", kSubTileH);
     W2E_CHECK_ARG(rgb->skip == nullptr || (rgb->host_taps1d && in_h % 2 == 0 && in_w % 2 == 0),
                   "modconv_tc2_rgb: skip needs taps and even H, W");
+    W2E_CHECK_ARG(rgb->rgb_dtype == W2E_F32 || (rgb->rgb_dtype == W2E_BF16 && Cout <= 256),
+                  "modconv_tc2_rgb: rgb_dtype must be W2E_F32, or W2E_BF16 with Cout <= 256");
     P.rgb_w = rgb->w; P.rgb_style = rgb->style; P.rgb_bias = rgb->bias; P.rgb_skip = rgb->skip; P.rgb = rgb->rgb;
+    P.rgb_bf16 = rgb->rgb_dtype == W2E_BF16 ? 1 : 0;
     if (rgb->skip)
       for (int i = 0; i < 4; ++i) P.kf[i] = rgb->host_taps1d[3 - i];
   }
@@ -1347,6 +1345,9 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // MMAs of the next tile overlap its drain of the current one (0.64 -> 0.57 ms at 64->32@512^2, the HBM floor is
   // 0.49).  Not for 64 channels: its weights are not resident and smaller tiles make the ring ingest-bound.
   if (transposed && P.bn <= 32 && !fb && !(g_flags & 16)) P.mt = 1;
+  // flag bit 5 (A/B): the same trade for the 64-channel transposed layer (two accumulator sets of 128 pixels instead
+  // of one of 256: MMA and epilogue overlap, at the price of weight blocks that feed half as many MMAs)
+  if (transposed && P.bn == 64 && Cout == 64 && !fb && (g_flags & 32)) P.mt = 1;
   const int acc_cols = P.ng * P.mt * P.bn;
   const int nbuf_plain = (acc_cols * 2 <= 512) ? 2 : 1;
   const int nbuf_ts = (acc_cols * 4 <= 512) ? 4 : nbuf_plain;   // TS flavour: two buffers per epilogue group
@@ -1449,7 +1450,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   W2E_CHECK_ARG(smem_bytes > 0, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
   if (P.mt == 4 && !ts)   // the direct-store epilogue has no 4-sub-tile variant: plan again with 256-pixel tiles
     return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                   in_h, in_w, transposed, act, rgb, stream, false);
+                   in_h, in_w, transposed, act, rgb, cfg, stream, false);
   W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
@@ -1565,26 +1566,28 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
 extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const float* bias,
                                const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
                                void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
-                               int transposed, int act, void* stream) {
+                               int transposed, int act, const w2e_tc2_config* cfg, void* stream) {
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                 in_h, in_w, transposed, act, nullptr, stream);
+                 in_h, in_w, transposed, act, nullptr, cfg, stream);
 }
 
 extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
                                    const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
                                    void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                                    int in_w, int act, const float* rgb_w, const float* rgb_style, const float* rgb_bias,
-                                   const float* rgb_skip, const float* host_taps1d, float* rgb, void* stream) {
-  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb};
+                                   const float* rgb_skip, const float* host_taps1d, void* rgb, int rgb_dtype,
+                                   const w2e_tc2_config* cfg, void* stream) {
+  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb, rgb_dtype};
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                 in_h, in_w, 0, act, &a, stream);
+                 in_h, in_w, 0, act, &a, cfg, stream);
 }
 
 
 extern "C" int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale, const float* host_taps,
                                       const float* bias, const float* noise, const float* noise_w, int noise_batch,
                                       const float* next_scale, void* out, void* out_mod, int* error_flag, int B,
-                                      int Cin, int Cout, int in_h, int in_w, int act, void* stream) {
+                                      int Cin, int Cout, int in_h, int in_w, int act, const w2e_tc2_config* cfg,
+                                      void* stream) {
   W2E_CHECK_ARG(host_taps, "modconv_tc2_upblur: null taps");
   // separable factorisation of the 4x4 kernel (rank-1 check as in w2e_blur_act_nhwc)
   int bi = 0, bj = 0;
@@ -1603,5 +1606,5 @@ extern "C" int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float
   FbArgs fb;
   for (int i = 0; i < 4; ++i) { fb.fv[i] = kv[3 - i]; fb.fh[i] = kh[3 - i]; }
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                 in_h, in_w, 1, act, nullptr, stream, false, &fb);
+                 in_h, in_w, 1, act, nullptr, cfg, stream, false, &fb);
 }

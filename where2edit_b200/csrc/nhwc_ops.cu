@@ -495,11 +495,11 @@ static int launch_blur_v2(const CUtensorMap& mz, const BlurParams& P, const Blur
                           cudaStream_t stream) {
 #define W2E_BLUR_V2_CASE(O, M)                                                                                        \
   {                                                                                                                    \
-    static bool configured = false;                                                                                    \
-    if (!configured) {                                                                                                 \
+    static PerDeviceOnce configured;                                                                                    \
+    if (!configured.done()) {                                                                                                 \
       W2E_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_v2_kernel<CT, O, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        100 * 1024));                                                                   \
-      configured = true;                                                                                               \
+      configured.mark();                                                                                               \
     }                                                                                                                  \
     blur_act_nhwc_v2_kernel<CT, O, M><<<(unsigned)blocks, 128, smem_bytes, stream>>>(mz, P, T);                        \
   }
@@ -689,7 +689,7 @@ extern "C" int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const
 extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const float* bias, const float* noise,
                                  const float* noise_w, int noise_batch, const float* next_scale, void* out,
                                  void* out_mod, int B, int C, int in_h, int in_w, int py0, int px0, int out_h,
-                                 int out_w, int act, void* stream) {
+                                 int out_w, int act, int variant, void* stream) {
   W2E_CHECK_ARG(z && host_taps && (out || out_mod), "blur_act_nhwc: null pointer");
   W2E_CHECK_ARG(B >= 0 && C > 0 && C % 8 == 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0,
                 "blur_act_nhwc: bad shape (C must be a multiple of 8)");
@@ -735,16 +735,16 @@ extern "C" int w2e_blur_act_nhwc(const void* z, const float* host_taps, const fl
     if (rc) return rc;
   }
   const int smem_bytes = (kBlurTY + 3) * (T.tx + 3) * T.ct * 2 + 128;
-  static const bool use_v2 = [] { const char* e = getenv("W2E_BLUR_V2"); return e && e[0] == '1'; }();
-  if (use_v2 && T.ct >= 32) {   // opt-in A/B variant (bit-identical results); default: the measured kernel below
+  const bool use_v2 = variant == 1;
+  if (use_v2 && T.ct >= 32) {   // the two kernels are bit-identical (tests/test_variants_gpu.py); `variant` picks one per call
     if (T.ct == 32) return launch_blur_v2<32>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
     if (T.ct == 64) return launch_blur_v2<64>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
     return launch_blur_v2<128>(mz, P, T, blocks, smem_bytes, (cudaStream_t)stream);
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
     W2E_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
+    configured.mark();
   }
   blur_act_nhwc_kernel<<<(unsigned)blocks, 128, smem_bytes, (cudaStream_t)stream>>>(mz, P, T);
   W2E_LAUNCH_OK();

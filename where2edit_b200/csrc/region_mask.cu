@@ -289,10 +289,10 @@ extern "C" int w2e_cluster_assign(const float* feature, const float* centres, in
   const int D = C + 2 * pos_channels;
   const size_t smem = (size_t)kAssignKC * ((D + 3) & ~3) * sizeof(float);
   W2E_CHECK_ARG(smem <= 200 * 1024, "cluster_assign: feature dimension too large for the shared-memory centre tile");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
     W2E_CUDA_OK(cudaFuncSetAttribute(cluster_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured.mark();
   }
   cluster_assign_kernel<<<dim3((unsigned)ceil_div(h * h, kAssignThreads), (unsigned)B), kAssignThreads, smem,
                           (cudaStream_t)stream>>>(feature, centres, low_ws, C, h, K, pos_channels);

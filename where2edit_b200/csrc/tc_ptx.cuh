@@ -236,12 +236,15 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder();  // modconv_tc.cu
+EncodeTiledFn tensor_map_encoder();  // tc_maps.cu
 // bf16 tiled tensor map; row_bytes selects the swizzle: 128 -> 128B, 64 -> 64B, anything else -> none
 int make_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int row_bytes);
 // fp32 tiled tensor map without swizzle (noise / skip-image boxes staged for the epilogue)
 int make_f32_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box);
+// fp32 operand map of the tf32 tensor-core mode (row_bytes 128 / 64 selects the swizzle like make_bf16_map)
+int make_f32_swizzled_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, int row_bytes);
 
 }  // namespace w2e

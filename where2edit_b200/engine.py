@@ -9,11 +9,11 @@ into the activation path: all samples share one bf16 weight tensor `[9][Cout][Ci
 the demodulation (model.py:242-243) is a per-(sample, channel) scale in the GEMM epilogue.
 
 Per resolution block (model.py:306-362):
-    up-conv   4 polyphase launches of w2e_modconv_tc (conv_transpose2d stride 2) -> z [(2h+1)^2]
+    up-conv   w2e_modconv_tc2 (transposed: the 4 parity classes of conv_transpose2d stride 2 in one pass) -> z [(2h+1)^2]
     blur      w2e_blur_act_nhwc: 4x4 FIR + noise + bias + lrelu*sqrt2, writes act * s_conv
-    conv      w2e_modconv_tc (9 taps) + demod + noise + bias + lrelu*sqrt2, writes act (for ToRGB /
-              feature capture) and act * s_next_up
-    ToRGB     w2e_torgb_nhwc: 1x1 modulated conv + bias + polyphase skip upsample, fp32 NCHW
+    conv      w2e_modconv_tc2[_rgb] (9 taps) + demod + noise + bias + lrelu*sqrt2 (+ the following ToRGB in the
+              epilogue), writes act (for ToRGB / feature capture) and act * s_next_up
+    ToRGB     fused above 16^2; w2e_torgb_nhwc otherwise: 1x1 modulated conv + bias + polyphase skip upsample
 Styles, demodulation coefficients and the tiny modulation linears stay fp32.
 """
 import os
@@ -24,36 +24,20 @@ from . import _native as N
 from . import functional as K
 from .op.upfirdn2d import kernel_taps
 
-_UP_AXIS = {0: [(0, 0), (-1, 2)], 1: [(0, 1)]}
-
-
-def _taps_plain():
-    taps = []
-    for ky in range(3):
-        for kx in range(3):
-            taps += [ky - 1, kx - 1, ky * 3 + kx]
-    return taps
-
-
-def _taps_up(py, px):
-    taps = []
-    for dy, ky in _UP_AXIS[py]:
-        for dx, kx in _UP_AXIS[px]:
-            taps += [dy, dx, ky * 3 + kx]
-    return taps
-
-
-_TAPS_PLAIN = _taps_plain()
-_TAPS_UP = {(py, px): _taps_up(py, px) for py in (0, 1) for px in (0, 1)}
-
 
 class SynthesisEngine:
     def __init__(self, gen):
         self.gen = gen
         self._w = {}
         self._err = N.ErrorFlag("libw2e modconv_tc2, bf16 synthesis engine")
-        # W2E_TC_V1=1 selects the first-generation kernel (one tile per CTA, 9 shifted TMA loads)
-        self.v1 = os.environ.get("W2E_TC_V1", "0") == "1"
+        # which of the two (bit-identical) blur kernels runs: W2E_BLUR_V2=0 selects the run-time-tile-shape one
+        self.blur_variant = int(os.environ.get("W2E_BLUR_V2", "0") == "1")
+        # per-call tuning / A-B switches of the tcgen05 convolution (_native.tc2_config(...)); None = defaults
+        self.tc2_cfg = None
+        # dtype of the image the LAST layer's epilogue writes (torch.float32 as the reference, or torch.bfloat16:
+        # half the bytes for a caller that gathers / copies the images out)
+        self.image_dtype = torch.float32
+        self.image_out = None   # optional caller-owned [B,3,H,W] buffer for the image (Generator.set_image_output)
         # W2E_FUSE_RGB=0 keeps ToRGB as its own kernel (w2e_torgb_nhwc) instead of the conv epilogue
         self.fuse_rgb = os.environ.get("W2E_FUSE_RGB", "1") == "1"
         # W2E_FUSE_UPBLUR=1 runs the up-convolution and its Blur as ONE kernel where w2e_modconv_tc2_upblur covers
@@ -170,25 +154,6 @@ class SynthesisEngine:
         return styles, demods
 
     # ------------------------------------------------------------------ kernel launches
-    def _conv(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, taps, in_hw, out_hw, grid_hw,
-              out_stride, py, px, act, out=None):
-        b = xs.shape[0]
-        dev = xs.device
-        nslots = pw.tc.shape[0]
-        if out is None and want_out:
-            out = torch.empty((b, out_hw[0], out_hw[1], pw.cout), device=dev, dtype=torch.bfloat16)
-        out_mod = torch.empty((b, out_hw[0], out_hw[1], pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
-        nb = 0 if noise is None else noise.shape[0]
-        ntaps = len(taps) // 3
-        N.note(kind="modconv", flops=2.0 * ntaps * pw.cin * pw.cout * b * grid_hw[0] * grid_hw[1],
-               tag=f"{pw.cin}->{pw.cout}@{grid_hw[0]}x{grid_hw[1]}x{ntaps}")
-        N.check(N.load().w2e_modconv_tc(
-            N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
-            N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, in_hw[0], in_hw[1],
-            out_hw[0], out_hw[1], grid_hw[0], grid_hw[1], out_stride, py, px, N.host_ints(taps), ntaps, nslots, act,
-            N.stream_ptr()), "modconv_tc")
-        return out, out_mod
-
     def _conv2(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, transposed, act):
         """Persistent v2 kernel: plain 3x3 (transposed=False) or the fused 4-class conv_transpose x2."""
         b, h, w, _ = xs.shape
@@ -203,17 +168,23 @@ class SynthesisEngine:
         N.check(N.load().w2e_modconv_tc2(
             N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
             N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w, int(transposed), act,
-            N.stream_ptr()), "modconv_tc2")
+            N.tc2_cfg(self.tc2_cfg), N.stream_ptr()), "modconv_tc2")
         return out, out_mod
 
-    def _conv2_rgb(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, rgb_module, rgb_style, skip):
+    def _conv2_rgb(self, xs, pw, d, noise, noise_w, bias, next_scale, want_out, want_mod, rgb_module, rgb_style, skip,
+                   rgb_dtype=torch.float32, rgb_out=None):
         """Plain 3x3 StyledConv with the following ToRGB fused into its epilogue."""
         b, h, w, _ = xs.shape
         dev = xs.device
         out = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
         out_mod = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
         # Cout > 256 runs as two channel blocks that ADD their partial ToRGB sums: the image starts at zero
-        rgb = (torch.zeros if pw.cout > 256 else torch.empty)((b, 3, h, w), device=dev, dtype=torch.float32)
+        if pw.cout > 256:
+            rgb_dtype = torch.float32
+        if rgb_out is not None and tuple(rgb_out.shape) == (b, 3, h, w) and rgb_out.dtype == rgb_dtype and pw.cout <= 256:
+            rgb = rgb_out
+        else:
+            rgb = (torch.zeros if pw.cout > 256 else torch.empty)((b, 3, h, w), device=dev, dtype=rgb_dtype)
         rpw = rgb_module.conv.packed()
         taps1d = None
         if skip is not None:
@@ -229,7 +200,8 @@ class SynthesisEngine:
             N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(next_scale),
             N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w, N.ACT_LRELU,
             N.ptr(rpw.rgb), N.ptr(rgb_style), N.ptr(rbias), N.ptr(skip),
-            N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb), N.stream_ptr()), "modconv_tc2_rgb")
+            N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb), N.dtype_code(rgb),
+            N.tc2_cfg(self.tc2_cfg), N.stream_ptr()), "modconv_tc2_rgb")
         return out, out_mod, rgb
 
     def _upblur(self, xs, pw, d, blur_kernel, pad, bias, noise, noise_w, next_scale, want_out, want_mod):
@@ -249,7 +221,7 @@ class SynthesisEngine:
         rc = N.load().w2e_modconv_tc2_upblur(
             N.ptr(xs), N.ptr(pw.tc), N.ptr(d), N.host_floats(taps), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
             N.ptr(next_scale), N.ptr(out), N.ptr(out_mod), N.ptr(self.error_flag(dev)), b, pw.cin, pw.cout, h, w,
-            N.ACT_LRELU, N.stream_ptr())
+            N.ACT_LRELU, N.tc2_cfg(self.tc2_cfg), N.stream_ptr())
         if rc == N.ERR_UNSUPPORTED:
             N.STATS.note = None
             return None
@@ -268,7 +240,7 @@ class SynthesisEngine:
         N.check(N.load().w2e_blur_act_nhwc(
             N.ptr(z), N.host_floats(kernel_taps(blur_kernel)), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
             N.ptr(next_scale), N.ptr(out), N.ptr(out_mod), b, c, ih, iw, pad[0], pad[0], out_hw[0], out_hw[1],
-            N.ACT_LRELU, N.stream_ptr()), "blur_act_nhwc")
+            N.ACT_LRELU, self.blur_variant, N.stream_ptr()), "blur_act_nhwc")
         return out, out_mod
 
     def _to_nchw(self, x):
@@ -389,37 +361,29 @@ class SynthesisEngine:
             next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
             need_out = next_is_rgb or want_features or blend_here
             need_mod = nxt is not None and not blend_here
-            fuse = (kind == "conv" and next_is_rgb and not self.v1 and self.fuse_rgb and pw.cout <= 512
+            fuse = (kind == "conv" and next_is_rgb and self.fuse_rgb and pw.cout <= 512
                     and hw[0] > 16 and not (attention_layer and attention_layer in (layer, layer + 1)))
             if fuse:
+                last = idx + 2 == len(layers)   # the image itself: written in the dtype the caller asked for
                 act, xs_next, fused_rgb = self._conv2_rgb(xs, pw, demods[idx], nz, noise_w, bias, nxt,
                                                           want_features, need_mod, layers[idx + 1][0],
-                                                          styles[idx + 1], skip)
+                                                          styles[idx + 1], skip,
+                                                          self.image_dtype if last else torch.float32,
+                                                          self.image_out if last else None)
             elif kind == "conv":
-                if self.v1:
-                    act, xs_next = self._conv(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
-                                              _TAPS_PLAIN, hw, hw, hw, 1, 0, 0, N.ACT_LRELU)
-                else:
-                    act, xs_next = self._conv2(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
-                                               False, N.ACT_LRELU)
+                act, xs_next = self._conv2(xs, pw, demods[idx], nz, noise_w, bias, nxt, need_out, need_mod,
+                                           False, N.ACT_LRELU)
             else:
                 h, w = hw
-                if self.v1:
-                    zh, zw = 2 * h + 1, 2 * w + 1
-                    z = torch.empty((batch, zh, zw, pw.cout), device=dev, dtype=torch.bfloat16)
-                    for (py, px), taps in _TAPS_UP.items():
-                        self._conv(xs, pw, demods[idx], None, None, None, None, True, False, taps, (h, w), (zh, zw),
-                                   (h + 1 - py, w + 1 - px), 2, py, px, N.ACT_NONE, out=z)
                 fused = None
-                if not self.v1 and self.fuse_upblur:
+                if self.fuse_upblur:
                     fused = self._upblur(xs, pw, demods[idx], conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt,
                                          need_out, need_mod)
                 hw = (2 * h, 2 * w)
                 if fused is not None:
                     act, xs_next = fused
                 else:
-                    if not self.v1:
-                        z, _ = self._conv2(xs, pw, demods[idx], None, None, None, None, True, False, True, N.ACT_NONE)
+                    z, _ = self._conv2(xs, pw, demods[idx], None, None, None, None, True, False, True, N.ACT_NONE)
                     act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, need_out,
                                               need_mod, hw)
             if blend_here:
@@ -429,4 +393,10 @@ class SynthesisEngine:
             if want_features:
                 captured.append(self._to_nchw(act))
             style_vector.append(s.reshape(batch, 1, -1, 1, 1))
+        if skip.dtype != self.image_dtype:   # image produced by an unfused ToRGB / blend (fp32): convert once
+            skip = skip.to(self.image_dtype)
+        if self.image_out is not None and skip.data_ptr() != self.image_out.data_ptr() \
+                and tuple(self.image_out.shape) == tuple(skip.shape):
+            self.image_out.copy_(skip)
+            skip = self.image_out
         return skip, style_vector, captured

@@ -198,9 +198,10 @@ def _tc_conv(xs, w, out_scale, cin, cout, transposed):
     b, h, wd, _ = xs.shape
     oh, ow = (2 * h + 1, 2 * wd + 1) if transposed else (h, wd)
     y = torch.empty((b, oh, ow, cout), device=xs.device, dtype=torch.bfloat16)
+    N.note(kind="modconv", flops=2.0 * 9 * cin * cout * b * h * wd, tag=f"{'up ' if transposed else ''}{cin}->{cout}@{h}x{wd} (autograd)")
     N.check(N.load().w2e_modconv_tc2(
         N.ptr(xs), N.ptr(w), N.ptr(out_scale), None, None, None, 0, None, N.ptr(y), None,
-        N.ptr(_tc_error_flag(xs.device)), b, cin, cout, h, wd, int(transposed), N.ACT_NONE, N.stream_ptr()),
+        N.ptr(_tc_error_flag(xs.device)), b, cin, cout, h, wd, int(transposed), N.ACT_NONE, None, N.stream_ptr()),
         "modconv_tc2")
     return y
 

@@ -335,6 +335,8 @@ class Generator(nn.Module):
         self.n_latent = self.log_size * 2 - 2
         self.precision = "fp32"
         self._engine = None
+        self.image_dtype = torch.float32   # dtype of the returned image in bf16 no-grad mode (set_image_output)
+        self.image_out = None              # optional caller-owned buffer the last layer writes the image into
         self.set_precision(precision)
 
     # ------------------------------------------------------------------ helpers kept from the reference
@@ -359,6 +361,18 @@ class Generator(nn.Module):
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
         self.precision = precision
+        return self
+
+    def set_image_output(self, dtype=torch.float32, buffer=None):
+        """bf16 no-grad mode only: the dtype the LAST layer's epilogue writes the image in (torch.float32 like the
+        reference, or torch.bfloat16: half the bytes for a caller that gathers or copies the images out) and,
+        optionally, a caller-owned contiguous [B,3,H,W] buffer of that dtype to write it into (e.g. this rank's slot
+        of a peer-mapped all-gather buffer, parallel.PeerGather.own).  The buffer is used when its batch matches."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("image dtype must be torch.float32 or torch.bfloat16")
+        if buffer is not None and (buffer.dtype != dtype or not buffer.is_contiguous()):
+            raise ValueError("image buffer must be contiguous and of the requested dtype")
+        self.image_dtype, self.image_out = dtype, buffer
         return self
 
     def assert_ok(self):
@@ -423,6 +437,7 @@ class Generator(nn.Module):
             from . import engine
             if self._engine is None:
                 self._engine = engine.SynthesisEngine(self)
+            self._engine.image_dtype, self._engine.image_out = self.image_dtype, self.image_out
             image, style_vector, captured = self._engine.run(
                 latent, input_is_stylespace, noise, want_features=return_features and not return_latents,
                 attention_layer=attention_layer if blending else 0, attention_map=attention_map,
