@@ -224,21 +224,29 @@ int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale
                            int Cin, int Cout, int in_h, int in_w, int act, const w2e_tc2_config* cfg,
                            void* stream);
 
-/* ---- layout transforms ----------------------------------------------------------------------
+/* tf32 mode (north_star (1): "bf16 and tf32 modes"): the same kernel with fp32 tensors in HBM (channels-last
+ * activations xs / out / out_mod, weights [9][Cout][Cin]) read by tcgen05.mma kind::tf32 (10-bit mantissa operands,
+ * fp32 accumulate); direct-store epilogue, no fused ToRGB.  Requires Cin % 16 == 0, Cout % 16 == 0.           */
+int w2e_modconv_tc2_tf32(const float* xs, const float* w, const float* out_scale, const float* bias,
+                         const float* noise, const float* noise_w, int noise_batch, const float* next_scale,
+                         float* out, float* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
+                         int in_w, int transposed, int act, const w2e_tc2_config* cfg, void* stream);
+
+/* ---- layout transforms (dtype = W2E_BF16 or W2E_F32: element type of the CHANNELS-LAST tensor) ----
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],
  * multiplied by style[b,c] when style != NULL.                                                */
 int w2e_nchw_to_nhwc_mod(const float* x, const float* style, void* y, int B, int Bx, int C,
-                         int64_t HW, void* stream);
+                         int64_t HW, int dtype, void* stream);
 /* x bf16 [B,HW,C] -> y fp32 [B,C,HW]  (feature capture, attention_model.py:542-543).          */
-int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, void* stream);
+int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, int dtype, void* stream);
 /* Pieces of the tensor-core dgrad of the transposed x2 convolution (autograd of model.py:249-259): the
  * output-parity class (py, px) of a fp32 NCHW gradient [B,C,H,W] as bf16 channels-last
  * y[b,j,i,c] = x[b,c,2j+py,2i+px]*scale[b,c] ([B,(H-py+1)/2,(W-px+1)/2,C]); and the sum of the four
  * per-class convolution results y_pq [B,h+1-p,w+1-q,C] over their common h x w region as fp32 NCHW.   */
 int w2e_nchw_class_to_nhwc_mod(const float* x, const float* scale, void* y, int B, int C, int H, int W, int py,
-                               int px, void* stream);
+                               int px, int dtype, void* stream);
 int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10, const void* y11, float* out,
-                              int B, int C, int h, int w, void* stream);
+                              int B, int C, int h, int w, int dtype, void* stream);
 
 /* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
  * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->

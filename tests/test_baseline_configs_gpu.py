@@ -8,8 +8,10 @@ the oracle -- not against this package's own fp32 path:
 
 Tolerances are the north star's: fp32 mode <= 1e-4 max-abs; bf16 mode <= 2e-2 max-abs and >= 45 dB PSNR after
 dividing both images by c = max|reference| (random-init images are not in [-1,1]).
+The tf32 mode (fp32 tensors, tcgen05 kind::tf32 convolutions) is held to the same image bar as bf16 and must beat it.
 Gradients: fp32 no further from the reference's fp64 gradient than twice the reference's own fp32 run; bf16
-(bf16 operands and bf16-stored convolution results) cosine >= 0.99 and relative L2 error <= 0.12 against fp64."""
+(bf16 operands and bf16-stored convolution results) cosine >= 0.99 and relative L2 error <= 0.12 against fp64; tf32
+cosine >= 0.9995 and relative L2 <= 0.03."""
 import os
 import types
 
@@ -28,6 +30,17 @@ from where2edit_b200 import mappers
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL32 = 1e-4
+PRECISIONS = ["fp32", "bf16", "tf32"]
+
+
+def record(name, **values):
+    """measured parity numbers, appended to gpurun_out/parity_measured.jsonl when that directory exists (DESIGN.md
+    quotes them); never affects the verdict"""
+    import json
+    d = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as fh:
+            fh.write(json.dumps({"test": name, **values}) + "\n")
 
 
 @pytest.fixture(scope="module")
@@ -50,9 +63,12 @@ def g1024():
     return build(1024)
 
 
-def check_image(img, ref_full, grid, stats, precision):
+def check_image(img, ref_full, grid, stats, precision, name=""):
     """img (GPU) against the oracle's full image and the reference's sub-grid / statistics."""
     img = img.float().cpu()
+    c0 = float(ref_full.abs().max())
+    record(name, precision=precision, max_abs_raw=max_abs(img, ref_full), max_abs_normalised=max_abs(img / c0, ref_full / c0),
+           psnr_db=psnr_db(img / c0, ref_full / c0, peak=2.0), max_abs_reference=c0)
     c = float(np.abs(stats[..., 2]).max())                    # max|reference image|
     assert abs(float(ref_full.abs().max()) - c) <= 1e-4       # the oracle and the reference agree on it
     g = torch.from_numpy(grid)
@@ -69,7 +85,7 @@ def check_image(img, ref_full, grid, stats, precision):
         assert not torch.equal(img, ref_full)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_cfg1_generator256_batch4(golden, precision):
     """BASELINE config 1: Generator(256, 512, 8), batch 4 from random W+."""
     gen, sd = build(256, precision)
@@ -78,10 +94,10 @@ def test_cfg1_generator256_batch4(golden, precision):
     with torch.no_grad():
         img, _ = gen([wplus.to(DEV)], input_is_latent=True, randomize_noise=False)
     gen.assert_ok()
-    check_image(img, ref, golden["cfg1/grid"], golden["cfg1/stats"], precision)
+    check_image(img, ref, golden["cfg1/grid"], golden["cfg1/stats"], precision, "cfg1")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_cfg2_ffhq1024_forward(g1024, golden, precision):
     """BASELINE config 2: FFHQ-1024 generator (channel_multiplier 2) from W+, fixed noise buffers; batch 2 here
     (the kernels are batch-invariant: tests/test_fullsize_gpu.py), checked against the oracle's full images."""
@@ -96,7 +112,7 @@ def test_cfg2_ffhq1024_forward(g1024, golden, precision):
         gen.assert_ok()
     finally:
         gen.set_precision("fp32")
-    check_image(img, ref, golden["cfg2/grid"], golden["cfg2/stats"], precision)
+    check_image(img, ref, golden["cfg2/grid"], golden["cfg2/stats"], precision, "cfg2")
     # captured features (consumers: run_attention.py:1108-1110, clustering_feature.py:373): every one of the 26
     assert len(feats) == 26
     for i, (f, r) in enumerate(zip(feats, ref_feats)):
@@ -138,22 +154,29 @@ def test_cfg3_levels_mapper_edit_with_region_blend(g1024, golden, precision):
         gen.set_precision("fp32")
     for s, r in zip(styles_hat, ref_styles):
         assert tuple(s.shape) == tuple(r.shape) and max_abs(s.cpu(), r) <= 1e-4 * max(1.0, float(r.abs().max()))
-    check_image(img, ref, golden["cfg3/grid"], golden["cfg3/stats"], precision)
+    check_image(img, ref, golden["cfg3/grid"], golden["cfg3/stats"], precision, "cfg3")
 
 
 def _grad_check(ours, ref32, ref64, precision, tag):
     ours, ref32, ref64 = (np.asarray(t, np.float64).reshape(-1) for t in (ours, ref32, ref64))
     scale = float(np.abs(ref64).max())
+    record("cfg4/" + tag, precision=precision, max_abs_over_scale=float(np.abs(ours - ref64).max()) / scale,
+           reference_fp32_max_abs_over_scale=float(np.abs(ref32 - ref64).max()) / scale,
+           cosine=float(ours @ ref64 / (np.linalg.norm(ours) * np.linalg.norm(ref64))),
+           rel_l2=float(np.linalg.norm(ours - ref64) / np.linalg.norm(ref64)))
     if precision == "fp32":
         err_ours, err_ref = float(np.abs(ours - ref64).max()), float(np.abs(ref32 - ref64).max())
         assert err_ours <= 2 * err_ref + 1e-4 * scale, (tag, err_ours, err_ref, scale)
     else:
         cos = float(ours @ ref64 / (np.linalg.norm(ours) * np.linalg.norm(ref64)))
         rel = float(np.linalg.norm(ours - ref64) / np.linalg.norm(ref64))
-        assert cos >= 0.99 and rel <= 0.12, (tag, cos, rel)
+        if precision == "tf32":
+            assert cos >= 0.9995 and rel <= 0.03, (tag, cos, rel)
+        else:
+            assert cos >= 0.99 and rel <= 0.12, (tag, cos, rel)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_cfg4_gradients_at_1024_match_reference_fp64_autograd(g1024, golden, precision):
     """BASELINE config 4 (CLIP-loss latent optimisation, run_attention.py:1419 / coach.py:91): dL/dW+ of the plain
     forward and dL/d(styles, mask) of the layer-13-blended stylespace forward for the seeded upstream dL/dimage,

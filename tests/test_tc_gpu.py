@@ -358,3 +358,78 @@ def test_tensor_core_dgrad_matches_fp32_engine(b, cin, cout, h, up):
     K.tc_assert_ok()
     assert got.shape == ref.shape and got.dtype == torch.float32
     assert norm_err(got.cpu(), ref.cpu()) <= 1e-2
+
+
+@pytest.mark.parametrize("b,cin,cout,h,up", [
+    (2, 64, 64, 16, False),      # 128-byte rows (32 fp32 channels per K chunk)
+    (1, 48, 32, 40, False),      # 64-byte rows (Cin % 32 != 0), ragged grid
+    (1, 512, 512, 8, False),     # 256-column tiles x 2, 16 K chunks
+    (2, 256, 128, 20, True),     # transposed x2, weight ring
+    (1, 64, 32, 36, True),       # transposed x2, resident weights
+])
+def test_tf32_modulated_conv_matches_oracle(b, cin, cout, h, up):
+    """w2e_modconv_tc2_tf32 (fp32 tensors in HBM, tcgen05 kind::tf32, north star item 1) through
+    functional.conv_forward_tc / conv_dgrad_tc against the fp64 oracle: 10-bit-mantissa operands, so ~1e-3 of the
+    output's range -- an order of magnitude inside the bf16 kernel's error on the same problem."""
+    pw = K.PackedWeight(synth.make_tensor((1, cout, cin, 3, 3), 81).to(DEV), 1 / (cin * 9) ** 0.5, None)
+    x = synth.make_tensor((b, cin, h, h), 82)
+    s = 1 + 0.3 * synth.make_tensor((b, cin), 83)
+    d = K.demod_coefficients(s.to(DEV), pw.wsq)
+    got = K.conv_forward_tc(x.to(DEV), s.to(DEV), d, pw, up, "tf32")
+    got16 = K.conv_forward_tc(x.to(DEV), s.to(DEV), d, pw, up, "bf16") if cin % 32 == 0 else None
+    K.tc_assert_ok()
+    w64 = synth.make_tensor((1, cout, cin, 3, 3), 81).double()
+    xs = x.double() * s.double()[:, :, None, None]
+    wt = w64[0] / (cin * 9) ** 0.5
+    if up:
+        ref = torch.nn.functional.conv_transpose2d(xs, wt.transpose(0, 1), stride=2)
+    else:
+        ref = torch.nn.functional.conv2d(xs, wt, padding=1)
+    ref = ref * d.double().cpu()[:, :, None, None]
+    e32 = norm_err(got.cpu(), ref)
+    e16 = norm_err(got16.cpu(), ref) if got16 is not None else 1.0
+    assert got.dtype == torch.float32 and tuple(got.shape) == tuple(ref.shape)
+    assert e32 <= 2e-3 and e32 < 0.5 * e16, (e32, e16)
+    # dgrad on the same kernel (flipped taps / the four parity classes of the transposed convolution)
+    gy = synth.make_tensor(tuple(ref.shape), 84)
+    gx = K.conv_dgrad_tc(gy.to(DEV), d, pw, up, (h, h), "tf32")
+    K.tc_assert_ok()
+    xs_ = xs.clone().requires_grad_(True)
+    out = (torch.nn.functional.conv_transpose2d(xs_, wt.transpose(0, 1), stride=2) if up
+           else torch.nn.functional.conv2d(xs_, wt, padding=1)) * d.double().cpu()[:, :, None, None]
+    (out * gy.double()).sum().backward()
+    assert norm_err(gx.cpu(), xs_.grad) <= 2e-3
+
+
+def test_tf32_generator_between_bf16_and_fp32(golden_g128):
+    """Generator(precision='tf32') at 128^2 against the reference golden: inside the bf16 tolerance and closer to the
+    reference than the bf16 engine; gradients flow through the tf32 dgrad."""
+    sd = synth.make_state_dict(128, channel_multiplier=1, seed=5, perturbed=True)
+    gen = w2e.Generator(128, 512, 8, channel_multiplier=1, precision="tf32")
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.to(DEV).eval()
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    wplus = synth.make_wplus(1, 12, seed=6).to(DEV)
+    ref = torch.from_numpy(golden_g128["img_wplus"])
+    c = float(ref.abs().max())
+    with torch.no_grad():
+        img, _ = gen([wplus], input_is_latent=True, randomize_noise=False)
+        gen.set_precision("bf16")
+        img16, _ = gen([wplus], input_is_latent=True, randomize_noise=False)
+    gen.assert_ok()
+    e32, e16 = max_abs(img.cpu() / c, ref / c), max_abs(img16.float().cpu() / c, ref / c)
+    assert e32 <= 5e-3 and e32 < e16 <= 2e-2, (e32, e16)
+    gen.set_precision("tf32")
+    wp = wplus.clone().requires_grad_(True)
+    img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+    img.square().mean().backward()
+    gen.assert_ok()
+    g_tf32 = wp.grad.double().flatten().cpu()
+    gen.set_precision("fp32")
+    wp2 = wplus.clone().requires_grad_(True)
+    img, _ = gen([wp2], input_is_latent=True, randomize_noise=False)
+    img.square().mean().backward()
+    g32 = wp2.grad.double().flatten().cpu()
+    cos = float(torch.dot(g_tf32, g32) / (g_tf32.norm() * g32.norm()))
+    assert cos >= 0.9995, cos

@@ -46,10 +46,11 @@ PROTOTYPES = {
     "w2e_modconv_tc2": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
     "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 6 + [_I, _P, _P]),
     "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P, _P]),
-    "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
-    "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _P]),
-    "w2e_nchw_class_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "w2e_nhwc_sum4_to_nchw_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "w2e_modconv_tc2_tf32": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
+    "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _I, _P]),
+    "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _I, _P]),
+    "w2e_nchw_class_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "w2e_nhwc_sum4_to_nchw_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "w2e_blur_act_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P] + [_I] * 10 + [_P]),
     "w2e_torgb_nhwc": (_I, [_P] * 7 + [_I, _I, _I, _I, _P]),
     "w2e_blend_nhwc": (_I, [_P] * 6 + [_I] * 6 + [_P]),

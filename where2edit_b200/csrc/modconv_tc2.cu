@@ -179,14 +179,18 @@ struct Ring {
   }
 };
 
-template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
+// TF32: fp32 activations / weights / results in HBM, tcgen05.mma kind::tf32 (the "tf32 mode" of the north star; only
+// with the direct-store epilogue).  The shared-memory BYTE geometry is that of the bf16 kernel: a 128-byte row holds
+// 32 fp32 channels instead of 64 bf16 ones and one MMA consumes 8 of them (32 bytes) instead of 16.
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS, bool TF32 = false>
 __global__ void __launch_bounds__(TS ? (WRES ? kT2ThreadsTS2 : kT2ThreadsTS) : kT2Threads, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ Tc2Params P, const __grid_constant__ Tc2Maps M) {
   constexpr int NG = TR ? 4 : 1;
   static_assert(!RGB || (!TR && (MT == 2 || (TS && MT == 4))), "fused ToRGB needs the plain conv with 2 (or 4) sub-tiles");
-  constexpr int kRowBytes = KSTEPS * 32;  // BK * 2 bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
-  constexpr int kBK = KSTEPS * 16;
+  static_assert(!TF32 || (!TS && !RGB), "the tf32 mode uses the direct-store epilogue without the fused ToRGB");
+  constexpr int kRowBytes = KSTEPS * 32;  // BK * element size: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  constexpr int kBK = KSTEPS * (TF32 ? 8 : 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;
@@ -375,7 +379,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // The whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform
     // registers); only tcgen05.mma / tcgen05.commit are issued, by one elected lane.
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((128u >> 4) << 24);
+    // (kind::tf32: A = B = tf32, format code 2)
+    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                           ((128u >> 4) << 24);
     const uint32_t a_hi = desc_hi(kRowBytes, kPitch * kRowBytes);
     const uint32_t b_hi = desc_hi(kRowBytes, 8 * kRowBytes);
     // descriptor low words (start address >> 4) are LINEAR in the address: one add per operand per MMA
@@ -459,8 +465,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
                 if (leader) {
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    if constexpr (TF32) umma_tf32_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                    else umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                  }
                 }
               }
             }
@@ -496,8 +504,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               }
               if (leader && mine) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if constexpr (TF32) umma_tf32_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                  else umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                }
               }
             }
             if (leader && mine) {
@@ -1132,8 +1142,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int64_t pix = valid ? ((int64_t)me.b * P.OH + oy) * P.OW + ox : 0;
         const float nzv = nw * me.nz[gmi];
         const uint32_t t_addr = t_tile + (uint32_t)gm * (uint32_t)P.bn;
-        __nv_bfloat16* o_row = P.out ? P.out + pix * P.Cout + me.co0 : nullptr;
-        __nv_bfloat16* m_row = P.out_mod ? P.out_mod + pix * P.Cout + me.co0 : nullptr;
+        __nv_bfloat16* o_row = (P.out && !TF32) ? P.out + pix * P.Cout + me.co0 : nullptr;
+        __nv_bfloat16* m_row = (P.out_mod && !TF32) ? P.out_mod + pix * P.Cout + me.co0 : nullptr;
+        // tf32 mode: the same tensors hold fp32
+        float* o_row32 = (P.out && TF32) ? reinterpret_cast<float*>(P.out) + pix * P.Cout + me.co0 : nullptr;
+        float* m_row32 = (P.out_mod && TF32) ? reinterpret_cast<float*>(P.out_mod) + pix * P.Cout + me.co0 : nullptr;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; c += 16) {
           uint32_t v[16];
@@ -1190,6 +1203,21 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               dst[0] = pk[0];
               dst[1] = pk[1];
             }
+            if constexpr (TF32) {
+              if (o_row32) {
+                float4* dst = reinterpret_cast<float4*>(o_row32 + c);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) dst[e4] = make_float4(f[4 * e4], f[4 * e4 + 1], f[4 * e4 + 2], f[4 * e4 + 3]);
+              }
+              if (m_row32) {
+                float4* dst = reinterpret_cast<float4*>(m_row32 + c);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 n4 = *reinterpret_cast<const float4*>(nx + c + 4 * e4);
+                  dst[e4] = make_float4(f[4 * e4] * n4.x, f[4 * e4 + 1] * n4.y, f[4 * e4 + 2] * n4.z, f[4 * e4 + 3] * n4.w);
+                }
+              }
+            }
           }
         }
         if (RGB && valid) {
@@ -1219,10 +1247,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS>
+template <bool TR, int MT, int KSTEPS, bool WRES, bool RGB, bool TS, bool TF32 = false>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Params& P, const Tc2Maps& M, int smem_bytes,
                       int max_ctas, cudaStream_t s) {
-  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB, TS>;
+  auto kern = modconv_tc2_kernel<TR, MT, KSTEPS, WRES, RGB, TS, TF32>;
   static PerDeviceOnce configured;
   if (!configured.done()) {
     W2E_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1283,7 +1311,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
                    const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
                    int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
                    const RgbArgs* rgb, const w2e_tc2_config* cfg, void* stream, bool allow_mt4 = true,
-                   const FbArgs* fb = nullptr) {
+                   const FbArgs* fb = nullptr, bool tf32 = false) {
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
@@ -1293,7 +1321,9 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
   W2E_CHECK_ARG(out_mod == nullptr || next_scale != nullptr, "modconv_tc2: out_mod needs next_scale");
   W2E_CHECK_ARG(B > 0 && in_h > 0 && in_w > 0, "modconv_tc2: bad shape");
-  W2E_CHECK_ARG(Cin % 32 == 0 && Cout % 16 == 0, "modconv_tc2: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
+  W2E_CHECK_ARG(Cin % (tf32 ? 16 : 32) == 0 && Cout % 16 == 0, "modconv_tc2: needs Cin %% %d == 0 and Cout %% 16 == 0 (got %d, %d)",
+                tf32 ? 16 : 32, Cin, Cout);
+  W2E_CHECK_ARG(!tf32 || (!rgb && !fb), "modconv_tc2_tf32: no fused ToRGB / blur in tf32 mode");
   W2E_CHECK_ARG(noise == nullptr || (noise_w != nullptr && (noise_batch == 1 || noise_batch == B)), "modconv_tc2: noise");
   W2E_CHECK_ARG(((uintptr_t)xs & 15) == 0 && ((uintptr_t)w & 15) == 0, "modconv_tc2: operands must be 16-byte aligned");
   if (!w2e_modconv_tc_supported()) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2: device is not sm_100");
@@ -1326,8 +1356,10 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   } else {
     P.OH = 2 * in_h + 1; P.OW = 2 * in_w + 1; P.grid_h = in_h + 1; P.grid_w = in_w + 1; P.out_stride = 2; P.ng = 4;
   }
-  P.bk = (Cin % 64 == 0) ? 64 : 32;
-  const int row_bytes = P.bk * 2;
+  // K chunk = one 128-byte (or 64-byte) swizzled row of channels: 64 / 32 bf16 or 32 / 16 fp32 (tf32 mode)
+  const int esize = tf32 ? 4 : 2;
+  P.bk = (Cin % (128 / esize) == 0) ? 128 / esize : 64 / esize;
+  const int row_bytes = P.bk * esize;
   P.mt = (P.grid_h > kSubTileH) ? 2 : 1;
   // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
   const bool mt4 = allow_mt4 && g_ts_mode != 0 && rgb && !out && !out_mod && Cin == 32 && Cout == 32 && in_h >= 64;
@@ -1382,7 +1414,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
 
   // TS epilogue eligibility (see the header): staging units of <= 64 channels, TMA-able strides
   const int n_out = (out ? 1 : 0) + (out_mod ? 1 : 0);
-  bool ts = g_ts_mode != 0 && (transposed || P.mt >= 2) && P.bn >= 32 && P.bn <= 128;
+  bool ts = !tf32 && g_ts_mode != 0 && (transposed || P.mt >= 2) && P.bn >= 32 && P.bn <= 128;
   if (rgb && nbuf_plain != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
   if (transposed && !fb) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
   if (noise && !fb) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
@@ -1450,22 +1482,26 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   W2E_CHECK_ARG(smem_bytes > 0, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
   if (P.mt == 4 && !ts)   // the direct-store epilogue has no 4-sub-tile variant: plan again with 256-pixel tiles
     return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                   in_h, in_w, transposed, act, rgb, cfg, stream, false);
+                   in_h, in_w, transposed, act, rgb, cfg, stream, false, fb, tf32);
   W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
   {
+    const uint64_t es = (uint64_t)esize;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)in_w * Cin * 2, (uint64_t)in_h * in_w * Cin * 2};
+    const uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
     const uint32_t box[4] = {(uint32_t)P.bk, (uint32_t)P.pitch, (uint32_t)P.box_rows, 1u};
-    int rc = make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
+    int rc = tf32 ? make_f32_swizzled_map(&ma, xs, 4, dims, strides, box, row_bytes)
+                  : make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
   {
+    const uint64_t es = (uint64_t)esize;
     const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
-    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    const uint64_t strides[2] = {(uint64_t)Cin * es, (uint64_t)Cout * Cin * es};
     const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)P.bn, 1u};
-    int rc = make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
+    int rc = tf32 ? make_f32_swizzled_map(&mb, w, 3, dims, strides, box, row_bytes)
+                  : make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
   Tc2Maps M;
@@ -1525,7 +1561,21 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int ks = P.bk / 16;
+  const int ks = row_bytes / 32;   // MMAs (K = 32 bytes each) per K chunk
+  if (tf32) {
+    if (P.cluster) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_tf32: no cluster mode");
+#define W2E_TC2_TF32(TR_, MT_, KS_, WR_) \
+  if ((transposed != 0) == TR_ && P.mt == MT_ && ks == KS_ && (P.wres != 0) == WR_) \
+    return launch_tc2<TR_, MT_, KS_, WR_, false, false, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);
+    W2E_TC2_TF32(false, 1, 4, false) W2E_TC2_TF32(false, 2, 4, false) W2E_TC2_TF32(false, 1, 2, false)
+    W2E_TC2_TF32(false, 2, 2, false) W2E_TC2_TF32(false, 1, 4, true) W2E_TC2_TF32(false, 2, 4, true)
+    W2E_TC2_TF32(false, 1, 2, true) W2E_TC2_TF32(false, 2, 2, true)
+    W2E_TC2_TF32(true, 1, 4, false) W2E_TC2_TF32(true, 2, 4, false) W2E_TC2_TF32(true, 1, 2, false)
+    W2E_TC2_TF32(true, 2, 2, false) W2E_TC2_TF32(true, 1, 4, true) W2E_TC2_TF32(true, 2, 4, true)
+    W2E_TC2_TF32(true, 1, 2, true) W2E_TC2_TF32(true, 2, 2, true)
+#undef W2E_TC2_TF32
+    return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_tf32: no kernel variant");
+  }
   if (rgb) {
     W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && (P.tiles_n == 1 || (P.tiles_n == 2 && !ts)),
                   "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
@@ -1569,6 +1619,17 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
                                int transposed, int act, const w2e_tc2_config* cfg, void* stream) {
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
                  in_h, in_w, transposed, act, nullptr, cfg, stream);
+}
+
+// tf32 mode (north star item 1: "bf16 and tf32 modes"): xs / w / out / out_mod are fp32 (channels-last activations,
+// [9][Cout][Cin] weights), the MMA reads them as tf32 and accumulates in fp32.
+extern "C" int w2e_modconv_tc2_tf32(const float* xs, const float* w, const float* out_scale, const float* bias,
+                                    const float* noise, const float* noise_w, int noise_batch,
+                                    const float* next_scale, float* out, float* out_mod, int* error_flag, int B, int Cin,
+                                    int Cout, int in_h, int in_w, int transposed, int act, const w2e_tc2_config* cfg,
+                                    void* stream) {
+  return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
+                 in_h, in_w, transposed, act, nullptr, cfg, stream, false, nullptr, true);
 }
 
 extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,

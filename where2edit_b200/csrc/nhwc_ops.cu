@@ -47,8 +47,9 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 
 // ------------------------------------------------------------------------------ layout transforms
 // x [Bx, C, HW] fp32 (Bx = 1 broadcasts over the batch) -> y [B, HW, C] bf16 * style[b, c]
+template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ style, __nv_bfloat16* __restrict__ y,
+nchw_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ style, T* __restrict__ y,
                         int Bx, int C, int64_t HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -70,14 +71,15 @@ nchw_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ s
     if (p < HW && c < C) {
       float v = tile[tx][r];
       if (style) v *= __ldg(style + (int64_t)b * C + c);
-      y[((int64_t)b * HW + p) * C + c] = __float2bfloat16_rn(v);
+      y[((int64_t)b * HW + p) * C + c] = from_f32<T>(v);
     }
   }
 }
 
-// x [B, HW, C] bf16 -> y [B, C, HW] fp32
+// x [B, HW, C] bf16 (or fp32) -> y [B, C, HW] fp32
+template <typename T>
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int64_t HW) {
+nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ y, int C, int64_t HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -87,7 +89,7 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
   for (int r = ty; r < 32; r += 8) {
     const int64_t p = p0 + r;
     const int c = c0 + tx;
-    tile[r][tx] = (p < HW && c < C) ? __bfloat162float(x[((int64_t)b * HW + p) * C + c]) : 0.f;
+    tile[r][tx] = (p < HW && c < C) ? to_f32<T>(x[((int64_t)b * HW + p) * C + c]) : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -101,8 +103,9 @@ nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__
 // Output-parity class (py, px) of a fp32 NCHW tensor x [B, C, H, W] as bf16 NHWC [B, hc, wc, C], times scale[b, c]:
 // y[b, j, i, c] = x[b, c, 2j+py, 2i+px] * scale[b, c].  (The dgrad of the transposed x2 convolution consumes the
 // upstream gradient class by class.)
+template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_class_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ scale, __nv_bfloat16* __restrict__ y,
+nchw_class_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
                               int C, int H, int W, int hc, int wc, int py, int px) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -129,16 +132,16 @@ nchw_class_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restri
     if (p < HWc && c < C) {
       float v = tile[tx][r];
       if (scale) v *= __ldg(scale + (int64_t)b * C + c);
-      y[((int64_t)b * HWc + p) * C + c] = __float2bfloat16_rn(v);
+      y[((int64_t)b * HWc + p) * C + c] = from_f32<T>(v);
     }
   }
 }
 
 // out[b, c, j, i] = sum over the four class results y_pq [B, h+1-p, w+1-q, C] (bf16 NHWC) at (j, i), fp32 NCHW [B, C, h, w]
+template <typename T>
 __global__ void __launch_bounds__(256)
-nhwc_sum4_to_nchw_kernel(const __nv_bfloat16* __restrict__ y00, const __nv_bfloat16* __restrict__ y01,
-                         const __nv_bfloat16* __restrict__ y10, const __nv_bfloat16* __restrict__ y11,
-                         float* __restrict__ out, int C, int h, int w) {
+nhwc_sum4_to_nchw_kernel(const T* __restrict__ y00, const T* __restrict__ y01, const T* __restrict__ y10,
+                         const T* __restrict__ y11, float* __restrict__ out, int C, int h, int w) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int64_t HW = (int64_t)h * w;
@@ -152,10 +155,10 @@ nhwc_sum4_to_nchw_kernel(const __nv_bfloat16* __restrict__ y00, const __nv_bfloa
     float v = 0.f;
     if (p < HW && c < C) {
       const int j = (int)(p / w), i = (int)(p - (int64_t)j * w);
-      v = __bfloat162float(y00[(((int64_t)b * (h + 1) + j) * (w + 1) + i) * C + c]) +
-          __bfloat162float(y01[(((int64_t)b * (h + 1) + j) * w + i) * C + c]) +
-          __bfloat162float(y10[(((int64_t)b * h + j) * (w + 1) + i) * C + c]) +
-          __bfloat162float(y11[(((int64_t)b * h + j) * w + i) * C + c]);
+      v = to_f32<T>(y00[(((int64_t)b * (h + 1) + j) * (w + 1) + i) * C + c]) +
+          to_f32<T>(y01[(((int64_t)b * (h + 1) + j) * w + i) * C + c]) +
+          to_f32<T>(y10[(((int64_t)b * h + j) * (w + 1) + i) * C + c]) +
+          to_f32<T>(y11[(((int64_t)b * h + j) * w + i) * C + c]);
     }
     tile[r][tx] = v;
   }
@@ -640,48 +643,61 @@ blend_nhwc_kernel(const __nv_bfloat16* __restrict__ edited, const __nv_bfloat16*
 using namespace w2e;
 
 extern "C" int w2e_nchw_to_nhwc_mod(const float* x, const float* style, void* y, int B, int Bx, int C, int64_t HW,
-                                    void* stream) {
+                                    int dtype, void* stream) {
+  W2E_CHECK_ARG(dtype == W2E_BF16 || dtype == W2E_F32, "nchw_to_nhwc_mod: dtype");
   W2E_CHECK_ARG(x && y, "nchw_to_nhwc_mod: null pointer");
   W2E_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && (Bx == 1 || Bx == B), "nchw_to_nhwc_mod: bad shape");
   W2E_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "nchw_to_nhwc_mod: batch/channels above 65535");
   if (B == 0) return W2E_OK;
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
-  nchw_to_nhwc_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, style, (__nv_bfloat16*)y, Bx, C, HW);
+  if (dtype == W2E_F32) nchw_to_nhwc_mod_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, style, (float*)y, Bx, C, HW);
+  else nchw_to_nhwc_mod_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, style, (__nv_bfloat16*)y, Bx, C, HW);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
 
-extern "C" int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, void* stream) {
+extern "C" int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64_t HW, int dtype, void* stream) {
   W2E_CHECK_ARG(x && y, "nhwc_to_nchw_f32: null pointer");
+  W2E_CHECK_ARG(dtype == W2E_BF16 || dtype == W2E_F32, "nhwc_to_nchw_f32: dtype");
   W2E_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && B <= 65535, "nhwc_to_nchw_f32: bad shape");
   if (B == 0) return W2E_OK;
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
-  nhwc_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
+  if (dtype == W2E_F32) nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, C, HW);
+  else nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
 
 extern "C" int w2e_nchw_class_to_nhwc_mod(const float* x, const float* scale, void* y, int B, int C, int H, int W, int py,
-                                          int px, void* stream) {
+                                          int px, int dtype, void* stream) {
   W2E_CHECK_ARG(x && y, "nchw_class_to_nhwc_mod: null pointer");
+  W2E_CHECK_ARG(dtype == W2E_BF16 || dtype == W2E_F32, "nchw_class_to_nhwc_mod: dtype");
   W2E_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && (py == 0 || py == 1) && (px == 0 || px == 1) && B <= 65535,
                 "nchw_class_to_nhwc_mod: bad shape");
   const int hc = (H - py + 1) / 2, wc = (W - px + 1) / 2;
   if (B == 0 || hc == 0 || wc == 0) return W2E_OK;
   dim3 grid((unsigned)ceil_div64((int64_t)hc * wc, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
-  nchw_class_to_nhwc_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, (__nv_bfloat16*)y, C, H, W, hc, wc, py, px);
+  if (dtype == W2E_F32)
+    nchw_class_to_nhwc_mod_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, (float*)y, C, H, W, hc, wc, py, px);
+  else
+    nchw_class_to_nhwc_mod_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, (__nv_bfloat16*)y, C, H, W, hc, wc, py, px);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }
 
 extern "C" int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10, const void* y11, float* out,
-                                         int B, int C, int h, int w, void* stream) {
+                                         int B, int C, int h, int w, int dtype, void* stream) {
   W2E_CHECK_ARG(y00 && y01 && y10 && y11 && out, "nhwc_sum4_to_nchw_f32: null pointer");
+  W2E_CHECK_ARG(dtype == W2E_BF16 || dtype == W2E_F32, "nhwc_sum4_to_nchw_f32: dtype");
   W2E_CHECK_ARG(B >= 0 && C > 0 && h > 0 && w > 0 && B <= 65535, "nhwc_sum4_to_nchw_f32: bad shape");
   if (B == 0) return W2E_OK;
   dim3 grid((unsigned)ceil_div64((int64_t)h * w, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
-  nhwc_sum4_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y00, (const __nv_bfloat16*)y01, (const __nv_bfloat16*)y10, (const __nv_bfloat16*)y11, out, C, h, w);
+  if (dtype == W2E_F32)
+    nhwc_sum4_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)y00, (const float*)y01, (const float*)y10,
+                                                                          (const float*)y11, out, C, h, w);
+  else
+    nhwc_sum4_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)y00, (const __nv_bfloat16*)y01, (const __nv_bfloat16*)y10, (const __nv_bfloat16*)y11, out, C, h, w);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

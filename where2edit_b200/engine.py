@@ -30,8 +30,12 @@ class SynthesisEngine:
         self.gen = gen
         self._w = {}
         self._err = N.ErrorFlag("libw2e modconv_tc2, bf16 synthesis engine")
-        # which of the two (bit-identical) blur kernels runs: W2E_BLUR_V2=0 selects the run-time-tile-shape one
-        self.blur_variant = int(os.environ.get("W2E_BLUR_V2", "0") == "1")
+        # which of the two (bit-identical) blur kernels runs.  Measured (B200, batch 32, tools/ab_layers.py): the templated
+        # kernel (variant 1) wins at >= 64 channels (0.442 -> 0.391 ms at 64@512^2, 0.230 -> 0.205 at 128@256^2), the
+        # run-time-tile-shape kernel (variant 0) at 32 channels (0.891 vs 1.172 ms at 32@1024^2): "auto" picks by the
+        # channel count; W2E_BLUR_V2=0 / 1 forces one kernel everywhere (A/B).
+        env = os.environ.get("W2E_BLUR_V2", "auto")
+        self.blur_variant = int(env) if env in ("0", "1") else "auto"
         # per-call tuning / A-B switches of the tcgen05 convolution (_native.tc2_config(...)); None = defaults
         self.tc2_cfg = None
         # dtype of the image the LAST layer's epilogue writes (torch.float32 as the reference, or torch.bfloat16:
@@ -240,14 +244,15 @@ class SynthesisEngine:
         N.check(N.load().w2e_blur_act_nhwc(
             N.ptr(z), N.host_floats(kernel_taps(blur_kernel)), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
             N.ptr(next_scale), N.ptr(out), N.ptr(out_mod), b, c, ih, iw, pad[0], pad[0], out_hw[0], out_hw[1],
-            N.ACT_LRELU, self.blur_variant, N.stream_ptr()), "blur_act_nhwc")
+            N.ACT_LRELU, (int(c >= 64) if self.blur_variant == "auto" else self.blur_variant), N.stream_ptr()),
+            "blur_act_nhwc")
         return out, out_mod
 
     def _to_nchw(self, x):
         b, h, w, c = x.shape
         y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
         N.note(kind="layout", bytes=6.0 * x.numel(), tag=f"nhwc->nchw {c}@{h}")
-        N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.stream_ptr()), "nhwc_to_nchw_f32")
+        N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.BF16, N.stream_ptr()), "nhwc_to_nchw_f32")
         return y
 
     def _to_nhwc(self, x, style, batch):
@@ -255,7 +260,7 @@ class SynthesisEngine:
         x = x.to(torch.float32).contiguous()
         y = torch.empty((batch, h, w, c), device=x.device, dtype=torch.bfloat16)
         N.note(kind="layout", bytes=4.0 * x.numel() + 2.0 * y.numel(), tag=f"nchw->nhwc {c}@{h}")
-        N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(style), N.ptr(y), batch, bx, c, h * w, N.stream_ptr()),
+        N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(style), N.ptr(y), batch, bx, c, h * w, N.BF16, N.stream_ptr()),
                 "nchw_to_nhwc_mod")
         return y
 

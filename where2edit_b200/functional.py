@@ -32,25 +32,33 @@ class PackedWeight:
         self.tc = None  # bf16 tensor-core layout, filled lazily by the engine
         self._tc_dgrad = None
 
-    def tc_fwd(self):
-        """bf16 [k*k][Cout][Cin] (equalised-lr scale folded in): operand of the tcgen05 forward convolution."""
+    def tc_fwd(self, dtype=torch.bfloat16):
+        """[k*k][Cout][Cin] (equalised-lr scale folded in): operand of the tcgen05 forward convolution, bf16 or
+        (tf32 mode) fp32 -- the fp32 layout is `dgr` itself."""
+        if dtype == torch.float32:
+            return self.dgr
         if self.tc is None:
             self.tc = self.dgr.to(torch.bfloat16).contiguous()
         return self.tc
 
-    def tc_dgrad(self):
-        """bf16 [k*k][Cin][Cout] with the taps flipped: the dgrad of a same-padded 3x3 convolution is the same
+    def tc_dgrad(self, dtype=torch.bfloat16):
+        """[k*k][Cin][Cout] with the taps flipped: the dgrad of a same-padded 3x3 convolution is the same
         convolution kernel run on the upstream gradient with input/output channels swapped."""
+        if dtype == torch.float32:
+            if getattr(self, "_tc_dgrad32", None) is None:
+                self._tc_dgrad32 = self.fwd.flip(0).contiguous()
+            return self._tc_dgrad32
         if self._tc_dgrad is None:
             self._tc_dgrad = self.fwd.flip(0).to(torch.bfloat16).contiguous()
         return self._tc_dgrad
 
-    def tc_dgrad_up(self):
+    def tc_dgrad_up(self, dtype=torch.bfloat16):
         """{(py, px): bf16 [9][Cin][Cout]} -- dgrad of the transposed (x2) convolution as four plain convolutions,
         one per output-parity class of the upstream gradient: class (py, px) holds gz[2j+py, 2i+px] and contributes
         gx[j, i] += gz_class[j+a, i+b] . W[ky, kx]^T with (a, ky) in {(0,0), (1,2)} for py = 0 and {(0,1)} for
         py = 1 (same for b, kx, px).  Offset (+a, +b) is tap (a+1, b+1) of the 3x3 kernel; the other taps are zero."""
-        if getattr(self, "_tc_dgrad_up", None) is None:
+        cache = "_tc_dgrad_up" + ("32" if dtype == torch.float32 else "")
+        if getattr(self, cache, None) is None:
             axis = {0: [(0, 0), (1, 2)], 1: [(0, 1)]}
             out = {}
             for py in (0, 1):
@@ -59,9 +67,9 @@ class PackedWeight:
                     for a, ky in axis[py]:
                         for b, kx in axis[px]:
                             w[(a + 1) * 3 + (b + 1)] = self.fwd[ky * 3 + kx]
-                    out[(py, px)] = w.to(torch.bfloat16).contiguous()
-            self._tc_dgrad_up = out
-        return self._tc_dgrad_up
+                    out[(py, px)] = w.to(dtype).contiguous()
+            setattr(self, cache, out)
+        return getattr(self, cache)
 
 
 def demod_coefficients(s, wsq):
@@ -145,7 +153,9 @@ def conv_dgrad(gy, d, pw, k, upsample, in_hw):
 # tcgen05 kernel (csrc/modconv_tc2.cu) between two layout passes; everything else of the backward
 # (activation, blur, ToRGB, style reductions) stays on the fp32 kernels.
 # --------------------------------------------------------------------------------------------
-TC_AUTOGRAD = False   # set by Generator._forward_modules for the duration of a bf16-precision autograd forward
+# set by Generator.forward for the duration of a tensor-core-precision forward through the module path:
+# False, "bf16" (bf16 operands) or "tf32" (fp32 tensors read as tf32 by the MMA; north star item 1)
+TC_AUTOGRAD = False
 _TC_ERR = {}
 
 
@@ -174,49 +184,62 @@ def tc_assert_ok():
         f.check()
 
 
-def _nhwc_mod(x, scale):
-    """fp32 NCHW -> bf16 NHWC, times scale[b, c] (None = 1)."""
+def _tc_dtype(mode):
+    return torch.float32 if mode == "tf32" else torch.bfloat16
+
+
+def _nhwc_mod(x, scale, dtype=torch.bfloat16):
+    """fp32 NCHW -> channels-last `dtype` (bf16, or fp32 in tf32 mode), times scale[b, c] (None = 1)."""
     b, c, h, w = x.shape
-    y = torch.empty((b, h, w, c), device=x.device, dtype=torch.bfloat16)
-    N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(scale), N.ptr(y), b, b, c, h * w, N.stream_ptr()),
-            "nchw_to_nhwc_mod")
+    y = torch.empty((b, h, w, c), device=x.device, dtype=dtype)
+    N.check(N.load().w2e_nchw_to_nhwc_mod(N.ptr(x), N.ptr(scale), N.ptr(y), b, b, c, h * w, N.dtype_code(y),
+                                          N.stream_ptr()), "nchw_to_nhwc_mod")
     return y
 
 
 def _nchw_f32(x):
     b, h, w, c = x.shape
     y = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
-    N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.stream_ptr()), "nhwc_to_nchw_f32")
+    N.check(N.load().w2e_nhwc_to_nchw_f32(N.ptr(x), N.ptr(y), b, c, h * w, N.dtype_code(x), N.stream_ptr()),
+            "nhwc_to_nchw_f32")
     return y
 
 
-def tc_supported(cin, cout, k):
-    return k == 3 and cin % 32 == 0 and cout % 16 == 0 and bool(N.load().w2e_modconv_tc_supported())
+def tc_supported(cin, cout, k, mode="bf16"):
+    return (k == 3 and cin % (16 if mode == "tf32" else 32) == 0 and cout % 16 == 0
+            and bool(N.load().w2e_modconv_tc_supported()))
 
 
 def _tc_conv(xs, w, out_scale, cin, cout, transposed):
+    """w2e_modconv_tc2 (bf16 tensors) or w2e_modconv_tc2_tf32 (fp32 tensors), by the dtype of xs."""
     b, h, wd, _ = xs.shape
     oh, ow = (2 * h + 1, 2 * wd + 1) if transposed else (h, wd)
-    y = torch.empty((b, oh, ow, cout), device=xs.device, dtype=torch.bfloat16)
-    N.note(kind="modconv", flops=2.0 * 9 * cin * cout * b * h * wd, tag=f"{'up ' if transposed else ''}{cin}->{cout}@{h}x{wd} (autograd)")
-    N.check(N.load().w2e_modconv_tc2(
-        N.ptr(xs), N.ptr(w), N.ptr(out_scale), None, None, None, 0, None, N.ptr(y), None,
-        N.ptr(_tc_error_flag(xs.device)), b, cin, cout, h, wd, int(transposed), N.ACT_NONE, None, N.stream_ptr()),
-        "modconv_tc2")
+    y = torch.empty((b, oh, ow, cout), device=xs.device, dtype=xs.dtype)
+    tf32 = xs.dtype == torch.float32
+    if w.dtype != xs.dtype:
+        raise RuntimeError("where2edit_b200: tensor-core convolution operands must share one dtype")
+    N.note(kind="modconv", flops=2.0 * 9 * cin * cout * b * h * wd,
+           tag=f"{'up ' if transposed else ''}{cin}->{cout}@{h}x{wd} ({'tf32' if tf32 else 'bf16'}, module path)")
+    fn = N.load().w2e_modconv_tc2_tf32 if tf32 else N.load().w2e_modconv_tc2
+    N.check(fn(N.ptr(xs), N.ptr(w), N.ptr(out_scale), None, None, None, 0, None, N.ptr(y), None,
+               N.ptr(_tc_error_flag(xs.device)), b, cin, cout, h, wd, int(transposed), N.ACT_NONE, None, N.stream_ptr()),
+            "modconv_tc2_tf32" if tf32 else "modconv_tc2")
     return y
 
 
-def conv_forward_tc(x, s, d, pw, upsample):
-    """conv_forward on the tensor cores: y = d * conv(bf16(x*s), bf16(W)), fp32 accumulate, bf16 result."""
-    return _nchw_f32(_tc_conv(_nhwc_mod(x, s), pw.tc_fwd(), d, pw.cin, pw.cout, upsample))
+def conv_forward_tc(x, s, d, pw, upsample, mode="bf16"):
+    """conv_forward on the tensor cores: y = d * conv(x*s, W) with bf16 (or tf32) operands, fp32 accumulate."""
+    dt = _tc_dtype(mode)
+    return _nchw_f32(_tc_conv(_nhwc_mod(x, s, dt), pw.tc_fwd(dt), d, pw.cin, pw.cout, upsample))
 
 
-def conv_dgrad_tc(gy, d, pw, upsample=False, in_hw=None):
+def conv_dgrad_tc(gy, d, pw, upsample=False, in_hw=None, mode="bf16"):
     """conv_dgrad on the tensor cores.  Plain (same-padded) 3x3 convolution: one launch with flipped taps.
     Transposed x2 convolution: its dgrad is a stride-2 convolution of the (2h+1)^2 upstream gradient, run as four
     plain convolutions over the gradient's output-parity classes (PackedWeight.tc_dgrad_up) and summed."""
+    dt = _tc_dtype(mode)
     if not upsample:
-        return _nchw_f32(_tc_conv(_nhwc_mod(gy, d), pw.tc_dgrad(), None, pw.cout, pw.cin, False))
+        return _nchw_f32(_tc_conv(_nhwc_mod(gy, d, dt), pw.tc_dgrad(dt), None, pw.cout, pw.cin, False))
     h, w = in_hw
     b, cout, zh, zw = gy.shape
     lib = N.load()
@@ -224,13 +247,13 @@ def conv_dgrad_tc(gy, d, pw, upsample=False, in_hw=None):
     for py in (0, 1):
         for px in (0, 1):
             hc, wc = (zh - py + 1) // 2, (zw - px + 1) // 2
-            g_c = torch.empty((b, hc, wc, cout), device=gy.device, dtype=torch.bfloat16)
+            g_c = torch.empty((b, hc, wc, cout), device=gy.device, dtype=dt)
             N.check(lib.w2e_nchw_class_to_nhwc_mod(N.ptr(gy), N.ptr(d), N.ptr(g_c), b, cout, zh, zw, py, px,
-                                                   N.stream_ptr()), "nchw_class_to_nhwc_mod")
-            ys.append(_tc_conv(g_c, pw.tc_dgrad_up()[(py, px)], None, pw.cout, pw.cin, False))
+                                                   N.dtype_code(g_c), N.stream_ptr()), "nchw_class_to_nhwc_mod")
+            ys.append(_tc_conv(g_c, pw.tc_dgrad_up(dt)[(py, px)], None, pw.cout, pw.cin, False))
     gxs = torch.empty((b, pw.cin, h, w), device=gy.device, dtype=torch.float32)
     N.check(lib.w2e_nhwc_sum4_to_nchw_f32(N.ptr(ys[0]), N.ptr(ys[1]), N.ptr(ys[2]), N.ptr(ys[3]), N.ptr(gxs), b, pw.cin,
-                                          h, w, N.stream_ptr()), "nhwc_sum4_to_nchw_f32")
+                                          h, w, N.dtype_code(ys[0]), N.stream_ptr()), "nhwc_sum4_to_nchw_f32")
     return gxs
 
 
@@ -254,10 +277,11 @@ def _rowdot(a, b, scale=None, want_prod=False):
 class _ModConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, s, d, pw, k, upsample):
-        tc = TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k)
-        y = conv_forward_tc(x, s, d, pw, upsample) if tc else conv_forward(x, s, d, pw, k, upsample)
+        mode = TC_AUTOGRAD
+        tc = bool(mode) and tc_supported(pw.cin, pw.cout, k, mode)
+        y = conv_forward_tc(x, s, d, pw, upsample, mode) if tc else conv_forward(x, s, d, pw, k, upsample)
         ctx.save_for_backward(x, s, d if d is not None else x.new_zeros(0), y)
-        ctx.cfg = (pw, k, upsample, d is not None, tc and tc_supported(pw.cout, pw.cin, k))
+        ctx.cfg = (pw, k, upsample, d is not None, mode if (tc and tc_supported(pw.cout, pw.cin, k, mode)) else False)
         return y
 
     @staticmethod
@@ -273,7 +297,7 @@ class _ModConv(torch.autograd.Function):
             gd = dot / d
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if tc_dgrad:
-                gxs = conv_dgrad_tc(gy, d_or_none, pw, upsample, (x.shape[2], x.shape[3]))
+                gxs = conv_dgrad_tc(gy, d_or_none, pw, upsample, (x.shape[2], x.shape[3]), tc_dgrad)
             else:
                 gxs = conv_dgrad(gy, d_or_none, pw, k, upsample, (x.shape[2], x.shape[3]))
             gs, gx = _rowdot(gxs, x, scale=s.contiguous(), want_prod=True)   # gs = sum_p gxs*x ; gx = gxs*s
@@ -288,8 +312,8 @@ def modulated_conv2d(x, s, d, pw, k, upsample):
         d = d.contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or s.requires_grad or (d is not None and d.requires_grad)):
         return _ModConv.apply(x, s, d, pw, k, upsample)
-    if TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k):
-        return conv_forward_tc(x, s, d, pw, upsample)
+    if TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k, TC_AUTOGRAD):
+        return conv_forward_tc(x, s, d, pw, upsample, TC_AUTOGRAD)
     return conv_forward(x, s, d, pw, k, upsample)
 
 

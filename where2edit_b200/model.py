@@ -356,10 +356,15 @@ class Generator(nn.Module):
         return self.style(input)
 
     def set_precision(self, precision):
-        """'fp32': exact CUDA-core path (differentiable).  'bf16': tcgen05 tensor-core path for
-        no-grad synthesis (falls back to nothing: raises if the device is not sm_100)."""
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        """'fp32': exact CUDA-core path (<= 1e-4 of the reference; differentiable).
+        'bf16': tcgen05 tensor-core path -- the channels-last bf16 engine for no-grad synthesis, bf16-operand
+                convolutions (forward and dgrad) inside the fp32 module path under autograd.
+        'tf32': the fp32 module path with every 3x3 modulated convolution (forward and dgrad) on tcgen05
+                kind::tf32 (fp32 tensors in HBM, 10-bit-mantissa operands, fp32 accumulate): about 8x closer to
+                the reference than bf16, for edits whose loss needs it.
+        There is no fallback: the tensor-core modes raise if the device is not sm_100."""
+        if precision not in ("fp32", "bf16", "tf32"):
+            raise ValueError(f"precision must be 'fp32', 'bf16' or 'tf32', got {precision!r}")
         self.precision = precision
         return self
 
@@ -446,7 +451,7 @@ class Generator(nn.Module):
             # precision "bf16" under autograd: the 3x3 convolutions (forward and dgrad) run on the tensor cores,
             # the rest of the differentiable path on the fp32 kernels (functional.TC_AUTOGRAD)
             prev = K.TC_AUTOGRAD
-            K.TC_AUTOGRAD = self.precision == "bf16"
+            K.TC_AUTOGRAD = self.precision if self.precision in ("bf16", "tf32") else False
             try:
                 if K.TC_AUTOGRAD:
                     K.tc_poll()   # a pipeline timeout of an earlier forward / backward raises here (no sync)
