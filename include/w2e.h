@@ -184,7 +184,8 @@ typedef struct w2e_tc2_config {
   int ts_mode;        /* 1 = shared-memory-staged TMA-store epilogue whenever eligible, 0 = direct stores    */
   int flags;          /* bit 0 no edge-tile tap masking (transposed), bit 1 a single MMA-issuing warp,
                          bit 3 64-column tiles for the transposed conv, bit 4 256-pixel tiles for the 32-channel
-                         transposed conv, bit 5 128-pixel tiles (two accumulator sets) for the 64-channel one   */
+                         transposed conv, bit 5 128-pixel tiles (two accumulator sets) for the 64-channel one,
+                         bit 6 one weight request per filter tap instead of one per tap row                     */
   int cluster_log2;   /* weight-ring kernels as clusters of 2^n CTAs with TMA-multicast weight blocks (0..3)  */
   void* timeline;     /* device long long[64][8] or NULL: clock64 stamps of CTA 0's first 64 tiles
                          (tools/tc2_timeline.py)                                                              */

@@ -79,4 +79,24 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return v;
 }
 
+// fp64 variants for the long, cancellation-heavy reductions of the backward (sums over up to 2^20 pixels of signed
+// gradient terms: condition number ~ sqrt(N); the kernels are memory-bound, the extra DADD per element is free)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum; result valid in thread 0.  `red` needs 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  v = warp_sum_d(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum_d(v);
+  __syncthreads();
+  return v;
+}
+
 }  // namespace w2e

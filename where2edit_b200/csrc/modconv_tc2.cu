@@ -62,6 +62,7 @@ struct Tc2Params {
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
+  int bgroup;               // weight-ring kernels, TS flavour: filter taps per weight REQUEST (1, or 3 = one tap row per TMA box)
   int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
   // fused ToRGB (models/stylegan2/model.py:353-362), RGB variants only
@@ -93,6 +94,7 @@ struct alignas(64) Tc2Maps {
   CUtensorMap noise;   // fp32 {OW, OH, noise_batch}, box {8, 16*MT, 1}
   CUtensorMap skip;    // fp32 {OW/2, OH/2, B*3}, box {12, 10, 3}
   CUtensorMap bh;      // cluster mode: weight map with a half-block box {BK, bn/2, 1}
+  CUtensorMap b3;      // grouped weight requests: box {BK, bn, 3} = the three taps of one kernel row
   CUtensorMap st[4];   // bf16 stores, box {unit_ch, 8, 16, 1}: plain [0] = out, [1] = out_mod; transposed [g] = class g of out
 };
 
@@ -176,6 +178,10 @@ struct Ring {
   uint32_t idx = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t n) {
     if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+  __device__ __forceinline__ void advance_by(uint32_t step, uint32_t n) {   // n is a multiple of step
+    idx += step;
+    if (idx >= n) { idx = 0; phase ^= 1u; }
   }
 };
 
@@ -324,6 +330,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int j0 = wk.ty * P.tile_dy + P.tile_o, i0 = wk.tx * P.tile_dx + P.tile_o, co0 = wk.tn * P.bn;
         const bool edge_y = TR && !(P.flags & 1) && !P.fb && j0 >= P.grid_h - 1;   // see the MMA issuer
         const bool edge_x = TR && !(P.flags & 1) && !P.fb && i0 >= P.grid_w - 1;
+        if (P.bgroup == 3) {
+          // One request per TAP ROW: a box {BK, bn, 3} fills three consecutive ring stages and signals the first
+          // stage's barrier.  A single thread issues a TMA request every ~330...400 cycles whatever its size
+          // (tools/tma_ingest_bench.cu), and a 16 KB block feeds only 256 cycles of MMAs: with per-tap requests the
+          // ring was bound by the REQUEST RATE, not by bytes.  (Edge-column tiles use only kx == 2 of each row: the
+          // whole row is still fetched.)
+          for (int kc = 0; kc < kchunks && ok; ++kc) {
+            for (int g = 0; g < 3; ++g) {
+              if (edge_y && g != 2) continue;
+              ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
+              if (!ok) break;
+              mbar_arrive_expect_tx(&bars->b_full[br.idx], 3u * (uint32_t)P.b_block_bytes);
+              tma_load_3d(b_base + (size_t)br.idx * P.b_block_bytes, &M.b3, &bars->b_full[br.idx], kc * kBK, co0, 3 * g);
+              br.advance_by(3, P.b_stages);
+            }
+          }
+          continue;
+        }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
@@ -475,6 +499,58 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             b_lo += b_block16;
           }
           if (leader) umma_commit(&bars->a_empty[ar.idx]);
+        } else if (TS && P.bgroup == 3) {
+          // grouped weight requests: one b_full / b_empty round trip (and one issue token) per TAP ROW of 3 blocks
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            if (edge_y && g != 2) continue;
+            const bool mine = !blk2 || (int)(nblk & 1u) == mw;
+            ++nblk;
+            if (mine) {
+              ok = mbar_wait_warp(&bars->b_full[br.idx], br.phase, abort_flag);
+              if (ok && blk2) ok = mbar_wait_warp(&bars->mma_turn[mw], mw == 0 ? (myblk & 1u) ^ 1u : (myblk & 1u), abort_flag);
+              if (!ok) break;
+              ++myblk;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int t = g * 3 + kx;
+              if (edge_x && kx != 2) continue;
+              const uint32_t b_lo = b_lo0 + (br.idx + (uint32_t)kx) * b_block16;
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                if (m == 1 && edge_y) continue;
+                constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                const int ai = tap_group<TR>(t) * MT + m;
+                const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+                uint32_t first = 1u;
+                if (TR) {
+                  first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
+                  started |= 1u << ai;
+                } else if (t == 0) {
+                  first = kc == 0 ? 0u : 1u;
+                }
+                if (leader && mine) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                }
+              }
+            }
+            if (leader && mine) {
+              umma_commit(&bars->b_empty[br.idx]);
+              if (!blk2 && g == 2) {
+                umma_commit(&bars->a_empty[ar.idx]);
+                if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
+              }
+              if (blk2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
+            }
+            br.advance_by(3, P.b_stages);
+          }
+          if (blk2 && ok && leader) {
+            umma_commit(&bars->a_empty[ar.idx]);
+            if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
+          }
         } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
@@ -1315,7 +1391,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
-  const int g_flags = cfg ? (cfg->flags & 59) : 0;
+  const int g_flags = cfg ? (cfg->flags & 123) : 0;
   const int g_cluster_mode = cfg ? (cfg->cluster_log2 < 0 ? 0 : (cfg->cluster_log2 > 3 ? 3 : cfg->cluster_log2)) : 0;
   long long* const g_dbg = cfg ? (long long*)cfg->timeline : nullptr;
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
@@ -1518,6 +1594,18 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)(P.bn >> clog), 1u};
     int rc = make_bf16_map(&M.bh, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
+  }
+  // grouped weight requests (one TMA box per tap row) for the weight-ring kernels of the TS flavour; flag bit 6 = off (A/B)
+  if (ts && !P.wres && !P.cluster && !tf32 && !(g_flags & 64) && P.b_stages >= 6) {
+    P.bgroup = 3;
+    P.b_stages -= P.b_stages % 3;
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9u};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    const uint32_t box[3] = {(uint32_t)P.bk, (uint32_t)P.bn, 3u};
+    int rc = make_bf16_map(&M.b3, w, 3, dims, strides, box, row_bytes);
+    if (rc) return rc;
+  } else {
+    P.bgroup = 1;
   }
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
   if (ts && !fb) {

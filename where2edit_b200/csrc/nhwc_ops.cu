@@ -45,6 +45,20 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 
+// Operand element of the tensor-core convolution: bf16 (round to nearest even), or fp32 rounded to tf32 with
+// cvt.rna (the tf32 MMA TRUNCATES the low 13 mantissa bits of its operands; truncation is a biased error that grows
+// coherently through the 17-layer chain -- measured: un-rounded tf32 was no closer to the reference than bf16)
+template <typename T>
+__device__ __forceinline__ T to_operand(float v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_operand<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ float to_operand<float>(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 // ------------------------------------------------------------------------------ layout transforms
 // x [Bx, C, HW] fp32 (Bx = 1 broadcasts over the batch) -> y [B, HW, C] bf16 * style[b, c]
 template <typename T>
@@ -71,7 +85,7 @@ nchw_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restrict__ s
     if (p < HW && c < C) {
       float v = tile[tx][r];
       if (style) v *= __ldg(style + (int64_t)b * C + c);
-      y[((int64_t)b * HW + p) * C + c] = from_f32<T>(v);
+      y[((int64_t)b * HW + p) * C + c] = to_operand<T>(v);
     }
   }
 }
@@ -132,7 +146,7 @@ nchw_class_to_nhwc_mod_kernel(const float* __restrict__ x, const float* __restri
     if (p < HWc && c < C) {
       float v = tile[tx][r];
       if (scale) v *= __ldg(scale + (int64_t)b * C + c);
-      y[((int64_t)b * HWc + p) * C + c] = from_f32<T>(v);
+      y[((int64_t)b * HWc + p) * C + c] = to_operand<T>(v);
     }
   }
 }

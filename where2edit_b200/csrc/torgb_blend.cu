@@ -70,21 +70,21 @@ __global__ void __launch_bounds__(256)
 torgb_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ style, float* __restrict__ gx, float* __restrict__ gstyle, int Cin,
                  int64_t HW) {
-  __shared__ float red[32];
+  __shared__ double red[32];
   const int c = blockIdx.x, b = blockIdx.y;
   const float w0 = __ldg(w + c), w1 = __ldg(w + Cin + c), w2 = __ldg(w + 2 * Cin + c);
   const float s = __ldg(style + (int64_t)b * Cin + c);
   const float* gp = g + (int64_t)b * 3 * HW;
   const float* xp = x + ((int64_t)b * Cin + c) * HW;
   float* gxp = gx + ((int64_t)b * Cin + c) * HW;
-  float acc = 0.f;
+  double acc = 0.0;
   for (int64_t p = threadIdx.x; p < HW; p += blockDim.x) {
     const float t = fmaf(gp[p], w0, fmaf(gp[HW + p], w1, gp[2 * HW + p] * w2));
     gxp[p] = t * s;
-    acc = fmaf(t, xp[p], acc);
+    acc += (double)(t * xp[p]);
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) gstyle[(int64_t)b * Cin + c] = acc;
+  acc = block_sum_d(acc, red);
+  if (threadIdx.x == 0) gstyle[(int64_t)b * Cin + c] = (float)acc;
 }
 
 // the same with every (c, b) plane split into nseg fixed segments (grid = nseg x Cin x B); the partial sums of
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256)
 torgb_bwd_seg_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ style, float* __restrict__ gx, float* __restrict__ partial, int Cin,
                      int64_t HW, int64_t seg_len, int nseg) {
-  __shared__ float red[32];
+  __shared__ double red[32];
   const int sg = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
   const float w0 = __ldg(w + c), w1 = __ldg(w + Cin + c), w2 = __ldg(w + 2 * Cin + c);
   const float s = __ldg(style + (int64_t)b * Cin + c);
@@ -101,7 +101,7 @@ torgb_bwd_seg_kernel(const float* __restrict__ g, const float* __restrict__ x, c
   const float* xp = x + ((int64_t)b * Cin + c) * HW;
   float* gxp = gx + ((int64_t)b * Cin + c) * HW;
   const int64_t p0 = (int64_t)sg * seg_len, p1 = min(HW, p0 + seg_len);
-  float acc = 0.f;
+  double acc = 0.0;
   for (int64_t p = p0 + (int64_t)threadIdx.x * 4; p < p1; p += (int64_t)blockDim.x * 4) {
     const float4 g0 = *reinterpret_cast<const float4*>(gp + p);
     const float4 g1 = *reinterpret_cast<const float4*>(gp + HW + p);
@@ -113,10 +113,10 @@ torgb_bwd_seg_kernel(const float* __restrict__ g, const float* __restrict__ x, c
     t.z = fmaf(g0.z, w0, fmaf(g1.z, w1, g2.z * w2));
     t.w = fmaf(g0.w, w0, fmaf(g1.w, w1, g2.w * w2));
     *reinterpret_cast<float4*>(gxp + p) = make_float4(t.x * s, t.y * s, t.z * s, t.w * s);
-    acc = fmaf(t.x, xv.x, acc); acc = fmaf(t.y, xv.y, acc); acc = fmaf(t.z, xv.z, acc); acc = fmaf(t.w, xv.w, acc);
+    acc += (double)(t.x * xv.x) + (double)(t.y * xv.y) + (double)(t.z * xv.z) + (double)(t.w * xv.w);
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) partial[((int64_t)b * Cin + c) * nseg + sg] = acc;
+  acc = block_sum_d(acc, red);
+  if (threadIdx.x == 0) partial[((int64_t)b * Cin + c) * nseg + sg] = (float)acc;
 }
 
 // ------------------------------------------------------------------------------------------ blend
@@ -178,19 +178,19 @@ __global__ void mask_grad_gather_kernel(const float* __restrict__ dsum, float* _
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ scale,
               float* __restrict__ prod, float* __restrict__ dot, int64_t inner) {
-  __shared__ float red[32];
+  __shared__ double red[32];
   const int64_t r = blockIdx.x;
   const float* ar = a + r * inner;
   const float* br = b + r * inner;
   const float s = scale ? __ldg(scale + r) : 1.f;
-  float acc = 0.f;
+  double acc = 0.0;   // fp64 accumulation: see block_sum_d
   for (int64_t p = threadIdx.x; p < inner; p += blockDim.x) {
     const float av = ar[p];
-    acc = fmaf(av, br[p], acc);
+    acc += (double)(av * br[p]);
     if (prod) prod[r * inner + p] = av * s;
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0 && dot) dot[r] = acc;
+  acc = block_sum_d(acc, red);
+  if (threadIdx.x == 0 && dot) dot[r] = (float)acc;
 }
 
 // Same reduction with every row split into nseg segments (grid = nseg x rows): long rows of the >= 256^2 layers
@@ -199,32 +199,32 @@ rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, const fl
 __global__ void __launch_bounds__(256)
 rowdot_seg_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ scale,
                   float* __restrict__ prod, float* __restrict__ partial, int64_t inner, int64_t seg_len, int nseg) {
-  __shared__ float red[32];
+  __shared__ double red[32];
   const int64_t r = blockIdx.y;
   const int sg = blockIdx.x;
   const int64_t p0 = (int64_t)sg * seg_len, p1 = min(inner, p0 + seg_len);
   const float* ar = a + r * inner;
   const float* br = b + r * inner;
   const float s = scale ? __ldg(scale + r) : 1.f;
-  float acc = 0.f;
+  double acc = 0.0;
   // seg_len and inner are multiples of 4 and the rows 16-byte aligned (checked by the launcher)
   for (int64_t p = p0 + (int64_t)threadIdx.x * 4; p < p1; p += (int64_t)blockDim.x * 4) {
     const float4 av = *reinterpret_cast<const float4*>(ar + p);
     const float4 bv = *reinterpret_cast<const float4*>(br + p);
-    acc = fmaf(av.x, bv.x, acc); acc = fmaf(av.y, bv.y, acc); acc = fmaf(av.z, bv.z, acc); acc = fmaf(av.w, bv.w, acc);
+    acc += (double)(av.x * bv.x) + (double)(av.y * bv.y) + (double)(av.z * bv.z) + (double)(av.w * bv.w);
     if (prod) *reinterpret_cast<float4*>(prod + r * inner + p) = make_float4(av.x * s, av.y * s, av.z * s, av.w * s);
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) partial[r * nseg + sg] = acc;
+  acc = block_sum_d(acc, red);
+  if (threadIdx.x == 0) partial[r * nseg + sg] = (float)acc;
 }
 
 __global__ void __launch_bounds__(256)
 rowdot_finish_kernel(const float* __restrict__ partial, float* __restrict__ dot, int64_t rows, int nseg) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  float acc = 0.f;
-  for (int sg = 0; sg < nseg; ++sg) acc += partial[r * nseg + sg];
-  dot[r] = acc;
+  double acc = 0.0;
+  for (int sg = 0; sg < nseg; ++sg) acc += (double)partial[r * nseg + sg];
+  dot[r] = (float)acc;
 }
 
 // one warp per (b, o): demod = rsqrt(sum_i style^2 * wsq + 1e-8)   (models/stylegan2/model.py:242)

@@ -4,6 +4,12 @@ models/stylegan2/model.py:239-274 and its backward).  No CPU path.
 """
 import torch
 
+# autocast safety (the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast, run_attention.py:1231):
+# the kernels take fp32 (or bf16) pointers, so half-precision tensors handed over by autocast-ed linears are cast to
+# fp32 at every custom Function and autocast is off inside it
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 from . import _native as N
 from .op.fused_act import _BiasAct
 from .op.upfirdn2d import _UpFirDn2d, kernel_taps
@@ -12,6 +18,13 @@ from .op.upfirdn2d import _UpFirDn2d, kernel_taps
 # --------------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------------
+def round_tf32(t):
+    """fp32 -> nearest tf32-representable fp32 (ties away from zero, like cvt.rna.tf32.f32): the tf32 MMA truncates
+    its operands, so they are rounded once when they are produced."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 class PackedWeight:
     """Batch-shared layouts of one ModulatedConv2d weight [1,Cout,Cin,k,k], pre-multiplied by the
     equalised-lr scale 1/sqrt(Cin*k*k) (model.py:216-217):
@@ -34,9 +47,11 @@ class PackedWeight:
 
     def tc_fwd(self, dtype=torch.bfloat16):
         """[k*k][Cout][Cin] (equalised-lr scale folded in): operand of the tcgen05 forward convolution, bf16 or
-        (tf32 mode) fp32 -- the fp32 layout is `dgr` itself."""
+        (tf32 mode) fp32 rounded to tf32."""
         if dtype == torch.float32:
-            return self.dgr
+            if getattr(self, "_tc32", None) is None:
+                self._tc32 = round_tf32(self.dgr)
+            return self._tc32
         if self.tc is None:
             self.tc = self.dgr.to(torch.bfloat16).contiguous()
         return self.tc
@@ -46,7 +61,7 @@ class PackedWeight:
         convolution kernel run on the upstream gradient with input/output channels swapped."""
         if dtype == torch.float32:
             if getattr(self, "_tc_dgrad32", None) is None:
-                self._tc_dgrad32 = self.fwd.flip(0).contiguous()
+                self._tc_dgrad32 = round_tf32(self.fwd.flip(0))
             return self._tc_dgrad32
         if self._tc_dgrad is None:
             self._tc_dgrad = self.fwd.flip(0).to(torch.bfloat16).contiguous()
@@ -67,7 +82,7 @@ class PackedWeight:
                     for a, ky in axis[py]:
                         for b, kx in axis[px]:
                             w[(a + 1) * 3 + (b + 1)] = self.fwd[ky * 3 + kx]
-                    out[(py, px)] = w.to(dtype).contiguous()
+                    out[(py, px)] = round_tf32(w) if dtype == torch.float32 else w.to(dtype).contiguous()
             setattr(self, cache, out)
         return getattr(self, cache)
 
@@ -76,8 +91,10 @@ def demod_coefficients(s, wsq):
     """d[b,o] = rsqrt(sum_i s[b,i]^2 * wsq[o,i] + 1e-8) (model.py:242).  Uses libw2e's kernel when no
     gradient is needed, plain torch ops (tiny [B,C] algebra) when autograd must see it."""
     if torch.is_grad_enabled() and s.requires_grad:
-        return torch.rsqrt((s * s) @ wsq.t() + 1e-8)
-    s = s.contiguous()
+        with torch.autocast("cuda", enabled=False):   # fp32 whatever the caller's autocast state
+            s32 = s.to(torch.float32)
+            return torch.rsqrt((s32 * s32) @ wsq.t() + 1e-8)
+    s = s.to(torch.float32).contiguous()
     d = torch.empty((s.shape[0], wsq.shape[0]), device=s.device, dtype=torch.float32)
     N.check(N.load().w2e_style_demod(N.ptr(s), N.ptr(wsq), N.ptr(d), s.shape[0], s.shape[1], wsq.shape[0],
                                      N.stream_ptr()), "style_demod")
@@ -276,6 +293,7 @@ def _rowdot(a, b, scale=None, want_prod=False):
 
 class _ModConv(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, s, d, pw, k, upsample):
         mode = TC_AUTOGRAD
         tc = bool(mode) and tc_supported(pw.cin, pw.cout, k, mode)
@@ -286,6 +304,7 @@ class _ModConv(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, gy):
         x, s, d, y = ctx.saved_tensors
         pw, k, upsample, has_d, tc_dgrad = ctx.cfg
@@ -307,9 +326,9 @@ class _ModConv(torch.autograd.Function):
 def modulated_conv2d(x, s, d, pw, k, upsample):
     """x [B,Cin,H,W] fp32, s [B,Cin], d [B,Cout] or None -> [B,Cout,H,W] (or (2H+1)^2 pre-blur)."""
     x = x.to(torch.float32).contiguous()
-    s = s.contiguous()
+    s = s.to(torch.float32).contiguous()     # (autocast hands over half-precision styles)
     if d is not None:
-        d = d.contiguous()
+        d = d.to(torch.float32).contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or s.requires_grad or (d is not None and d.requires_grad)):
         return _ModConv.apply(x, s, d, pw, k, upsample)
     if TC_AUTOGRAD and tc_supported(pw.cin, pw.cout, k, TC_AUTOGRAD):
@@ -357,6 +376,7 @@ class _WeightGradTap(torch.autograd.Function):
     `weight` (the convolution kernels themselves take the weight as a packed, detached constant)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, y, weight, x, s, d, scale, k, upsample):
         ctx.save_for_backward(y, weight, x, s, d if d is not None else y.new_zeros(0))
         ctx.cfg = (scale, k, upsample, d is not None)
@@ -364,6 +384,7 @@ class _WeightGradTap(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, gy):
         y, weight, x, s, d = ctx.saved_tensors
         scale, k, upsample, has_d = ctx.cfg
@@ -413,6 +434,7 @@ def separable_taps(kernel2d):
 
 class _ToRGB(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, s, skip, w_rgb, bias, taps2d, taps1d):
         b, cin, h, w = x.shape
         rgb = torch.empty((b, 3, h, w), device=x.device, dtype=torch.float32)
@@ -425,6 +447,7 @@ class _ToRGB(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, g):
         x, s = ctx.saved_tensors
         w_rgb, taps2d, has_skip = ctx.cfg
@@ -455,7 +478,7 @@ def to_rgb(x, s, pw, bias, skip, up_kernel):
     x = x.contiguous()
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
-    s = s.contiguous()
+    s = s.to(torch.float32).contiguous()
     taps2d = taps1d = None
     if skip is not None:
         taps2d = kernel_taps(up_kernel)
@@ -474,6 +497,7 @@ def to_rgb(x, s, pw, bias, skip, up_kernel):
 # --------------------------------------------------------------------------------------------
 class _MaskBlend(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, edited, orig, mask):
         b, c, h, w = edited.shape
         out = torch.empty_like(edited)
@@ -485,6 +509,7 @@ class _MaskBlend(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, g):
         edited, orig, mask = ctx.saved_tensors
         b, c, h, w = edited.shape

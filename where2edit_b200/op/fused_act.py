@@ -2,6 +2,12 @@
 models/stylegan2/op/fused_act.py:11-39, executed by libw2e (csrc/bias_act.cu) in ONE pass instead
 of the reference's add / leaky_relu / mul chain.  No CPU implementation."""
 import torch
+
+# autocast safety (the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast, run_attention.py:1231):
+# the kernels take fp32 (or bf16) pointers, so half-precision tensors handed over by autocast-ed linears are cast to
+# fp32 at every custom Function and autocast is off inside it
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
 from torch import nn
 
 from .. import _native as N
@@ -54,6 +60,7 @@ def bias_act_backward(gy, y, bias_shape_c, want_gbias, layout, slope, scale):
 
 class _BiasActBackward(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, gy, y, want_gbias, layout, slope, scale):
         ctx.save_for_backward(y)
         ctx.cfg = (layout, slope, scale)
@@ -63,6 +70,7 @@ class _BiasActBackward(torch.autograd.Function):
         return gx, gbias
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, ggx, ggbias):
         # second order: d(gx)/d(gy) is the same mask; the op is piecewise linear in y
         (y,) = ctx.saved_tensors
@@ -77,6 +85,7 @@ class _BiasAct(torch.autograd.Function):
     """y = lrelu(x + bias + noise_w*noise) * scale; gradients to x and bias (noise terms are buffers)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, bias, noise, noise_w, slope, scale):
         y = bias_act_forward(x, bias, noise, noise_w, slope, scale)
         ctx.save_for_backward(y)
@@ -85,6 +94,7 @@ class _BiasAct(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
         slope, scale = ctx.cfg

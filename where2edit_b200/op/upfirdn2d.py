@@ -4,6 +4,12 @@ import weakref
 
 import torch
 
+# autocast safety (the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast, run_attention.py:1231):
+# the kernels take fp32 (or bf16) pointers, so half-precision tensors handed over by autocast-ed linears are cast to
+# fp32 at every custom Function and autocast is off inside it
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 from .. import _native as N
 
 _TAPS_CACHE = {}
@@ -55,11 +61,13 @@ def _run(x, taps, kh, kw, geom, backward=False, in_hw=None):
 
 class _UpFirDn2dBackward(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, gy, taps, kh, kw, geom, in_hw):
         ctx.cfg = (taps, kh, kw, geom)
         return _run(gy.contiguous(), taps, kh, kw, geom, backward=True, in_hw=in_hw)
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, ggx):
         taps, kh, kw, geom = ctx.cfg
         # the operator is linear: the gradient of its adjoint is the operator itself
@@ -68,11 +76,13 @@ class _UpFirDn2dBackward(torch.autograd.Function):
 
 class _UpFirDn2d(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, taps, kh, kw, geom):
         ctx.cfg = (taps, kh, kw, geom, (x.shape[2], x.shape[3]))
         return _run(x, taps, kh, kw, geom)
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, gy):
         taps, kh, kw, geom, in_hw = ctx.cfg
         return _UpFirDn2dBackward.apply(gy, taps, kh, kw, geom, in_hw), None, None, None, None

@@ -16,6 +16,12 @@ Both run hand-written CUDA through libw2e's C ABI (include/w2e.h); there is no C
 
 import torch
 
+# autocast safety (the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast, run_attention.py:1231):
+# the kernels take fp32 (or bf16) pointers, so half-precision tensors handed over by autocast-ed linears are cast to
+# fp32 at every custom Function and autocast is off inside it
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 from . import _native as N
 
 GAUSSIAN_KSIZE = 5
@@ -71,6 +77,7 @@ def assign_clusters(blend_feature, initial_state, size, clusters=None):
 
 class _RegionAttention(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, each, ids, clusters, threshold, margin):
         b, s, _ = each.shape
         dev = each.device
@@ -89,6 +96,7 @@ class _RegionAttention(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, g_final, g_same, g_reg, g_tv):
         each, ids, same, stats = ctx.saved_tensors
         clusters, margin = ctx.cfg

@@ -10,11 +10,18 @@ reference's two hyper-parameters.  CUDA only (libw2e.so, include/w2e.h: w2e_box_
 """
 import torch
 
+# autocast safety (the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast, run_attention.py:1231):
+# the kernels take fp32 (or bf16) pointers, so half-precision tensors handed over by autocast-ed linears are cast to
+# fp32 at every custom Function and autocast is off inside it
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 from . import _native as N
 
 
 class _BoxResample(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, up, pool):
         b, c, h, w = x.shape
         y = torch.empty((b, c, h * up // pool, w * up // pool), device=x.device, dtype=torch.float32)
@@ -25,6 +32,7 @@ class _BoxResample(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_amp_bwd
     def backward(ctx, gy):
         b, c, h, w, up, pool = ctx.cfg
         gy = gy.to(torch.float32).contiguous()
