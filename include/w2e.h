@@ -185,7 +185,8 @@ typedef struct w2e_tc2_config {
   int flags;          /* bit 0 no edge-tile tap masking (transposed), bit 1 a single MMA-issuing warp,
                          bit 3 64-column tiles for the transposed conv, bit 4 256-pixel tiles for the 32-channel
                          transposed conv, bit 5 128-pixel tiles (two accumulator sets) for the 64-channel one,
-                         bit 6 one weight request per filter tap instead of one per tap row                     */
+                         bit 6 one weight request per filter tap instead of one per tap row, bit 7 one 256-column
+                         tile instead of two 128-column tiles for the 256-channel conv with fused ToRGB          */
   int cluster_log2;   /* weight-ring kernels as clusters of 2^n CTAs with TMA-multicast weight blocks (0..3)  */
   void* timeline;     /* device long long[64][8] or NULL: clock64 stamps of CTA 0's first 64 tiles
                          (tools/tc2_timeline.py)                                                              */
@@ -203,7 +204,7 @@ int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const
  * rgb_w: float [3,Cout] pre-scaled by 1/sqrt(Cout); rgb_skip: float [B,3,in_h/2,in_w/2] or NULL;
  * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: [B,3,in_h,in_w] of rgb_dtype
  * (W2E_F32 or W2E_BF16: the image in the dtype the caller wants, straight from the epilogue).
- * Needs Cout <= 512 (the rgb image must be fp32 and zero-initialised when Cout > 256: two channel blocks add
+ * Needs Cout <= 512 (the rgb image must be fp32 and zero-initialised when Cout >= 256: two channel blocks add
  * into it) and in_h > 16.                                                                        */
 int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,
                         const float* noise, const float* noise_w, int noise_batch,

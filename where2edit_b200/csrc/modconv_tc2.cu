@@ -879,7 +879,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (RGB) {
               const float rs = __ldg(P.rgb_style + bc);
 #pragma unroll
-              for (int o = 0; o < 3; ++o) cst[384 + o * 128 + gt] = __ldg(P.rgb_w + o * P.Cout + gt) * rs;
+              for (int o = 0; o < 3; ++o) cst[384 + o * 128 + gt] = __ldg(P.rgb_w + o * P.Cout + c) * rs;
             }
           }
           named_bar_sync(bar_group, kT2EpiThreads);
@@ -897,13 +897,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
         for (int p = 0; p < NP; ++p)
 #pragma unroll
-          for (int o = 0; o < 3; ++o) { racc[p][o] = 0ull; rgb_init[p][o] = rgbb[o]; }
+          for (int o = 0; o < 3; ++o) { racc[p][o] = 0ull; rgb_init[p][o] = tn == 0 ? rgbb[o] : 0.f; }
         if (has_noise) {
 #pragma unroll
           for (int m = 0; m < NZ; ++m)
             nzm[m] = nw * lds_f32(eb + noise_off + (uint32_t)(((RGB ? half * NP : 0) + m) * kSubTileH * kTileW * 4));
         }
-        if (has_skip) {
+        if (has_skip && tn == 0) {   // (several channel blocks: the first one adds bias + skip, see the final store)
           // upfirdn2d(skip, up=2, pad=(2,1)) = a 2x2-tap polyphase filter on rows ya, ya+1 / columns xa, xa+1.
           // The box starts one row and FOUR columns before the sub-tile's first source pixel: the innermost
           // start coordinate of a TMA box must be 16-byte aligned (x0 - 1 faults with an illegal instruction).
@@ -1063,7 +1063,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 float lo, hi;
                 unpack2(racc[p][o], lo, hi);
                 const float v = rgb_init[p][o] + (lo + hi);
-                if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di + o * plane] = __float2bfloat16_rn(v);
+                // two channel blocks (Cout = 256 as two 128-column tiles): both ADD their partial sums to the zero-
+                // initialised image; two addends commute, so the result does not depend on the arrival order
+                if (P.tiles_n > 1) atomicAdd(reinterpret_cast<float*>(P.rgb) + di + o * plane, v);
+                else if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di + o * plane] = __float2bfloat16_rn(v);
                 else reinterpret_cast<float*>(P.rgb)[di + o * plane] = v;
               }
             }
@@ -1391,7 +1394,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
-  const int g_flags = cfg ? (cfg->flags & 123) : 0;
+  const int g_flags = cfg ? (cfg->flags & 251) : 0;
   const int g_cluster_mode = cfg ? (cfg->cluster_log2 < 0 ? 0 : (cfg->cluster_log2 > 3 ? 3 : cfg->cluster_log2)) : 0;
   long long* const g_dbg = cfg ? (long long*)cfg->timeline : nullptr;
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
@@ -1418,8 +1421,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
                   "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 512 and more than %d rows", kSubTileH);
     W2E_CHECK_ARG(rgb->skip == nullptr || (rgb->host_taps1d && in_h % 2 == 0 && in_w % 2 == 0),
                   "modconv_tc2_rgb: skip needs taps and even H, W");
-    W2E_CHECK_ARG(rgb->rgb_dtype == W2E_F32 || (rgb->rgb_dtype == W2E_BF16 && Cout <= 256),
-                  "modconv_tc2_rgb: rgb_dtype must be W2E_F32, or W2E_BF16 with Cout <= 256");
+    W2E_CHECK_ARG(rgb->rgb_dtype == W2E_F32 || (rgb->rgb_dtype == W2E_BF16 && Cout < 256),
+                  "modconv_tc2_rgb: rgb_dtype must be W2E_F32, or W2E_BF16 with Cout < 256");
     P.rgb_w = rgb->w; P.rgb_style = rgb->style; P.rgb_bias = rgb->bias; P.rgb_skip = rgb->skip; P.rgb = rgb->rgb;
     P.rgb_bf16 = rgb->rgb_dtype == W2E_BF16 ? 1 : 0;
     if (rgb->skip)
@@ -1444,7 +1447,13 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // (MT 1, bn 128) beats (MT 2, bn 64) on every >=128-channel up-layer (0.48 vs 0.59 ms at 512->256@64^2) although
   // its 16 KB weight blocks feed only 4 MMAs each and the ring is then bound by the SM's TMA ingest (~42 B/clk:
   // 385 cycles per block against 256 cycles of MMAs) -- bn 64 serialises MMA and epilogue on one accumulator set.
-  const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : 256;
+  // Plain conv + fused ToRGB at Cout == 256 (256 -> 256 @128^2): two 128-column tiles instead of one 256-column tile.
+  // A 256-pixel x 256-column tile fills the 512 TMEM columns, so MMA and epilogue alternate (measured 0.51 ms against
+  // 0.27 ms of MMAs); 128 columns leave room for two accumulator sets and the staged 16-warp epilogue, and the two
+  // column tiles add their partial ToRGB sums into the zero-initialised image.  Flag bit 7 = off (A/B).
+  const bool rgb_split = !transposed && rgb && Cout == 256 && g_ts_mode != 0 && !(g_flags & 128) && in_h > kSubTileH &&
+                         rgb->rgb_dtype == W2E_F32;
+  const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : (rgb_split ? 128 : 256);
   P.bn = 16;
   for (int cand : {256, 128, 64, 32, 16})
     if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
@@ -1497,7 +1506,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   if (rgb && rgb->skip) ts = ts && ((P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
   if (out) ts = ts && (((uintptr_t)out & 15) == 0);
   if (out_mod) ts = ts && (((uintptr_t)out_mod & 15) == 0);
-  if (rgb && P.bn != Cout) ts = false;
+  if (rgb && P.bn != Cout && !rgb_split) ts = false;
 
   // shared-memory plan: resident weights when small, else a ring of weight blocks; with the TS
   // epilogue also the output staging slots (per epilogue group and half) and the two stages of
@@ -1665,7 +1674,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_tf32: no kernel variant");
   }
   if (rgb) {
-    W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && (P.tiles_n == 1 || (P.tiles_n == 2 && !ts)),
+    W2E_CHECK_ARG((P.mt == 2 || P.mt == 4) && (P.tiles_n == 1 || (P.tiles_n == 2 && (!ts || rgb_split))),
                   "modconv_tc2_rgb: unsupported tiling (mt %d, n tiles %d)", P.mt, P.tiles_n);
     if (P.mt == 4) {
       if (P.wres) return launch_tc2<false, 4, 2, true, true, true>(ma, mb, P, M, smem_bytes, g_max_ctas, st);

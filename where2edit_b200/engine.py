@@ -182,13 +182,13 @@ class SynthesisEngine:
         dev = xs.device
         out = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_out else None
         out_mod = torch.empty((b, h, w, pw.cout), device=dev, dtype=torch.bfloat16) if want_mod else None
-        # Cout > 256 runs as two channel blocks that ADD their partial ToRGB sums: the image starts at zero
-        if pw.cout > 256:
+        # Cout >= 256 runs as two channel blocks that ADD their partial ToRGB sums: the image starts at zero
+        if pw.cout >= 256:
             rgb_dtype = torch.float32
-        if rgb_out is not None and tuple(rgb_out.shape) == (b, 3, h, w) and rgb_out.dtype == rgb_dtype and pw.cout <= 256:
+        if rgb_out is not None and tuple(rgb_out.shape) == (b, 3, h, w) and rgb_out.dtype == rgb_dtype and pw.cout < 256:
             rgb = rgb_out
         else:
-            rgb = (torch.zeros if pw.cout > 256 else torch.empty)((b, 3, h, w), device=dev, dtype=rgb_dtype)
+            rgb = (torch.zeros if pw.cout >= 256 else torch.empty)((b, 3, h, w), device=dev, dtype=rgb_dtype)
         rpw = rgb_module.conv.packed()
         taps1d = None
         if skip is not None:
