@@ -669,14 +669,28 @@ def main():
     # ---------------- per-kernel roofline from one traced step (CUDA events around every launch)
     roofline = roofline_up = None
     kinds = {}
+    TRACED = 5
     if rank == 0:
         step(0, dev_w[0], gather=False)   # rank-0 only: must not enter a collective
         torch.cuda.synchronize()
         N.STATS.trace = []
-        step(1, dev_w[1], gather=False)
+        for i in range(TRACED):           # the AVERAGE launch duration over several steps, not one sample
+            step(i, dev_w[i % 2], gather=False)
         torch.cuda.synchronize()
         trace, N.STATS.trace = N.STATS.trace, None
         roofline, roofline_up, kinds, layers = roofline_from_trace(trace, peaks, B, args.size, B == 32 and args.size == 1024)
+        for k in kinds.values():          # per step
+            k["ms"] /= TRACED
+            k["launches"] //= TRACED
+            k["flops"] /= TRACED
+            k["bytes"] /= TRACED
+        for r in (roofline, roofline_up):
+            if r is not None:
+                r["launches"] //= TRACED
+                for key in ("algorithmic_flops", "algorithmic_bytes"):
+                    if key in r:
+                        r[key] /= TRACED
+                r["traced_steps"] = TRACED
         if args.layers_out:
             with open(args.layers_out, "w") as fh:
                 json.dump({"batch": B, "size": args.size, "precision": args.precision, "launches": layers,

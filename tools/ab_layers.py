@@ -23,7 +23,8 @@ def main():
     # (name, ts_mode, flags, cluster_log2, blur variant): per-call switches, no library-global state
     settings = [("default", 1, 0, 0, "auto"), ("per-tap weight requests", 1, 64, 0, "auto"), ("blur kernel 0", 1, 0, 0, 0)]
     if len(sys.argv) > 2:
-        settings = [("default", 1, 0, 0, "auto")] + [(a, *[int(v) for v in a.split(",")]) for a in sys.argv[2:]]
+        settings = [("default", 1, 0, 0, "auto")] + [(a, *[(v if v == "auto" else int(v)) for v in a.split(",")])
+                                                     for a in sys.argv[2:]]
     results = {}
     for name, ts, flags, clus, blur in settings:
         eng.tc2_cfg = N.tc2_config(ts_mode=ts, flags=flags, cluster_log2=clus)
