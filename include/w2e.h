@@ -226,6 +226,15 @@ int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale
                            int Cin, int Cout, int in_h, int in_w, int act, const w2e_tc2_config* cfg,
                            void* stream);
 
+/* Plain 3x3 convolution of w2e_modconv_tc2 over a STRIDED VIEW of a channels-last bf16 tensor (strides in elements,
+ * multiples of 8) using only the filter taps whose bit is set in tap_mask (bit ky*3+kx).  Used by the dgrad of the
+ * transposed x2 convolution (autograd of models/stylegan2/model.py:249-259): four launches, one per output-parity class
+ * of the (2h+1)^2 upstream gradient, added by w2e_sum4_nhwc.  No noise / bias / activation.                         */
+int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, const float* next_scale,
+                         void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
+                         int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
+                         const w2e_tc2_config* cfg, void* stream);
+
 /* tf32 mode (north_star (1): "bf16 and tf32 modes"): the same kernel with fp32 tensors in HBM (channels-last
  * activations xs / out / out_mod, weights [9][Cout][Cin]) read by tcgen05.mma kind::tf32 (10-bit mantissa operands,
  * fp32 accumulate); direct-store epilogue, no fused ToRGB.  Requires Cin % 16 == 0, Cout % 16 == 0.           */
@@ -249,6 +258,26 @@ int w2e_nchw_class_to_nhwc_mod(const float* x, const float* scale, void* y, int 
                                int px, int dtype, void* stream);
 int w2e_nhwc_sum4_to_nchw_f32(const void* y00, const void* y01, const void* y10, const void* y11, float* out,
                               int B, int C, int h, int w, int dtype, void* stream);
+
+/* ---- channels-last bf16 backward (BASELINE config 4; csrc/bwd_nhwc.cu; math: SURVEY.md appendix C) -------------
+ * grad_assemble: one pass over the output a [B,HW,C] of a styled layer that turns the gradient w.r.t. the modulated
+ * input of the NEXT convolution (gxs, style s_next; either may be NULL) and the gradient of a ToRGB reading a
+ * (g_rgb [B,3,HW] fp32 with w_rgb [3,C], s_rgb [B,C]; or NULL) into gz = dL/d(pre-activation) * demod (bf16, the
+ * operand of this layer's dgrad; may be NULL), and reduces sums[b,0,c] = sum_p gxs*a (direct term of dL/ds_next),
+ * sums[b,1,c] = sum_p (sum_o g_rgb[o] w_rgb[o,c]) * a (dL/ds_rgb) and, when demod != NULL,
+ * sums[b,2,c] = sum_p dL/dy * (y - noise_w*noise - bias) (= demod * dL/ddemod).  act_kind: W2E_ACT_LRELU inverts
+ * a = lrelu(y)*sqrt2 (op/fused_act.py:23-39).  workspace: w2e_grad_assemble_workspace(B,HW,C) floats.            */
+int64_t w2e_grad_assemble_workspace(int B, int64_t HW, int C);
+int w2e_grad_assemble_nhwc(const void* gxs, const float* s_next, const void* act, const float* g_rgb,
+                           const float* w_rgb, const float* s_rgb, const float* noise, const float* noise_w,
+                           int noise_batch, const float* bias, const float* demod, int act_kind, void* gz,
+                           float* sums, float* workspace, int B, int64_t HW, int C, void* stream);
+/* dot[b,c] = sum_p a[b,p,c] * b[b or 0,p,c] (bf16 channels-last; b_batch == 1 broadcasts b); same workspace.   */
+int w2e_rowdot_nhwc(const void* a, const void* b, int b_batch, float* dot, float* workspace, int B, int64_t HW,
+                    int C, void* stream);
+/* out [B,h,w,C] = y00 [B,h+1,w+1,C] + y01 [B,h+1,w,C] + y10 [B,h,w+1,C] + y11 [B,h,w,C] over the h x w region.   */
+int w2e_sum4_nhwc(const void* y00, const void* y01, const void* y10, const void* y11, void* out, int B, int h,
+                  int w, int C, void* stream);
 
 /* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
  * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->

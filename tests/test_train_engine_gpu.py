@@ -1,0 +1,164 @@
+"""The channels-last bf16 forward + backward engine (train_engine.py; BASELINE config 4) against the reference's autograd
+gradients (tests/golden/generator32.npz, written by the unmodified reference) and against this package's exact fp32
+path; its kernels (grad_assemble, rowdot, sum4, the strided-view convolution) against plain torch formulas."""
+import numpy as np
+import pytest
+import torch
+
+import where2edit_b200 as w2e
+from conftest import max_abs
+from oracle import synth
+from where2edit_b200 import _native as N
+from where2edit_b200 import functional as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(size, cm=2, precision="bf16"):
+    gen = w2e.Generator(size, 512, 8, channel_multiplier=cm, precision=precision)
+    gen.load_state_dict(synth.make_state_dict(size, seed=0, perturbed=True, channel_multiplier=cm), strict=True)
+    gen = gen.to(DEV).eval()
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    return gen
+
+
+def cos_rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(torch.dot(a, b) / (a.norm() * b.norm())), float((a - b).norm() / b.norm())
+
+
+def test_wplus_gradient_matches_reference_autograd(golden_g32):
+    gen = build(32)
+    wplus = synth.make_wplus(2, 8, seed=2)
+    upstream = (synth.make_tensor((2, 3, 32, 32), 4) / (2 * 3 * 32 * 32)).to(DEV)
+    wp = wplus.to(DEV).requires_grad_(True)
+    img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+    assert img.dtype == torch.float32 and img.grad_fn is not None and "Synthesis" in type(img.grad_fn).__name__
+    (img * upstream).sum().backward()
+    gen.assert_ok()
+    c = float(np.abs(golden_g32["img_wplus"]).max())
+    assert max_abs(img.detach().cpu() / c, torch.from_numpy(golden_g32["img_wplus"]) / c) <= 2e-2
+    cos, rel = cos_rel(wp.grad, torch.from_numpy(golden_g32["grad_wplus"]))
+    assert cos >= 0.99 and rel <= 0.12, (cos, rel)
+    # deterministic: a second run is bit-identical
+    wp2 = wplus.to(DEV).requires_grad_(True)
+    img2, _ = gen([wp2], input_is_latent=True, randomize_noise=False)
+    (img2 * upstream).sum().backward()
+    assert torch.equal(img2, img) and torch.equal(wp2.grad, wp.grad)
+
+
+@pytest.mark.parametrize("size,cm", [(64, 2), (256, 1)])
+def test_stylespace_gradients_track_the_fp32_path(size, cm):
+    """every one of the per-layer style gradients (3x3 convolutions: direct + demodulation term; ToRGB) against the
+    exact fp32 kernels, which tests/test_generator_gpu.py pins to the reference's autograd"""
+    gen = build(size, cm)
+    w = synth.make_wplus(2, gen.n_latent, seed=2).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    upstream = (torch.randn(2, 3, size, size, generator=g) / (3 * size * size)).to(DEV)
+    with torch.no_grad():
+        _, _, styles = gen([w], input_is_latent=True, randomize_noise=False, return_latents=True)
+    grads = {}
+    for mode in ("engine", "fp32"):
+        gen.set_precision("bf16" if mode == "engine" else "fp32")
+        st = [s.detach().clone().requires_grad_(True) for s in styles]
+        img, _ = gen([st], input_is_stylespace=True, randomize_noise=False)
+        (img * upstream).sum().backward()
+        grads[mode] = [s.grad for s in st]
+    gen.set_precision("bf16")
+    gen.assert_ok()
+    total = cos_rel(torch.cat([x.flatten() for x in grads["engine"]]), torch.cat([x.flatten() for x in grads["fp32"]]))
+    assert total[0] >= 0.99 and total[1] <= 0.12, total
+    for i, (a, b) in enumerate(zip(grads["engine"], grads["fp32"])):
+        assert a.shape == b.shape
+        cos, rel = cos_rel(a, b)
+        assert cos >= 0.97, (i, cos, rel)
+    # batch invariance of the backward: sample 1 alone gives the same gradient rows, bit for bit
+    st1 = [s.detach()[1:2].clone().requires_grad_(True) for s in styles]
+    img1, _ = gen([st1], input_is_stylespace=True, randomize_noise=False)
+    (img1 * upstream[1:2]).sum().backward()
+    for a, b in zip(st1, grads["engine"]):
+        assert torch.equal(a.grad, b[1:2])
+
+
+def test_module_path_is_kept_where_the_engine_does_not_apply():
+    gen = build(32)
+    w = synth.make_wplus(1, 8, seed=2).to(DEV)
+    with torch.no_grad():
+        _, _, styles, feats = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
+    st = [s.detach().clone().requires_grad_(True) for s in styles]
+    mask = torch.rand(1, 1, 8, 8, device=DEV, requires_grad=True)
+    img, _ = gen([st], input_is_stylespace=True, randomize_noise=False, attention_layer=5, attention_map=mask,
+                 feature_map=feats)
+    assert "Synthesis" not in type(img.grad_fn).__name__
+    img.square().mean().backward()
+    assert mask.grad is not None and torch.isfinite(mask.grad).all()
+    gen.bf16_backward = "modules"
+    wp = w.clone().requires_grad_(True)
+    img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+    assert "Synthesis" not in type(img.grad_fn).__name__
+
+
+def test_backward_kernels_against_torch_formulas():
+    lib = N.load()
+    torch.manual_seed(0)
+    b, h, w, c = 3, 20, 12, 64
+    act = torch.randn(b, h, w, c, device=DEV).to(torch.bfloat16)
+    gxs = torch.randn(b, h, w, c, device=DEV).to(torch.bfloat16)
+    s_next, s_rgb, d = (1 + 0.3 * torch.randn(b, c, device=DEV) for _ in range(3))
+    g_rgb = torch.randn(b, 3, h, w, device=DEV)
+    w_rgb = torch.randn(3, c, device=DEV)
+    noise = torch.randn(1, 1, h, w, device=DEV)
+    nw = torch.tensor([0.3], device=DEV)
+    bias = 0.1 * torch.randn(c, device=DEV)
+    gz = torch.empty_like(act)
+    sums = torch.empty(b, 3, c, device=DEV)
+    ws = torch.empty(int(lib.w2e_grad_assemble_workspace(b, h * w, c)), device=DEV)
+    N.check(lib.w2e_grad_assemble_nhwc(N.ptr(gxs), N.ptr(s_next), N.ptr(act), N.ptr(g_rgb), N.ptr(w_rgb), N.ptr(s_rgb),
+                                       N.ptr(noise), N.ptr(nw), 1, N.ptr(bias), N.ptr(d), N.ACT_LRELU, N.ptr(gz), N.ptr(sums),
+                                       N.ptr(ws), b, h * w, c, N.stream_ptr()), "grad_assemble")
+    a64, g64 = act.double(), gxs.double()
+    t = torch.einsum("bohw,oc->bhwc", g_rgb.double(), w_rgb.double())
+    ga = g64 * s_next.double()[:, None, None] + t * s_rgb.double()[:, None, None]
+    pos = a64 > 0
+    gp = ga * torch.where(pos, 2 ** 0.5, 0.2 * 2 ** 0.5)
+    y = a64 / torch.where(pos, 2 ** 0.5, 0.2 * 2 ** 0.5)
+    r3 = (gp * (y - 0.3 * noise.double()[0, 0, :, :, None] - bias.double())).sum((1, 2))
+    want_gz = gp * d.double()[:, None, None]
+    scale = float(want_gz.abs().max())
+    assert max_abs(gz.double().cpu(), want_gz.cpu()) <= 1e-2 * scale          # bf16 rounding of the result
+    for r, want in enumerate(((g64 * a64).sum((1, 2)), (t * a64).sum((1, 2)), r3)):
+        assert max_abs(sums[:, r].cpu(), want.cpu()) <= 1e-4 * float(want.abs().max()), r
+    # rowdot (with a batch-broadcast second operand) and sum4
+    dot = torch.empty(b, c, device=DEV)
+    N.check(lib.w2e_rowdot_nhwc(N.ptr(gxs), N.ptr(act[:1].contiguous()), 1, N.ptr(dot), N.ptr(ws), b, h * w, c, N.stream_ptr()),
+            "rowdot")
+    want = (g64 * a64[:1]).sum((1, 2))
+    assert max_abs(dot.cpu(), want.cpu()) <= 1e-4 * float(want.abs().max())
+    ys = [torch.randn(b, h + 1 - p, w + 1 - q, c, device=DEV).to(torch.bfloat16) for p in (0, 1) for q in (0, 1)]
+    out = torch.empty(b, h, w, c, device=DEV, dtype=torch.bfloat16)
+    N.check(lib.w2e_sum4_nhwc(*[N.ptr(y) for y in ys], N.ptr(out), b, h, w, c, N.stream_ptr()), "sum4")
+    want = sum(y[:, :h, :w].float() for y in ys).to(torch.bfloat16)
+    assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8)])
+def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
+    """four strided-view launches with 4 / 2 / 2 / 1 taps + sum4 == the gradient of conv_transpose2d(stride 2)"""
+    from where2edit_b200 import train_engine
+    gen = w2e.Generator(8, 512, 1, precision="bf16").to(DEV)
+    eng = train_engine.TrainEngine(gen)
+    b = 2
+    weight = synth.make_tensor((1, cout, cin, 3, 3), 91).to(DEV)
+    pw = K.PackedWeight(weight, 1 / (cin * 9) ** 0.5, None)
+    gz = torch.randn(b, 2 * h + 1, 2 * h + 1, cout, device=DEV).to(torch.bfloat16)
+    got = eng._dgrad_up(gz, pw, h, h)
+    eng.assert_ok()
+    x = torch.zeros(b, cin, h, h, device=DEV, dtype=torch.float64, requires_grad=True)
+    wt = (weight[0].double() / (cin * 9) ** 0.5).to(torch.bfloat16).double()
+    y = torch.nn.functional.conv_transpose2d(x, wt.transpose(0, 1), stride=2)
+    (y * gz.double().permute(0, 3, 1, 2)).sum().backward()
+    want = x.grad.permute(0, 2, 3, 1)
+    scale = float(want.abs().max())
+    assert max_abs(got.double().cpu(), want.cpu()) <= 1.5e-2 * scale

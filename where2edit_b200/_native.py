@@ -47,6 +47,11 @@ PROTOTYPES = {
     "w2e_modconv_tc2_rgb": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P] * 6 + [_I, _P, _P]),
     "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P, _P]),
     "w2e_modconv_tc2_tf32": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
+    "w2e_modconv_tc2_view": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _I, _P, _P]),
+    "w2e_grad_assemble_workspace": (_L, [_I, _L, _I]),
+    "w2e_grad_assemble_nhwc": (_I, [_P] * 8 + [_I, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P]),
+    "w2e_rowdot_nhwc": (_I, [_P, _P, _I, _P, _P, _I, _L, _I, _P]),
+    "w2e_sum4_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _I, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _I, _P]),
     "w2e_nchw_class_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -63,7 +68,7 @@ PROTOTYPES = {
 
 # entry points that enqueue no kernel (host queries)
 _HOST_ONLY = {"w2e_version", "w2e_last_error_string", "w2e_device_info", "w2e_bias_act_bwd_workspace", "w2e_rowdot_segments",
-              "w2e_modconv_tc_supported"}
+              "w2e_modconv_tc_supported", "w2e_grad_assemble_workspace"}
 
 
 class Tc2Config(ctypes.Structure):

@@ -62,6 +62,8 @@ struct Tc2Params {
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
+  int tap_mask;             // plain conv: bit t set = filter tap t is used (0x1ff = all); class convolutions of the
+                            // transposed convolution's dgrad use 4 / 2 / 2 / 1 of the 9 taps
   int bgroup;               // weight-ring kernels, TS flavour: filter taps per weight REQUEST (1, or 3 = one tap row per TMA box)
   int flags;                // A/B switches (w2e_modconv_tc2_flags): 1 = no edge-tile tap masking, 2 = one MMA issuer
   long long* dbg;           // optional timeline of CTA 0 (tools/tc2_timeline.py): [tile][8] clock64 stamps
@@ -306,6 +308,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const bool edge_x = TR && !(P.flags & 1) && i0 >= P.grid_w - 1;
             for (int t = 0; t < 9; ++t) {
               if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
+              if (!TR && !((P.tap_mask >> t) & 1)) continue;
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], (uint32_t)P.b_block_bytes);
@@ -339,6 +342,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int kc = 0; kc < kchunks && ok; ++kc) {
             for (int g = 0; g < 3; ++g) {
               if (edge_y && g != 2) continue;
+              if (!TR && !((P.tap_mask >> (3 * g)) & 7)) continue;   // no tap of this row is used
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], 3u * (uint32_t)P.b_block_bytes);
@@ -351,6 +355,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kc = 0; kc < kchunks && ok; ++kc) {
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
+            if (!TR && !((P.tap_mask >> t) & 1)) continue;
             if (pj == 0) {
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
@@ -412,6 +417,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t a_lo0 = (smem_u32(a_base) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(b_base) & 0x3FFFFu) >> 4;
     const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4, b_block16 = (uint32_t)P.b_block_bytes >> 4;
     const uint32_t bn = (uint32_t)P.bn;
+    const int first_tap = __ffs(P.tap_mask) - 1;   // plain conv: the first USED tap overwrites the accumulator
+    const int last_tap = TR ? 8 : 31 - __clz(P.tap_mask);
     Ring ar, br, cr;
     bool ok = true;
     // warp-uniform issue: every lane runs the loops (descriptors stay in uniform registers, per-tile state stays
@@ -473,7 +480,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           uint32_t b_lo = b_lo0 + (uint32_t)(kc * 9) * b_block16;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2))) {
+            if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) && (TR || ((P.tap_mask >> t) & 1))) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
                 if (m == 1 && edge_y) continue;
@@ -484,7 +491,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (TR) {
                   first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
                   started |= 1u << ai;
-                } else if (t == 0) {
+                } else if (t == first_tap) {
                   first = kc == 0 ? 0u : 1u;
                 }
                 if (leader) {
@@ -504,6 +511,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             if (edge_y && g != 2) continue;
+            if (!TR && !((P.tap_mask >> (3 * g)) & 7)) continue;
             const bool mine = !blk2 || (int)(nblk & 1u) == mw;
             ++nblk;
             if (mine) {
@@ -516,6 +524,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int kx = 0; kx < 3; ++kx) {
               const int t = g * 3 + kx;
               if (edge_x && kx != 2) continue;
+              if (!TR && !((P.tap_mask >> t) & 1)) continue;
               const uint32_t b_lo = b_lo0 + (br.idx + (uint32_t)kx) * b_block16;
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
@@ -527,7 +536,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (TR) {
                   first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
                   started |= 1u << ai;
-                } else if (t == 0) {
+                } else if (t == first_tap) {
                   first = kc == 0 ? 0u : 1u;
                 }
                 if (leader && mine) {
@@ -539,7 +548,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             if (leader && mine) {
               umma_commit(&bars->b_empty[br.idx]);
-              if (!blk2 && g == 2) {
+              if (!blk2 && g == last_tap / 3) {
                 umma_commit(&bars->a_empty[ar.idx]);
                 if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
               }
@@ -555,6 +564,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
+            if (!TR && !((P.tap_mask >> t) & 1)) continue;
             const bool mine = !blk2 || (int)(nblk & 1u) == mw;
             ++nblk;
             if (mine) {
@@ -575,7 +585,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               if (TR) {
                 first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
                 started |= 1u << ai;
-              } else if (t == 0) {
+              } else if (t == first_tap) {
                 first = kc == 0 ? 0u : 1u;
               }
               if (leader && mine) {
@@ -589,7 +599,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (leader && mine) {
               if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)((1u << (1 << cl)) - 1u));   // free once ALL CTAs consumed it
               else umma_commit(&bars->b_empty[br.idx]);
-              if (!blk2 && t == 8) {
+              if (!blk2 && t == last_tap) {
                 umma_commit(&bars->a_empty[ar.idx]);
                 if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);   // last block of the tile
               }
@@ -1386,11 +1396,16 @@ struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped
   float fv[4], fh[4];
 };
 
+struct ViewArgs {   // plain conv on a strided view of a channels-last tensor, with a subset of the 9 filter taps
+  int64_t stride_x, stride_y, stride_b;   // in elements: between pixels of a row, rows, samples
+  int tap_mask;
+};
+
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
                    const float* noise_w, int noise_batch, const float* next_scale, void* out, void* out_mod,
                    int* error_flag, int B, int Cin, int Cout, int in_h, int in_w, int transposed, int act,
                    const RgbArgs* rgb, const w2e_tc2_config* cfg, void* stream, bool allow_mt4 = true,
-                   const FbArgs* fb = nullptr, bool tf32 = false) {
+                   const FbArgs* fb = nullptr, bool tf32 = false, const ViewArgs* view = nullptr) {
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
@@ -1430,6 +1445,14 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   }
   P.pitch = kPitch;
   P.ntaps = 9;
+  P.tap_mask = 0x1ff;
+  if (view) {
+    W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_view: plain bf16 convolution only");
+    W2E_CHECK_ARG(view->tap_mask > 0 && view->tap_mask <= 0x1ff, "modconv_tc2_view: tap mask %d", view->tap_mask);
+    W2E_CHECK_ARG(view->stride_x > 0 && (view->stride_x * 2) % 16 == 0 && (view->stride_y * 2) % 16 == 0 &&
+                      (view->stride_b * 2) % 16 == 0, "modconv_tc2_view: strides must be multiples of 8 elements");
+    P.tap_mask = view->tap_mask;
+  }
   if (!transposed) {
     P.OH = in_h; P.OW = in_w; P.grid_h = in_h; P.grid_w = in_w; P.out_stride = 1; P.ng = 1;
   } else {
@@ -1567,14 +1590,18 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   W2E_CHECK_ARG(smem_bytes > 0, "modconv_tc2: shared memory plan does not fit (Cin %d Cout %d)", Cin, Cout);
   if (P.mt == 4 && !ts)   // the direct-store epilogue has no 4-sub-tile variant: plan again with 256-pixel tiles
     return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
-                   in_h, in_w, transposed, act, rgb, cfg, stream, false, fb, tf32);
+                   in_h, in_w, transposed, act, rgb, cfg, stream, false, fb, tf32, view);
   W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
   {
     const uint64_t es = (uint64_t)esize;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
+    uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
+    if (view) {
+      strides[0] = (uint64_t)view->stride_x * es; strides[1] = (uint64_t)view->stride_y * es;
+      strides[2] = (uint64_t)view->stride_b * es;
+    }
     const uint32_t box[4] = {(uint32_t)P.bk, (uint32_t)P.pitch, (uint32_t)P.box_rows, 1u};
     int rc = tf32 ? make_f32_swizzled_map(&ma, xs, 4, dims, strides, box, row_bytes)
                   : make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
@@ -1716,6 +1743,19 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
                                int transposed, int act, const w2e_tc2_config* cfg, void* stream) {
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
                  in_h, in_w, transposed, act, nullptr, cfg, stream);
+}
+
+// Plain 3x3 convolution over a STRIDED VIEW of a channels-last bf16 tensor with a subset of the nine taps: the dgrad of
+// the transposed x2 convolution is a stride-2 convolution of the (2h+1)^2 upstream gradient, run as four such launches --
+// one per output-parity class of the gradient (a view with doubled pixel / row strides) with the 4 / 2 / 2 / 1 taps
+// that class feeds -- whose results w2e_sum4_nhwc adds.
+extern "C" int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, const float* next_scale,
+                                    void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
+                                    int in_w, int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
+                                    const w2e_tc2_config* cfg, void* stream) {
+  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask};
+  return run_tc2(xs, w, out_scale, nullptr, nullptr, nullptr, 0, next_scale, out, out_mod, error_flag, B, Cin, Cout, in_h,
+                 in_w, 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
 
 // tf32 mode (north star item 1: "bf16 and tf32 modes"): xs / w / out / out_mod are fp32 (channels-last activations,

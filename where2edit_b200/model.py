@@ -337,6 +337,7 @@ class Generator(nn.Module):
         self._engine = None
         self.image_dtype = torch.float32   # dtype of the returned image in bf16 no-grad mode (set_image_output)
         self.image_out = None              # optional caller-owned buffer the last layer writes the image into
+        self.bf16_backward = "engine"      # "modules": keep the fp32 module path under autograd even when the engine applies
         self.set_precision(precision)
 
     # ------------------------------------------------------------------ helpers kept from the reference
@@ -379,6 +380,24 @@ class Generator(nn.Module):
             raise ValueError("image buffer must be contiguous and of the requested dtype")
         self.image_dtype, self.image_out = dtype, buffer
         return self
+
+    def _bf16_engine(self):
+        from . import train_engine
+        if self._engine is None:
+            self._engine = train_engine.TrainEngine(self)
+        self._engine.image_dtype, self._engine.image_out = self.image_dtype, self.image_out
+        return self._engine
+
+    def _train_engine_applies(self, latent, stylespace, noise, blending, want_features):
+        """The channels-last backward engine covers the latent / style optimisation loops: frozen generator, fixed
+        noise buffers, gradient to the W+ latent or the stylespace codes.  Anything else (region blend under
+        autograd, feature capture, trainable generator parameters, per-sample random noise) takes the module path."""
+        if blending or want_features or any(n is None for n in noise) or self.bf16_backward == "modules":
+            return False
+        if any(p.requires_grad for p in self.parameters()):
+            return False
+        inputs = latent if stylespace else [latent]
+        return any(t.requires_grad for t in inputs)
 
     def assert_ok(self):
         """Synchronising check that no tensor-core kernel of this generator reported a pipeline timeout (the
@@ -439,17 +458,19 @@ class Generator(nn.Module):
 
         blending = attention_map is not None
         if self.precision == "bf16" and not torch.is_grad_enabled():
-            from . import engine
-            if self._engine is None:
-                self._engine = engine.SynthesisEngine(self)
-            self._engine.image_dtype, self._engine.image_out = self.image_dtype, self.image_out
-            image, style_vector, captured = self._engine.run(
+            image, style_vector, captured = self._bf16_engine().run(
                 latent, input_is_stylespace, noise, want_features=return_features and not return_latents,
                 attention_layer=attention_layer if blending else 0, attention_map=attention_map,
                 feature_map=feature_map)
+        elif self.precision == "bf16" and self._train_engine_applies(latent, input_is_stylespace, noise, blending,
+                                                                      return_features and not return_latents):
+            # under autograd: channels-last bf16 forward + backward engine (train_engine.py)
+            from . import train_engine
+            image, style_vector = train_engine.synthesize_with_grad(self._bf16_engine(), latent, input_is_stylespace, noise)
+            captured = []
         else:
-            # precision "bf16" under autograd: the 3x3 convolutions (forward and dgrad) run on the tensor cores,
-            # the rest of the differentiable path on the fp32 kernels (functional.TC_AUTOGRAD)
+            # module path.  precision "bf16" / "tf32": the 3x3 convolutions (forward and dgrad) run on the tensor
+            # cores between layout passes, the rest of the differentiable path on the fp32 kernels
             prev = K.TC_AUTOGRAD
             K.TC_AUTOGRAD = self.precision if self.precision in ("bf16", "tf32") else False
             try:
