@@ -326,6 +326,34 @@ def extra_pipelines(gen, dev, size, n_lat):
     except Exception as exc:
         out["edit_pipeline_cfg3"] = {"error": repr(exc)[:300]}
     torch.cuda.empty_cache()
+    # cfg4: forward + backward of the latent-optimisation step (python bench.py --workload train is the full contract line)
+    try:
+        tb = 16
+        train_mapper = make_levels_mapper(dev).train()
+        wt = torch.randn(tb, n_lat, 512, generator=g).to(dev)
+        gimg = (torch.randn(tb, 3, size, size, generator=g) / (3 * size * size)).to(dev)
+        frozen = [p.requires_grad for p in gen.parameters()]
+        for p in gen.parameters():
+            p.requires_grad_(False)
+
+        def train_step():
+            for p in train_mapper.parameters():
+                p.grad = None
+            img, _ = gen([wt + 0.1 * train_mapper(wt)], input_is_latent=True, randomize_noise=False)
+            (img * gimg).sum().backward()
+        ms = gpu_ms(train_step, 3, warm=2)
+        with torch.no_grad():
+            fwd = gpu_ms(lambda: gen([wt], input_is_latent=True, randomize_noise=False), 3, warm=1)
+        for p, r in zip(gen.parameters(), frozen):
+            p.requires_grad_(r)
+        out["train_step_cfg4"] = {
+            "what": "LevelsMapper edit -> 1024^2 forward + backward to the mapper parameters (channels-last bf16 engine), "
+                    "seeded synthetic dL/dimage", "batch": tb, "ms": ms, "images_per_s": tb / ms * 1e3,
+            "forward_only_ms": fwd, "ratio_to_forward": ms / fwd}
+        del train_mapper, wt, gimg
+    except Exception as exc:
+        out["train_step_cfg4"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
     # CUDA graph: B = 1 latency
     try:
         w1 = w[:1].contiguous()

@@ -279,6 +279,11 @@ int w2e_rowdot_nhwc(const void* a, const void* b, int b_batch, float* dot, float
 int w2e_sum4_nhwc(const void* y00, const void* y01, const void* y10, const void* y11, void* out, int B, int h,
                   int w, int C, void* stream);
 
+/* Gradient of the ToRGB skip upsample (upfirdn2d(skip, outer(k1,k1), up 2, pad (2,1)), model.py:31-49,358) for a
+ * separable 4-tap kernel: g [planes,2h,2w] fp32 -> g_skip [planes,h,w]; host_taps1d = k1 (4 floats, with gain).  */
+int w2e_skip_grad(const float* g, float* g_skip, const float* host_taps1d, int64_t planes, int h, int w,
+                  void* stream);
+
 /* ---- Blur + NoiseInjection + FusedLeakyReLU, channels-last (model.py:200-206,260,279-290) ---
  * z bf16 [B,in_h,in_w,C] --(4x4 separable FIR `host_taps` [16], unflipped; pad py0/px0 before)-->
  * [B,out_h,out_w,C]; then the same epilogue as w2e_modconv_tc2 (no demodulation).

@@ -74,12 +74,14 @@ def test_stylespace_gradients_track_the_fp32_path(size, cm):
         assert a.shape == b.shape
         cos, rel = cos_rel(a, b)
         assert cos >= 0.97, (i, cos, rel)
-    # batch invariance of the backward: sample 1 alone gives the same gradient rows, bit for bit
+    # batch invariance of the backward: sample 1 alone gives the same gradient rows (the kernels and their reductions
+    # are bit-identical per sample; the small [B,C] demodulation algebra goes through library GEMMs whose algorithm
+    # may depend on the batch, hence a tolerance of a few fp32 ulps of the gradient's range)
     st1 = [s.detach()[1:2].clone().requires_grad_(True) for s in styles]
     img1, _ = gen([st1], input_is_stylespace=True, randomize_noise=False)
     (img1 * upstream[1:2]).sum().backward()
     for a, b in zip(st1, grads["engine"]):
-        assert torch.equal(a.grad, b[1:2])
+        assert max_abs(a.grad.cpu(), b[1:2].cpu()) <= 1e-5 * float(b.abs().max())
 
 
 def test_module_path_is_kept_where_the_engine_does_not_apply():
@@ -141,6 +143,16 @@ def test_backward_kernels_against_torch_formulas():
     N.check(lib.w2e_sum4_nhwc(*[N.ptr(y) for y in ys], N.ptr(out), b, h, w, c, N.stream_ptr()), "sum4")
     want = sum(y[:, :h, :w].float() for y in ys).to(torch.bfloat16)
     assert torch.equal(out, want)
+    # gradient of the ToRGB skip upsample against autograd of the public upfirdn2d
+    skip = torch.randn(2, 3, 10, 14, device=DEV, requires_grad=True)
+    kern = w2e.make_kernel([1, 3, 3, 1]).to(DEV) * 4
+    up = w2e.upfirdn2d(skip, kern, up=2, down=1, pad=(2, 1))
+    gup = torch.randn_like(up)
+    up.backward(gup)
+    got = torch.empty(2, 3, 10, 14, device=DEV)
+    N.check(lib.w2e_skip_grad(N.ptr(gup.contiguous()), N.ptr(got), N.host_floats([0.25, 0.75, 0.75, 0.25]), 6, 10, 14,
+                              N.stream_ptr()), "skip_grad")
+    assert max_abs(got.cpu(), skip.grad.cpu()) <= 1e-5
 
 
 @pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8)])

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "w2e_grad_assemble_nhwc": (_I, [_P] * 8 + [_I, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P]),
     "w2e_rowdot_nhwc": (_I, [_P, _P, _I, _P, _P, _I, _L, _I, _P]),
     "w2e_sum4_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "w2e_skip_grad": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "w2e_nchw_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _L, _I, _P]),
     "w2e_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _L, _I, _P]),
     "w2e_nchw_class_to_nhwc_mod": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -64,86 +64,128 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// grid (nchunks, B); thread = (pixel lane, 8-channel group); shared: 3 * lanes * C floats for the lane reduction
-__global__ void __launch_bounds__(kGaThreads)
+// grid (nchunks, B); thread = (pixel lane, 8-channel group).  Per-channel constants live in shared memory (read back
+// with 128-bit loads) so that the register budget goes to loads in flight: two pixels per thread are fetched before
+// either is consumed, three CTAs per SM.  Shared: 9 * C floats of constants + 3 * lanes * C floats for the reduction.
+template <bool RGB, bool R3>
+__global__ void __launch_bounds__(kGaThreads, RGB ? 2 : 3)
 grad_assemble_nhwc_kernel(const GaParams P) {
-  extern __shared__ float red[];
-  const int groups = P.C >> 3;
-  const int lanes = kGaThreads / groups;          // pixel lanes per CTA (C <= 2048, C % 8 == 0, groups | 256)
+  extern __shared__ float smem_f[];
+  const int C = P.C;
+  float* c_sn = smem_f;            // s_next
+  float* c_dm = c_sn + C;          // demod
+  float* c_bs = c_dm + C;          // bias
+  float* c_sr = c_bs + C;          // s_rgb
+  float* c_wr = c_sr + C;          // w_rgb [3][C]
+  float* red = c_wr + 3 * C + 2 * C;   // (two spare rows keep the block 16-byte aligned for any C % 8 == 0)
+  const int groups = C >> 3;
+  const int lanes = kGaThreads / groups;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
   const int b = blockIdx.y;
   const int c0 = g * 8;
-  const int64_t p_begin = (int64_t)blockIdx.x * P.chunk;
-  const int64_t p_end = min(P.HW, p_begin + P.chunk);
-  float sn[8], ws[3][8], wr[3][8], dm[8], bs[8];
+  for (int c = threadIdx.x; c < C; c += kGaThreads) {
+    c_sn[c] = P.s_next ? __ldg(P.s_next + (int64_t)b * C + c) : 1.f;
+    c_dm[c] = P.demod ? __ldg(P.demod + (int64_t)b * C + c) : 1.f;
+    c_bs[c] = P.bias ? __ldg(P.bias + c) : 0.f;
+    if (RGB) {
+      c_sr[c] = __ldg(P.s_rgb + (int64_t)b * C + c);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = c0 + k;
-    sn[k] = P.s_next ? __ldg(P.s_next + (int64_t)b * P.C + c) : 1.f;
-    dm[k] = P.demod ? __ldg(P.demod + (int64_t)b * P.C + c) : 1.f;
-    bs[k] = P.bias ? __ldg(P.bias + c) : 0.f;
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      wr[o][k] = P.g_rgb ? __ldg(P.w_rgb + o * P.C + c) : 0.f;
-      ws[o][k] = P.g_rgb ? wr[o][k] * __ldg(P.s_rgb + (int64_t)b * P.C + c) : 0.f;
+      for (int o = 0; o < 3; ++o) c_wr[o * C + c] = __ldg(P.w_rgb + o * C + c);
     }
   }
+  __syncthreads();
+  const int64_t p_begin = (int64_t)blockIdx.x * P.chunk;
+  const int64_t p_end = min(P.HW, p_begin + P.chunk);
   const float nw = P.noise ? __ldg(P.noise_w) : 0.f;
   const float gain = P.lrelu ? 1.41421356237309515f : 1.f;
   const float neg = P.lrelu ? 0.2f : 1.f;
+  const float dpos = gain, dneg = gain * neg, ipos = 1.f / gain, ineg = 1.f / (gain * neg);
   float r1[8], r2[8], r3[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) r1[k] = r2[k] = r3[k] = 0.f;
   const int64_t base = (int64_t)b * P.HW;
-  for (int64_t p = p_begin + lane; p < p_end; p += lanes) {
-    const int64_t e = (base + p) * P.C + c0;
-    float a[8], gx[8];
-    unpack8(*reinterpret_cast<const uint4*>(P.act + e), a);
-    if (P.gxs) unpack8(*reinterpret_cast<const uint4*>(P.gxs + e), gx);
-    else {
+  const float* nzp = P.noise ? P.noise + (P.noise_per_sample ? (int64_t)b * P.HW : 0) : nullptr;
+  const float* grp = RGB ? P.g_rgb + (int64_t)b * 3 * P.HW : nullptr;
+
+  auto consume = [&](int64_t p, const uint4 av, const uint4 gv, const float gr0, const float gr1, const float gr2, const float nz) {
+    float a[8], gx[8], out[8];
+    unpack8(av, a);
+    unpack8(gv, gx);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gx[k] = 0.f;
-    }
-    float gr[3] = {0.f, 0.f, 0.f};
-    if (P.g_rgb) {
-#pragma unroll
-      for (int o = 0; o < 3; ++o) gr[o] = __ldg(P.g_rgb + ((int64_t)b * 3 + o) * P.HW + p);
-    }
-    const float nz = P.noise ? nw * __ldg(P.noise + (P.noise_per_sample ? (int64_t)b * P.HW : 0) + p) : 0.f;
-    float out[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float t = fmaf(gr[0], wr[0][k], fmaf(gr[1], wr[1][k], gr[2] * wr[2][k]));      // unmodulated ToRGB pull-back
-      const float ga = fmaf(gx[k], sn[k], fmaf(gr[0], ws[0][k], fmaf(gr[1], ws[1][k], gr[2] * ws[2][k])));
-      r1[k] = fmaf(gx[k], a[k], r1[k]);
-      r2[k] = fmaf(t, a[k], r2[k]);
-      const bool pos = a[k] > 0.f;
-      const float gp = ga * (pos ? gain : gain * neg);                 // gradient w.r.t. the pre-activation y
-      if (P.want_r3) {
-        const float y = a[k] * (pos ? 1.f / gain : 1.f / (gain * neg));
-        r3[k] = fmaf(gp, y - nz - bs[k], r3[k]);
+    for (int h = 0; h < 2; ++h) {
+      const float4 sn = *reinterpret_cast<const float4*>(c_sn + c0 + 4 * h);
+      const float4 dm = *reinterpret_cast<const float4*>(c_dm + c0 + 4 * h);
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sr = bs, w0 = bs, w1 = bs, w2 = bs;
+      if (R3) bs = *reinterpret_cast<const float4*>(c_bs + c0 + 4 * h);
+      if (RGB) {
+        sr = *reinterpret_cast<const float4*>(c_sr + c0 + 4 * h);
+        w0 = *reinterpret_cast<const float4*>(c_wr + c0 + 4 * h);
+        w1 = *reinterpret_cast<const float4*>(c_wr + C + c0 + 4 * h);
+        w2 = *reinterpret_cast<const float4*>(c_wr + 2 * C + c0 + 4 * h);
       }
-      out[k] = gp * dm[k];
+      const float snv[4] = {sn.x, sn.y, sn.z, sn.w}, dmv[4] = {dm.x, dm.y, dm.z, dm.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+      const float srv[4] = {sr.x, sr.y, sr.z, sr.w}, w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+      const float w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = 4 * h + q;
+        float ga = gx[k] * snv[q];
+        r1[k] = fmaf(gx[k], a[k], r1[k]);
+        if (RGB) {
+          const float t = fmaf(gr0, w0v[q], fmaf(gr1, w1v[q], gr2 * w2v[q]));   // unmodulated ToRGB pull-back
+          ga = fmaf(t, srv[q], ga);
+          r2[k] = fmaf(t, a[k], r2[k]);
+        }
+        const bool pos = a[k] > 0.f;
+        const float gp = ga * (pos ? dpos : dneg);                             // gradient w.r.t. the pre-activation y
+        if (R3) r3[k] = fmaf(gp, fmaf(a[k], pos ? ipos : ineg, -nz) - bsv[q], r3[k]);
+        out[k] = gp * dmv[q];
+      }
     }
-    if (P.gz) *reinterpret_cast<uint4*>(P.gz + e) = pack8(out);
+    if (P.gz) *reinterpret_cast<uint4*>(P.gz + (base + p) * C + c0) = pack8(out);
+  };
+
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  int64_t p = p_begin + lane;
+  for (; p + lanes < p_end; p += 2 * lanes) {      // two pixels in flight per thread
+    const int64_t q = p + lanes;
+    const uint4 a0 = *reinterpret_cast<const uint4*>(P.act + (base + p) * C + c0);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(P.act + (base + q) * C + c0);
+    const uint4 g0 = P.gxs ? *reinterpret_cast<const uint4*>(P.gxs + (base + p) * C + c0) : zero4;
+    const uint4 g1 = P.gxs ? *reinterpret_cast<const uint4*>(P.gxs + (base + q) * C + c0) : zero4;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, y0 = 0.f, y1 = 0.f, y2 = 0.f;
+    if (RGB) {
+      x0 = __ldg(grp + p); x1 = __ldg(grp + P.HW + p); x2 = __ldg(grp + 2 * P.HW + p);
+      y0 = __ldg(grp + q); y1 = __ldg(grp + P.HW + q); y2 = __ldg(grp + 2 * P.HW + q);
+    }
+    const float n0 = (R3 && nzp) ? nw * __ldg(nzp + p) : 0.f, n1 = (R3 && nzp) ? nw * __ldg(nzp + q) : 0.f;
+    consume(p, a0, g0, x0, x1, x2, n0);
+    consume(q, a1, g1, y0, y1, y2, n1);
+  }
+  if (p < p_end) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(P.act + (base + p) * C + c0);
+    const uint4 g0 = P.gxs ? *reinterpret_cast<const uint4*>(P.gxs + (base + p) * C + c0) : zero4;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (RGB) { x0 = __ldg(grp + p); x1 = __ldg(grp + P.HW + p); x2 = __ldg(grp + 2 * P.HW + p); }
+    consume(p, a0, g0, x0, x1, x2, (R3 && nzp) ? nw * __ldg(nzp + p) : 0.f);
   }
   // deterministic reduction over the pixel lanes (lane order), per channel
   float* s1 = red;
-  float* s2 = red + (size_t)lanes * P.C;
-  float* s3 = red + (size_t)2 * lanes * P.C;
+  float* s2 = red + (size_t)lanes * C;
+  float* s3 = red + (size_t)2 * lanes * C;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    s1[lane * P.C + c0 + k] = r1[k];
-    s2[lane * P.C + c0 + k] = r2[k];
-    s3[lane * P.C + c0 + k] = r3[k];
+    s1[lane * C + c0 + k] = r1[k];
+    s2[lane * C + c0 + k] = r2[k];
+    s3[lane * C + c0 + k] = r3[k];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * P.C; i += kGaThreads) {
-    const int r = i / P.C, c = i - r * P.C;
-    const float* src = red + (size_t)r * lanes * P.C + c;
+  for (int i = threadIdx.x; i < 3 * C; i += kGaThreads) {
+    const int r = i / C, c = i - r * C;
+    const float* src = red + (size_t)r * lanes * C + c;
     float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += src[(size_t)l * P.C];
-    P.partial[(((int64_t)b * P.nchunks + blockIdx.x) * 3 + r) * P.C + c] = acc;
+    for (int l = 0; l < lanes; ++l) acc += src[(size_t)l * C];
+    P.partial[(((int64_t)b * P.nchunks + blockIdx.x) * 3 + r) * C + c] = acc;
   }
 }
 
@@ -213,6 +255,45 @@ sum4_nhwc_kernel(const __nv_bfloat16* __restrict__ y00, const __nv_bfloat16* __r
   }
 }
 
+// Gradient of the ToRGB skip path: skip_up = upfirdn2d(skip, outer(k1, k1), up 2, pad (2,1)) (model.py:31-49, 358) is the
+// 2x2-tap polyphase filter  up[2m] = f0 x[m-1] + f2 x[m],  up[2m+1] = f1 x[m] + f3 x[m+1]  per axis (f = flipped k1), so
+//   g_skip[m] = f3 g[2m-1] + f2 g[2m] + f1 g[2m+1] + f0 g[2m+2]      (a 4-tap stride-2 filter per axis, zero outside)
+// planes = B * 3 image planes of fp32 [2h, 2w] -> [h, w]; thread = 4 adjacent outputs of a row.
+__global__ void __launch_bounds__(256)
+skip_grad_kernel(const float* __restrict__ g, float* __restrict__ gx, int h, int w, int64_t total, float f0, float f1,
+                 float f2, float f3) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int wq = (w + 3) >> 2;
+  const int xq = (int)(t % wq);
+  const int y = (int)((t / wq) % h);
+  const int64_t plane = t / ((int64_t)wq * h);
+  const int W2 = 2 * w, H2 = 2 * h;
+  const float* gp = g + plane * (int64_t)H2 * W2;
+  const float fy[4] = {f3, f2, f1, f0};
+  const int x0 = xq * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 4; ++dy) {
+    const int Y = 2 * y - 1 + dy;
+    if (Y < 0 || Y >= H2) continue;
+    const float* row = gp + (int64_t)Y * W2;
+    float v[10];                                   // columns 2*x0-1 .. 2*x0+8
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int X = 2 * x0 - 1 + i;
+      v[i] = (X >= 0 && X < W2) ? __ldg(row + X) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      acc[k] = fmaf(fy[dy], fmaf(f3, v[2 * k], fmaf(f2, v[2 * k + 1], fmaf(f1, v[2 * k + 2], f0 * v[2 * k + 3]))), acc[k]);
+  }
+  float* out = gx + (plane * h + y) * (int64_t)w + x0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (x0 + k < w) out[k] = acc[k];
+}
+
 // pixel chunks: a function of the image size ONLY (never of the batch), so that a sample's partial sums -- and with
 // them its gradients -- are bit-identical whatever batch it is part of: at most 128 chunks of at least 256 pixels
 int64_t plan_chunks(int B, int64_t HW, int64_t* chunk_out) {
@@ -258,10 +339,14 @@ extern "C" int w2e_grad_assemble_nhwc(const void* gxs, const float* s_next, cons
   P.want_r3 = demod != nullptr ? 1 : 0;
   P.nchunks = (int)plan_chunks(B, HW, &P.chunk);
   const int lanes = kGaThreads / (C / 8);
-  const size_t smem = (size_t)3 * lanes * C * sizeof(float);
-  // (lanes * C == 2048 floats whatever C: 24 KB)
+  const size_t smem = ((size_t)9 * C + (size_t)3 * lanes * C) * sizeof(float);   // constants + 24 KB of lane partials
+  W2E_CHECK_ARG(smem <= 48 * 1024, "grad_assemble_nhwc: shared memory");
   cudaStream_t st = (cudaStream_t)stream;
-  grad_assemble_nhwc_kernel<<<dim3((unsigned)P.nchunks, (unsigned)B), kGaThreads, smem, st>>>(P);
+  const dim3 grid((unsigned)P.nchunks, (unsigned)B);
+  if (g_rgb && demod) grad_assemble_nhwc_kernel<true, true><<<grid, kGaThreads, smem, st>>>(P);
+  else if (g_rgb) grad_assemble_nhwc_kernel<true, false><<<grid, kGaThreads, smem, st>>>(P);
+  else if (demod) grad_assemble_nhwc_kernel<false, true><<<grid, kGaThreads, smem, st>>>(P);
+  else grad_assemble_nhwc_kernel<false, false><<<grid, kGaThreads, smem, st>>>(P);
   W2E_LAUNCH_OK();
   const int64_t total = (int64_t)B * 3 * C;
   reduce_chunks_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(workspace, sums, P.nchunks, 3 * C, total);
@@ -301,6 +386,19 @@ extern "C" int w2e_sum4_nhwc(const void* y00, const void* y01, const void* y10, 
   sum4_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y00, (const __nv_bfloat16*)y01, (const __nv_bfloat16*)y10, (const __nv_bfloat16*)y11,
       (__nv_bfloat16*)out, h, w, C, total);
+  W2E_LAUNCH_OK();
+  return W2E_OK;
+}
+
+extern "C" int w2e_skip_grad(const float* g, float* g_skip, const float* host_taps1d, int64_t planes, int h, int w,
+                             void* stream) {
+  W2E_CHECK_ARG(g && g_skip && host_taps1d, "skip_grad: null pointer");
+  W2E_CHECK_ARG(planes >= 0 && h > 0 && w > 0, "skip_grad: bad shape");
+  if (planes == 0) return W2E_OK;
+  const int64_t total = planes * h * ((w + 3) / 4);
+  // flipped 1-D taps f[i] = k1[3 - i] (the forward's polyphase coefficients, csrc/torgb_blend.cu)
+  skip_grad_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      g, g_skip, h, w, total, host_taps1d[3], host_taps1d[2], host_taps1d[1], host_taps1d[0]);
   W2E_LAUNCH_OK();
   return W2E_OK;
 }

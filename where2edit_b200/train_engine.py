@@ -197,9 +197,15 @@ class TrainEngine(SynthesisEngine):
                 if hasattr(module, "upsample"):     # the skip path: gradient of upfirdn2d(skip, up=2, pad=(2,1))
                     b, _, h, w = g_rgb.shape
                     taps2d = kernel_taps(module.upsample.kernel)
+                    taps1d = K.separable_taps(taps2d) if len(taps2d) == 16 else None
                     g_skip = torch.empty((b, 3, h // 2, w // 2), device=dev, dtype=torch.float32)
-                    N.check(lib.w2e_upfirdn2d_bwd(N.ptr(g_rgb), N.ptr(g_skip), N.host_floats(taps2d), b * 3, h // 2, w // 2,
-                                                  4, 4, 2, 2, 1, 1, 2, 1, 2, 1, N.F32, N.stream_ptr()), "upfirdn2d_bwd")
+                    N.note(kind="bwd_elementwise", bytes=4.0 * 1.25 * g_rgb.numel(), tag=f"skip grad @{h}")
+                    if taps1d is not None:
+                        N.check(lib.w2e_skip_grad(N.ptr(g_rgb), N.ptr(g_skip), N.host_floats(taps1d), b * 3, h // 2, w // 2,
+                                                  N.stream_ptr()), "skip_grad")
+                    else:   # unusual (non-separable) upsample filter: the generic upfirdn2d backward
+                        N.check(lib.w2e_upfirdn2d_bwd(N.ptr(g_rgb), N.ptr(g_skip), N.host_floats(taps2d), b * 3, h // 2, w // 2,
+                                                      4, 4, 2, 2, 1, 1, 2, 1, 2, 1, N.F32, N.stream_ptr()), "upfirdn2d_bwd")
                     g_rgb = g_skip
                 else:
                     g_rgb = None
