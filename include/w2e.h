@@ -229,11 +229,14 @@ int w2e_modconv_tc2_upblur(const void* xs, const void* w, const float* out_scale
 /* Plain 3x3 convolution of w2e_modconv_tc2 over a STRIDED VIEW of a channels-last bf16 tensor (strides in elements,
  * multiples of 8) using only the filter taps whose bit is set in tap_mask (bit ky*3+kx).  Used by the dgrad of the
  * transposed x2 convolution (autograd of models/stylegan2/model.py:249-259): four launches, one per output-parity class
- * of the (2h+1)^2 upstream gradient, added by w2e_sum4_nhwc.  No noise / bias / activation.                         */
+ * of the (2h+1)^2 upstream gradient.  out is [B,out_h,out_w,Cout] with out_h <= in_h, out_w <= in_w (the rest of the
+ * convolution grid is clipped); accumulate != 0 ADDS the result to out (TMA reduce-add, bf16) so that the four class
+ * launches accumulate in place; a clipped or accumulating output needs more than 16 rows (else W2E_ERR_UNSUPPORTED:
+ * run with out_h = in_h, out_w = in_w and add the parts with w2e_sum4_nhwc).  No noise / bias / activation.        */
 int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, const float* next_scale,
                          void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
-                         int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
-                         const w2e_tc2_config* cfg, void* stream);
+                         int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask, int out_h, int out_w,
+                         int accumulate, const w2e_tc2_config* cfg, void* stream);
 
 /* tf32 mode (north_star (1): "bf16 and tf32 modes"): the same kernel with fp32 tensors in HBM (channels-last
  * activations xs / out / out_mod, weights [9][Cout][Cin]) read by tcgen05.mma kind::tf32 (10-bit mantissa operands,

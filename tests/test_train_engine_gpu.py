@@ -155,7 +155,7 @@ def test_backward_kernels_against_torch_formulas():
     assert max_abs(got.cpu(), skip.grad.cpu()) <= 1e-5
 
 
-@pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8)])
+@pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8), (64, 32, 40), (256, 128, 32)])
 def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     """four strided-view launches with 4 / 2 / 2 / 1 taps + sum4 == the gradient of conv_transpose2d(stride 2)"""
     from where2edit_b200 import train_engine
@@ -165,8 +165,11 @@ def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     weight = synth.make_tensor((1, cout, cin, 3, 3), 91).to(DEV)
     pw = K.PackedWeight(weight, 1 / (cin * 9) ** 0.5, None)
     gz = torch.randn(b, 2 * h + 1, 2 * h + 1, cout, device=DEV).to(torch.bfloat16)
-    got = eng._dgrad_up(gz, pw, h, h)
+    got = eng._dgrad_up(gz, pw, h, h)          # (h >= 32: accumulated in place by TMA reduce-add)
     eng.assert_ok()
+    eng.dgrad_up_in_place = False
+    parts = eng._dgrad_up(gz, pw, h, h)
+    assert max_abs(got.float().cpu(), parts.float().cpu()) <= 2e-2 * float(parts.float().abs().max())
     x = torch.zeros(b, cin, h, h, device=DEV, dtype=torch.float64, requires_grad=True)
     wt = (weight[0].double() / (cin * 9) ** 0.5).to(torch.bfloat16).double()
     y = torch.nn.functional.conv_transpose2d(x, wt.transpose(0, 1), stride=2)

@@ -62,6 +62,7 @@ struct Tc2Params {
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
+  int reduce_add;           // TS epilogue: `out` boxes are ADDED to global memory (TMA reduce) instead of stored
   int tap_mask;             // plain conv: bit t set = filter tap t is used (0x1ff = all); class convolutions of the
                             // transposed convolution's dgrad use 4 / 2 / 2 / 1 of the 9 taps
   int bgroup;               // weight-ring kernels, TS flavour: filter taps per weight REQUEST (1, or 3 = one tap row per TMA box)
@@ -1038,7 +1039,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (TR) {
                   tma_store_4d(&M.st[acc / MT], slot_o, cc, i0, yy, b);
                 } else {
-                  if (OUT) tma_store_4d(&M.st[0], slot_o, cc, i0, yy, b);
+                  if (OUT) {
+                    if (P.reduce_add) tma_reduce_add_4d(&M.st[0], slot_o, cc, i0, yy, b);
+                    else tma_store_4d(&M.st[0], slot_o, cc, i0, yy, b);
+                  }
                   if (MOD) tma_store_4d(&M.st[1], slot_m, cc, i0, yy, b);
                 }
                 bulk_commit();
@@ -1399,6 +1403,8 @@ struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped
 struct ViewArgs {   // plain conv on a strided view of a channels-last tensor, with a subset of the 9 filter taps
   int64_t stride_x, stride_y, stride_b;   // in elements: between pixels of a row, rows, samples
   int tap_mask;
+  int out_h, out_w;   // extent of the `out` buffer ([B,out_h,out_w,Cout], <= the convolution grid: the rest is clipped)
+  int reduce;         // 1: add the result to `out` (TMA reduce) instead of storing it
 };
 
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
@@ -1451,7 +1457,9 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     W2E_CHECK_ARG(view->tap_mask > 0 && view->tap_mask <= 0x1ff, "modconv_tc2_view: tap mask %d", view->tap_mask);
     W2E_CHECK_ARG(view->stride_x > 0 && (view->stride_x * 2) % 16 == 0 && (view->stride_y * 2) % 16 == 0 &&
                       (view->stride_b * 2) % 16 == 0, "modconv_tc2_view: strides must be multiples of 8 elements");
+    W2E_CHECK_ARG(view->out_h > 0 && view->out_h <= in_h && view->out_w > 0 && view->out_w <= in_w, "modconv_tc2_view: out extent");
     P.tap_mask = view->tap_mask;
+    P.reduce_add = view->reduce ? 1 : 0;
   }
   if (!transposed) {
     P.OH = in_h; P.OW = in_w; P.grid_h = in_h; P.grid_w = in_w; P.out_stride = 1; P.ng = 1;
@@ -1474,9 +1482,10 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // A 256-pixel x 256-column tile fills the 512 TMEM columns, so MMA and epilogue alternate (measured 0.51 ms against
   // 0.27 ms of MMAs); 128 columns leave room for two accumulator sets and the staged 16-warp epilogue, and the two
   // column tiles add their partial ToRGB sums into the zero-initialised image.  Flag bit 7 = off (A/B).
+  const bool clipped_out = view && (view->reduce || view->out_h != in_h || view->out_w != in_w);   // needs the TMA-store epilogue
   const bool rgb_split = !transposed && rgb && Cout == 256 && g_ts_mode != 0 && !(g_flags & 128) && in_h > kSubTileH &&
                          rgb->rgb_dtype == W2E_F32;
-  const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : (rgb_split ? 128 : 256);
+  const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : ((rgb_split || clipped_out) ? 128 : 256);
   P.bn = 16;
   for (int cand : {256, 128, 64, 32, 16})
     if (cand <= bn_max && Cout % cand == 0) { P.bn = cand; break; }
@@ -1644,6 +1653,9 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     P.bgroup = 1;
   }
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
+  if (clipped_out && !ts)
+    return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_view: a clipped / accumulating output needs the TMA-store epilogue "
+                                          "(more than 16 rows, 32..128-column tiles)");
   if (ts && !fb) {
     if (noise) {
       const uint64_t dims[3] = {(uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)noise_batch};
@@ -1662,8 +1674,9 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     }
     const uint32_t sbox[4] = {(uint32_t)P.ts_unit_ch, (uint32_t)kTileW, (uint32_t)kSubTileH, 1u};
     if (!transposed) {
-      const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)B};
-      const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)P.OW * Cout * 2, (uint64_t)P.OH * P.OW * Cout * 2};
+      const uint64_t ow = view ? (uint64_t)view->out_w : (uint64_t)P.OW, oh = view ? (uint64_t)view->out_h : (uint64_t)P.OH;
+      const uint64_t dims[4] = {(uint64_t)Cout, ow, oh, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)Cout * 2, ow * Cout * 2, oh * ow * Cout * 2};
       if (out) {
         int rc = make_bf16_map(&M.st[0], out, 4, dims, strides, sbox, P.ts_unit_ch * 2);
         if (rc) return rc;
@@ -1752,8 +1765,8 @@ extern "C" int w2e_modconv_tc2(const void* xs, const void* w, const float* out_s
 extern "C" int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, const float* next_scale,
                                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                                     int in_w, int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
-                                    const w2e_tc2_config* cfg, void* stream) {
-  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask};
+                                    int out_h, int out_w, int accumulate, const w2e_tc2_config* cfg, void* stream) {
+  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate};
   return run_tc2(xs, w, out_scale, nullptr, nullptr, nullptr, 0, next_scale, out, out_mod, error_flag, B, Cin, Cout, in_h,
                  in_w, 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }

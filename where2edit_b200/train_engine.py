@@ -37,6 +37,8 @@ class _Saved:
 
 
 class TrainEngine(SynthesisEngine):
+    dgrad_up_in_place = True   # A/B switch: False = always separate class results + w2e_sum4_nhwc
+
     # ------------------------------------------------------------------ forward (keeps what the backward needs)
     def forward_train(self, latent, stylespace, noise):
         gen = self.gen
@@ -147,21 +149,27 @@ class TrainEngine(SynthesisEngine):
         b, zh, zw, c = gz.shape
         lib = N.load()
         wts = pw.tc_dgrad_up()
+        out = torch.empty((b, h, w, pw.cin), device=gz.device, dtype=torch.bfloat16)
+        # >= 32 rows: the four class launches accumulate IN PLACE (class 00 stores the h x w region, the others add to
+        # it through TMA reduce-add); smaller maps: separate results + w2e_sum4_nhwc
+        in_place = self.dgrad_up_in_place and h >= 32
         parts = []
         for py in (0, 1):
             for px in (0, 1):
                 hc, wc = h + 1 - py, w + 1 - px
                 view = gz.reshape(-1)[(py * zw + px) * c:]
-                y = torch.empty((b, hc, wc, pw.cin), device=gz.device, dtype=torch.bfloat16)
+                y = out if in_place else torch.empty((b, hc, wc, pw.cin), device=gz.device, dtype=torch.bfloat16)
                 ntaps = bin(_CLASS_TAPS[(py, px)]).count("1")
                 N.note(kind="modconv", flops=2.0 * ntaps * pw.cin * pw.cout * b * hc * wc,
                        tag=f"dgrad up {pw.cout}->{pw.cin}@{hc}x{wc} class {py}{px}")
                 N.check(lib.w2e_modconv_tc2_view(
                     N.ptr(view), N.ptr(wts[(py, px)]), None, None, N.ptr(y), None, N.ptr(self.error_flag(gz.device)),
                     b, pw.cout, pw.cin, hc, wc, 2 * c, 2 * zw * c, zh * zw * c, _CLASS_TAPS[(py, px)],
+                    h if in_place else hc, w if in_place else wc, int(in_place and (py, px) != (0, 0)),
                     N.tc2_cfg(self.tc2_cfg), N.stream_ptr()), "modconv_tc2_view (dgrad up)")
                 parts.append(y)
-        out = torch.empty((b, h, w, pw.cin), device=gz.device, dtype=torch.bfloat16)
+        if in_place:
+            return out
         N.note(kind="bwd_elementwise", bytes=2.0 * 5 * out.numel(), tag=f"sum4 {pw.cin}@{h}")
         N.check(lib.w2e_sum4_nhwc(N.ptr(parts[0]), N.ptr(parts[1]), N.ptr(parts[2]), N.ptr(parts[3]), N.ptr(out), b, h, w,
                                   pw.cin, N.stream_ptr()), "sum4_nhwc")
