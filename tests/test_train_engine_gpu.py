@@ -155,7 +155,8 @@ def test_backward_kernels_against_torch_formulas():
     assert max_abs(got.cpu(), skip.grad.cpu()) <= 1e-5
 
 
-@pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8), (64, 32, 40), (256, 128, 32)])
+@pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8), (64, 32, 40), (256, 128, 32),
+                                        (128, 64, 36), (512, 256, 32), (512, 512, 33)])
 def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     """four strided-view launches with 4 / 2 / 2 / 1 taps + sum4 == the gradient of conv_transpose2d(stride 2)"""
     from where2edit_b200 import train_engine

@@ -1582,7 +1582,11 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       P.b_stages = 1;
       b_bytes = w_bytes;
     } else {
-      const int avail = smem_limit - P.a_stages * P.a_stage_bytes - ts_bytes;
+      int avail = smem_limit - P.a_stages * P.a_stage_bytes - ts_bytes;
+      if (use_ts && P.a_stages > 2 && avail / P.b_block_bytes < 4) {   // a third A stage is a luxury: the ring comes first
+        P.a_stages = 2;
+        avail = smem_limit - P.a_stages * P.a_stage_bytes - ts_bytes;
+      }
       P.b_stages = avail / P.b_block_bytes;
       if (P.b_stages > kT2MaxB) P.b_stages = kT2MaxB;
       if (P.b_stages < (use_ts ? 4 : 2)) continue;
