@@ -234,33 +234,47 @@ class TrainEngine(SynthesisEngine):
             if pending is not None:
                 gs[pending[1]] = sums[:, 1]
                 pending = None
+            # demodulation term of this layer's style gradient (appendix C): with G = sum g_y * y (y = demodulated conv
+            # output), dL/dd = G / d and gs_demod = 2 s ((-G d^2 / 2) @ wsq) = -s ((G d^2) @ wsq)
             if kind == "conv":
-                big_g = sums[:, 2]                              # G = sum g_y * y  (y = demodulated conv output)
+                gd2 = sums[:, 2] * d * d                        # G = sums[:, 2]
                 gxs = self._dgrad_plain(gz, pw)
             else:
                 h2, w2 = sv.hw[idx]
                 h, w = h2 // 2, w2 // 2
                 gzu = self._blur_t(gz, conv.blur.kernel, d, (2 * h + 1, 2 * w + 1))
-                big_g = self._rowdot(gzu, sv.z[idx]) / d        # gzu = g_y * d, z = y
+                gd2 = self._rowdot(gzu, sv.z[idx]) * d          # gzu = g_y * d, z = y: sum gzu*z = G d
                 gxs = self._dgrad_up(gzu, pw, h, w)
-            # demodulation term of this layer's style gradient: 2 * s * ((-G d^2 / 2) @ wsq)   (appendix C)
-            gq = -0.5 * big_g * d * d
-            demod_terms[idx] = 2.0 * styles[idx] * (gq @ pw.wsq)
+            demod_terms[idx] = gd2 @ pw.wsq
             gxs_next, s_next, next_idx = gxs, styles[idx], idx
         # first layer: its input is the constant
         gs[conv_ids[0]] = self._rowdot(gxs_next, sv.const)
         for idx in conv_ids:
-            gs[idx] = gs[idx] + demod_terms[idx]
+            gs[idx] = torch.addcmul(gs[idx], styles[idx], demod_terms[idx], value=-1.0)
         return gs
 
     def latent_gradient(self, sv, gs, latent_shape):
         """dL/dW+ [B, n_latent, style_dim] from the per-layer style gradients, through the modulation linears
         s_l = w[:, row_l] @ (W_l * scale)^T + b_l (models/stylegan2/model.py:149-159, 238)."""
         plan = self._plan
-        g = torch.zeros(latent_shape, device=gs[0].device, dtype=torch.float32)
-        for (choff, cin, _), row, gl in zip(plan["seg"], sv.rows, gs):
-            g[:, row] += gl @ plan["w_all"][choff:choff + cin]
-        return g
+        # layers that read the same W+ row (a ToRGB and the next block's first convolution) are neighbours in the
+        # concatenated modulation weight: one GEMM per row
+        gs_all = torch.cat(gs, dim=1)
+        per_row = {}
+        for (choff, cin, _), row in zip(plan["seg"], sv.rows):
+            lo, hi = per_row.get(row, (choff, choff))
+            per_row[row] = (min(lo, choff), max(hi, choff + cin))
+        zero = None
+        cols = []
+        for row in range(latent_shape[1]):
+            if row in per_row:
+                lo, hi = per_row[row]
+                cols.append(gs_all[:, lo:hi] @ plan["w_all"][lo:hi])
+            else:
+                if zero is None:
+                    zero = torch.zeros((latent_shape[0], latent_shape[2]), device=gs_all.device, dtype=torch.float32)
+                cols.append(zero)
+        return torch.stack(cols, dim=1)
 
 
 class _SynthesisFn(torch.autograd.Function):
