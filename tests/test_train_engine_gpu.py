@@ -84,22 +84,66 @@ def test_stylespace_gradients_track_the_fp32_path(size, cm):
         assert max_abs(a.grad.cpu(), b[1:2].cpu()) <= 1e-5 * float(b.abs().max())
 
 
+def test_blended_stylespace_gradients_match_reference_autograd(golden_g32):
+    """the reference's training forward (run_attention.py:1245): stylespace codes + region blend at a convolution layer
+    and the following ToRGB; gradients w.r.t. the 11 styles AND the attention map against the reference's autograd"""
+    g = golden_g32
+    gen = build(32)
+    wplus = synth.make_wplus(2, 8, seed=2).to(DEV)
+    upstream = (synth.make_tensor((2, 3, 32, 32), 4) / (2 * 3 * 32 * 32)).to(DEV)
+    gen.set_precision("fp32")
+    with torch.no_grad():
+        _, _, _, feats = gen([wplus], input_is_latent=True, randomize_noise=False, return_features=True)
+    gen.set_precision("bf16")
+    ref_styles = [torch.from_numpy(g[f"style_{i}"]) for i in range(11)]
+    edited = [(s * (1 + 0.05 * synth.make_tensor(tuple(s.shape), 500 + i))).to(DEV).requires_grad_(True)
+              for i, s in enumerate(ref_styles)]
+    mask = synth.make_mask(2, 16, seed=10).to(DEV).requires_grad_(True)
+    img, _ = gen([edited], input_is_stylespace=True, randomize_noise=False, attention_layer=7, attention_map=mask,
+                 feature_map=feats)
+    assert "Synthesis" in type(img.grad_fn).__name__
+    (img * upstream).sum().backward()
+    gen.assert_ok()
+    got = torch.cat([s.grad.flatten() for s in edited])
+    want = torch.cat([torch.from_numpy(g[f"grad_style_{i}"]).flatten() for i in range(11)])
+    cos, rel = cos_rel(got, want)
+    assert cos >= 0.99 and rel <= 0.12, (cos, rel)
+    cos_m, rel_m = cos_rel(mask.grad, torch.from_numpy(g["grad_mask"]))
+    assert cos_m >= 0.99 and rel_m <= 0.12, (cos_m, rel_m)
+    # a blend at a ToRGB layer only (layer 8 = the RGB image at 16^2), and at an up-convolution (layer 6)
+    for layer, msize in ((8, 16), (6, 8)):
+        st = [s.detach().clone().requires_grad_(True) for s in edited]
+        mk = synth.make_mask(2, msize, seed=3 + layer).to(DEV).requires_grad_(True)
+        out, _ = gen([st], input_is_stylespace=True, randomize_noise=False, attention_layer=layer, attention_map=mk,
+                     feature_map=feats)
+        (out * upstream).sum().backward()
+        gen.set_precision("fp32")
+        st32 = [s.detach().clone().requires_grad_(True) for s in edited]
+        mk32 = mk.detach().clone().requires_grad_(True)
+        out32, _ = gen([st32], input_is_stylespace=True, randomize_noise=False, attention_layer=layer, attention_map=mk32,
+                       feature_map=feats)
+        (out32 * upstream).sum().backward()
+        gen.set_precision("bf16")
+        c1, r1 = cos_rel(torch.cat([s.grad.flatten() for s in st]), torch.cat([s.grad.flatten() for s in st32]))
+        c2, r2 = cos_rel(mk.grad, mk32.grad)
+        assert c1 >= 0.99 and c2 >= 0.99, (layer, c1, r1, c2, r2)
+    gen.assert_ok()
+
+
 def test_module_path_is_kept_where_the_engine_does_not_apply():
     gen = build(32)
     w = synth.make_wplus(1, 8, seed=2).to(DEV)
-    with torch.no_grad():
-        _, _, styles, feats = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
-    st = [s.detach().clone().requires_grad_(True) for s in styles]
-    mask = torch.rand(1, 1, 8, 8, device=DEV, requires_grad=True)
-    img, _ = gen([st], input_is_stylespace=True, randomize_noise=False, attention_layer=5, attention_map=mask,
-                 feature_map=feats)
-    assert "Synthesis" not in type(img.grad_fn).__name__
-    img.square().mean().backward()
-    assert mask.grad is not None and torch.isfinite(mask.grad).all()
     gen.bf16_backward = "modules"
     wp = w.clone().requires_grad_(True)
     img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
     assert "Synthesis" not in type(img.grad_fn).__name__
+    gen.bf16_backward = "engine"
+    gen.conv1.conv.weight.requires_grad_(True)          # a trainable generator parameter: not the engine's case
+    wp = w.clone().requires_grad_(True)
+    img, _ = gen([wp], input_is_latent=True, randomize_noise=False)
+    assert "Synthesis" not in type(img.grad_fn).__name__
+    img.square().mean().backward()
+    assert torch.isfinite(wp.grad).all()
 
 
 def test_backward_kernels_against_torch_formulas():

@@ -388,15 +388,18 @@ class Generator(nn.Module):
         self._engine.image_dtype, self._engine.image_out = self.image_dtype, self.image_out
         return self._engine
 
-    def _train_engine_applies(self, latent, stylespace, noise, blending, want_features):
+    def _train_engine_applies(self, latent, stylespace, noise, blending, want_features, attention_map=None, feature_map=None):
         """The channels-last backward engine covers the latent / style optimisation loops: frozen generator, fixed
-        noise buffers, gradient to the W+ latent or the stylespace codes.  Anything else (region blend under
-        autograd, feature capture, trainable generator parameters, per-sample random noise) takes the module path."""
-        if blending or want_features or any(n is None for n in noise) or self.bf16_backward == "modules":
+        noise buffers, gradient to the W+ latent or the stylespace codes and, with a region blend
+        (run_attention.py:1245), to the attention map.  Anything else (feature capture, trainable generator
+        parameters, per-sample random noise, original features that require grad) takes the module path."""
+        if want_features or any(n is None for n in noise) or self.bf16_backward == "modules":
             return False
         if any(p.requires_grad for p in self.parameters()):
             return False
-        inputs = latent if stylespace else [latent]
+        if blending and (feature_map is None or any(torch.is_tensor(f) and f.requires_grad for f in feature_map)):
+            return False     # (the reference computes the original features under no_grad, run_attention.py:1195-1203)
+        inputs = list(latent if stylespace else [latent]) + ([attention_map] if blending else [])
         return any(t.requires_grad for t in inputs)
 
     def assert_ok(self):
@@ -463,10 +466,13 @@ class Generator(nn.Module):
                 attention_layer=attention_layer if blending else 0, attention_map=attention_map,
                 feature_map=feature_map)
         elif self.precision == "bf16" and self._train_engine_applies(latent, input_is_stylespace, noise, blending,
-                                                                      return_features and not return_latents):
+                                                                      return_features and not return_latents, attention_map,
+                                                                      feature_map):
             # under autograd: channels-last bf16 forward + backward engine (train_engine.py)
             from . import train_engine
-            image, style_vector = train_engine.synthesize_with_grad(self._bf16_engine(), latent, input_is_stylespace, noise)
+            image, style_vector = train_engine.synthesize_with_grad(
+                self._bf16_engine(), latent, input_is_stylespace, noise, attention_layer if blending else 0, attention_map,
+                feature_map)
             captured = []
         else:
             # module path.  precision "bf16" / "tf32": the 3x3 convolutions (forward and dgrad) run on the tensor

@@ -40,7 +40,7 @@ class TrainEngine(SynthesisEngine):
     dgrad_up_in_place = True   # A/B switch: False = always separate class results + w2e_sum4_nhwc
 
     # ------------------------------------------------------------------ forward (keeps what the backward needs)
-    def forward_train(self, latent, stylespace, noise):
+    def forward_train(self, latent, stylespace, noise, attention_layer=0, attention_map=None, feature_map=None):
         gen = self.gen
         layers = gen.styled_layers()
         rows = gen.latent_rows(stylespace)
@@ -58,6 +58,9 @@ class TrainEngine(SynthesisEngine):
         sv.batch, sv.stylespace, sv.styles, sv.demods = batch, stylespace, styles, demods
         sv.layers, sv.rows = layers, rows
         sv.act, sv.z, sv.noise, sv.hw = {}, {}, {}, {}
+        sv.blend = {}        # layer index -> (tensor before the blend, original feature, kind): region blend sites
+        sv.mask = attention_map.detach().to(torch.float32).contiguous() if attention_layer else None
+        carry = False
         const = gen.input.input.detach()
         sv.const = self._to_nhwc(const, None, 1)                     # unmodulated, batch-broadcast
         xs = self._to_nhwc(const, styles[0], batch)
@@ -73,6 +76,11 @@ class TrainEngine(SynthesisEngine):
                     skip, fused_rgb = fused_rgb, None
                 else:
                     skip = self._torgb(act, module, s, skip)
+                if attention_layer and (idx + 1 == attention_layer or carry):     # attention_model.py:558-561 (`or this_layer`)
+                    carry = False
+                    orig = feature_map[idx].detach().to(torch.float32).contiguous()
+                    sv.blend[idx] = (skip, orig, "rgb")
+                    skip = K.mask_blend(skip, orig, sv.mask)
                 style_vector.append(s.reshape(batch, 1, -1, 1, 1))
                 continue
             conv = module.conv
@@ -83,9 +91,11 @@ class TrainEngine(SynthesisEngine):
             bias = module.activate.bias.detach().to(torch.float32).contiguous()
             nxt = consumer_style(idx)
             next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
-            need_mod = nxt is not None
+            blend_here = bool(attention_layer) and idx + 1 == attention_layer
+            need_mod = nxt is not None and not blend_here
             if kind == "conv":
-                fuse = next_is_rgb and self.fuse_rgb and pw.cout <= 512 and hw[0] > 16
+                fuse = (next_is_rgb and self.fuse_rgb and pw.cout <= 512 and hw[0] > 16
+                        and not (attention_layer and attention_layer in (idx + 1, idx + 2)))
                 if fuse:
                     act, xs_next, fused_rgb = self._conv2_rgb(xs, pw, demods[idx], nz, noise_w, bias, nxt, True, need_mod,
                                                               layers[idx + 1][0], styles[idx + 1], skip)
@@ -99,6 +109,13 @@ class TrainEngine(SynthesisEngine):
                 act, xs_next = self._blur(z, conv.blur.kernel, conv.blur.pad, bias, nz, noise_w, nxt, True, need_mod, hw)
                 sv.z[idx] = z
             sv.act[idx], sv.noise[idx], sv.hw[idx] = act, (nz, noise_w, bias), hw
+            if blend_here:      # attention_model.py:546-549: m * out + (1 - m) * original feature, consumed by what follows
+                carry = True
+                blended, xs_next = self._blend(act, feature_map[idx], sv.mask, nxt, nxt is not None)
+                sv.blend[idx] = (blended, None, "conv")
+                sv.blend_orig = getattr(sv, "blend_orig", {})
+                sv.blend_orig[idx] = feature_map[idx]
+                act = blended   # the following ToRGB (and the next convolution, through xs_next) read the blended tensor
             xs = xs_next
             style_vector.append(s.reshape(batch, 1, -1, 1, 1))
         return skip, style_vector, sv
@@ -111,7 +128,7 @@ class TrainEngine(SynthesisEngine):
             ws = self._ws = torch.empty(max(n, 1), device=dev, dtype=torch.float32)
         return ws
 
-    def _assemble(self, gxs, s_next, act, g_rgb, w_rgb, s_rgb, noise, demod, want_gz=True):
+    def _assemble(self, gxs, s_next, act, g_rgb, w_rgb, s_rgb, noise, demod, want_gz=True, act_kind=N.ACT_LRELU):
         b, h, w, c = act.shape
         dev = act.device
         gz = torch.empty_like(act) if want_gz else None
@@ -120,7 +137,7 @@ class TrainEngine(SynthesisEngine):
         N.note(kind="bwd_elementwise", bytes=2.0 * act.numel() * (2 + int(gxs is not None)), tag=f"grad_assemble {c}@{h}")
         N.check(N.load().w2e_grad_assemble_nhwc(
             N.ptr(gxs), N.ptr(s_next), N.ptr(act), N.ptr(g_rgb), N.ptr(w_rgb), N.ptr(s_rgb), N.ptr(nz), N.ptr(noise_w),
-            0 if nz is None else nz.shape[0], N.ptr(bias), N.ptr(demod), N.ACT_LRELU, N.ptr(gz), N.ptr(sums),
+            0 if nz is None else nz.shape[0], N.ptr(bias), N.ptr(demod), act_kind, N.ptr(gz), N.ptr(sums),
             N.ptr(self._workspace(b, h * w, c, dev)), b, h * w, c, N.stream_ptr()), "grad_assemble_nhwc")
         return gz, sums
 
@@ -187,12 +204,28 @@ class TrainEngine(SynthesisEngine):
             N.stream_ptr()), "blur_act_nhwc (transposed)")
         return out
 
-    def backward_train(self, sv, g_img):
+    def _blend_backward(self, g_blended, act, orig_nchw, mask):
+        """g w.r.t. m * act + (1 - m) * orig (channels-last bf16, one layer of <= 64^2 in the published configuration)
+        -> (g_act bf16 channels-last, g_mask [B,1,mh,mw]) through the fp32 blend-backward kernel between two layout
+        passes (attention_model.py:548-549; no gradient to the original feature, run_attention.py:1195-1203)."""
+        b, h, w, c = act.shape
+        lib = N.load()
+        g32, a32 = self._to_nchw(g_blended), self._to_nchw(act)
+        o32 = orig_nchw.detach().to(torch.float32).contiguous()
+        ge = torch.empty_like(g32)
+        gm = torch.empty_like(mask)
+        ws = torch.empty((b, h, w), device=g32.device, dtype=torch.float32)
+        N.check(lib.w2e_mask_blend_bwd(N.ptr(g32), N.ptr(a32), N.ptr(o32), N.ptr(mask), N.ptr(ge), N.ptr(gm), N.ptr(ws), b, c, h,
+                                       w, mask.shape[2], mask.shape[3], N.stream_ptr()), "mask_blend_bwd")
+        return self._to_nhwc(ge, None, b), gm
+
+    def backward_train(self, sv, g_img, feature_map=None):
         gen = self.gen
         layers, styles, demods, batch = sv.layers, sv.styles, sv.demods, sv.batch
         dev = g_img.device
         lib = N.load()
         g_rgb = g_img.detach().to(torch.float32).contiguous()
+        g_mask = None
         gs = [None] * len(layers)        # dL/d(style) per styled layer, [B, Cin]
         gxs_next, s_next, next_idx = None, None, None
         pending = None                   # (g_rgb at this resolution, rgb layer index)
@@ -201,6 +234,16 @@ class TrainEngine(SynthesisEngine):
         for idx in range(len(layers) - 1, -1, -1):
             module, kind = layers[idx]
             if kind == "rgb":
+                if idx in sv.blend:      # blended skip image: g_skip = m * g, g_mask += sum g * (skip - orig)
+                    skip_pre, orig, _ = sv.blend[idx]
+                    b, _, h, w = g_rgb.shape
+                    ge, gm = torch.empty_like(g_rgb), torch.empty_like(sv.mask)
+                    ws = torch.empty((b, h, w), device=dev, dtype=torch.float32)
+                    N.check(lib.w2e_mask_blend_bwd(N.ptr(g_rgb), N.ptr(skip_pre), N.ptr(orig), N.ptr(sv.mask), N.ptr(ge), N.ptr(gm),
+                                                   N.ptr(ws), b, 3, h, w, sv.mask.shape[2], sv.mask.shape[3], N.stream_ptr()),
+                            "mask_blend_bwd")
+                    g_rgb = ge
+                    g_mask = gm if g_mask is None else g_mask + gm
                 pending = (g_rgb, idx)
                 if hasattr(module, "upsample"):     # the skip path: gradient of upfirdn2d(skip, up=2, pad=(2,1))
                     b, _, h, w = g_rgb.shape
@@ -227,8 +270,20 @@ class TrainEngine(SynthesisEngine):
                 gr, ridx = pending
                 rpw = layers[ridx][0].conv.packed()
                 rgb_args = (gr, rpw.rgb, styles[ridx])
-            gz, sums = self._assemble(gxs_next, s_next, act, rgb_args[0], rgb_args[1], rgb_args[2],
-                                      sv.noise[idx] if kind == "conv" else None, d if kind == "conv" else None)
+            if idx in sv.blend:
+                # the consumers read the BLENDED tensor: pull their gradients back to it (no activation, no demodulation:
+                # act_kind NONE), through the blend to the layer's own output, then through the activation
+                blended = sv.blend[idx][0]
+                g_bl, sums = self._assemble(gxs_next, s_next, blended, rgb_args[0], rgb_args[1], rgb_args[2], None, None,
+                                            act_kind=N.ACT_NONE)
+                g_act, gm = self._blend_backward(g_bl, act, sv.blend_orig[idx], sv.mask)
+                g_mask = gm if g_mask is None else g_mask + gm
+                gz, sums2 = self._assemble(g_act, None, act, None, None, None, sv.noise[idx] if kind == "conv" else None,
+                                           d if kind == "conv" else None)
+                sums = torch.stack([sums[:, 0], sums[:, 1], sums2[:, 2]], dim=1)
+            else:
+                gz, sums = self._assemble(gxs_next, s_next, act, rgb_args[0], rgb_args[1], rgb_args[2],
+                                          sv.noise[idx] if kind == "conv" else None, d if kind == "conv" else None)
             if next_idx is not None:
                 gs[next_idx] = sums[:, 0]                       # direct term of the NEXT convolution's style gradient
             if pending is not None:
@@ -251,6 +306,7 @@ class TrainEngine(SynthesisEngine):
         gs[conv_ids[0]] = self._rowdot(gxs_next, sv.const)
         for idx in conv_ids:
             gs[idx] = torch.addcmul(gs[idx], styles[idx], demod_terms[idx], value=-1.0)
+        sv.g_mask = g_mask
         return gs
 
     def latent_gradient(self, sv, gs, latent_shape):
@@ -282,12 +338,16 @@ class _SynthesisFn(torch.autograd.Function):
 
     @staticmethod
     @K._amp_fwd
-    def forward(ctx, engine, stylespace, noise, *inputs):
+    def forward(ctx, engine, stylespace, noise, blend, mask, *inputs):
         latent = list(inputs) if stylespace else inputs[0]
         with torch.no_grad():
-            image, style_vector, sv = engine.forward_train(latent, stylespace, noise)
+            if blend is None:
+                image, style_vector, sv = engine.forward_train(latent, stylespace, noise)
+            else:
+                image, style_vector, sv = engine.forward_train(latent, stylespace, noise, blend[0], mask, blend[1])
         ctx.engine, ctx.sv, ctx.stylespace = engine, sv, stylespace
         ctx.shapes = [tuple(t.shape) for t in inputs]
+        ctx.has_mask = mask is not None
         ctx.mark_non_differentiable(*style_vector)
         return (image, *style_vector)
 
@@ -302,14 +362,18 @@ class _SynthesisFn(torch.autograd.Function):
                 grads = [g.reshape(shape) for g, shape in zip(gs, ctx.shapes)]
             else:
                 grads = [engine.latent_gradient(sv, gs, ctx.shapes[0])]
+        g_mask = sv.g_mask if (ctx.has_mask and ctx.needs_input_grad[4]) else None
         ctx.sv = None
         engine._err.publish()
-        return (None, None, None, *grads)
+        return (None, None, None, None, g_mask, *grads)
 
 
-def synthesize_with_grad(engine, latent, stylespace, noise):
+def synthesize_with_grad(engine, latent, stylespace, noise, attention_layer=0, attention_map=None, feature_map=None):
+    """image (differentiable w.r.t. the W+ latent / the stylespace codes and, with a region blend, the attention map)
+    and the detached post-modulation styles."""
     inputs = list(latent) if stylespace else [latent]
     engine._err.poll()
+    blend = (int(attention_layer), list(feature_map)) if attention_layer else None
     with torch.cuda.device(engine.gen.input.input.device):
-        out = _SynthesisFn.apply(engine, stylespace, noise, *inputs)
+        out = _SynthesisFn.apply(engine, stylespace, noise, blend, attention_map if attention_layer else None, *inputs)
     return out[0], list(out[1:])
