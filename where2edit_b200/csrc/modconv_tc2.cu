@@ -62,6 +62,8 @@ struct Tc2Params {
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
+  int percls;               // transposed conv, one accumulator set (4 classes x MT x bn = 512 TMEM columns): the classes
+                            // are handed over one by one (see "per-class hand-over" in the kernel)
   int reduce_add;           // TS epilogue: `out` boxes are ADDED to global memory (TMA reduce) instead of stored
   int tap_mask;             // plain conv: bit t set = filter tap t is used (0x1ff = all); class convolutions of the
                             // transposed convolution's dgrad use 4 / 2 / 2 / 1 of the 9 taps
@@ -248,7 +250,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int s = 0; s < P.b_stages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1u << cl); }
       // TS flavour with a single accumulator buffer: both epilogue groups drain every tile (unit-split mode)
       const uint32_t epi_arrivals = (TS && (P.nbuf == 1 || P.fb)) ? 2 * kT2EpiThreads : kT2EpiThreads;
-      for (int s = 0; s < P.nbuf; ++s) { mbar_init(&bars->acc_full[s], n_issuers); mbar_init(&bars->acc_empty[s], epi_arrivals); }
+      // (per-class hand-over: the four entries are the four parity classes of the single accumulator set)
+      for (int s = 0; s < (P.percls ? 4 : P.nbuf); ++s) { mbar_init(&bars->acc_full[s], n_issuers); mbar_init(&bars->acc_empty[s], epi_arrivals); }
       mbar_init(&bars->w_full, 1);
       mbar_init(&bars->mma_turn[0], 1);
       mbar_init(&bars->mma_turn[1], 1);
@@ -341,7 +344,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // ring was bound by the REQUEST RATE, not by bytes.  (Edge-column tiles use only kx == 2 of each row: the
           // whole row is still fetched.)
           for (int kc = 0; kc < kchunks && ok; ++kc) {
-            for (int g = 0; g < 3; ++g) {
+            for (int gi = 0; gi < 3; ++gi) {
+              const int g = TR ? (gi == 0 ? 1 : (gi == 1 ? 0 : 2)) : gi;   // transposed: tap rows in the order 1, 0, 2 (see the issuer)
               if (edge_y && g != 2) continue;
               if (!TR && !((P.tap_mask >> (3 * g)) & 7)) continue;   // no tap of this row is used
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
@@ -455,8 +459,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // Their untouched accumulators belong to classes whose rows/columns are clipped by the stores.
       const bool edge_y = TR && !(P.flags & 1) && !P.fb && wk.ty * (kSubTileH * MT) >= P.grid_h - 1;
       const bool edge_x = TR && !(P.flags & 1) && !P.fb && wk.tx * kTileW >= P.grid_w - 1;
-      ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
-      if (!ok) break;
+      // PER-CLASS HAND-OVER (transposed conv whose 4 classes x MT x bn accumulators fill all 512 TMEM columns, so there is
+      // no second accumulator set): the tap rows are issued in the order 1, 0, 2 -- row 1 feeds exactly the classes
+      // (1,0) and (1,1), rows 0 and 2 the classes (0,0) and (0,1) -- so in the last K chunk classes 2 and 3 are complete
+      // after the FIRST row (they are committed there and the epilogue starts draining them while rows 0 and 2 still run)
+      // and in the first K chunk of the next tile row 1 only needs classes 2 and 3 drained, rows 0 / 2 classes 0 and 1.
+      // Measured before: MMA phase and a ~4.5k-cycle drain strictly alternated (tools/tc2_timeline.py).
+      if (!(TR && P.percls)) {
+        ok = mbar_wait_warp(&bars->acc_empty[cr.idx], cr.phase ^ 1u, abort_flag);
+        if (!ok) break;
+      }
       tc_fence_after();
       const bool dbg_on = TS && P.dbg && blockIdx.x == 0 && tile / (int)gridDim.x < 64 && lane == 0;
       if (dbg_on) P.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
@@ -510,9 +522,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         } else if (TS && P.bgroup == 3) {
           // grouped weight requests: one b_full / b_empty round trip (and one issue token) per TAP ROW of 3 blocks
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            if (edge_y && g != 2) continue;
-            if (!TR && !((P.tap_mask >> (3 * g)) & 7)) continue;
+          for (int gi = 0; gi < 3; ++gi) {
+            const int g = TR ? (gi == 0 ? 1 : (gi == 1 ? 0 : 2)) : gi;
+            if (TR && P.percls && kc == 0 && gi < 2) {
+              // first K chunk: the classes this row starts must have been drained (row 1: classes 2, 3; row 0: 0, 1)
+              const int c0 = gi == 0 ? 2 : 0;
+              ok = mbar_wait_warp(&bars->acc_empty[c0], cr.phase ^ 1u, abort_flag) &&
+                   mbar_wait_warp(&bars->acc_empty[c0 + 1], cr.phase ^ 1u, abort_flag);
+              if (!ok) break;
+              tc_fence_after();
+            }
+            const bool skip_row = (edge_y && g != 2) || (!TR && !((P.tap_mask >> (3 * g)) & 7));
+            if (TR && P.percls && kc == kchunks - 1 && skip_row && leader && gi != 1) {
+              // (a skipped row still is a commit point of its classes: the hand-over protocol is the same for every tile)
+              const int c0 = gi == 0 ? 2 : 0;
+              umma_commit(&bars->acc_full[c0]);
+              umma_commit(&bars->acc_full[c0 + 1]);
+            }
+            if (skip_row) continue;
             const bool mine = !blk2 || (int)(nblk & 1u) == mw;
             ++nblk;
             if (mine) {
@@ -551,15 +578,22 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               umma_commit(&bars->b_empty[br.idx]);
               if (!blk2 && g == last_tap / 3) {
                 umma_commit(&bars->a_empty[ar.idx]);
-                if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
+                if (kc == kchunks - 1 && !(TR && P.percls)) umma_commit(&bars->acc_full[cr.idx]);
               }
               if (blk2) mbar_arrive(&bars->mma_turn[mw ^ 1]);
+            }
+            if (TR && P.percls && kc == kchunks - 1 && leader && gi != 1 && (blk2 || mine)) {
+              // last K chunk: row 1 completed classes 2 and 3, row 2 (the last one) classes 0 and 1.  Every issuer commits
+              // (the barrier counts the issuers), each covering the MMAs it issued itself.
+              const int c0 = gi == 0 ? 2 : 0;
+              umma_commit(&bars->acc_full[c0]);
+              umma_commit(&bars->acc_full[c0 + 1]);
             }
             br.advance_by(3, P.b_stages);
           }
           if (blk2 && ok && leader) {
             umma_commit(&bars->a_empty[ar.idx]);
-            if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);
+            if (kc == kchunks - 1 && !(TR && P.percls)) umma_commit(&bars->acc_full[cr.idx]);
           }
         } else {
 #pragma unroll
@@ -936,14 +970,17 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // of its next tile run while it still drains this one
         const uint32_t ci = seq & nbuf_mask;
         const uint32_t t_tile = t_lane + ci * (uint32_t)(NACC * P.bn);
-        if (ok) ok = mbar_wait(&bars->acc_full[ci], (seq >> nbuf_shift) & 1u, abort_flag);
-        tc_fence_after();
+        const bool percls = TR && P.percls;
+        if (!percls) {
+          if (ok) ok = mbar_wait(&bars->acc_full[ci], (seq >> nbuf_shift) & 1u, abort_flag);
+          tc_fence_after();
+        }
         if (dbg_on) P.dbg[seq * 8 + 6] = clock64();
         const int nunits = RGB ? chunks : NACC * chunks;
-        bool released = false;
-        auto run_units = [&](auto out_tag, auto mod_tag) {
+        bool released = percls;   // (per-class hand-over releases class by class below)
+        auto run_units = [&](auto out_tag, auto mod_tag, const int u_begin, const int u_end) {
           constexpr bool OUT = decltype(out_tag)::value, MOD = decltype(mod_tag)::value;
-          for (int ui = unit0; ui < nunits; ui += unit_step) {
+          for (int ui = u_begin + unit0; ui < u_end; ui += unit_step) {
             const int acc = RGB ? half * NP : ui / chunks;     // (first) accumulator of this unit
             const int chunk = RGB ? ui : ui - acc * chunks;
             const int m = acc % MT;
@@ -957,7 +994,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const uint32_t slot_o =
                 stage0 + (uint32_t)(((OUT && MOD) ? 0 : (int)(un & (uint32_t)(P.ts_slots - 1))) * P.ts_unit_bytes);
             const uint32_t slot_m = OUT ? stage0 + (uint32_t)P.ts_unit_bytes : slot_o;
-            const bool last_unit = ui + unit_step >= nunits;
+            const bool last_unit = !percls && ui + unit_step >= u_end;
             for (int c16 = 0; c16 < UC; c16 += 16) {
               uint32_t v[NP][16];
 #pragma unroll
@@ -1053,13 +1090,25 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         };
         using T1 = std::true_type;
         using T0 = std::false_type;
-        if (TR) {
-          run_units(T1{}, T0{});
+        if (percls) {
+          // classes in the order the issuer completes them: 2, 3 (tap row 1), then 0, 1
+          const int per_class = MT * chunks;
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            const int cls = (q + 2) & 3;
+            if (ok) ok = mbar_wait(&bars->acc_full[cls], seq & 1u, abort_flag);
+            tc_fence_after();
+            run_units(T1{}, T0{}, cls * per_class, (cls + 1) * per_class);
+            tc_fence_before();
+            mbar_arrive(&bars->acc_empty[cls]);
+          }
+        } else if (TR) {
+          run_units(T1{}, T0{}, 0, nunits);
         } else if (has_out) {
-          if (has_mod) run_units(T1{}, T1{}); else run_units(T1{}, T0{});
+          if (has_mod) run_units(T1{}, T1{}, 0, nunits); else run_units(T1{}, T0{}, 0, nunits);
         } else {
-          if (has_mod) run_units(T0{}, T1{});
-          else if (RGB) run_units(T0{}, T0{});
+          if (has_mod) run_units(T0{}, T1{}, 0, nunits);
+          else if (RGB) run_units(T0{}, T0{}, 0, nunits);
         }
         if (!released) {
           tc_fence_before();
@@ -1415,7 +1464,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
-  const int g_flags = cfg ? (cfg->flags & 251) : 0;
+  const int g_flags = cfg ? (cfg->flags & 507) : 0;
   const int g_cluster_mode = cfg ? (cfg->cluster_log2 < 0 ? 0 : (cfg->cluster_log2 > 3 ? 3 : cfg->cluster_log2)) : 0;
   long long* const g_dbg = cfg ? (long long*)cfg->timeline : nullptr;
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
@@ -1548,13 +1597,18 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   const int w_bytes = 9 * kchunks * P.b_block_bytes;
   int smem_bytes = 0;
   struct Cand { int unit_ch, slots; };
-  const Cand cands[5] = {{64, 2}, {64, 1}, {32, 2}, {32, 1}, {0, 0}};
+  // transposed conv with a single accumulator set (per-class hand-over): 32-channel units, so that all four
+  // half-groups of epilogue warps have a unit of every class (and the weight ring gets the shared memory)
+  const bool small_units = transposed && !fb && acc_cols == 512 && !(g_flags & 256) && P.bn >= 64;
+  const Cand cands_std[5] = {{64, 2}, {64, 1}, {32, 2}, {32, 1}, {0, 0}};
+  const Cand cands_small[5] = {{32, 2}, {32, 1}, {64, 2}, {64, 1}, {0, 0}};
+  const Cand* cands = small_units ? cands_small : cands_std;
   for (int ci = ts ? 0 : 4; ci < 5 && smem_bytes == 0; ++ci) {
     const bool use_ts = cands[ci].unit_ch != 0;
     int extra = 0, ts_bytes = 0;
     if (use_ts) {
       P.ts_unit_ch = P.bn < cands[ci].unit_ch ? P.bn : cands[ci].unit_ch;
-      if (ci >= 2 && P.bn <= 32) continue;   // same unit as candidates 0/1
+      if (cands[ci].unit_ch == 32 && !small_units && P.bn <= 32) continue;   // same unit as the 64-channel candidates
       P.ts_slots = cands[ci].slots;
       if (!fb && n_out > P.ts_slots) continue;
       P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
@@ -1656,6 +1710,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   } else {
     P.bgroup = 1;
   }
+  // per-class accumulator hand-over (transposed conv with a single accumulator set); flag bit 8 = off (A/B)
+  P.percls = (transposed && ts && !fb && P.nbuf == 1 && P.bgroup == 3 && !(g_flags & 256)) ? 1 : 0;
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
   if (clipped_out && !ts)
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_view: a clipped / accumulating output needs the TMA-store epilogue "
