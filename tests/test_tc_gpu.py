@@ -206,6 +206,9 @@ def test_bf16_batch_invariance():
     (2, 64, 64, 32, True, True, True), (1, 32, 32, 40, False, False, True), (2, 128, 256, 24, True, False, True),
     (1, 64, 32, 72, True, True, True),
     (2, 32, 32, 136, True, False, False),   # RGB-only last layer: 512-pixel tiles, two pixels per epilogue thread
+    (2, 32, 32, 144, True, False, False),   # RGB-only last layer on pixel pairs (w2e_modconv_tc2_rgb_pair), ragged rows
+    (1, 32, 32, 48, False, False, False),   # pixel pairs, no skip image
+    (3, 32, 32, 80, True, False, False),    # pixel pairs, 5 x 3 tiles per image
     (1, 64, 64, 64, True, False, True),     # one staging slot per epilogue half
     (3, 128, 128, 48, True, False, True),   # weight ring + staged epilogue, 64-channel units
     (2, 512, 512, 24, True, True, True),    # two channel blocks adding their partial ToRGB sums
@@ -250,6 +253,42 @@ def test_conv_with_fused_torgb_matches_oracle(eng, b, cin, cout, h, with_skip, w
         assert norm_err(eng._to_nchw(out).cpu(), ref) <= 1e-2
     else:
         assert out is None
+
+
+@pytest.mark.parametrize("b,h,rgb_dtype", [(2, 64, torch.float32), (1, 144, torch.bfloat16)])
+def test_pixel_pair_last_layer_agrees_with_the_pixel_kernel(eng, b, h, rgb_dtype):
+    """w2e_modconv_tc2_rgb_pair (N = 64 MMAs on pixel pairs) is the same arithmetic as w2e_modconv_tc2_rgb on the
+    32-channel RGB-only layer up to the fp32 summation order inside the tensor core and the ToRGB dot product"""
+    layer = _Layer(32, 32, False, 61)
+    rgbm = w2e.ToRGB(32, 16)
+    with torch.no_grad():
+        rgbm.conv.weight.copy_(synth.make_tensor((1, 3, 32, 1, 1), 62))
+        rgbm.bias.copy_(0.1 * synth.make_tensor((1, 3, 1, 1), 63))
+    rgbm = rgbm.to(DEV)
+    x = synth.make_tensor((b, 32, h, h), 64)
+    s = 1 + 0.3 * synth.make_tensor((b, 32), 65)
+    s_rgb = (1 + 0.3 * synth.make_tensor((b, 32), 66)).to(DEV).contiguous()
+    noise = synth.make_tensor((1, 1, h, h), 67).to(DEV)
+    skip = synth.make_tensor((b, 3, h // 2, h // 2), 68).to(DEV)
+    m = layer.m
+    pw = eng._tc_weight(m.conv)
+    d = K.demod_coefficients(s.to(DEV), pw.wsq)
+    xs = eng._to_nhwc(x.to(DEV), s.to(DEV).contiguous(), b)
+    got = {}
+    try:
+        for pair in (True, False):
+            eng.pair_mode = pair
+            before = N.STATS.launches.get("w2e_modconv_tc2_rgb_pair", 0)
+            _, _, rgb = eng._conv2_rgb(xs, pw, d, noise, m.noise.weight.detach(), m.activate.bias.detach(), None, False,
+                                       False, rgbm, s_rgb, skip, rgb_dtype=rgb_dtype)
+            eng.assert_ok()
+            assert (N.STATS.launches.get("w2e_modconv_tc2_rgb_pair", 0) - before) == (1 if pair else 0)
+            assert rgb.dtype == rgb_dtype
+            got[pair] = rgb.float().cpu()
+    finally:
+        eng.pair_mode = True
+    tol = 1e-5 if rgb_dtype == torch.float32 else 8e-3   # bf16 image: one rounding step of the stored value
+    assert norm_err(got[True], got[False]) <= tol
 
 
 @pytest.mark.parametrize("b,cin,cout,h,up", [(2, 64, 32, 40, True), (1, 128, 64, 24, True), (2, 256, 128, 20, True),

@@ -21,7 +21,7 @@ def main():
     gen._engine = E.SynthesisEngine(gen)
     eng = gen._engine
     # (name, ts_mode, flags, cluster_log2, blur variant): per-call switches, no library-global state
-    settings = [("default", 1, 0, 0, "auto"), ("no per-class hand-over", 1, 256, 0, "auto"), ("per-tap weight requests", 1, 64, 0, "auto")]
+    settings = [("default", 1, 0, 0, "auto"), ("no per-class hand-over", 1, 256, 0, "auto"), ("last layer not on pixel pairs", 1, 0, 0, "auto")]
     if len(sys.argv) > 2:
         settings = [("default", 1, 0, 0, "auto")] + [(a, *[(v if v == "auto" else int(v)) for v in a.split(",")])
                                                      for a in sys.argv[2:]]
@@ -29,6 +29,7 @@ def main():
     for name, ts, flags, clus, blur in settings:
         eng.tc2_cfg = N.tc2_config(ts_mode=ts, flags=flags, cluster_log2=clus)
         eng.blur_variant = blur
+        eng.pair_mode = "not on pixel pairs" not in name
         with torch.no_grad():
             for _ in range(2):
                 gen([w], input_is_latent=True, randomize_noise=False)
@@ -44,6 +45,7 @@ def main():
                 N.STATS.trace = None
         results[name] = {k: min(v) for k, v in acc.items()}
     eng.tc2_cfg = None
+    eng.pair_mode = True
     base = results["default"]
     names = [s_[0] for s_ in settings]
     print(f"{'launch':30s} " + " ".join(f"{n:>22s}" for n in names))

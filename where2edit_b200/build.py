@@ -43,7 +43,7 @@ def _fingerprint():
     h = hashlib.sha256()
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "w2e.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())   # relative: the snapshot on a GPU box lives under another root
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -61,6 +61,20 @@ def build(force=False, verbose=False, jobs=None):
     """Compile every .cu under csrc/ to an object and link libw2e.so.  Returns the library path."""
     if not force and is_current():
         return LIB
+    # one builder at a time: with one process per GPU (torchrun) every rank may find the library stale at once
+    import fcntl
+    lock = open(os.path.join(PKG, ".build_lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if is_current():            # another process built it while this one waited
+            return LIB
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose=False):
     nvcc = _nvcc()
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -82,11 +96,13 @@ def build(force=False, verbose=False, jobs=None):
             failed.append((src, out))
     if failed:
         raise RuntimeError("nvcc failed:\n" + "\n".join(f"--- {s}\n{o}" for s, o in failed))
+    tmp = LIB + f".tmp{os.getpid()}"
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+            "-Xcompiler", "-fPIC", "-o", tmp, *objs]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)
+    os.replace(tmp, LIB)            # atomic: a concurrent loader sees the old or the new library, never a partial one
     with open(STAMP, "w") as fh:
         fh.write(_fingerprint())
     return LIB

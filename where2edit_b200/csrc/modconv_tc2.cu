@@ -62,6 +62,9 @@ struct Tc2Params {
   float fbv[4], fbh[4];
   int tile_dy, tile_dx, tile_o;   // tile (ty, tx) starts at input position (ty*tile_dy + tile_o, tx*tile_dx + tile_o)
   int cluster;              // log2 of the cluster size (0 = no clusters): multicast weight blocks
+  int pair;                 // x-pair mode of the 32-channel RGB-only layer (see run_tc2): accumulator row = TWO adjacent pixels
+  int OW_real;              // pair mode: width of the image in pixels (OW counts pixel pairs)
+  int skip_box_bytes;       // bytes of one sub-tile's skip patch in the epilogue-input stage
   int percls;               // transposed conv, one accumulator set (4 classes x MT x bn = 512 TMEM columns): the classes
                             // are handed over one by one (see "per-class hand-over" in the kernel)
   int reduce_add;           // TS epilogue: `out` boxes are ADDED to global memory (TMA reduce) instead of stored
@@ -294,7 +297,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (RGB && P.rgb_skip) {
 #pragma unroll
             for (int m = 0; m < MT; ++m)
-              tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
+              tma_load_3d(eb + P.e_noise_bytes + m * P.skip_box_bytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
                           ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
           }
           er.advance(kEStages);
@@ -397,12 +400,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint8_t* eb = smem + P.e_off + (size_t)er.idx * P.e_stage_bytes;
         *reinterpret_cast<int4*>(eb + P.e_info_off) = make_int4(b, j0, i0, wk.tn);
         mbar_arrive_expect_tx(&bars->e_full[er.idx], (uint32_t)P.e_bytes);   // release: orders the info store
-        if (P.noise && !P.fb) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], i0, j0, P.noise_per_sample ? b : 0);
+        // (pair mode: i0 counts pixel pairs = columns of the half-resolution skip image; the noise patch is 16 pixels wide)
+        if (P.noise && !P.fb) tma_load_3d(eb, &M.noise, &bars->e_full[er.idx], P.pair ? 2 * i0 : i0, j0, P.noise_per_sample ? b : 0);
         if (RGB && P.rgb_skip) {
 #pragma unroll
           for (int m = 0; m < MT; ++m)
-            tma_load_3d(eb + P.e_noise_bytes + m * kSkipBoxBytes, &M.skip, &bars->e_full[er.idx], (i0 >> 1) - 4,
-                        ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
+            tma_load_3d(eb + P.e_noise_bytes + m * P.skip_box_bytes, &M.skip, &bars->e_full[er.idx],
+                        (P.pair ? i0 : (i0 >> 1)) - 4, ((j0 + m * kSubTileH) >> 1) - 1, b * 3);
         }
         er.advance(kEStages);
       }
@@ -508,10 +512,15 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   first = kc == 0 ? 0u : 1u;
                 }
                 if (leader) {
+                  // pair mode (KSTEPS == 4: K = [pixel 2i | pixel 2i+1] x 32 channels): the left neighbour pair (t % 3 == 0)
+                  // contributes only its RIGHT pixel (K steps 2, 3), the right neighbour pair only its LEFT pixel (0, 1)
+                  const bool pr = KSTEPS == 4 && P.pair;
+                  const int kfirst = (pr && t % 3 == 0) ? 2 : 0;
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
-                    if constexpr (TF32) umma_tf32_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
-                    else umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? first : 1u);
+                    if (pr && ((t % 3 == 0 && k < 2) || (t % 3 == 2 && k >= 2))) continue;
+                    if constexpr (TF32) umma_tf32_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == kfirst ? first : 1u);
+                    else umma_bf16_lohi(dcol[ai], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == kfirst ? first : 1u);
                   }
                 }
               }
@@ -889,7 +898,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // shares every per-channel constant it reads from shared memory between them
       constexpr int NP = RGB ? MT / 2 : 1;
       const uint32_t skip_off = (uint32_t)P.e_noise_bytes +
-                                (uint32_t)(half * NP * kSkipBoxBytes + (((sy + 1) >> 1) * kSkipBoxW + ((sx + 1) >> 1) + 3) * 4);
+                                (uint32_t)(half * NP * P.skip_box_bytes + (((sy + 1) >> 1) * kSkipBoxW + ((sx + 1) >> 1) + 3) * 4);
       const uint32_t noise_off = (uint32_t)((sy * kTileW + sx) * 4);
       float rgbb[3] = {0.f, 0.f, 0.f};
       if (RGB && P.rgb_bias) {
@@ -917,19 +926,123 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           gen ^= 1u;
           if (gt < P.bn) {
             float* cst = bars->ts_consts(group, (int)gen);
-            const int c = tn * P.bn + gt, bc = b * P.Cout + c;
+            // (pair mode: accumulator column gt = pixel (gt >> 5) of the pair, channel gt & 31 of the 32-channel arrays)
+            const int nch = P.pair ? (P.Cout >> 1) : P.Cout;
+            const int c = P.pair ? (gt & 31) : tn * P.bn + gt, bc = b * nch + c;
             cst[gt] = (P.out_scale ? __ldg(P.out_scale + bc) : 1.f) * gain;
             cst[128 + gt] = (P.bias ? __ldg(P.bias + c) : 0.f) * gain;
             cst[256 + gt] = P.next_scale ? __ldg(P.next_scale + bc) : 0.f;
             if (RGB) {
               const float rs = __ldg(P.rgb_style + bc);
 #pragma unroll
-              for (int o = 0; o < 3; ++o) cst[384 + o * 128 + gt] = __ldg(P.rgb_w + o * P.Cout + c) * rs;
+              for (int o = 0; o < 3; ++o) cst[384 + o * 128 + gt] = __ldg(P.rgb_w + o * nch + c) * rs;
             }
           }
           named_bar_sync(bar_group, kT2EpiThreads);
         }
         const uint32_t sc_a = smem_u32(bars->ts_consts(group, (int)gen));
+
+        if constexpr (!TR && MT == 2 && KSTEPS == 4 && WRES && RGB) {
+          if (P.pair) {
+            // ---------------------------------------------------------------- x-pair mode (32-channel RGB-only layer)
+            // Accumulator row r = the pixel PAIR (j0 + 16*half + sy, 2*(i0 + sx) + a): columns [0,32) hold pixel a = 0,
+            // [32,64) pixel a = 1 (the per-channel constants were staged from arrays expanded to 64 entries).  Both
+            // pixels are finished here: noise, bias, leaky-ReLU, ToRGB dot product, skip upsample, image store.
+            constexpr int kW = 16, kPlane = 10 * kW * 4, kRow = kW * 4;
+            const int m = half;
+            float nzp[2] = {0.f, 0.f};
+            if (has_noise) {
+#pragma unroll
+              for (int a = 0; a < 2; ++a)
+                nzp[a] = nw * lds_f32(eb + (uint32_t)((((m * kSubTileH + sy) * kW) + 2 * sx + a) * 4));
+            }
+            float init[2][3];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int o = 0; o < 3; ++o) init[a][o] = rgbb[o];
+            if (has_skip) {
+              // half-resolution column of pixel (.., 2*(i0+sx)+a) is i0 + sx + a - 1; the box starts at column i0 - 4
+              const uint32_t sb0 = eb + (uint32_t)P.e_noise_bytes + (uint32_t)(m * P.skip_box_bytes) +
+                                   (uint32_t)((((sy + 1) >> 1) * kW + sx + 3) * 4);
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                const float ax0 = a ? P.kf[1] : P.kf[0], ax1 = a ? P.kf[3] : P.kf[2];
+                const uint32_t sb = sb0 + (uint32_t)(a * 4);
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                  const float t00 = lds_f32(sb + o * kPlane), t01 = lds_f32(sb + o * kPlane + 4);
+                  const float t10 = lds_f32(sb + o * kPlane + kRow), t11 = lds_f32(sb + o * kPlane + kRow + 4);
+                  init[a][o] += cy0 * fmaf(ax1, t01, ax0 * t00) + cy1 * fmaf(ax1, t11, ax0 * t10);
+                }
+              }
+            }
+            mbar_arrive(&bars->e_empty[es]);
+            const uint32_t ci = seq & nbuf_mask;
+            const uint32_t t_addr = t_lane + ci * (uint32_t)(NG * MT * P.bn) + (uint32_t)(m * P.bn);
+            if (ok) ok = mbar_wait(&bars->acc_full[ci], (seq >> nbuf_shift) & 1u, abort_flag);
+            tc_fence_after();
+            if (dbg_on) P.dbg[seq * 8 + 6] = clock64();
+            uint64_t racc[2][3];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int o = 0; o < 3; ++o) racc[a][o] = 0ull;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              const uint64_t nz2 = pack2(nzp[a], nzp[a]);
+#pragma unroll
+              for (int c16 = 0; c16 < 32; c16 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + (uint32_t)(a * 32 + c16), v);
+                tmem_ld_wait();
+                if (a == 1 && c16 == 16) {   // this thread's last TMEM read of the tile: hand the buffer back
+                  tc_fence_before();
+                  mbar_arrive(&bars->acc_empty[ci]);
+                }
+                const uint32_t ca = sc_a + (uint32_t)((a * 32 + c16) * 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint64_t a01, a23, b01, b23, w01[3], w23[3];
+                  lds_2x2(ca + e * 16, a01, a23);
+                  lds_2x2(ca + 512 + e * 16, b01, b23);
+#pragma unroll
+                  for (int o = 0; o < 3; ++o) lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01[o], w23[o]);
+                  uint64_t f01 = add2(fma2(pack2u(v[4 * e], v[4 * e + 1]), a01, b01), nz2);
+                  uint64_t f23 = add2(fma2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23, b23), nz2);
+                  const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
+                  float x0, x1, x2, x3, y0, y1, y2, y3;
+                  unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                  unpack2(g01, y0, y1); unpack2(g23, y2, y3);
+                  f01 = pack2(fmaxf(x0, y0), fmaxf(x1, y1));
+                  f23 = pack2(fmaxf(x2, y2), fmaxf(x3, y3));
+#pragma unroll
+                  for (int o = 0; o < 3; ++o) racc[a][o] = fma2(f23, w23[o], fma2(f01, w01[o], racc[a][o]));
+                }
+              }
+            }
+            const int oy = j0 + m * kSubTileH + sy, ox = 2 * (i0 + sx);
+            if (oy < P.OH && ox < P.OW_real && ok) {
+              const int64_t plane = (int64_t)P.OH * P.OW_real;
+              const int64_t di = ((int64_t)b * 3 * P.OH + oy) * P.OW_real + ox;
+#pragma unroll
+              for (int o = 0; o < 3; ++o) {
+                float l0, h0, l1, h1;
+                unpack2(racc[0][o], l0, h0);
+                unpack2(racc[1][o], l1, h1);
+                const float v0 = init[0][o] + (l0 + h0), v1 = init[1][o] + (l1 + h1);
+                if (P.rgb_bf16) {
+                  *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(P.rgb) + di + o * plane) =
+                      __floats2bfloat162_rn(v0, v1);
+                } else {
+                  *reinterpret_cast<float2*>(reinterpret_cast<float*>(P.rgb) + di + o * plane) = make_float2(v0, v1);
+                }
+              }
+            }
+            if (dbg_on) P.dbg[seq * 8 + 7] = clock64();
+            continue;
+          }
+        }
 
         // epilogue inputs staged by the producer's TMA boxes
         // noise of this thread's pixel(s): fused ToRGB -> sub-tiles half*NP + p; otherwise one value per sub-tile
@@ -955,7 +1068,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           constexpr int kPlane = 10 * kSkipBoxW * 4, kRow = kSkipBoxW * 4;
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
-            const uint32_t sb = eb + skip_off + (uint32_t)(p * kSkipBoxBytes);
+            const uint32_t sb = eb + skip_off + (uint32_t)(p * P.skip_box_bytes);
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
               const float t00 = lds_f32(sb + o * kPlane), t01 = lds_f32(sb + o * kPlane + 4);
@@ -1443,6 +1556,7 @@ using namespace w2e;
 
 struct RgbArgs {
   const float* w; const float* style; const float* bias; const float* skip; const float* host_taps1d; void* rgb; int rgb_dtype;
+  int pair;   // x-pair mode: the tensors describe pixel PAIRS (Cin = Cout = 64, in_w = image width / 2), see w2e_modconv_tc2_rgb_pair
 };
 
 struct FbArgs {   // fused up-convolution + Blur: the separable 4x4 FIR (flipped taps)
@@ -1521,6 +1635,13 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   const int row_bytes = P.bk * esize;
   P.mt = (P.grid_h > kSubTileH) ? 2 : 1;
   // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
+  const bool pair = rgb && rgb->pair;
+  if (pair) {
+    W2E_CHECK_ARG(!transposed && !out && !out_mod && Cin == 64 && Cout == 64 && in_h > kSubTileH && in_h % 2 == 0 && !tf32 && !view,
+                  "modconv_tc2_rgb_pair: needs the RGB-only 32-channel layer (as 64-channel pixel pairs), even height");
+    P.pair = 1;
+    P.OW_real = 2 * in_w;
+  }
   const bool mt4 = allow_mt4 && g_ts_mode != 0 && rgb && !out && !out_mod && Cin == 32 && Cout == 32 && in_h >= 64;
   if (mt4) P.mt = 4;
   // Transposed conv: 4 parity classes x MT sub-tiles x bn columns must fit 512 TMEM columns.  Measured (B=32):
@@ -1584,7 +1705,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   if (rgb && nbuf_plain != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
   if (transposed && !fb) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
   if (noise && !fb) ts = ts && (P.OW * 4) % 16 == 0 && (((uintptr_t)noise & 15) == 0);
-  if (rgb && rgb->skip) ts = ts && ((P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
+  if (rgb && rgb->skip) ts = ts && ((pair ? P.OW : P.OW / 2) * 4) % 16 == 0 && (((uintptr_t)rgb->skip & 15) == 0);
   if (out) ts = ts && (((uintptr_t)out & 15) == 0);
   if (out_mod) ts = ts && (((uintptr_t)out_mod & 15) == 0);
   if (rgb && P.bn != Cout && !rgb_split) ts = false;
@@ -1613,10 +1734,12 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       if (!fb && n_out > P.ts_slots) continue;
       P.ts_unit_bytes = 128 * P.ts_unit_ch * 2;
       P.use_e = 1;
-      P.e_noise_bytes = P.mt == 4 ? 2048 : 1024;
-      P.e_info_off = P.e_noise_bytes + ((rgb && rgb->skip) ? P.mt * kSkipBoxBytes : 0);
+      P.e_noise_bytes = (P.mt == 4 || pair) ? 2048 : 1024;
+      P.skip_box_bytes = pair ? 2048 : kSkipBoxBytes;
+      const int skip_w = pair ? 16 : kSkipBoxW, noise_w_px = pair ? 2 * kTileW : kTileW;
+      P.e_info_off = P.e_noise_bytes + ((rgb && rgb->skip) ? P.mt * P.skip_box_bytes : 0);
       P.e_stage_bytes = P.e_info_off + 128;
-      P.e_bytes = (noise ? kTileW * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * kSkipBoxW * 4 : 0);
+      P.e_bytes = (noise ? noise_w_px * kSubTileH * P.mt * 4 : 0) + ((rgb && rgb->skip) ? P.mt * 3 * 10 * skip_w * 4 : 0);
       ts_bytes = fb ? 64 * 1024 : (n_out ? 2 * 2 * P.ts_slots * P.ts_unit_bytes : 0);
       if (fb) { P.e_bytes = 0; P.e_info_off = 0; P.e_stage_bytes = 128; }
       extra = 1024 /*alignment of the staging area*/ + kEStages * P.e_stage_bytes;
@@ -1713,22 +1836,25 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-class accumulator hand-over (transposed conv with a single accumulator set); flag bit 8 = off (A/B)
   P.percls = (transposed && ts && !fb && P.nbuf == 1 && P.bgroup == 3 && !(g_flags & 256)) ? 1 : 0;
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
+  if (pair && !(ts && P.wres && P.mt == 2 && P.bk == 64))
+    return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_rgb_pair: needs the staged epilogue with resident weights");
   if (clipped_out && !ts)
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_view: a clipped / accumulating output needs the TMA-store epilogue "
                                           "(more than 16 rows, 32..128-column tiles)");
   if (ts && !fb) {
     if (noise) {
-      const uint64_t dims[3] = {(uint64_t)P.OW, (uint64_t)P.OH, (uint64_t)noise_batch};
-      const uint64_t strides[2] = {(uint64_t)P.OW * 4, (uint64_t)P.OH * P.OW * 4};
-      const uint32_t box[3] = {(uint32_t)kTileW, (uint32_t)(kSubTileH * P.mt), 1u};
+      const uint64_t ow = pair ? (uint64_t)P.OW_real : (uint64_t)P.OW;
+      const uint64_t dims[3] = {ow, (uint64_t)P.OH, (uint64_t)noise_batch};
+      const uint64_t strides[2] = {ow * 4, (uint64_t)P.OH * ow * 4};
+      const uint32_t box[3] = {(uint32_t)(pair ? 2 * kTileW : kTileW), (uint32_t)(kSubTileH * P.mt), 1u};
       int rc = make_f32_map(&M.noise, noise, 3, dims, strides, box);
       if (rc) return rc;
     }
     if (rgb && rgb->skip) {
-      const uint64_t h2 = (uint64_t)P.OH / 2, w2 = (uint64_t)P.OW / 2;
+      const uint64_t h2 = (uint64_t)P.OH / 2, w2 = pair ? (uint64_t)P.OW : (uint64_t)P.OW / 2;   // (pairs = half-res columns)
       const uint64_t dims[3] = {w2, h2, (uint64_t)B * 3};
       const uint64_t strides[2] = {w2 * 4, h2 * w2 * 4};
-      const uint32_t box[3] = {(uint32_t)kSkipBoxW, 10u, 3u};
+      const uint32_t box[3] = {(uint32_t)(pair ? 16 : kSkipBoxW), 10u, 3u};
       int rc = make_f32_map(&M.skip, rgb->skip, 3, dims, strides, box);
       if (rc) return rc;
     }
@@ -1848,9 +1974,29 @@ extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* o
                                    int in_w, int act, const float* rgb_w, const float* rgb_style, const float* rgb_bias,
                                    const float* rgb_skip, const float* host_taps1d, void* rgb, int rgb_dtype,
                                    const w2e_tc2_config* cfg, void* stream) {
-  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb, rgb_dtype};
+  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb, rgb_dtype, 0};
   return run_tc2(xs, w, out_scale, bias, noise, noise_w, noise_batch, next_scale, out, out_mod, error_flag, B, Cin, Cout,
                  in_h, in_w, 0, act, &a, cfg, stream);
+}
+
+// x-pair mode of the RGB-only 32 -> 32 channel layer (the last layer of the 1024^2 generator: 13 % of a step).  A
+// tcgen05.mma with N = 32 costs 44 cycles, one with N = 64 only 48 (operand fetch, tools/umma_bench.cu), so the layer is
+// run on PIXEL PAIRS: the channels-last input [B,H,W,32] IS [B,H,W/2,64] (a pair's 2 x 32 channels are contiguous), the
+// output pair has 2 x 32 = 64 channels, and the 3x3 kernel becomes a 3x3 kernel over pairs whose left / right taps use
+// only one pixel of the neighbouring pair: 3 x (2 + 4 + 2) K steps of N = 64 per 128 pairs instead of 2 x 18 of N = 32
+// per 256 pixels (1152 vs 1584 cycles).  w_pair: bf16 [9][64][64] pair weights,
+// w_pair[ky*3+dj+1][a*32+o][b*32+c] = W[ky][2dj+b-a+1][o][c] (zero where that tap index falls outside 0..2);
+// out_scale [B,32], bias [32], rgb_w [3,32], rgb_style [B,32]: the ordinary 32-channel arrays (the epilogue indexes them
+// with column & 31); H, W: the image size in pixels (W a multiple of 16); everything else as w2e_modconv_tc2_rgb.
+extern "C" int w2e_modconv_tc2_rgb_pair(const void* xs, const void* w_pair, const float* out_scale, const float* bias,
+                                        const float* noise, const float* noise_w, int noise_batch, int* error_flag, int B,
+                                        int H, int W, int act, const float* rgb_w, const float* rgb_style,
+                                        const float* rgb_bias, const float* rgb_skip, const float* host_taps1d, void* rgb,
+                                        int rgb_dtype, const w2e_tc2_config* cfg, void* stream) {
+  W2E_CHECK_ARG(W > 0 && W % 16 == 0, "modconv_tc2_rgb_pair: the width must be a multiple of 16");
+  const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb, rgb_dtype, 1};
+  return run_tc2(xs, w_pair, out_scale, bias, noise, noise_w, noise_batch, nullptr, nullptr, nullptr, error_flag, B, 64, 64,
+                 H, W / 2, 0, act, &a, cfg, stream);
 }
 
 

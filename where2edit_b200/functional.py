@@ -56,6 +56,23 @@ class PackedWeight:
             self.tc = self.dgr.to(torch.bfloat16).contiguous()
         return self.tc
 
+    def tc_pair(self):
+        """bf16 [9][2*Cout][2*Cin]: the 3x3 kernel over horizontally adjacent PIXEL PAIRS (w2e_modconv_tc2_rgb_pair):
+        pair tap (ky, dj) connects input pixel b of pair i+dj to output pixel a of pair i through kx = 2*dj + b - a + 1."""
+        if getattr(self, "_tc_pair", None) is None:
+            w = self.dgr                                   # [9][Cout][Cin] fp32, tap = ky*3 + kx
+            co, ci = self.cout, self.cin
+            wp = torch.zeros((9, 2 * co, 2 * ci), device=w.device, dtype=torch.float32)
+            for ky in range(3):
+                for dj in (-1, 0, 1):
+                    for a in (0, 1):
+                        for b in (0, 1):
+                            kx = 2 * dj + b - a + 1
+                            if 0 <= kx <= 2:
+                                wp[ky * 3 + dj + 1, a * co:(a + 1) * co, b * ci:(b + 1) * ci] = w[ky * 3 + kx]
+            self._tc_pair = wp.to(torch.bfloat16).contiguous()
+        return self._tc_pair
+
     def tc_dgrad(self, dtype=torch.bfloat16):
         """[k*k][Cin][Cout] with the taps flipped: the dgrad of a same-padded 3x3 convolution is the same
         convolution kernel run on the upstream gradient with input/output channels swapped."""
