@@ -492,8 +492,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (32; 16 for --workload train)")
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--image-dtype", default="bf16", choices=["bf16", "fp32"],
-                    help="dtype of the images the last layer writes / the caller receives")
+    ap.add_argument("--image-dtype", default="bf16", choices=["bf16", "fp32", "u8"],
+                    help="dtype of the images the last layer writes / the caller receives (u8: the save_image quantisation)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="images of the CPU-baseline sample (0 = skip)")
     ap.add_argument("--layers-out", default=None, help="write the per-launch trace of one step to this JSON file")
     ap.add_argument("--verify", action="store_true", help="N > 1: check the gathered images slot by slot (default on)")
@@ -528,8 +528,10 @@ def main():
     from where2edit_b200 import _native as N
     from where2edit_b200 import parallel
     gen = make_generator(args.size, args.precision, dev)
-    img_dtype = torch.bfloat16 if (args.image_dtype == "bf16" and args.precision == "bf16") else torch.float32
-    img_name = "bf16" if img_dtype == torch.bfloat16 else "f32"
+    img_dtype = torch.float32
+    if args.precision == "bf16" and args.image_dtype != "fp32":
+        img_dtype = torch.bfloat16 if args.image_dtype == "bf16" else torch.uint8
+    img_name = {torch.bfloat16: "bf16", torch.float32: "f32", torch.uint8: "u8"}[img_dtype]
     gen.set_image_output(img_dtype)
     # Multi-GPU: the persistent convolution kernels normally occupy every SM, so the NCCL all-gather kernels of
     # the previous step could only run in the gaps between them; leaving a few SMs free lets the collective
@@ -687,12 +689,40 @@ def main():
 
     e2e_value, d2h = measure_e2e(img_dtype, K_)
     h2d = host_w[0].numel() * 4
-    e2e_f32 = None
+    e2e_f32 = e2e_u8 = None
     if dist is None and img_dtype != torch.float32:
         v32, d32 = measure_e2e(torch.float32, max(5, K_ // 3))
         e2e_f32 = {"value": v32, "unit": UNIT, "d2h_bytes_per_step": d32,
                    "note": "same, with fp32 images (the reference's output dtype) copied out: PCIe-bound"}
+    if img_dtype != torch.uint8 and args.precision == "bf16" and (dist is None or peer is None):
+        v8, d8 = measure_e2e(torch.uint8, max(5, K_ // 3))
+        e2e_u8 = {"value": v8, "unit": UNIT, "d2h_bytes_per_step": d8,
+                  "note": "same, with uint8 images (the save_image quantisation the reference applies to its results, "
+                          "done by the last layer's epilogue) copied out"}
     gen.set_image_output(img_dtype)
+
+    # ---------------- the host side's ceiling for `e2e`: the same device-to-host copies with NO kernels running, all ranks
+    # at once (pinned buffers of one step's images, as in the e2e loop).  e2e cannot exceed images / this time.
+    def d2h_ceiling(dtype, steps):
+        src = torch.zeros((B, 3, args.size, args.size), device=dev, dtype=dtype)
+        dst = [torch.empty(src.shape, dtype=dtype).pin_memory() for _ in range(2)]
+        for i in range(2):
+            dst[i].copy_(src, non_blocking=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            dst[i % 2].copy_(src, non_blocking=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item()) / 1e3
+        nbytes = src.numel() * src.element_size()
+        return {"aggregate_gb_per_s": world * nbytes * steps / sec / 1e9, "images_per_s_ceiling": world * B * steps / sec,
+                "image_dtype": {torch.bfloat16: "bf16", torch.float32: "f32", torch.uint8: "u8"}[dtype]}
+
+    host_ceiling = d2h_ceiling(img_dtype, max(5, K_ // 3))
 
     # ---------------- per-kernel roofline from one traced step (CUDA events around every launch)
     roofline = roofline_up = None
@@ -767,6 +797,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "image_dtype": img_name},
             "e2e_fp32_images": e2e_f32,
+            "e2e_u8_images": e2e_u8,
+            "e2e_d2h_ceiling": host_ceiling,
             "gpu_launches": launches,
             "gather_ok": gather_ok,
             "roofline": roofline, "roofline_upfirdn2d": roofline_up,

@@ -38,6 +38,9 @@ extern "C" {
 
 #define W2E_F32 0
 #define W2E_BF16 1
+#define W2E_U8 2   /* image outputs only: uint8 by the quantisation of torchvision.utils.save_image(normalize=True,
+                      range=(-1, 1)), which the reference applies to its results (attention/run_attention.py:1470, 1535):
+                      u8 = trunc(clamp((clamp(v, -1, 1) + 1) / 2 * 255 + 0.5, 0, 255))                              */
 
 #define W2E_ACT_NONE 0
 #define W2E_ACT_LRELU 1
@@ -204,7 +207,7 @@ int w2e_modconv_tc2(const void* xs, const void* w, const float* out_scale, const
  * is produced without re-reading the activation; out and out_mod may then both be NULL.
  * rgb_w: float [3,Cout] pre-scaled by 1/sqrt(Cout); rgb_skip: float [B,3,in_h/2,in_w/2] or NULL;
  * host_taps1d: the 4 taps of the separable skip filter (with gain); rgb: [B,3,in_h,in_w] of rgb_dtype
- * (W2E_F32 or W2E_BF16: the image in the dtype the caller wants, straight from the epilogue).
+ * (W2E_F32, W2E_BF16 or W2E_U8: the image in the dtype the caller wants, straight from the epilogue).
  * Needs Cout <= 512 (the rgb image must be fp32 and zero-initialised when Cout >= 256: two channel blocks add
  * into it) and in_h > 16.                                                                        */
 int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, const float* bias,

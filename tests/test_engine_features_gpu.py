@@ -86,6 +86,36 @@ def test_image_in_the_callers_dtype_and_buffer():
         gen.set_image_output(torch.float16)
 
 
+@pytest.mark.parametrize("size", [64, 256, 1024])
+def test_uint8_image_is_the_save_image_quantisation_of_the_fp32_image(size):
+    """set_image_output(torch.uint8): the last layer's epilogue (64^2: the conversion after an fp32 ToRGB sum; 256^2: the
+    staged epilogue; 1024^2: the pixel-pair kernel) quantises exactly like torchvision.utils.save_image(normalize=True,
+    range=(-1, 1)) quantises the reference's results (run_attention.py:1470) -- bit-exact against that arithmetic applied
+    to the fp32 image of the same kernels"""
+    gen = build(size)
+    w = synth.make_wplus(1, gen.n_latent, seed=4).to(DEV)
+    with torch.no_grad():
+        img, _ = gen([w], input_is_latent=True, randomize_noise=False)
+        c = float(img.abs().max()) / 1.25          # the image is linear in the ToRGB weights: bring it to about [-1.25, 1.25]
+        for m in [gen.to_rgb1] + list(gen.to_rgbs):
+            m.conv.weight.div_(c)
+            m.bias.div_(c)
+        gen._engine = None
+        img32, _ = gen([w], input_is_latent=True, randomize_noise=False)
+        assert 1.0 < float(img32.abs().max()) < 1.6
+        gen.set_image_output(torch.uint8)
+        img8, _ = gen([w], input_is_latent=True, randomize_noise=False)
+        gen.assert_ok()
+    assert img8.dtype == torch.uint8 and img8.shape == img32.shape
+    t = img32.clone().clamp_(min=-1.0, max=1.0)     # torchvision make_grid norm_ip(img, low, high)
+    t.sub_(-1.0).div_(max(1.0 - (-1.0), 1e-5))
+    want = t.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)   # torchvision save_image
+    assert torch.equal(img8, want)
+    hist = torch.bincount(img8.flatten().long(), minlength=256)
+    assert int((hist > 0).sum()) > 200               # the whole range is exercised, a clamped end included
+    assert int(hist[0]) + int(hist[255]) > 0
+
+
 @pytest.mark.parametrize("amp_dtype", [torch.float16, torch.bfloat16])
 def test_public_modules_under_autocast(amp_dtype):
     """the reference's --amp wraps mapper + generator in torch.cuda.amp.autocast (run_attention.py:1231,1386): the

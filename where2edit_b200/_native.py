@@ -17,7 +17,7 @@ _I = ctypes.c_int
 _L = ctypes.c_int64
 _F = ctypes.c_float
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_LRELU = 0, 1
 
 # name -> (restype, argtypes)   -- must mirror include/w2e.h exactly (tests check every symbol)
@@ -284,6 +284,8 @@ def dtype_code(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.uint8:   # image outputs only (W2E_U8)
+        return U8
     raise RuntimeError(f"where2edit_b200: unsupported dtype {t.dtype} (float32 or bfloat16)")
 
 

@@ -78,8 +78,9 @@ struct Tc2Params {
   const float* rgb_style;   // [B,Cout]
   const float* rgb_bias;    // [3] or null
   const float* rgb_skip;    // [B,3,OH/2,OW/2] fp32 NCHW or null
-  void* rgb;                // [B,3,OH,OW] NCHW, fp32 or (rgb_bf16) bf16: the image in the dtype the caller wants
-  int rgb_bf16;
+  void* rgb;                // [B,3,OH,OW] NCHW, fp32, (rgb_bf16 == 1) bf16 or (rgb_bf16 == 2) uint8: the image in the dtype
+  int rgb_bf16;             // the caller wants; uint8 = the quantisation of torchvision.utils.save_image(normalize=True,
+                            // range=(-1, 1)) that the reference applies to its results (run_attention.py:1470, 1535)
   float kf[4];              // flipped 1-D taps of the skip upsample filter
   int noise_per_sample;
   int B, Cin, Cout, OH, OW;
@@ -124,6 +125,15 @@ struct Tc2Bars {
   __device__ __forceinline__ float* ts_consts(int group, int cb) { return &ep_scale[0][0] + (group * 2 + cb) * 768; }
 };
 static_assert(offsetof(Tc2Bars, ep_rgb) - offsetof(Tc2Bars, ep_scale) == 3 * 512 * sizeof(float), "ep arrays must be contiguous");
+
+// uint8 image: exactly the fp32 operation sequence of torchvision's make_grid(normalize=True, value_range=(-1, 1)) followed
+// by save_image's mul(255).add_(0.5).clamp_(0, 255).to(uint8): clamp, - low, / (high - low), * 255, + 0.5, clamp, truncate.
+__device__ __forceinline__ uint8_t quant_u8(float v) {
+  float t = fminf(fmaxf(v, -1.f), 1.f);
+  t = __fmul_rn(__fadd_rn(t, 1.f), 0.5f);   // (division by 2 is exact)
+  t = __fadd_rn(__fmul_rn(t, 255.f), 0.5f);
+  return (uint8_t)fminf(fmaxf(t, 0.f), 255.f);
+}
 
 // Tile coordinates advanced without divisions: tile = ((tn*B + b)*tiles_y + ty)*tiles_x + tx and
 // the per-CTA stride is decomposed once in the same mixed radix.
@@ -1031,7 +1041,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 unpack2(racc[0][o], l0, h0);
                 unpack2(racc[1][o], l1, h1);
                 const float v0 = init[0][o] + (l0 + h0), v1 = init[1][o] + (l1 + h1);
-                if (P.rgb_bf16) {
+                if (P.rgb_bf16 == 2) {
+                  *reinterpret_cast<uchar2*>(reinterpret_cast<uint8_t*>(P.rgb) + di + o * plane) =
+                      make_uchar2(quant_u8(v0), quant_u8(v1));
+                } else if (P.rgb_bf16) {
                   *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(P.rgb) + di + o * plane) =
                       __floats2bfloat162_rn(v0, v1);
                 } else {
@@ -1242,6 +1255,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 // two channel blocks (Cout = 256 as two 128-column tiles): both ADD their partial sums to the zero-
                 // initialised image; two addends commute, so the result does not depend on the arrival order
                 if (P.tiles_n > 1) atomicAdd(reinterpret_cast<float*>(P.rgb) + di + o * plane, v);
+                else if (P.rgb_bf16 == 2) reinterpret_cast<uint8_t*>(P.rgb)[di + o * plane] = quant_u8(v);
                 else if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di + o * plane] = __float2bfloat16_rn(v);
                 else reinterpret_cast<float*>(P.rgb)[di + o * plane] = v;
               }
@@ -1479,7 +1493,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             const int64_t di = (((int64_t)me.b * 3 + o) * P.OH + oy) * P.OW + ox;
-            if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di] = __float2bfloat16_rn(rgb_acc[o]);   // (tiles_n == 1)
+            if (P.rgb_bf16 == 2) reinterpret_cast<uint8_t*>(P.rgb)[di] = quant_u8(rgb_acc[o]);   // (tiles_n == 1)
+            else if (P.rgb_bf16) reinterpret_cast<__nv_bfloat16*>(P.rgb)[di] = __float2bfloat16_rn(rgb_acc[o]);
             else if (P.tiles_n > 1) atomicAdd(reinterpret_cast<float*>(P.rgb) + di, rgb_acc[o]);
             else reinterpret_cast<float*>(P.rgb)[di] = rgb_acc[o];
           }
@@ -1605,10 +1620,10 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
                   "modconv_tc2_rgb: the fused ToRGB needs a plain conv with Cout <= 512 and more than %d rows", kSubTileH);
     W2E_CHECK_ARG(rgb->skip == nullptr || (rgb->host_taps1d && in_h % 2 == 0 && in_w % 2 == 0),
                   "modconv_tc2_rgb: skip needs taps and even H, W");
-    W2E_CHECK_ARG(rgb->rgb_dtype == W2E_F32 || (rgb->rgb_dtype == W2E_BF16 && Cout < 256),
-                  "modconv_tc2_rgb: rgb_dtype must be W2E_F32, or W2E_BF16 with Cout < 256");
+    W2E_CHECK_ARG(rgb->rgb_dtype == W2E_F32 || ((rgb->rgb_dtype == W2E_BF16 || rgb->rgb_dtype == W2E_U8) && Cout < 256),
+                  "modconv_tc2_rgb: rgb_dtype must be W2E_F32, or W2E_BF16 / W2E_U8 with Cout < 256");
     P.rgb_w = rgb->w; P.rgb_style = rgb->style; P.rgb_bias = rgb->bias; P.rgb_skip = rgb->skip; P.rgb = rgb->rgb;
-    P.rgb_bf16 = rgb->rgb_dtype == W2E_BF16 ? 1 : 0;
+    P.rgb_bf16 = rgb->rgb_dtype == W2E_BF16 ? 1 : (rgb->rgb_dtype == W2E_U8 ? 2 : 0);
     if (rgb->skip)
       for (int i = 0; i < 4; ++i) P.kf[i] = rgb->host_taps1d[3 - i];
   }

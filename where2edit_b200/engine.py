@@ -416,7 +416,7 @@ class SynthesisEngine:
                 captured.append(self._to_nchw(act))
             style_vector.append(s.reshape(batch, 1, -1, 1, 1))
         if skip.dtype != self.image_dtype:   # image produced by an unfused ToRGB / blend (fp32): convert once
-            skip = skip.to(self.image_dtype)
+            skip = K.quantize_u8(skip) if self.image_dtype == torch.uint8 else skip.to(self.image_dtype)
         if self.image_out is not None and skip.data_ptr() != self.image_out.data_ptr() \
                 and tuple(self.image_out.shape) == tuple(skip.shape):
             self.image_out.copy_(skip)

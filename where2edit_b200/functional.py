@@ -25,6 +25,14 @@ def round_tf32(t):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def quantize_u8(img):
+    """fp32 image in [-1, 1] -> uint8 exactly as torchvision.utils.save_image(normalize=True, range=(-1, 1)) quantises the
+    reference's results (run_attention.py:1470, 1535): clamp, (v + 1) / 2, * 255, + 0.5, clamp, truncate.  The last
+    layer's epilogue does this in registers (W2E_U8); this is the same arithmetic for images that did not come out of it."""
+    t = img.to(torch.float32).clamp(-1.0, 1.0).add(1.0).mul(0.5)
+    return t.mul(255.0).add(0.5).clamp(0.0, 255.0).to(torch.uint8)
+
+
 class PackedWeight:
     """Batch-shared layouts of one ModulatedConv2d weight [1,Cout,Cin,k,k], pre-multiplied by the
     equalised-lr scale 1/sqrt(Cin*k*k) (model.py:216-217):

@@ -371,11 +371,13 @@ class Generator(nn.Module):
 
     def set_image_output(self, dtype=torch.float32, buffer=None):
         """bf16 no-grad mode only: the dtype the LAST layer's epilogue writes the image in (torch.float32 like the
-        reference, or torch.bfloat16: half the bytes for a caller that gathers or copies the images out) and,
+        reference; torch.bfloat16: half the bytes for a caller that gathers or copies the images out; torch.uint8: a
+        quarter -- the quantisation torchvision.utils.save_image(normalize=True, range=(-1, 1)) applies when the
+        reference writes its results, run_attention.py:1470/1535, functional.quantize_u8 is the same arithmetic) and,
         optionally, a caller-owned contiguous [B,3,H,W] buffer of that dtype to write it into (e.g. this rank's slot
         of a peer-mapped all-gather buffer, parallel.PeerGather.own).  The buffer is used when its batch matches."""
-        if dtype not in (torch.float32, torch.bfloat16):
-            raise ValueError("image dtype must be torch.float32 or torch.bfloat16")
+        if dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            raise ValueError("image dtype must be torch.float32, torch.bfloat16 or torch.uint8")
         if buffer is not None and (buffer.dtype != dtype or not buffer.is_contiguous()):
             raise ValueError("image buffer must be contiguous and of the requested dtype")
         self.image_dtype, self.image_out = dtype, buffer
