@@ -253,6 +253,13 @@ int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, 
                          void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h, int in_w,
                          int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask, int out_h, int out_w,
                          int accumulate, const w2e_tc2_config* cfg, void* stream);
+/* Fused dgrad of the transposed x2 convolution (conv_transpose2d(stride 2) of models/stylegan2/model.py:249-258; autograd
+ * reaches it from attention/run_attention.py:1419 and mapper/training/coach.py:91): gx [B,h,w,Cout] from the upstream
+ * gradient gz [B,2h+1,2w+1,Cin] (channels-last bf16) in one launch, gx[j,i] = sum_{ky,kx} gz[2j+ky,2i+kx] . w[ky*3+kx] with
+ * w bf16 [9][Cout][Cin]; out_scale [B,Cout] or NULL.  W2E_ERR_UNSUPPORTED when the weights do not fit in shared memory
+ * next to the four parity-class tiles of gz (use w2e_modconv_tc2_view per class then).                                 */
+int w2e_modconv_tc2_dgrad_up(const void* gz, const void* w, const float* out_scale, void* gx, int* error_flag, int B,
+                             int Cin, int Cout, int h, int w_, const w2e_tc2_config* cfg, void* stream);
 
 /* tf32 mode (north_star (1): "bf16 and tf32 modes"): the same kernel with fp32 tensors in HBM (channels-last
  * activations xs / out / out_mod, weights [9][Cout][Cin]) read by tcgen05.mma kind::tf32 (10-bit mantissa operands,

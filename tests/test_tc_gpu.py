@@ -292,7 +292,7 @@ def test_pixel_pair_last_layer_agrees_with_the_pixel_kernel(eng, b, h, rgb_dtype
 
 
 @pytest.mark.parametrize("b,cin,cout,h,up", [(2, 64, 32, 40, True), (1, 128, 64, 24, True), (2, 256, 128, 20, True),
-                                             (2, 64, 64, 48, False)])
+                                             (2, 64, 64, 48, False), (2, 32, 32, 72, False)])
 def test_staged_and_direct_epilogues_agree_bitwise(eng, b, cin, cout, h, up):
     """the TMA-store epilogue (two MMA issuers, edge-tile tap masking, unit split) and the direct-store
     epilogue are two schedules of the same arithmetic: results must be bit-identical"""

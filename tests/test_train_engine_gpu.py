@@ -200,7 +200,7 @@ def test_backward_kernels_against_torch_formulas():
 
 
 @pytest.mark.parametrize("cin,cout,h", [(64, 32, 20), (256, 128, 24), (512, 512, 8), (64, 32, 40), (256, 128, 32),
-                                        (128, 64, 36), (512, 256, 32), (512, 512, 33)])
+                                        (128, 64, 36), (512, 256, 32), (512, 512, 33), (64, 32, 129)])
 def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     """four strided-view launches with 4 / 2 / 2 / 1 taps + sum4 == the gradient of conv_transpose2d(stride 2)"""
     from where2edit_b200 import train_engine
@@ -210,6 +210,12 @@ def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     weight = synth.make_tensor((1, cout, cin, 3, 3), 91).to(DEV)
     pw = K.PackedWeight(weight, 1 / (cin * 9) ** 0.5, None)
     gz = torch.randn(b, 2 * h + 1, 2 * h + 1, cout, device=DEV).to(torch.bfloat16)
+    # 64 -> 32 channels: ONE launch (w2e_modconv_tc2_dgrad_up: four class tiles, one accumulator); otherwise per class
+    before = N.STATS.launches.get("w2e_modconv_tc2_dgrad_up", 0)
+    fused = eng._dgrad_up(gz, pw, h, h)
+    eng.assert_ok()
+    assert N.STATS.launches.get("w2e_modconv_tc2_dgrad_up", 0) - before == (1 if (cin, cout) == (64, 32) and h > 16 else 0)
+    eng.dgrad_up_fused = False
     got = eng._dgrad_up(gz, pw, h, h)          # (h >= 32: accumulated in place by TMA reduce-add)
     eng.assert_ok()
     eng.dgrad_up_in_place = False
@@ -222,3 +228,5 @@ def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     want = x.grad.permute(0, 2, 3, 1)
     scale = float(want.abs().max())
     assert max_abs(got.double().cpu(), want.cpu()) <= 1.5e-2 * scale
+    # the fused launch rounds once (fp32 accumulation of all nine taps), the per-class launches once per class
+    assert max_abs(fused.double().cpu(), want.cpu()) <= 8e-3 * scale

@@ -21,7 +21,8 @@ def main():
     gen._engine = E.SynthesisEngine(gen)
     eng = gen._engine
     # (name, ts_mode, flags, cluster_log2, blur variant): per-call switches, no library-global state
-    settings = [("default", 1, 0, 0, "auto"), ("no per-class hand-over", 1, 256, 0, "auto"), ("last layer not on pixel pairs", 1, 0, 0, "auto")]
+    settings = [("default", 1, 0, 0, "auto"), ("no per-class hand-over", 1, 256, 0, "auto"),
+                ("last layer not on pixel pairs", 1, 0, 0, "auto")]
     if len(sys.argv) > 2:
         settings = [("default", 1, 0, 0, "auto")] + [(a, *[(v if v == "auto" else int(v)) for v in a.split(",")])
                                                      for a in sys.argv[2:]]

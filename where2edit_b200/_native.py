@@ -48,6 +48,7 @@ PROTOTYPES = {
     "w2e_modconv_tc2_rgb_pair": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P, _P]),
     "w2e_modconv_tc2_tf32": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
+    "w2e_modconv_tc2_dgrad_up": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "w2e_modconv_tc2_view": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P, _P]),
     "w2e_grad_assemble_workspace": (_L, [_I, _L, _I]),
     "w2e_grad_assemble_nhwc": (_I, [_P] * 8 + [_I, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P]),
@@ -170,6 +171,9 @@ def load():
             return _lib
         path = _build.LIB
         stale = os.path.exists(path) and os.path.exists(_build.STAMP) and not _build.is_current()
+        alt = os.environ.get("W2E_LIB_PATH")   # kernel A/B only (tools/): another build of the same ABI
+        if alt:
+            path, stale = alt, False
         if not os.path.exists(path) or stale or (os.environ.get("W2E_REBUILD") == "1"):
             # a stale library would be called through mismatched prototypes: rebuild it, or refuse to load it
             try:
@@ -185,12 +189,16 @@ def load():
             try:
                 fn = getattr(lib, name)
             except AttributeError as e:
+                if alt:        # an older build under test (tools/): entry points added since are simply absent
+                    continue
                 raise RuntimeError(f"where2edit_b200: {path} does not export {name}") from e
             fn.restype = res
             fn.argtypes = args
         proxy = _Lib()
         proxy.cdll = lib
         for name in PROTOTYPES:
+            if alt and not hasattr(lib, name):
+                continue
             setattr(proxy, name, _wrap(name, getattr(lib, name)))
         _lib = proxy
     return _lib

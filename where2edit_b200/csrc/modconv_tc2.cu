@@ -65,6 +65,8 @@ struct Tc2Params {
   int pair;                 // x-pair mode of the 32-channel RGB-only layer (see run_tc2): accumulator row = TWO adjacent pixels
   int OW_real;              // pair mode: width of the image in pixels (OW counts pixel pairs)
   int skip_box_bytes;       // bytes of one sub-tile's skip patch in the epilogue-input stage
+  int dg4, cls16;           // fused dgrad of the transposed convolution (w2e_modconv_tc2_dgrad_up): an A stage holds the FOUR
+                            // parity-class tiles of the upstream gradient, cls16 = bytes of one class tile >> 4
   int percls;               // transposed conv, one accumulator set (4 classes x MT x bn = 512 TMEM columns): the classes
                             // are handed over one by one (see "per-class hand-over" in the kernel)
   int reduce_add;           // TS epilogue: `out` boxes are ADDED to global memory (TMA reduce) instead of stored
@@ -104,6 +106,7 @@ struct alignas(64) Tc2Maps {
   CUtensorMap skip;    // fp32 {OW/2, OH/2, B*3}, box {12, 10, 3}
   CUtensorMap bh;      // cluster mode: weight map with a half-block box {BK, bn/2, 1}
   CUtensorMap b3;      // grouped weight requests: box {BK, bn, 3} = the three taps of one kernel row
+  CUtensorMap a4[3];   // fused dgrad of the transposed convolution: parity classes (0,1), (1,0), (1,1) of the gradient (map_a = (0,0))
   CUtensorMap st[4];   // bf16 stores, box {unit_ch, 8, 16, 1}: plain [0] = out, [1] = out_mod; transposed [g] = class g of out
 };
 
@@ -189,6 +192,12 @@ template <bool TR>
 __device__ __forceinline__ constexpr bool tap_first(int t) {  // first tap (in issue order) of its accumulator
   return TR ? (t == 0 || t == 1 || t == 3 || t == 4) : (t == 0);
 }
+
+// Fused dgrad of the transposed x2 convolution: gx[j,i] = sum_{ky,kx} gz[2j+ky, 2i+kx] . W[ky,kx]^T.  With the gradient
+// split into its four parity classes gzc_(py,px)[r,s] = gz[2r+py, 2s+px] (strided TMA views), tap (ky,kx) reads class
+// (ky & 1, kx & 1) at offset (ky == 2, kx == 2): nine shifted reads of four class tiles, ONE accumulator.
+__device__ __forceinline__ constexpr int dg4_class(int t) { return ((t / 3) & 1) * 2 + ((t % 3) & 1); }
+__device__ __forceinline__ constexpr int dg4_rows(int t) { return ((t / 3) == 2 ? kPitch : 0) + ((t % 3) == 2 ? 1 : 0); }
 
 __device__ __forceinline__ uint32_t e_base_fb(uint8_t* smem, const Tc2Params& P) { return smem_u32(smem + P.e_off); }
 
@@ -317,8 +326,17 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (!ok) break;
           if (TS && P.dbg && blockIdx.x == 0 && kc == 0 && tile / (int)gridDim.x < 64) P.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
           mbar_arrive_expect_tx(&bars->a_full[ar.idx], (uint32_t)P.a_box_bytes);
-          tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
-                      j0 - 1, b);
+          if (!TR && !TS && MT == 1 && !RGB && !TF32 && P.dg4) {   // (compile-time gate: only this instantiation has the mode)
+            // the four parity-class tiles of the gradient (rows j0 .. j0+16*MT, columns i0 .. i0+8 of every class view)
+            uint8_t* dst = a_base + (size_t)ar.idx * P.a_stage_bytes;
+            tma_load_4d(dst, &map_a, &bars->a_full[ar.idx], kc * kBK, i0, j0, b);
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+              tma_load_4d(dst + ((size_t)(c * P.cls16) << 4), &M.a4[c - 1], &bars->a_full[ar.idx], kc * kBK, i0, j0, b);
+          } else {
+            tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
+                        j0 - 1, b);
+          }
           ar.advance(P.a_stages);
           if (!WRES && !TS) {
             const bool edge_y = TR && !(P.flags & 1) && j0 >= P.grid_h - 1;   // see the MMA issuer
@@ -505,6 +523,36 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (dbg_on && kc == 0) P.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
         if (WRES) {
           uint32_t b_lo = b_lo0 + (uint32_t)(kc * 9) * b_block16;
+          if constexpr (!TR && TS) {
+            // plain conv: the three tap ROWS as a rolled loop (a third of the code: the issuing warp shares its scheduler's
+            // instruction cache with four epilogue warps)
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t a_row = a_lo + (uint32_t)(ky * kPitch * kRowBytes / 16);
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int t = ky * 3 + kx;
+                if ((P.tap_mask >> t) & 1) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m) {
+                    constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
+                    const uint32_t a_tap = a_row + (uint32_t)(kx * kRowBytes / 16 + m * kSub16);
+                    const uint32_t first = (t == first_tap && kc == 0) ? 0u : 1u;
+                    if (leader) {
+                      const bool pr = KSTEPS == 4 && P.pair;
+                      const int kfirst = (pr && kx == 0) ? 2 : 0;
+#pragma unroll
+                      for (int k = 0; k < KSTEPS; ++k) {
+                        if (pr && ((kx == 0 && k < 2) || (kx == 2 && k >= 2))) continue;
+                        umma_bf16_lohi(dcol[m], a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == kfirst ? first : 1u);
+                      }
+                    }
+                  }
+                }
+                b_lo += b_block16;
+              }
+            }
+          } else {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if (!((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) && (TR || ((P.tap_mask >> t) & 1))) {
@@ -513,7 +561,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (m == 1 && edge_y) continue;
                 constexpr int kSub16 = kSubTileH * kPitch * kRowBytes / 16;
                 const int ai = tap_group<TR>(t) * MT + m;
-                const uint32_t a_tap = a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
+                // (the fused dgrad of the transposed convolution only exists in this instantiation: the issue loop of the
+                // 32-channel kernels is issue-bound, and a run-time select per MMA cost them 0.50 -> 0.73 ms at 1024^2)
+                constexpr bool kDg4 = !TR && !TS && MT == 1 && !RGB && !TF32;
+                const uint32_t a_tap = (kDg4 && P.dg4)
+                    ? a_lo + (uint32_t)(dg4_class(t) * P.cls16 + dg4_rows(t) * kRowBytes / 16 + m * kSub16)
+                    : a_lo + (uint32_t)(tap_rows<TR>(t) * kRowBytes / 16 + m * kSub16);
                 uint32_t first = 1u;
                 if (TR) {
                   first = (kc == 0 && !((started >> ai) & 1u)) ? 0u : 1u;
@@ -536,6 +589,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               }
             }
             b_lo += b_block16;
+          }
           }
           if (leader) umma_commit(&bars->a_empty[ar.idx]);
         } else if (TS && P.bgroup == 3) {
@@ -1427,10 +1481,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int e4 = 0; e4 < 4; ++e4) {
               const float4 a4 = *reinterpret_cast<const float4*>(sc + c + 4 * e4);
               const float4 b4 = *reinterpret_cast<const float4*>(sh + c + 4 * e4);
-              f[4 * e4 + 0] = fmaf(__uint_as_float(v[4 * e4 + 0]), a4.x, b4.x + nzv);
-              f[4 * e4 + 1] = fmaf(__uint_as_float(v[4 * e4 + 1]), a4.y, b4.y + nzv);
-              f[4 * e4 + 2] = fmaf(__uint_as_float(v[4 * e4 + 2]), a4.z, b4.z + nzv);
-              f[4 * e4 + 3] = fmaf(__uint_as_float(v[4 * e4 + 3]), a4.w, b4.w + nzv);
+              // (acc * scale + bias) + noise, the operation order of the staged epilogue: the two are bit-identical
+              f[4 * e4 + 0] = fmaf(__uint_as_float(v[4 * e4 + 0]), a4.x, b4.x) + nzv;
+              f[4 * e4 + 1] = fmaf(__uint_as_float(v[4 * e4 + 1]), a4.y, b4.y) + nzv;
+              f[4 * e4 + 2] = fmaf(__uint_as_float(v[4 * e4 + 2]), a4.z, b4.z) + nzv;
+              f[4 * e4 + 3] = fmaf(__uint_as_float(v[4 * e4 + 3]), a4.w, b4.w) + nzv;
             }
             if (lrelu) {
 #pragma unroll
@@ -1583,6 +1638,8 @@ struct ViewArgs {   // plain conv on a strided view of a channels-last tensor, w
   int tap_mask;
   int out_h, out_w;   // extent of the `out` buffer ([B,out_h,out_w,Cout], <= the convolution grid: the rest is clipped)
   int reduce;         // 1: add the result to `out` (TMA reduce) instead of storing it
+  int dg4;            // fused dgrad of the transposed convolution: xs = the (2 in_h + 1) x (2 in_w + 1) upstream gradient, read
+                      // through its four parity-class views; the strides / tap mask above are not used
 };
 
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
@@ -1630,7 +1687,11 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.pitch = kPitch;
   P.ntaps = 9;
   P.tap_mask = 0x1ff;
-  if (view) {
+  const bool dg4 = view && view->dg4;
+  if (dg4) {
+    W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_dgrad_up: plain bf16 convolution only");
+    P.dg4 = 1;
+  } else if (view) {
     W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_view: plain bf16 convolution only");
     W2E_CHECK_ARG(view->tap_mask > 0 && view->tap_mask <= 0x1ff, "modconv_tc2_view: tap mask %d", view->tap_mask);
     W2E_CHECK_ARG(view->stride_x > 0 && (view->stride_x * 2) % 16 == 0 && (view->stride_y * 2) % 16 == 0 &&
@@ -1657,6 +1718,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     P.pair = 1;
     P.OW_real = 2 * in_w;
   }
+  // fused dgrad of the transposed convolution: an A stage is four class tiles, so 128-pixel tiles (direct-store epilogue)
+  if (dg4) P.mt = 1;
   const bool mt4 = allow_mt4 && g_ts_mode != 0 && rgb && !out && !out_mod && Cin == 32 && Cout == 32 && in_h >= 64;
   if (mt4) P.mt = 4;
   // Transposed conv: 4 parity classes x MT sub-tiles x bn columns must fit 512 TMEM columns.  Measured (B=32):
@@ -1667,7 +1730,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // A 256-pixel x 256-column tile fills the 512 TMEM columns, so MMA and epilogue alternate (measured 0.51 ms against
   // 0.27 ms of MMAs); 128 columns leave room for two accumulator sets and the staged 16-warp epilogue, and the two
   // column tiles add their partial ToRGB sums into the zero-initialised image.  Flag bit 7 = off (A/B).
-  const bool clipped_out = view && (view->reduce || view->out_h != in_h || view->out_w != in_w);   // needs the TMA-store epilogue
+  const bool clipped_out = view && !dg4 && (view->reduce || view->out_h != in_h || view->out_w != in_w);   // needs the TMA-store epilogue
   const bool rgb_split = !transposed && rgb && Cout == 256 && g_ts_mode != 0 && !(g_flags & 128) && in_h > kSubTileH &&
                          rgb->rgb_dtype == W2E_F32;
   const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : ((rgb_split || clipped_out) ? 128 : 256);
@@ -1694,6 +1757,11 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.box_rows = kSubTileH * P.mt + 2;
   P.a_box_bytes = P.box_rows * P.pitch * row_bytes;
   P.a_stage_bytes = (P.a_box_bytes + 1023) / 1024 * 1024;
+  if (dg4) {
+    P.cls16 = P.a_stage_bytes >> 4;
+    P.a_box_bytes *= 4;
+    P.a_stage_bytes *= 4;
+  }
   P.b_block_bytes = P.bn * row_bytes;
   P.tiles_x = ceil_div(P.grid_w, kTileW);
   P.tiles_y = ceil_div(P.grid_h, kSubTileH * P.mt);
@@ -1799,18 +1867,35 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   W2E_CHECK_ARG(smem_bytes > 0 && smem_bytes <= 227 * 1024, "modconv_tc2: %d bytes of shared memory needed", smem_bytes);
 
   CUtensorMap ma, mb;
+  Tc2Maps M;
+  memset(&M, 0, sizeof(M));
+  if (dg4 && !P.wres)
+    return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_dgrad_up: needs weights resident in shared memory (Cin %d, Cout %d)", Cin, Cout);
   {
     const uint64_t es = (uint64_t)esize;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
-    if (view) {
+    if (view && !dg4) {
       strides[0] = (uint64_t)view->stride_x * es; strides[1] = (uint64_t)view->stride_y * es;
       strides[2] = (uint64_t)view->stride_b * es;
     }
     const uint32_t box[4] = {(uint32_t)P.bk, (uint32_t)P.pitch, (uint32_t)P.box_rows, 1u};
-    int rc = tf32 ? make_f32_swizzled_map(&ma, xs, 4, dims, strides, box, row_bytes)
-                  : make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
-    if (rc) return rc;
+    if (dg4) {
+      // class (py, px) of the [B, 2h+1, 2w+1, Cin] gradient: pixels (2r+py, 2s+px), extent (h+1-py) x (w+1-px)
+      const uint64_t zh = 2 * (uint64_t)in_h + 1, zw = 2 * (uint64_t)in_w + 1;
+      const uint64_t cstrides[3] = {2 * (uint64_t)Cin * es, 2 * zw * Cin * es, zh * zw * Cin * es};
+      for (int c = 0; c < 4; ++c) {
+        const int py = c >> 1, px = c & 1;
+        const uint64_t cdims[4] = {(uint64_t)Cin, (uint64_t)(in_w + 1 - px), (uint64_t)(in_h + 1 - py), (uint64_t)B};
+        const __nv_bfloat16* base = (const __nv_bfloat16*)xs + ((int64_t)py * (int64_t)zw + px) * Cin;
+        int rc = make_bf16_map(c == 0 ? &ma : &M.a4[c - 1], base, 4, cdims, cstrides, box, row_bytes);
+        if (rc) return rc;
+      }
+    } else {
+      int rc = tf32 ? make_f32_swizzled_map(&ma, xs, 4, dims, strides, box, row_bytes)
+                    : make_bf16_map(&ma, xs, 4, dims, strides, box, row_bytes);
+      if (rc) return rc;
+    }
   }
   {
     const uint64_t es = (uint64_t)esize;
@@ -1821,8 +1906,6 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
                   : make_bf16_map(&mb, w, 3, dims, strides, box, row_bytes);
     if (rc) return rc;
   }
-  Tc2Maps M;
-  memset(&M, 0, sizeof(M));
   // 2-CTA clusters: the pair works on the same tile of two consecutive samples and shares every weight block
   int clog = g_cluster_mode;
   while (clog > 0 && (B % (1 << clog) != 0 || (P.bn >> clog) < 8)) --clog;
@@ -1967,9 +2050,25 @@ extern "C" int w2e_modconv_tc2_view(const void* xs, const void* w, const float* 
                                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                                     int in_w, int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
                                     int out_h, int out_w, int accumulate, const w2e_tc2_config* cfg, void* stream) {
-  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate};
+  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate, 0};
   return run_tc2(xs, w, out_scale, nullptr, nullptr, nullptr, 0, next_scale, out, out_mod, error_flag, B, Cin, Cout, in_h,
                  in_w, 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
+}
+
+// Fused dgrad of the transposed x2 convolution (conv_transpose2d(stride 2), models/stylegan2/model.py:249-258): the input
+// gradient gx [B,h,w,Cout] from the upstream gradient gz [B,2h+1,2w+1,Cin] in ONE launch,
+//   gx[j,i] = sum_{ky,kx} gz[2j+ky, 2i+kx] . w[ky*3+kx],   w: bf16 [9][Cout][Cin] (the forward weight, equalised-lr scale folded in),
+// the four parity classes of gz read through strided TMA views and all nine taps accumulated in one TMEM accumulator:
+// gz is read once and gx written once (w2e_modconv_tc2_view x 4 re-reads gx three times through its reduce-adds).
+// Returns W2E_ERR_UNSUPPORTED when the nine weight blocks do not fit in shared memory next to the four class tiles
+// (then the per-class launches are the path).  out_scale [B,Cout] (or NULL) multiplies the result.
+extern "C" int w2e_modconv_tc2_dgrad_up(const void* gz, const void* w, const float* out_scale, void* gx, int* error_flag,
+                                        int B, int Cin, int Cout, int h, int w_, const w2e_tc2_config* cfg, void* stream) {
+  ViewArgs v;
+  memset(&v, 0, sizeof(v));
+  v.tap_mask = 0x1ff; v.out_h = h; v.out_w = w_; v.dg4 = 1;
+  return run_tc2(gz, w, out_scale, nullptr, nullptr, nullptr, 0, nullptr, gx, nullptr, error_flag, B, Cin, Cout, h, w_, 0,
+                 W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
 
 // tf32 mode (north star item 1: "bf16 and tf32 modes"): xs / w / out / out_mod are fp32 (channels-last activations,

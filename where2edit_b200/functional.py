@@ -92,6 +92,13 @@ class PackedWeight:
             self._tc_dgrad = self.fwd.flip(0).to(torch.bfloat16).contiguous()
         return self._tc_dgrad
 
+    def tc_dgrad_up_fused(self):
+        """bf16 [9][Cin][Cout] (tap = ky*3 + kx of the forward kernel): operand of w2e_modconv_tc2_dgrad_up, the one-launch
+        dgrad of the transposed (x2) convolution -- gx[j,i] = sum gz[2j+ky, 2i+kx] . W[ky,kx]^T."""
+        if getattr(self, "_tc_dgrad_up_fused", None) is None:
+            self._tc_dgrad_up_fused = self.fwd.to(torch.bfloat16).contiguous()
+        return self._tc_dgrad_up_fused
+
     def tc_dgrad_up(self, dtype=torch.bfloat16):
         """{(py, px): bf16 [9][Cin][Cout]} -- dgrad of the transposed (x2) convolution as four plain convolutions,
         one per output-parity class of the upstream gradient: class (py, px) holds gz[2j+py, 2i+px] and contributes

@@ -37,6 +37,7 @@ class _Saved:
 
 
 class TrainEngine(SynthesisEngine):
+    dgrad_up_fused = True      # A/B switch: False = never the one-launch dgrad of the transposed convolution
     dgrad_up_in_place = True   # A/B switch: False = always separate class results + w2e_sum4_nhwc
 
     # ------------------------------------------------------------------ forward (keeps what the backward needs)
@@ -165,8 +166,21 @@ class TrainEngine(SynthesisEngine):
         run per output-parity class of gz (strided views) with the taps that class feeds, then summed."""
         b, zh, zw, c = gz.shape
         lib = N.load()
-        wts = pw.tc_dgrad_up()
         out = torch.empty((b, h, w, pw.cin), device=gz.device, dtype=torch.bfloat16)
+        if self.dgrad_up_fused and 9 * pw.cin * pw.cout * 2 <= 80 * 1024 and h > 16:
+            # one launch: the four parity-class tiles of gz feed one accumulator (gz read once, gx written once); only
+            # where the nine weight blocks fit in shared memory next to them (the 64 -> 32 channel layer)
+            N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"dgrad up {pw.cout}->{pw.cin}@{h}x{w} fused")
+            rc = lib.w2e_modconv_tc2_dgrad_up(N.ptr(gz), N.ptr(pw.tc_dgrad_up_fused()), None, N.ptr(out),
+                                              N.ptr(self.error_flag(gz.device)), b, pw.cout, pw.cin, h, w,
+                                              N.tc2_cfg(self.tc2_cfg), N.stream_ptr())
+            if rc != N.ERR_UNSUPPORTED:
+                N.check(rc, "modconv_tc2_dgrad_up")
+                return out
+            N.STATS.launches["w2e_modconv_tc2_dgrad_up"] -= 1
+            if N.STATS.trace:
+                N.STATS.trace.pop()
+        wts = pw.tc_dgrad_up()
         # >= 32 rows: the four class launches accumulate IN PLACE (class 00 stores the h x w region, the others add to
         # it through TMA reduce-add); smaller maps: separate results + w2e_sum4_nhwc
         in_place = self.dgrad_up_in_place and h >= 32
