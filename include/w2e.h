@@ -269,6 +269,30 @@ int w2e_modconv_tc2_tf32(const float* xs, const float* w, const float* out_scale
                          float* out, float* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                          int in_w, int transposed, int act, const w2e_tc2_config* cfg, void* stream);
 
+/* ---- grouped region-attention heads of the cluster-style mapper ----
+ * attention/run_attention.py:803-806, 829-841: per captured generator feature map one 1x1 StyledConv(C_h -> 32)
+ * (models/stylegan2/model.py:234-290, 306-340, stylespace input) followed by F.interpolate(nearest) to size x size and
+ * the concatenation of all results.  ONE launch for all heads, evaluated only at the pixels that survive the resize:
+ *   out[b, 32 h + o, Y, X] = lrelu(d[b,o] * sum_c weight_h[o,c] style_h[b,c] feat_h[b,c,y,x] + nw_h noise_h + bias_h[o]) * sqrt2
+ * feat / weight / style / bias / noise_w / noise: HOST arrays of nheads device pointers -- feat_h float [B,chans[h],res[h],
+ * res[h]], weight_h [32,chans[h]] (equalised-lr scale folded in), style_h [B,chans[h]], bias_h [32], noise_w_h a device
+ * scalar, noise_h [B,r,r] with r = min(res[h], size) or NULL (noise / noise_w may be NULL altogether).
+ * out: float [B, 32 nheads, size, size]; demod: float [nheads, B, 32] (written; the backward reads it).  nheads <= 24.   */
+int w2e_attn_heads_fwd(int nheads, const float* const* feat, const int* chans, const int* res,
+                       const float* const* weight, const float* const* style, const float* const* bias,
+                       const float* const* noise_w, const float* const* noise, float* out, float* demod, int B, int size,
+                       void* stream);
+/* Backward of the above (the reference trains the heads, run_attention.py:725-735; the feature maps come from the frozen
+ * generator under no_grad, :1196-1203): gout / out [B, 32 nheads, size, size]; gacc: scratch of the same size;
+ * red: float [nheads, B, 3, 32] (written): [.,.,0,o] = d bias_h[o], [.,.,1,o] internal, [.,.,2,0] = d noise_w_h, per sample
+ * (the caller sums over B); dW / ds: HOST arrays of device pointers to the [32,chans[h]] / [B,chans[h]] gradients of
+ * weight_h / style_h (written, demodulation terms included).  Fixed-order reductions, no atomics.                       */
+int w2e_attn_heads_bwd(int nheads, const float* const* feat, const int* chans, const int* res,
+                       const float* const* weight, const float* const* style, const float* const* bias,
+                       const float* const* noise_w, const float* const* noise, const float* gout, const float* out,
+                       const float* demod, float* gacc, float* red, float* const* dW, float* const* ds, int B, int size,
+                       void* stream);
+
 /* ---- layout transforms (dtype = W2E_BF16 or W2E_F32: element type of the CHANNELS-LAST tensor) ----
  * x fp32 [Bx,C,HW] (Bx == 1 broadcasts, e.g. ConstantInput, model.py:293-303) -> y bf16 [B,HW,C],
  * multiplied by style[b,c] when style != NULL.                                                */

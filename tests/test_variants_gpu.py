@@ -113,3 +113,76 @@ def test_cluster_style_mapper_trains_every_parameter():
                if p.grad is None and not n.startswith("mapper_textca_") and ".conv.modulation." not in n]
     assert not missing, missing
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+def _cluster_mapper_setup(noise_weight):
+    import torch
+    sys.path.insert(0, ROOT)
+    import where2edit_b200 as w2e
+    from oracle import synth
+    from where2edit_b200 import mappers
+    dev = "cuda:0"
+    gen = w2e.Generator(64, 512, 8, channel_multiplier=2)
+    gen.load_state_dict(synth.make_state_dict(64, seed=0, perturbed=True), strict=True)
+    gen = gen.to(dev).eval()
+    with torch.no_grad():
+        _, _, styles, feats = gen([synth.make_wplus(3, gen.n_latent, seed=2).to(dev)], input_is_latent=True,
+                                  randomize_noise=False, return_features=True)
+        feats = list(feats) + [gen.input.input.repeat(3, 1, 1, 1)]
+    torch.manual_seed(5)
+    m = mappers.ClusterStyleMapper(gen.n_latent, 1024, 512, attention_layer=7, cluster_layer=7, clusters=4, channel_multiplier=2,
+                                   cluster_dim=feats[6].shape[1] + 2 * (feats[6].shape[1] // 16)).to(dev).train()
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.endswith("noise.weight"):
+                p.fill_(noise_weight)
+            elif name.endswith("activate.bias"):
+                p.normal_(0, 0.2)
+    text = torch.randn(3, 512, device=dev)
+    x = [torch.cat([text.unsqueeze(1), s[:, :, :, 0, 0]], dim=-1) for s in styles]
+    return m, x, feats
+
+
+@pytest.mark.parametrize("size,noise_weight", [(16, 0.0), (24, 0.3), (64, 0.3)])
+def test_grouped_attention_heads_match_the_per_head_modules(size, noise_weight):
+    """w2e_attn_heads_fwd / _bwd (one launch for all heads, only the pixels that survive the nearest resize) against one
+    StyledConv module call per head on the full-resolution maps -- the reference's formulation, run_attention.py:803-841:
+    outputs, and the gradient of every trained parameter.  Sizes below / between / at the feature resolutions
+    (4^2..64^2, non-integer ratios included); the noise of both paths comes from the same generator state."""
+    import torch
+    m, x, feats = _cluster_mapper_setup(noise_weight)
+    results = {}
+    for fused in (True, False):
+        m.fused_heads, m.sample_first = fused, fused
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(11)
+        out, final, (loss_delta, loss_reg, loss_tv) = m(x, feats, size)
+        loss = final.square().mean() + 0.1 * loss_reg + 0.1 * loss_tv + sum(s.square().mean() for s in out)
+        loss.backward()
+        results[fused] = (final.detach(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+    f1, g1 = results[True]
+    f0, g0 = results[False]
+    # (with noise the full-resolution modules draw it at the feature resolution and the resize keeps one value in k^2:
+    #  another sample of the same distribution -- only the noise-free case is comparable value by value)
+    if noise_weight == 0.0:
+        assert float((f1 - f0).abs().max()) <= 1e-5
+        assert set(g1) == set(g0)
+        for n in g0:
+            if n.endswith("noise.weight"):   # d/d(noise weight) = sum g * noise: other noise values at full resolution
+                continue
+            scale = float(g0[n].abs().max()) + 1e-12
+            assert float((g1[n] - g0[n]).abs().max()) <= 2e-3 * scale + 1e-9, n
+    else:
+        # same noise values in both paths when nothing is down-sampled after the head: sample_first on the module path
+        m.fused_heads, m.sample_first = False, True
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(11)
+        out, final, (loss_delta, loss_reg, loss_tv) = m(x, feats, size)
+        loss = final.square().mean() + 0.1 * loss_reg + 0.1 * loss_tv + sum(s.square().mean() for s in out)
+        loss.backward()
+        g2 = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+        assert float((f1 - final.detach()).abs().max()) <= 1e-5
+        assert set(g1) == set(g2)
+        for n in g2:
+            scale = float(g2[n].abs().max()) + 1e-12
+            assert float((g1[n] - g2[n]).abs().max()) <= 2e-3 * scale + 1e-9, n

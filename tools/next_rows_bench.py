@@ -156,6 +156,38 @@ def measure(iters=20):
     e_np, i_np = each[:4].cpu().numpy(), (ids[:4]).cpu().numpy()
     t0 = time.time()
     ro.region_attention(e_np, i_np, k)
+    # ---- cluster-style mapper (run_attention.py:703-893) over the features of a 1024^2 generator: attention heads on the
+    # pixels that survive the nearest resize to 64^2 against heads on the full-resolution maps (the reference's order)
+    try:
+        import where2edit_b200 as w2e
+        from where2edit_b200 import mappers
+        mb = 4
+        gen = w2e.Generator(1024, 512, 8, channel_multiplier=2, precision="bf16").to(dev).eval()
+        with torch.no_grad():
+            _, _, styles, feats = gen([torch.randn(mb, gen.n_latent, 512, device=dev)], input_is_latent=True,
+                                      randomize_noise=False, return_features=True)
+            feats = list(feats) + [gen.input.input.repeat(mb, 1, 1, 1)]
+        cl = next(i for i, f in enumerate(feats) if f.shape[1] >= 256 and f.shape[-1] == 64) + 1   # a 64^2 convolution feature
+        cdim = feats[cl - 1].shape[1] + 2 * (feats[cl - 1].shape[1] // 16)
+        cm = mappers.ClusterStyleMapper(gen.n_latent, 1024, 512, attention_layer=11, cluster_layer=cl, channel_multiplier=2,
+                                        clusters=10, cluster_dim=cdim).to(dev).eval()
+        text = torch.randn(mb, 512, device=dev)
+        xin = [torch.cat([text.unsqueeze(1), s_[:, :, :, 0, 0]], dim=-1) for s_ in styles]
+        res = {}
+        with torch.no_grad():
+            for fused, sample in ((True, True), (False, True), (False, False)):
+                cm.fused_heads, cm.sample_first = fused, sample
+                res[(fused, sample)] = gpu_ms(lambda: cm(xin, feats, 64), 3, warmup=1)
+        cm.fused_heads, cm.sample_first = True, True
+        out["cluster_style_mapper_fwd"] = {"shape": f"B={mb}, 26 feature maps of the 1024^2 generator, 64^2 attention map",
+                                           "ms": res[(True, True)], "per_head_modules_on_sampled_pixels_ms": res[(False, True)],
+                                           "per_head_modules_on_full_resolution_ms": res[(False, False)],
+                                           "note": "grouped launch of all attention heads (w2e_attn_heads_fwd) vs one "
+                                                   "StyledConv module call per head"}
+        del gen, cm, feats, styles
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["cluster_style_mapper_fwd"] = {"error": repr(exc)[:200]}
     out["region_attention_fwd"]["cpu_oracle_ms_per_64"] = (time.time() - t0) * 1e3 * 16
     x1 = small[:1].cpu().numpy()
     t0 = time.time()

@@ -48,6 +48,8 @@ PROTOTYPES = {
     "w2e_modconv_tc2_rgb_pair": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "w2e_modconv_tc2_upblur": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P, _P]),
     "w2e_modconv_tc2_tf32": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P] + [_I] * 7 + [_P, _P]),
+    "w2e_attn_heads_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "w2e_attn_heads_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "w2e_modconv_tc2_dgrad_up": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "w2e_modconv_tc2_view": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P, _P]),
     "w2e_grad_assemble_workspace": (_L, [_I, _L, _I]),
@@ -300,6 +302,11 @@ def dtype_code(t):
 def host_floats(values):
     arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
     return arr
+
+
+def host_ptrs(tensors):
+    """Host array of device pointers (NULL for None) for the grouped entry points."""
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
 
 
 def host_ints(values):

@@ -84,6 +84,8 @@ class ClusterStyleMapper(nn.Module):
     unmodified reference).  The reference trains the attention heads, so their convolution-weight gradients are
     switched on here (the frozen generator's stay off)."""
 
+    fused_heads = True    # A/B switch: False = one StyledConv module call per attention head (_attend)
+    sample_first = True   # A/B switch of _attend: False = the heads run on the full-resolution feature maps (as the reference)
     LAYER_NUM = (0, 2, 3, 5, 6, 8, 9, 11, 12, 14, 15, 17, 18, 20, 21, 23, 24)
     STYLE_LAYERS = (0, 2, 2, 3, 5, 5, 6, 8, 8, 9, 11, 11, 12, 14, 14, 15, 17, 17, 18, 20, 20, 21, 23, 23, 24, 26, 26)
 
@@ -127,9 +129,33 @@ class ClusterStyleMapper(nn.Module):
         self.initial_state = initial_state.to(self.initial_bias.device)
 
     def _attend(self, name, feature, text, size):
+        """One attention head: 1x1 StyledConv over a captured feature map, nearest-resized to `size`
+        (run_attention.py:803-806, 829-839).  A 1x1 modulated convolution, its noise / bias / leaky-ReLU and a
+        nearest-neighbour DOWN-sampling commute exactly (every output pixel depends on one input pixel), so a feature
+        map larger than `size` is sampled FIRST: the head then runs on size^2 pixels instead of up to 1024^2 (the
+        reference evaluates all of them and keeps one in 256).  Fresh noise (noise=None, model.py:286-288) is drawn for
+        the pixels that are kept.  Feature maps smaller than `size` go through the head first, as in the reference."""
         style = getattr(self, f"attention_textca_{name}")(text)
+        if self.sample_first and size is not None and feature.shape[-2] > size and feature.shape[-1] > size:
+            feature = torch.nn.functional.interpolate(feature, size)
         res, _ = getattr(self, f"attention_{name}")(feature, style.view(style.shape[0], 1, -1, 1, 1), input_is_stylespace=True)
-        return res if size is None else torch.nn.functional.interpolate(res, size)
+        if size is None or tuple(res.shape[-2:]) == (size, size):
+            return res
+        return torch.nn.functional.interpolate(res, size)
+
+    def _attend_all(self, names, features, text, size):
+        """Every attention head in ONE launch (region.attention_heads -> w2e_attn_heads_fwd / _bwd): the 18 stylespace
+        inputs from one GEMM over the concatenated `attention_textca_*` weights (they all read the same text feature),
+        the 1x1 StyledConvs + nearest resize + concatenation from one kernel that only evaluates the surviving pixels."""
+        from . import region
+        lins = [getattr(self, f"attention_textca_{n}") for n in names]
+        w = torch.cat([m.weight * m.scale for m in lins])
+        bias = torch.cat([m.bias * m.lr_mul for m in lins])
+        styles = torch.nn.functional.linear(text, w, bias).split([m.weight.shape[0] for m in lins], dim=1)
+        heads = [getattr(self, f"attention_{n}") for n in names]
+        weights = [h.conv.weight[0, :, :, 0, 0] * h.conv.scale for h in heads]
+        return region.attention_heads(features, weights, list(styles), [h.activate.bias for h in heads],
+                                      [h.noise.weight for h in heads], size)
 
     def forward(self, x, feature_map, size, attention_text=None):
         from . import region
@@ -138,7 +164,11 @@ class ClusterStyleMapper(nn.Module):
         if attention_text is None:
             attention_text = x_text
         choice_cluster = region.assign_clusters(feature_map[self.cluster_layer - 1], self.initial_state, size, self.clusters)
-        maps = [self._attend("first", feature_map[-1], attention_text, size)]
+        names = ["first"] + [c for c in range(len(x)) if c in self.LAYER_NUM]
+        head_feats = [feature_map[-1]] + [feature_map[c] for c in names[1:]]
+        fused = (self.fused_heads and len(names) <= 24 and
+                 all(f.is_cuda and not f.requires_grad and f.ndim == 4 and f.shape[2] == f.shape[3] for f in head_feats))
+        maps = [] if fused else [self._attend("first", feature_map[-1], attention_text, size)]
         styles, loss_delta = [], 0
         for c in range(len(x)):
             x_c = x[c][:, :, self.latent_dim:]
@@ -149,9 +179,10 @@ class ClusterStyleMapper(nn.Module):
                 loss_delta = loss_delta + torch.mean(torch.norm(x_new - x_c, dim=-1)) / float(self.mapper_layer)
                 x_c = x_new
             styles.append(x_c.unsqueeze(3).unsqueeze(3))
-            if c in self.LAYER_NUM:
+            if c in self.LAYER_NUM and not fused:
                 maps.append(self._attend(c, feature_map[c], attention_text, size))
-        logits = self._attend("last", torch.cat(maps, dim=1), attention_text, None)
+        all_maps = self._attend_all(names, head_feats, attention_text, size) if fused else torch.cat(maps, dim=1)
+        logits = self._attend("last", all_maps, attention_text, None)
         each = torch.sigmoid(logits + self.initial_bias).view(batch, size, size)
         final_map, _, loss_reg, loss_tv = region.region_attention(each, choice_cluster, self.clusters)
         return styles, final_map, [loss_delta, loss_reg, loss_tv]

@@ -152,4 +152,76 @@ def region_attention(each_attention_map, choice_cluster, clusters, threshold=0.8
     return _RegionAttention.apply(each, choice_cluster.contiguous(), clusters, float(threshold), float(margin))
 
 
-__all__ = ["assign_clusters", "region_attention", "gaussian_taps"]
+__all__ = ["assign_clusters", "region_attention", "gaussian_taps", "attention_heads"]
+
+
+class _AttentionHeads(torch.autograd.Function):
+    """All region-attention heads of the cluster-style mapper in one launch (csrc/attn_heads.cu): forward w2e_attn_heads_fwd,
+    backward w2e_attn_heads_bwd (gradients to every head's weight, style, bias and noise weight; the feature maps come
+    from the frozen generator and get none)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, size, feats, noises, *params):
+        n = len(feats)
+        weights, styles, biases, noise_ws = (list(params[i * n:(i + 1) * n]) for i in range(4))
+        weights = [w.contiguous() for w in weights]
+        styles = [s.contiguous() for s in styles]
+        biases = [b.contiguous() for b in biases]
+        noise_ws = [w.reshape(1).contiguous() for w in noise_ws]
+        b = feats[0].shape[0]
+        dev = feats[0].device
+        out = torch.empty((b, 32 * n, size, size), device=dev, dtype=torch.float32)
+        demod = torch.empty((n, b, 32), device=dev, dtype=torch.float32)
+        chans = [int(f.shape[1]) for f in feats]
+        res = [int(f.shape[2]) for f in feats]
+        N.check(N.load().w2e_attn_heads_fwd(
+            n, N.host_ptrs(feats), N.host_ints(chans), N.host_ints(res), N.host_ptrs(weights), N.host_ptrs(styles),
+            N.host_ptrs(biases), N.host_ptrs(noise_ws), N.host_ptrs(noises), N.ptr(out), N.ptr(demod), b, size,
+            N.stream_ptr()), "attn_heads_fwd")
+        ctx.heads = (size, feats, noises, weights, styles, biases, noise_ws, chans, res)
+        ctx.save_for_backward(out, demod)
+        return out
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, gout):
+        size, feats, noises, weights, styles, biases, noise_ws, chans, res = ctx.heads
+        out, demod = ctx.saved_tensors
+        n = len(feats)
+        b = out.shape[0]
+        gout = gout.to(torch.float32).contiguous()
+        gacc = torch.empty_like(out)
+        red = torch.empty((n, b, 3, 32), device=out.device, dtype=torch.float32)
+        dws = [torch.empty_like(w) for w in weights]
+        dss = [torch.empty_like(s) for s in styles]
+        N.check(N.load().w2e_attn_heads_bwd(
+            n, N.host_ptrs(feats), N.host_ints(chans), N.host_ints(res), N.host_ptrs(weights), N.host_ptrs(styles),
+            N.host_ptrs(biases), N.host_ptrs(noise_ws), N.host_ptrs(noises), N.ptr(gout), N.ptr(out), N.ptr(demod),
+            N.ptr(gacc), N.ptr(red), N.host_ptrs(dws), N.host_ptrs(dss), b, size, N.stream_ptr()), "attn_heads_bwd")
+        per_head = red.sum(1)                                   # [n, 3, 32]: the per-sample partials, summed over the batch
+        dbias = [per_head[h, 0] for h in range(n)]
+        dnw = [per_head[h, 2, 0:1] if noises[h] is not None else None for h in range(n)]
+        return (None, None, None, *dws, *dss, *dbias, *dnw)
+
+
+def attention_heads(feats, weights, styles, biases, noise_weights, size, noises=None):
+    """Grouped launch of the 1x1 StyledConv attention heads + nearest resize + concatenation (attention/run_attention.py:
+    803-806, 829-841).  feats[h]: [B,C_h,H_h,H_h] fp32 captured feature maps (no gradient: they come from the frozen
+    generator under no_grad, :1196-1203); weights[h]: [32,C_h] with the equalised-lr scale folded in; styles[h]: [B,C_h];
+    biases[h]: [32]; noise_weights[h]: scalar tensors; noises[h]: [B,r,r] with r = min(H_h, size), or None = fresh normal
+    noise at the head's own resolution (model.py:286-288).  Returns [B, 32 * len(feats), size, size]."""
+    N.require_cuda(*feats)
+    size = int(size)
+    fs = []
+    for f in feats:
+        if f.ndim != 4 or f.shape[2] != f.shape[3]:
+            raise ValueError(f"attention_heads: feature maps must be [B,C,H,H], got {tuple(f.shape)}")
+        if f.requires_grad:
+            raise ValueError("attention_heads: feature maps must not require grad (use the per-head modules instead)")
+        fs.append(f.detach().to(torch.float32).contiguous())
+    b = fs[0].shape[0]
+    if noises is None:
+        noises = [f.new_empty(b, 1, min(f.shape[2], size), min(f.shape[2], size)).normal_() for f in fs]   # (as NoiseInjection)
+    noises = [None if z is None else z.detach().to(torch.float32).contiguous() for z in noises]
+    return _AttentionHeads.apply(size, fs, noises, *weights, *styles, *biases, *noise_weights)
