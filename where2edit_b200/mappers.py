@@ -157,6 +157,25 @@ class ClusterStyleMapper(nn.Module):
         return region.attention_heads(features, weights, list(styles), [h.activate.bias for h in heads],
                                       [h.noise.weight for h in heads], size)
 
+    def _text_branches(self, x_text, n):
+        """`mapper_text_{c}(x_text).unsqueeze(1)` for c < n (run_attention.py:816-817): every branch reads the same text
+        feature, so the n first linears are ONE GEMM over the concatenated weights and the n second ones one batched
+        GEMM, each followed by one fused bias + leaky-ReLU launch over all branches."""
+        if n == 0:
+            return []
+        seqs = [getattr(self, f"mapper_text_{c}") for c in range(n)]
+        if not (self.fused_heads and x_text.is_cuda):
+            return [s(x_text).unsqueeze(1) for s in seqs]
+        from .op.fused_act import fused_leaky_relu
+        b = x_text.shape[0]
+        hid = seqs[0][0].weight.shape[0]
+        w1 = torch.cat([s[0].weight * s[0].scale for s in seqs])
+        h1 = fused_leaky_relu(torch.nn.functional.linear(x_text, w1), torch.cat([s[0].bias * s[0].lr_mul for s in seqs]))
+        w2 = torch.stack([s[1].weight * s[1].scale for s in seqs])                       # [n, 512, hid]
+        o2 = torch.bmm(h1.view(b, n, hid).transpose(0, 1), w2.transpose(1, 2))           # [n, B, 512]
+        o2 = fused_leaky_relu(o2.transpose(0, 1).reshape(b, -1), torch.cat([s[1].bias * s[1].lr_mul for s in seqs]))
+        return list(o2.view(b, n, 1, -1).unbind(1))
+
     def forward(self, x, feature_map, size, attention_text=None):
         from . import region
         batch = x[0].shape[0]
@@ -169,11 +188,12 @@ class ClusterStyleMapper(nn.Module):
         fused = (self.fused_heads and len(names) <= 24 and
                  all(f.is_cuda and not f.requires_grad and f.ndim == 4 and f.shape[2] == f.shape[3] for f in head_feats))
         maps = [] if fused else [self._attend("first", feature_map[-1], attention_text, size)]
+        text_hiddens = self._text_branches(x_text, min(len(x), self.mapper_layer))
         styles, loss_delta = [], 0
         for c in range(len(x)):
             x_c = x[c][:, :, self.latent_dim:]
             if c < self.mapper_layer:
-                text_hidden = getattr(self, f"mapper_text_{c}")(x_text).unsqueeze(1)
+                text_hidden = text_hiddens[c]
                 mixed = getattr(self, f"mapper_all_{c}")(torch.cat([getattr(self, f"mapper_{c}")(x_c), text_hidden], dim=-1))
                 x_new = x_c + 0.1 * (mixed - x_c)
                 loss_delta = loss_delta + torch.mean(torch.norm(x_new - x_c, dim=-1)) / float(self.mapper_layer)
