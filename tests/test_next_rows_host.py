@@ -101,3 +101,48 @@ def test_cluster_style_mapper_state_dict_equals_the_reference_layout():
         assert {k: list(v.shape) for k, v in m.state_dict().items()} == json.loads(str(g[f"{name}/keys"]))
         with pytest.raises(ValueError):
             m.store_clusters(torch.zeros(clusters + 1, 576))
+
+
+def test_save_image_oracle_equals_torchvision():
+    """oracle/save_image_oracle.py (the uint8 image output's checker) against torchvision.utils itself: make_grid's
+    normalisation followed by save_image's conversion, on values that cover both clamps and every level"""
+    import torchvision
+    from oracle import save_image_oracle as so
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand(1, 3, 64, 96, generator=g) * 2.6 - 1.3)
+    img[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, -0.999999, 0.999999, 1e-8, -1.5, 1.5])
+    grid = torchvision.utils.make_grid(img.clone(), nrow=1, normalize=True, value_range=(-1, 1), padding=0)
+    want = grid.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8).numpy()
+    got = so.quantise_ref(img[0].numpy())
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    assert len(np.unique(got)) == 256
+    # the host-side helper of the package is the same arithmetic (used when the image did not come out of the fused epilogue)
+    from where2edit_b200 import functional as K
+    assert np.array_equal(K.quantize_u8(img[0]).numpy(), want)
+
+
+def test_new_entry_points_reject_bad_arguments_without_touching_the_gpu():
+    """w2e_modconv_tc2_rgb_pair / _dgrad_up / w2e_attn_heads_fwd/_bwd: validation before any CUDA call"""
+    import ctypes
+    from where2edit_b200 import _native as N
+    lib = N.load()
+    one = 0x1000
+    INVALID = 1
+    # pair kernel: the width must be a multiple of 16
+    assert lib.w2e_modconv_tc2_rgb_pair(one, one, one, one, None, None, 0, None, 1, 64, 24, 1, one, one, None, None, None, one,
+                                        0, None, None) == INVALID
+    assert "multiple of 16" in N.last_error()
+    # fused transposed dgrad: null pointers
+    assert lib.w2e_modconv_tc2_dgrad_up(None, None, None, None, None, 1, 32, 64, 32, 32, None, None) == INVALID
+    # attention heads: head count, null tables, a head without feature map
+    ptrs = (ctypes.c_void_p * 1)(one)
+    null = (ctypes.c_void_p * 1)(None)
+    ints = (ctypes.c_int * 1)(32)
+    assert lib.w2e_attn_heads_fwd(0, ptrs, ints, ints, ptrs, ptrs, ptrs, None, None, one, one, 1, 16, None) == INVALID
+    assert lib.w2e_attn_heads_fwd(25, ptrs, ints, ints, ptrs, ptrs, ptrs, None, None, one, one, 1, 16, None) == INVALID
+    assert lib.w2e_attn_heads_fwd(1, None, ints, ints, ptrs, ptrs, ptrs, None, None, one, one, 1, 16, None) == INVALID
+    assert lib.w2e_attn_heads_fwd(1, null, ints, ints, ptrs, ptrs, ptrs, None, None, one, one, 1, 16, None) == INVALID
+    assert lib.w2e_attn_heads_fwd(1, ptrs, ints, ints, ptrs, ptrs, ptrs, None, ptrs, one, one, 1, 16, None) == INVALID  # noise, no weight
+    assert "noise" in N.last_error()
+    assert lib.w2e_attn_heads_bwd(1, ptrs, ints, ints, ptrs, ptrs, ptrs, None, None, one, one, one, one, one, None, None, 1, 16,
+                                  None) == INVALID

@@ -186,3 +186,47 @@ def test_grouped_attention_heads_match_the_per_head_modules(size, noise_weight):
         for n in g2:
             scale = float(g2[n].abs().max()) + 1e-12
             assert float((g1[n] - g2[n]).abs().max()) <= 2e-3 * scale + 1e-9, n
+
+
+@pytest.mark.parametrize("size", [12, 20, 32])
+def test_grouped_attention_heads_match_the_oracle(size):
+    """region.attention_heads (w2e_attn_heads_fwd) against the CPU oracle's restatement of one reference head
+    (StyledConv(C, 32, 1) with a stylespace input, run_attention.py:805 / :837) + F.interpolate(nearest): feature maps
+    below, at and above `size`, non-integer resize ratios, explicit noise"""
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import cluster_mapper_oracle as cmo
+    from oracle import stylegan2_oracle as orc
+    from where2edit_b200 import region
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(size)
+    b = 2
+    shapes = [(512, 4), (256, 16), (64, 32), (32, 48)]
+    feats, weights, styles, biases, nws, noises, want = [], [], [], [], [], [], []
+    for i, (c, h) in enumerate(shapes):
+        f = torch.randn(b, c, h, h, generator=g)
+        w = torch.randn(1, 32, c, 1, 1, generator=g)
+        st = 1 + 0.3 * torch.randn(b, c, generator=g)
+        bias = 0.2 * torch.randn(32, generator=g)
+        nw = torch.tensor([0.25 * (i + 1)])
+        r = min(h, size)
+        nz = torch.randn(b, 1, r, r, generator=g)
+        # oracle: the head at the feature's own resolution with the noise it would have drawn there, then the resize.  For a
+        # map larger than `size` the kept pixels' noise is what matters: place the [r, r] noise at the kept positions.
+        idx = torch.nn.functional.interpolate(torch.arange(h * h, dtype=torch.float32).view(1, 1, h, h), size).long().view(-1)
+        full = torch.zeros(b, 1, h * h)
+        if h > size:
+            full[:, :, idx] = nz.view(b, 1, -1)
+        else:
+            full = nz.view(b, 1, -1).clone()
+        sd = {"p.conv.weight": w, "p.conv.modulation.weight": None, "p.conv.modulation.bias": None,
+              "p.noise.weight": nw, "p.activate.bias": bias}
+        out, _ = orc._styled_conv({k: (v.double() if v is not None else None) for k, v in sd.items()}, "p", f.double(),
+                                  st.double().view(b, 1, -1, 1, 1), full.view(b, 1, h, h).double(), False, True)
+        want.append(torch.nn.functional.interpolate(out, size))
+        feats.append(f.to(dev)); weights.append((w[0, :, :, 0, 0] / c ** 0.5).to(dev)); styles.append(st.to(dev))
+        biases.append(bias.to(dev)); nws.append(nw.to(dev)); noises.append(nz.to(dev))
+    got = region.attention_heads(feats, weights, styles, biases, nws, size, noises=noises).cpu().double()
+    want = torch.cat(want, dim=1)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
