@@ -190,7 +190,8 @@ typedef struct w2e_tc2_config {
                          transposed conv, bit 5 128-pixel tiles (two accumulator sets) for the 64-channel one,
                          bit 6 one weight request per filter tap instead of one per tap row, bit 7 one 256-column
                          tile instead of two 128-column tiles for the 256-channel conv with fused ToRGB, bit 8 no
-                         per-class accumulator hand-over in the transposed conv                                  */
+                         per-class accumulator hand-over in the transposed conv, bit 9 no second planning pass with the
+                         weight ring when the staged epilogue does not fit next to resident weights              */
   int cluster_log2;   /* weight-ring kernels as clusters of 2^n CTAs with TMA-multicast weight blocks (0..3)  */
   void* timeline;     /* device long long[64][8] or NULL: clock64 stamps of CTA 0's first 64 tiles
                          (tools/tc2_timeline.py)                                                              */

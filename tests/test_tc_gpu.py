@@ -305,7 +305,8 @@ def test_staged_and_direct_epilogues_agree_bitwise(eng, b, cin, cout, h, up):
     try:
         # (ts_mode, flags, cluster_log2): the per-call w2e_tc2_config switches (include/w2e.h)
         for ts_mode, flags, clus in [(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (1, 0, 1), (0, 0, 1), (1, 8, 0),
-                                     (1, 16, 0), (1, 32, 0), (1, 64, 0), (1, 66, 0), (1, 256, 0), (1, 258, 0), (1, 257, 0)]:
+                                     (1, 16, 0), (1, 32, 0), (1, 64, 0), (1, 66, 0), (1, 256, 0), (1, 258, 0), (1, 257, 0),
+                                     (1, 512, 0)]:
             eng.tc2_cfg = N.tc2_config(ts_mode=ts_mode, flags=flags, cluster_log2=clus)
             outs.append(run_layer(eng, layer, x, s, noise, nxt))
     finally:

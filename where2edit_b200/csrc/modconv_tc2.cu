@@ -1650,7 +1650,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-call tuning / A-B switches (include/w2e.h: w2e_tc2_config); NULL = defaults
   const int g_max_ctas = cfg ? cfg->max_ctas : 0;
   const int g_ts_mode = cfg ? cfg->ts_mode : 1;
-  const int g_flags = cfg ? (cfg->flags & 507) : 0;
+  const int g_flags = cfg ? (cfg->flags & 1019) : 0;
   const int g_cluster_mode = cfg ? (cfg->cluster_log2 < 0 ? 0 : (cfg->cluster_log2 > 3 ? 3 : cfg->cluster_log2)) : 0;
   long long* const g_dbg = cfg ? (long long*)cfg->timeline : nullptr;
   W2E_CHECK_ARG(xs && w && (out || out_mod || rgb), "modconv_tc2: null pointer");
@@ -1807,7 +1807,18 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   const Cand cands_std[5] = {{64, 2}, {64, 1}, {32, 2}, {32, 1}, {0, 0}};
   const Cand cands_small[5] = {{32, 2}, {32, 1}, {64, 2}, {64, 1}, {0, 0}};
   const Cand* cands = small_units ? cands_small : cands_std;
-  for (int ci = ts ? 0 : 4; ci < 5 && smem_bytes == 0; ++ci) {
+  // Candidates 0..3 (staged epilogue) are tried twice when the weights could be resident: first with resident weights, then
+  // -- if no staged plan fits next to them -- with the weight RING, which needs less shared memory; only then the direct-
+  // store epilogue.  (64 -> 64 @512^2 with both outputs and the fused ToRGB, the training forward: 74 KB of weights + two
+  // A stages leave no room for the staging slots, and the 8-warp direct-store epilogue took 0.74 ms at batch 16 against
+  // 0.31 ms for the one-output inference launch.)  Flag bit 9 = off (A/B).
+  const bool can_be_resident = Cout / P.bn == 1 && w_bytes <= 80 * 1024;
+  const bool ring_retry = ts && can_be_resident && !fb && !pair && !dg4 && !(g_flags & 512);
+  const int n_plans = ring_retry ? 9 : 5;
+  for (int pi = ts ? 0 : (n_plans - 1); pi < n_plans && smem_bytes == 0; ++pi) {
+    // plan index -> (candidate, weights may be resident): 0..3 staged + resident, [4..7 staged + ring,] last = direct store
+    const int ci = pi == n_plans - 1 ? 4 : pi % 4;
+    const bool allow_wres = !(ring_retry && pi >= 4 && pi < 8);
     const bool use_ts = cands[ci].unit_ch != 0;
     int extra = 0, ts_bytes = 0;
     if (use_ts) {
@@ -1831,7 +1842,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     }
     const int smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - kBarsBytes - extra;
     P.a_stages = kchunks == 1 ? 3 : 2;
-    P.wres = (P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
+    P.wres = (allow_wres && P.tiles_n == 1 && w_bytes <= 80 * 1024) ? 1 : 0;
     int b_bytes = 0;
     if (P.wres) {
       if (use_ts) P.a_stages = kT2MaxA;   // epilogue-bound layers: a deep A ring hides the DRAM latency of the tile loads
