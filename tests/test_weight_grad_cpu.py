@@ -71,3 +71,18 @@ def test_enable_weight_gradients_marks_every_modulated_conv():
     assert all(c.conv.weight_grad for c in m)
     w2e.enable_weight_gradients(m, False)
     assert not any(c.conv.weight_grad for c in m)
+
+
+def test_trained_weights_are_repacked_after_a_data_write():
+    """Optimisers that write through `.data` (the reference's Ranger, mapper/training/ranger.py:155-162) do not bump the
+    tensor's version counter; a module whose weight is being trained must not serve a cached layout of the old weight."""
+    import where2edit_b200 as w2e
+    m = w2e.ModulatedConv2d(8, 4, 1, 8)
+    m.weight_grad = True
+    before = m.packed().rgb.clone()
+    v = m.weight._version
+    m.weight.data.copy_(m.weight.data * 2)
+    assert m.weight._version == v                        # the hazard: nothing tells the cache that the weight changed
+    assert torch.allclose(m.packed().rgb, 2 * before)
+    m.weight_grad = False                                # frozen modules keep the cache (keyed on pointer / version / device)
+    assert m.packed() is m.packed()

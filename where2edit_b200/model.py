@@ -189,7 +189,10 @@ class ModulatedConv2d(nn.Module):
         """Batch-shared weight layouts (K.PackedWeight), cached per weight version/device."""
         w = self.weight
         key = (w.data_ptr(), w._version, str(w.device))
-        if self._packed is None or self._packed.key != key:
+        # A weight that is being TRAINED (weight_grad, e.g. the cluster mapper's attention heads) is repacked on every
+        # call: optimisers that write through `.data` (the reference's Ranger, mapper/training/ranger.py:155-162) do not
+        # bump the version counter, and a stale layout would silently keep the old weights.
+        if self._packed is None or self._packed.key != key or self.weight_grad:
             self._packed = K.PackedWeight(w.detach(), self.scale, key)
         return self._packed
 
