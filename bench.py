@@ -344,12 +344,22 @@ def extra_pipelines(gen, dev, size, n_lat):
         ms = gpu_ms(train_step, 3, warm=2)
         with torch.no_grad():
             fwd = gpu_ms(lambda: gen([wt], input_is_latent=True, randomize_noise=False), 3, warm=1)
+        graphed = None
+        try:   # the same step as one CUDA-graph launch (where2edit_b200.GraphedStep)
+            def graph_step(w_in):
+                img, _ = gen([w_in + 0.1 * train_mapper(w_in)], input_is_latent=True, randomize_noise=False)
+                (img * gimg).sum().backward()
+            fast_step = w2e.GraphedStep(graph_step, [wt], params=train_mapper.parameters())
+            graphed = gpu_ms(lambda: fast_step(wt), 3, warm=2)
+            del fast_step
+        except Exception as exc:
+            graphed = repr(exc)[:200]
         for p, r in zip(gen.parameters(), frozen):
             p.requires_grad_(r)
         out["train_step_cfg4"] = {
             "what": "LevelsMapper edit -> 1024^2 forward + backward to the mapper parameters (channels-last bf16 engine), "
                     "seeded synthetic dL/dimage", "batch": tb, "ms": ms, "images_per_s": tb / ms * 1e3,
-            "forward_only_ms": fwd, "ratio_to_forward": ms / fwd}
+            "forward_only_ms": fwd, "ratio_to_forward": ms / fwd, "cuda_graph_ms": graphed}
         del train_mapper, wt, gimg
     except Exception as exc:
         out["train_step_cfg4"] = {"error": repr(exc)[:300]}
@@ -464,6 +474,42 @@ def run_train(args, world, rank, dev, dist, peaks):
                 json.dump({"batch": B, "size": args.size, "workload": "train", "launches": layers, "kinds": kinds}, fh, indent=1)
         with torch.no_grad():   # the forward alone (same precision, module path) for the fwd+bwd : fwd ratio
             fwd_ms = gpu_ms(lambda: gen([dev_w[0]], input_is_latent=True, randomize_noise=False), 3, warm=1)
+    # the same step as ONE CUDA-graph launch (where2edit_b200.GraphedStep; N = 1: a second, hook-free copy of the mapper)
+    graph_info = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and os.environ.get("W2E_BENCH_GRAPH", "1") == "1":
+        try:
+            import where2edit_b200 as w2e
+            mapper2 = make_levels_mapper(dev).train()
+
+            def plain(w):
+                img, _ = gen([w + 0.1 * mapper2(w)], input_is_latent=True, randomize_noise=False)
+                loss = (img * gimg).sum()
+                loss.backward()
+                return loss
+            fast = w2e.GraphedStep(plain, [dev_w[0]], params=mapper2.parameters())
+            for i in range(3):
+                fast(dev_w[i % 2])
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(K_):
+                fast(dev_w[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / K_
+            fast(dev_w[0])
+            torch.cuda.synchronize()
+            got = [p.grad.detach().clone() for p in mapper2.parameters()]
+            for p in mapper2.parameters():
+                p.grad = None
+            plain(dev_w[0])
+            torch.cuda.synchronize()
+            same = all(torch.equal(a, p.grad) for a, p in zip(got, mapper2.parameters()))
+            graph_info = {"ms_per_step": gms, "images_per_s": B / gms * 1e3, "gradients_bit_identical_to_eager": bool(same),
+                          "what": "the same step (mapper forward, generator forward, loss, backward) captured once and "
+                                  "replayed as one CUDA-graph launch per step, latents copied into the graph's input buffer"}
+            del fast
+        except Exception as exc:   # an auxiliary number must never cost the contract line
+            graph_info = {"error": repr(exc)[:300]}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
@@ -475,6 +521,7 @@ def run_train(args, world, rank, dev, dist, peaks):
             "gpu_launches": launches, "roofline": roofline,
             "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in kinds.items()},
             "forward_only_ms_same_path": fwd_ms,
+            "cuda_graph": graph_info,
             "mapper_gradient_floats": int(reducer.flat.numel()), "gradient_buckets": len(reducer.buckets),
             "cpu_baseline": None,
         }))

@@ -86,6 +86,63 @@ def test_image_in_the_callers_dtype_and_buffer():
         gen.set_image_output(torch.float16)
 
 
+def test_cuda_graph_of_the_whole_optimisation_step():
+    """GraphedStep: mapper forward -> generator forward -> loss -> backward as one graph launch; the gradients of the
+    mapper parameters (and, second case, of a W+ latent optimised directly, run_attention.py:1233-1424) are bit-identical
+    to the eager step, replay after replay, for new inputs"""
+    import types
+    from where2edit_b200 import mappers
+    gen = build(64)
+    torch.manual_seed(5)
+    mapper = mappers.LevelsMapper(types.SimpleNamespace(no_coarse_mapper=False, no_medium_mapper=False,
+                                                        no_fine_mapper=False)).to(DEV).train()
+    ws = [synth.make_wplus(2, gen.n_latent, seed=s).to(DEV) for s in (3, 4, 5)]
+    gimg = synth.make_tensor((2, 3, 64, 64), 9).to(DEV) / (3 * 64 * 64)
+
+    def step(w):
+        img, _ = gen([w + 0.1 * mapper(w)], input_is_latent=True, randomize_noise=False)
+        loss = (img * gimg).sum()
+        loss.backward()
+        return loss
+
+    def eager(w):
+        for p in mapper.parameters():
+            p.grad = None
+        loss = step(w)
+        return loss.detach().clone(), [p.grad.detach().clone() for p in mapper.parameters()]
+
+    want = [eager(w) for w in ws]
+    fast = w2e.GraphedStep(step, [ws[0]], params=mapper.parameters())
+    for w, (loss_ref, grads_ref) in list(zip(ws, want)) + [(ws[0], want[0])]:
+        loss = fast(w)
+        torch.cuda.synchronize()
+        assert torch.equal(loss.detach(), loss_ref)
+        assert all(torch.equal(p.grad, g) for p, g in zip(mapper.parameters(), grads_ref))
+    gen.assert_ok()
+    # a latent optimised directly: the leaf is closed over, no inputs
+    latent = ws[1].clone().requires_grad_(True)
+
+    def latent_step():
+        img, _ = gen([latent], input_is_latent=True, randomize_noise=False)
+        (img * gimg).sum().backward()
+
+    latent_step()
+    ref = latent.grad.detach().clone()
+    fast2 = w2e.GraphedStep(latent_step, [], params=[latent])
+    fast2()
+    torch.cuda.synchronize()
+    assert torch.equal(latent.grad, ref)
+    with torch.no_grad():
+        latent.add_(0.01)                      # an optimiser step in place: the next replay sees the new latent
+    fast2()
+    g_graph = latent.grad.detach().clone()
+    torch.cuda.synchronize()
+    lat2 = latent.detach().clone().requires_grad_(True)
+    img, _ = gen([lat2], input_is_latent=True, randomize_noise=False)
+    (img * gimg).sum().backward()
+    assert torch.equal(g_graph, lat2.grad)
+
+
 @pytest.mark.parametrize("size", [64, 256, 1024])
 def test_uint8_image_is_the_save_image_quantisation_of_the_fp32_image(size):
     """set_image_output(torch.uint8): the last layer's epilogue (64^2: the conversion after an fp32 ToRGB sum; 256^2: the

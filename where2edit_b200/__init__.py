@@ -9,7 +9,7 @@ from . import _native
 from .model import (Blur, ConstantInput, Downsample, EqualConv2d, EqualLinear, Generator, ModulatedConv2d,
                     NoiseInjection, PixelNorm, ScaledLeakyReLU, StyledConv, ToRGB, Upsample, make_kernel)
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d, upfirdn2d_native
-from .graph import GraphedGenerator
+from .graph import GraphedGenerator, GraphedStep
 
 __version__ = "0.1.0"
 
@@ -67,4 +67,4 @@ def install_as_reference():
 __all__ = ["Generator", "ModulatedConv2d", "StyledConv", "ToRGB", "EqualLinear", "EqualConv2d", "PixelNorm",
            "Blur", "Upsample", "Downsample", "NoiseInjection", "ConstantInput", "ScaledLeakyReLU", "make_kernel",
            "FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "upfirdn2d_native", "install_as_reference",
-           "enable_weight_gradients", "GraphedGenerator"]
+           "enable_weight_gradients", "GraphedGenerator", "GraphedStep"]

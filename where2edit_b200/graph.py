@@ -10,6 +10,10 @@ noise buffers, no host synchronisation anywhere on the path) with static input /
 Inputs may be a W+ / z tensor list or a stylespace list; `attention_map` / `feature_map` (the blended edit forward,
 attention/attention_model.py:546-549) are static buffers too and are refreshed by passing new values to the call.
 The outputs are the graph's own buffers: they are overwritten by the next replay.
+
+`GraphedStep` does the same for a whole optimisation step -- mapper forward, generator forward, loss, `backward()` to the
+mapper parameters or latents (attention/run_attention.py:1233-1424, mapper/training/coach.py:81-92): ~140 launches at
+1024^2 whose low-resolution half is shorter than the host time to enqueue it.
 """
 import torch
 
@@ -67,5 +71,62 @@ class GraphedGenerator:
             _copy_tree(self.attention_map, attention_map)
         if feature_map is not None:
             _copy_tree(self.feature_map, list(feature_map))
+        self.graph.replay()
+        return self.outputs
+
+
+class GraphedStep:
+    """One forward + backward of the optimisation loop as ONE CUDA-graph launch.
+
+        def step(w):                                   # any callable that ends in backward(); returns tensors to keep
+            img, _ = gen([w + 0.1 * mapper(w)], input_is_latent=True, randomize_noise=False)
+            loss = criterion(img)
+            loss.backward()
+            return loss
+        fast = GraphedStep(step, [w], params=mapper.parameters())
+        loss = fast(w_new)                             # copy-in + graph launch; p.grad of every parameter is refreshed
+        optimizer.step()
+
+    `params`: the leaves whose `.grad` the step produces.  Their gradients are cleared before the capture, so
+    `backward()` allocates them inside the graph's memory pool and every replay OVERWRITES them (PyTorch's whole-network
+    capture recipe): zero_grad() between replays is neither needed nor allowed to free them (use set_to_none=False, or
+    none at all).  The frozen bf16 engine path (precision="bf16", fixed noise buffers) has no host synchronisation, which
+    is what makes the step capturable; gradients are bit-identical to the eager step (tests/test_engine_features_gpu.py).
+    Inputs must keep their shapes; the returned tensors are the graph's own buffers."""
+
+    def __init__(self, fn, example_inputs, params, warmup=3):
+        self.fn = fn
+        self.params = [p for p in params]
+        self.inputs = _clone_tree(list(example_inputs))   # (may be empty: a step that closes over its leaves)
+        if not self.params:
+            raise ValueError("GraphedStep: `params` must name the leaves whose gradients the step produces")
+        dev = self.params[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        # (the warm-up runs on a side stream, as PyTorch's capture recipe asks; gradient accumulators created by earlier
+        # eager steps live on the default stream, which autograd reports once per run -- not an error here)
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(max(1, int(warmup))):   # cached layouts, allocator and library workspaces warm before the capture
+                    self._clear()
+                    self.fn(*self.inputs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._clear()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.outputs = self.fn(*self.inputs)
+        finally:
+            if quiet is not None:
+                quiet(True)
+
+    def _clear(self):
+        for p in self.params:
+            p.grad = None
+
+    def __call__(self, *inputs):
+        _copy_tree(self.inputs, list(inputs))
         self.graph.replay()
         return self.outputs
