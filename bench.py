@@ -310,19 +310,43 @@ def extra_pipelines(gen, dev, size, n_lat):
     mask = torch.rand(eb, 1, 64, 64, generator=g).to(dev)
 
     def edit():
+        # the W+ flow of attention/run_attention.py:1196-1245: original forward with its features, mapper edit of the
+        # latent, edited forward blended with the original's features through the attention mask
         with torch.no_grad():
             _, _, _, feats = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
             w_hat = w + 0.1 * mapper(w)
-            _, _, styles = gen([w_hat], input_is_latent=True, randomize_noise=False, return_latents=True)
-            img, _ = gen([styles], input_is_stylespace=True, randomize_noise=False, attention_layer=13,
+            img, _ = gen([w_hat], input_is_latent=True, randomize_noise=False, attention_layer=13,
+                         attention_map=mask, feature_map=feats)
+        return img
+
+    def edit_only():   # the per-step part of the optimisation loop: features of the original are computed once (:1196-1203)
+        with torch.no_grad():
+            w_hat = w + 0.1 * mapper(w)
+            img, _ = gen([w_hat], input_is_latent=True, randomize_noise=False, attention_layer=13,
+                         attention_map=mask, feature_map=feats_once)
+        return img
+    def edit_one_map():   # the same pipeline bringing back only the feature maps the blend reads (capture_layers)
+        with torch.no_grad():
+            _, _, _, feats = gen([w], input_is_latent=True, randomize_noise=False, return_features=True,
+                                 capture_layers=gen.blend_feature_layers(13))
+            w_hat = w + 0.1 * mapper(w)
+            img, _ = gen([w_hat], input_is_latent=True, randomize_noise=False, attention_layer=13,
                          attention_map=mask, feature_map=feats)
         return img
     try:
         ms = gpu_ms(edit, 3, warm=2)
+        ms_one = gpu_ms(edit_one_map, 3, warm=2)
+        with torch.no_grad():
+            _, _, _, feats_once = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
+        ms_edit = gpu_ms(edit_only, 3, warm=2)
+        del feats_once
         out["edit_pipeline_cfg3"] = {
-            "what": "LevelsMapper edit + original forward with all 26 features captured (fp32 NCHW) + styles of the "
-                    "edited code + edited forward blended at layer 13 through a 64^2 mask, bf16 engine",
-            "batch": eb, "ms": ms, "edited_images_per_s": eb / ms * 1e3}
+            "what": "original forward with all 26 features captured (fp32 NCHW, as the reference returns them) + "
+                    "LevelsMapper edit of the W+ code + edited forward blended at layer 13 through a 64^2 mask "
+                    "(run_attention.py:1196-1245), bf16 engine",
+            "batch": eb, "ms": ms, "edited_images_per_s": eb / ms * 1e3,
+            "capturing_only_the_blend_layer_ms": ms_one, "capturing_only_the_blend_layer_images_per_s": eb / ms_one * 1e3,
+            "edited_forward_only_ms": ms_edit, "edited_forward_only_images_per_s": eb / ms_edit * 1e3}
     except Exception as exc:
         out["edit_pipeline_cfg3"] = {"error": repr(exc)[:300]}
     torch.cuda.empty_cache()

@@ -86,6 +86,37 @@ def test_image_in_the_callers_dtype_and_buffer():
         gen.set_image_output(torch.float16)
 
 
+def test_capture_layers_returns_only_the_requested_feature_maps():
+    """Generator.forward(return_features=True, capture_layers=[...]): the requested maps are bit-identical to the full
+    capture, the others are None, image and styles unchanged; the blended forward works from the one map it reads"""
+    gen = build(128)
+    w = synth.make_wplus(2, gen.n_latent, seed=6).to(DEV)
+    mask = torch.rand(2, 1, 16, 16, device=DEV)
+    with torch.no_grad():
+        img_a, _, styles_a, feats_a = gen([w], input_is_latent=True, randomize_noise=False, return_features=True)
+        layer = 9
+        need = gen.blend_feature_layers(layer)
+        assert need == [8, 10]                 # the up-convolution of layer 9 and the image of the next ToRGB (carry)
+        img_b, _, styles_b, feats_b = gen([w], input_is_latent=True, randomize_noise=False, return_features=True,
+                                          capture_layers=need + [2])
+        assert torch.equal(img_a, img_b) and len(feats_b) == len(feats_a)
+        assert all(torch.equal(a, b) for a, b in zip(styles_a, styles_b))
+        for i, (a, b) in enumerate(zip(feats_a, feats_b)):
+            assert (b is None) == (i not in need + [2])
+            if b is not None:
+                assert torch.equal(a, b)
+        w2 = synth.make_wplus(2, gen.n_latent, seed=7).to(DEV)
+        want, _ = gen([w2], input_is_latent=True, randomize_noise=False, attention_layer=layer, attention_map=mask,
+                      feature_map=feats_a)
+        got, _ = gen([w2], input_is_latent=True, randomize_noise=False, attention_layer=layer, attention_map=mask,
+                     feature_map=feats_b)
+        assert torch.equal(want, got)
+    gen.set_precision("fp32")   # module path: same contract
+    with torch.no_grad():
+        _, _, _, feats_c = gen([w], input_is_latent=True, randomize_noise=False, return_features=True, capture_layers=[0])
+    assert feats_c[0] is not None and all(f is None for f in feats_c[1:])
+
+
 def test_cuda_graph_of_the_whole_optimisation_step():
     """GraphedStep: mapper forward -> generator forward -> loss -> backward as one graph launch; the gradients of the
     mapper parameters (and, second case, of a W+ latent optimised directly, run_attention.py:1233-1424) are bit-identical

@@ -319,17 +319,20 @@ class SynthesisEngine:
     # ------------------------------------------------------------------ the forward
     @torch.no_grad()
     def run(self, latent, stylespace, noise, want_features=False, attention_layer=0, attention_map=None,
-            feature_map=None):
+            feature_map=None, capture_layers=None):
         """One forward.  Launches on the generator's device (made current for the call, so a model on cuda:1
         works while cuda:0 is current); a pipeline timeout of an EARLIER call raises here (no synchronisation)."""
         self._err.poll()
         with torch.cuda.device(self.gen.input.input.device):
-            out = self._run(latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map)
+            out = self._run(latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map,
+                            capture_layers)
             self._err.publish()
         return out
 
-    def _run(self, latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map):
+    def _run(self, latent, stylespace, noise, want_features, attention_layer, attention_map, feature_map,
+             capture_layers=None):
         gen = self.gen
+        keep = None if capture_layers is None else set(int(i) for i in capture_layers)   # positions of the returned list
         layers = gen.styled_layers()
         rows = gen.latent_rows(stylespace)
         pick = (lambda r: latent[r]) if stylespace else (lambda r: latent[:, r])
@@ -366,9 +369,10 @@ class SynthesisEngine:
                 if attention_layer and (blend_here or carry):
                     carry = False
                     skip = K.mask_blend(skip, feature_map[layer - 1], attention_map)
-                captured.append(skip)
+                captured.append(skip if (keep is None or idx in keep) else None)
                 style_vector.append(s.reshape(batch, 1, -1, 1, 1))
                 continue
+            want_here = want_features and (keep is None or idx in keep)   # this layer's map goes back to the caller
             conv = module.conv
             pw = self._tc_weight(conv)
             nz = noise[noise_idx]
@@ -381,14 +385,14 @@ class SynthesisEngine:
             bias = module.activate.bias.detach().to(torch.float32).contiguous()
             nxt = consumer_style(idx)
             next_is_rgb = idx + 1 < len(layers) and layers[idx + 1][1] == "rgb"
-            need_out = next_is_rgb or want_features or blend_here
+            need_out = next_is_rgb or want_here or blend_here
             need_mod = nxt is not None and not blend_here
             fuse = (kind == "conv" and next_is_rgb and self.fuse_rgb and pw.cout <= 512
                     and hw[0] > 16 and not (attention_layer and attention_layer in (layer, layer + 1)))
             if fuse:
                 last = idx + 2 == len(layers)   # the image itself: written in the dtype the caller asked for
                 act, xs_next, fused_rgb = self._conv2_rgb(xs, pw, demods[idx], nz, noise_w, bias, nxt,
-                                                          want_features, need_mod, layers[idx + 1][0],
+                                                          want_here, need_mod, layers[idx + 1][0],
                                                           styles[idx + 1], skip,
                                                           self.image_dtype if last else torch.float32,
                                                           self.image_out if last else None)
@@ -413,7 +417,7 @@ class SynthesisEngine:
                 act, xs_next = self._blend(act, feature_map[layer - 1], attention_map, nxt, nxt is not None)
             xs = xs_next
             if want_features:
-                captured.append(self._to_nchw(act))
+                captured.append(self._to_nchw(act) if want_here else None)
             style_vector.append(s.reshape(batch, 1, -1, 1, 1))
         if skip.dtype != self.image_dtype:   # image produced by an unfused ToRGB / blend (fp32): convert once
             skip = K.quantize_u8(skip) if self.image_dtype == torch.uint8 else skip.to(self.image_dtype)

@@ -453,9 +453,27 @@ class Generator(nn.Module):
             i += 3 if input_is_stylespace else 2
         return rows
 
+    def blend_feature_layers(self, attention_layer):
+        """Positions of the feature list that a forward blended at `attention_layer` reads (attention_model.py:546-561): the
+        map of that layer and, when it is a convolution, the image of the next ToRGB (the `this_layer` carry) -- what to
+        pass as `capture_layers` to the forward that produces the original's features."""
+        kinds = [k for _, k in self.styled_layers()]
+        if not 1 <= attention_layer <= len(kinds):
+            raise ValueError(f"attention_layer must be in 1..{len(kinds)}")
+        need = [attention_layer - 1]
+        if kinds[attention_layer - 1] != "rgb":
+            nxt = next((i for i in range(attention_layer, len(kinds)) if kinds[i] == "rgb"), None)
+            if nxt is not None:
+                need.append(nxt)
+        return need
+
     def forward(self, styles, return_latents=False, return_features=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, input_is_stylespace=False, noise=None,
-                randomize_noise=True, attention_layer=0, attention_map=None, feature_map=None):
+                randomize_noise=True, attention_layer=0, attention_map=None, feature_map=None, capture_layers=None):
+        """attention/attention_model.py:473-676.  One addition to the reference's signature: `capture_layers`, positions of
+        the returned feature list to fill when `return_features=True` (None = all 26, as the reference; the others are
+        None) -- the blended forward only reads the maps `blend_feature_layers(attention_layer)` names, and bringing
+        every layer back as fp32 NCHW costs as much as the forward itself at 1024^2."""
         latent = self._assemble_latent(styles, inject_index, truncation, truncation_latent, input_is_latent,
                                        input_is_stylespace)
         if noise is None:
@@ -469,7 +487,7 @@ class Generator(nn.Module):
             image, style_vector, captured = self._bf16_engine().run(
                 latent, input_is_stylespace, noise, want_features=return_features and not return_latents,
                 attention_layer=attention_layer if blending else 0, attention_map=attention_map,
-                feature_map=feature_map)
+                feature_map=feature_map, capture_layers=capture_layers)
         elif self.precision == "bf16" and self._train_engine_applies(latent, input_is_stylespace, noise, blending,
                                                                       return_features and not return_latents, attention_map,
                                                                       feature_map):
@@ -497,6 +515,9 @@ class Generator(nn.Module):
         if return_latents:
             return image, latent, style_vector
         if return_features:
+            if capture_layers is not None:   # (the module / training paths capture everything: drop what was not asked for)
+                keep = set(int(i) for i in capture_layers)
+                captured = [c if i in keep else None for i, c in enumerate(captured)]
             return image, latent, style_vector, captured
         return image, None
 
