@@ -124,6 +124,16 @@ def test_torgb_nhwc_and_layouts(eng):
     assert norm_err(rgb0, ref0) <= 1e-5
 
 
+@pytest.mark.parametrize("b,c,h,w", [(2, 32, 8, 8), (3, 64, 37, 37), (1, 128, 16, 24), (2, 512, 9, 7), (2, 32, 5, 5),
+                                     (1, 48, 16, 16), (2, 256, 64, 64)])
+def test_channels_last_to_nchw_is_an_exact_transpose(eng, b, c, h, w):
+    """w2e_nhwc_to_nchw_f32 (captured feature maps go back to the caller through it): both kernels -- 64 x 64 tiles with
+    16-byte loads, 32 x 32 tiles for the other shapes -- against a torch permute, ragged pixel counts included"""
+    x = synth.make_tensor((b, h, w, c), 31).to(torch.bfloat16).to(DEV)
+    got = eng._to_nchw(x)
+    assert got.dtype == torch.float32 and torch.equal(got, x.float().permute(0, 3, 1, 2).contiguous())
+
+
 def _check_image(img, ref):
     c = float(ref.abs().max())
     assert max_abs(img.double() / c, ref.double() / c) <= 2e-2

@@ -114,6 +114,45 @@ nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ y, int C, i
   }
 }
 
+// The same transpose with 16-byte loads and 64 x 64 tiles (C % 64 == 0 or C == 32 -> CH = 32; bf16 input): every captured
+// feature map of a forward goes through it when the caller asks for the reference's fp32 NCHW maps (25 GB of traffic at
+// 1024^2, batch 32: as much time as the forward itself), and the 32 x 32 tile kernel above moves 64-byte rows.
+template <int CH>
+__global__ void __launch_bounds__(256)
+nhwc_bf16_to_nchw_f32_v2_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int64_t HW) {
+  constexpr int PIX = 64, CG = CH / 8;
+  __shared__ float tile[CH][PIX + 1];
+  const int b = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * PIX;
+  const int c0 = blockIdx.y * CH;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int q = tid; q < PIX * CG; q += 256) {
+    const int px = q / CG, cg = q - px * CG;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + px < HW) v = __ldg(reinterpret_cast<const uint4*>(x + ((int64_t)b * HW + p0 + px) * C + c0 + cg * 8));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tile[cg * 8 + 2 * j][px] = __uint_as_float(w[j] << 16);
+      tile[cg * 8 + 2 * j + 1][px] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool full = p0 + PIX <= HW && (HW & 1) == 0;
+#pragma unroll
+  for (int c = warp; c < CH; c += 8) {
+    float* dst = y + ((int64_t)b * C + c0 + c) * HW + p0;
+    if (full) {
+      *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(tile[c][2 * lane], tile[c][2 * lane + 1]);
+    } else {
+      if (p0 + 2 * lane < HW) dst[2 * lane] = tile[c][2 * lane];
+      if (p0 + 2 * lane + 1 < HW) dst[2 * lane + 1] = tile[c][2 * lane + 1];
+    }
+  }
+}
+
 // Output-parity class (py, px) of a fp32 NCHW tensor x [B, C, H, W] as bf16 NHWC [B, hc, wc, C], times scale[b, c]:
 // y[b, j, i, c] = x[b, c, 2j+py, 2i+px] * scale[b, c].  (The dgrad of the transposed x2 convolution consumes the
 // upstream gradient class by class.)
@@ -675,6 +714,14 @@ extern "C" int w2e_nhwc_to_nchw_f32(const void* x, float* y, int B, int C, int64
   W2E_CHECK_ARG(dtype == W2E_BF16 || dtype == W2E_F32, "nhwc_to_nchw_f32: dtype");
   W2E_CHECK_ARG(B >= 0 && C > 0 && HW > 0 && B <= 65535, "nhwc_to_nchw_f32: bad shape");
   if (B == 0) return W2E_OK;
+  if (dtype == W2E_BF16 && (C % 64 == 0 || C == 32) && HW >= 64 && (((uintptr_t)x & 15) == 0) && (((uintptr_t)y & 7) == 0)) {
+    const int ch = C % 64 == 0 ? 64 : 32;
+    dim3 grid2((unsigned)ceil_div64(HW, 64), (unsigned)(C / ch), (unsigned)B);
+    if (ch == 64) nhwc_bf16_to_nchw_f32_v2_kernel<64><<<grid2, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
+    else nhwc_bf16_to_nchw_f32_v2_kernel<32><<<grid2, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
+    W2E_LAUNCH_OK();
+    return W2E_OK;
+  }
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
   if (dtype == W2E_F32) nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, C, HW);
   else nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW);
