@@ -230,3 +230,25 @@ def test_grouped_attention_heads_match_the_oracle(size):
     want = torch.cat(want, dim=1)
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
+def test_cluster_style_mapper_forward_as_one_cuda_graph():
+    """GraphedStep without parameters: the whole mapper forward (assign_clusters, grouped heads, text branches, region
+    block) replayed as one graph launch gives the eager result, also after the inputs change"""
+    import torch
+    import where2edit_b200 as w2e
+    m, x, feats = _cluster_mapper_setup(0.0)
+    m.eval()
+    with torch.no_grad():
+        want_styles, want_map, want_losses = m(x, feats, 16)
+        fast = w2e.GraphedStep(lambda xs, fs: m(xs, fs, 16), [x, feats])
+        got_styles, got_map, got_losses = fast(x, feats)
+        torch.cuda.synchronize()
+        assert torch.equal(got_map, want_map)
+        assert all(torch.equal(a, b) for a, b in zip(got_styles, want_styles))
+        assert all(torch.equal(torch.as_tensor(a), torch.as_tensor(b)) for a, b in zip(got_losses, want_losses))
+        x2 = [t * 1.1 for t in x]
+        want2 = m(x2, feats, 16)[1].clone()
+        got2 = fast(x2, feats)[1]
+        torch.cuda.synchronize()
+        assert torch.equal(got2, want2)

@@ -179,8 +179,17 @@ def measure(iters=20):
                 cm.fused_heads, cm.sample_first = fused, sample
                 res[(fused, sample)] = gpu_ms(lambda: cm(xin, feats, 64), 3, warmup=1)
         cm.fused_heads, cm.sample_first = True, True
+        graphed_ms = None
+        try:   # the same forward as one CUDA-graph launch (no host synchronisation anywhere on the path)
+            with torch.no_grad():
+                fast = w2e.GraphedStep(lambda xs_, fs_: cm(xs_, fs_, 64), [xin, feats])
+                graphed_ms = gpu_ms(lambda: fast.graph.replay(), 5, warmup=2)
+            del fast
+        except Exception as exc:
+            graphed_ms = repr(exc)[:200]
         out["cluster_style_mapper_fwd"] = {"shape": f"B={mb}, 26 feature maps of the 1024^2 generator, 64^2 attention map",
-                                           "ms": res[(True, True)], "per_head_modules_on_sampled_pixels_ms": res[(False, True)],
+                                           "ms": res[(True, True)], "cuda_graph_ms": graphed_ms,
+                                           "per_head_modules_on_sampled_pixels_ms": res[(False, True)],
                                            "per_head_modules_on_full_resolution_ms": res[(False, False)],
                                            "note": "grouped launch of all attention heads (w2e_attn_heads_fwd) vs one "
                                                    "StyledConv module call per head"}

@@ -87,20 +87,32 @@ class GraphedStep:
         loss = fast(w_new)                             # copy-in + graph launch; p.grad of every parameter is refreshed
         optimizer.step()
 
-    `params`: the leaves whose `.grad` the step produces.  Their gradients are cleared before the capture, so
+    `params`: the leaves whose `.grad` the step produces (empty for a no-grad callable, e.g. the cluster-style mapper's
+    forward in an edit application: ~250 small launches, host-bound when run eagerly).  Their gradients are cleared before the capture, so
     `backward()` allocates them inside the graph's memory pool and every replay OVERWRITES them (PyTorch's whole-network
     capture recipe): zero_grad() between replays is neither needed nor allowed to free them (use set_to_none=False, or
     none at all).  The frozen bf16 engine path (precision="bf16", fixed noise buffers) has no host synchronisation, which
     is what makes the step capturable; gradients are bit-identical to the eager step (tests/test_engine_features_gpu.py).
     Inputs must keep their shapes; the returned tensors are the graph's own buffers."""
 
-    def __init__(self, fn, example_inputs, params, warmup=3):
+    def __init__(self, fn, example_inputs, params=(), warmup=3):
         self.fn = fn
         self.params = [p for p in params]
         self.inputs = _clone_tree(list(example_inputs))   # (may be empty: a step that closes over its leaves)
-        if not self.params:
-            raise ValueError("GraphedStep: `params` must name the leaves whose gradients the step produces")
-        dev = self.params[0].device
+
+        def first_tensor(x):
+            if isinstance(x, torch.Tensor):
+                return x
+            if isinstance(x, (list, tuple)):
+                for v in x:
+                    t = first_tensor(v)
+                    if t is not None:
+                        return t
+            return None
+        anchor = self.params[0] if self.params else first_tensor(self.inputs)
+        if anchor is None:
+            raise ValueError("GraphedStep: needs `params` or at least one tensor input (to find the device)")
+        dev = anchor.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         # (the warm-up runs on a side stream, as PyTorch's capture recipe asks; gradient accumulators created by earlier
