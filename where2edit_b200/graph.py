@@ -93,7 +93,8 @@ class GraphedStep:
     capture recipe): zero_grad() between replays is neither needed nor allowed to free them (use set_to_none=False, or
     none at all).  The frozen bf16 engine path (precision="bf16", fixed noise buffers) has no host synchronisation, which
     is what makes the step capturable; gradients are bit-identical to the eager step (tests/test_engine_features_gpu.py).
-    Inputs must keep their shapes; the returned tensors are the graph's own buffers."""
+    Inputs must keep their shapes; the returned tensors are the graph's own buffers.  One process, one device: a step that
+    issues collectives (parallel.GradBucketReducer) is run eagerly -- all-reduce the refreshed `.grad`s after the replay."""
 
     def __init__(self, fn, example_inputs, params=(), warmup=3):
         self.fn = fn
