@@ -498,9 +498,12 @@ def run_train(args, world, rank, dev, dist, peaks):
                 json.dump({"batch": B, "size": args.size, "workload": "train", "launches": layers, "kinds": kinds}, fh, indent=1)
         with torch.no_grad():   # the forward alone (same precision, module path) for the fwd+bwd : fwd ratio
             fwd_ms = gpu_ms(lambda: gen([dev_w[0]], input_is_latent=True, randomize_noise=False), 3, warm=1)
-    # the same step as ONE CUDA-graph launch (where2edit_b200.GraphedStep; N = 1: a second, hook-free copy of the mapper)
+    # the same step as ONE CUDA-graph launch (where2edit_b200.GraphedStep) on a second, hook-free copy of the mapper; at
+    # N > 1 the refreshed gradients are all-reduced after the replay (one flat 12.6 MB buffer: ~0.1 ms, no overlap needed).
+    # Every rank takes part (collectives), a rank whose capture failed makes all of them skip the measurement.
     graph_info = None
-    if rank == 0 and world == 1 and args.precision == "bf16" and os.environ.get("W2E_BENCH_GRAPH", "1") == "1":
+    if args.precision == "bf16" and os.environ.get("W2E_BENCH_GRAPH", "1") == "1":
+        fast = err = None
         try:
             import where2edit_b200 as w2e
             mapper2 = make_levels_mapper(dev).train()
@@ -511,29 +514,52 @@ def run_train(args, world, rank, dev, dist, peaks):
                 loss.backward()
                 return loss
             fast = w2e.GraphedStep(plain, [dev_w[0]], params=mapper2.parameters())
+        except Exception as exc:   # an auxiliary number must never cost the contract line
+            err = repr(exc)[:300]
+        ok_flag = torch.tensor([1 if fast is not None else 0], device=dev)
+        if dist is not None:
+            dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+        if int(ok_flag.item()) == 1:
+            params2 = list(mapper2.parameters())
+            sizes = [p.numel() for p in params2]
+
+            def graphed_step(w):
+                loss = fast(w)
+                if dist is not None:   # average the mapper gradients over the ranks (DDP semantics, run_attention.py:1022-1030)
+                    grads = [p.grad for p in params2]
+                    flat = torch.cat([g.reshape(-1) for g in grads])
+                    dist.all_reduce(flat)
+                    flat.div_(world)
+                    torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split(sizes), grads)])
+                return loss
             for i in range(3):
-                fast(dev_w[i % 2])
-            torch.cuda.synchronize()
+                graphed_step(dev_w[i % 2])
+            barrier()
             e0.record()
             for i in range(K_):
-                fast(dev_w[i % 2])
+                graphed_step(dev_w[i % 2])
             e1.record()
-            torch.cuda.synchronize()
-            gms = e0.elapsed_time(e1) / K_
+            barrier()
+            gt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+            gms = float(gt.item()) / K_
             fast(dev_w[0])
             torch.cuda.synchronize()
-            got = [p.grad.detach().clone() for p in mapper2.parameters()]
-            for p in mapper2.parameters():
+            got = [p.grad.detach().clone() for p in params2]
+            for p in params2:
                 p.grad = None
             plain(dev_w[0])
             torch.cuda.synchronize()
-            same = all(torch.equal(a, p.grad) for a, p in zip(got, mapper2.parameters()))
-            graph_info = {"ms_per_step": gms, "images_per_s": B / gms * 1e3, "gradients_bit_identical_to_eager": bool(same),
+            same = all(torch.equal(a, p.grad) for a, p in zip(got, params2))
+            graph_info = {"ms_per_step": gms, "images_per_s": world * B / gms * 1e3,
+                          "gradients_bit_identical_to_eager": bool(same),
                           "what": "the same step (mapper forward, generator forward, loss, backward) captured once and "
-                                  "replayed as one CUDA-graph launch per step, latents copied into the graph's input buffer"}
-            del fast
-        except Exception as exc:   # an auxiliary number must never cost the contract line
-            graph_info = {"error": repr(exc)[:300]}
+                                  "replayed as one CUDA-graph launch per step, latents copied into the graph's input buffer"
+                                  + ("; the mapper gradients all-reduced (one flat buffer) after every replay" if dist is not None else "")}
+        else:
+            graph_info = {"error": err or "capture failed on another rank"}
+        del fast
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
