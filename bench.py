@@ -304,7 +304,7 @@ def extra_pipelines(gen, dev, size, n_lat):
     mapper = make_levels_mapper(dev).eval()
     for p in mapper.parameters():
         p.requires_grad_(False)
-    eb = 32
+    eb = 64   # BASELINE.json configs[2]: "batch 64 edit pipeline"
     g = torch.Generator().manual_seed(11)
     w = torch.randn(eb, n_lat, 512, generator=g).to(dev)
     mask = torch.rand(eb, 1, 64, 64, generator=g).to(dev)
