@@ -388,6 +388,21 @@ def extra_pipelines(gen, dev, size, n_lat):
     except Exception as exc:
         out["train_step_cfg4"] = {"error": repr(exc)[:300]}
     torch.cuda.empty_cache()
+    # tf32 mode (BASELINE config 2 names "bf16/tf32"): the fp32 module path with the 3x3 convolutions on tcgen05 kind::tf32
+    try:
+        tb32 = 8
+        w32 = w[:tb32].contiguous()
+        gen.set_precision("tf32")
+        with torch.no_grad():
+            ms32 = gpu_ms(lambda: gen([w32], input_is_latent=True, randomize_noise=False), 3, warm=2)
+        out["tf32_forward"] = {"batch": tb32, "ms": ms32, "images_per_s": tb32 / ms32 * 1e3,
+                               "note": "an accuracy mode (1.4e-3 of the reference at 1024^2 against 1.2e-2 in bf16): fp32 "
+                                       "tensors, layout passes and fp32 elementwise kernels around every convolution"}
+    except Exception as exc:
+        out["tf32_forward"] = {"error": repr(exc)[:300]}
+    finally:
+        gen.set_precision("bf16")
+    torch.cuda.empty_cache()
     # CUDA graph: B = 1 latency
     try:
         w1 = w[:1].contiguous()
