@@ -26,25 +26,30 @@ def main():
     if len(sys.argv) > 2:
         settings = [("default", 1, 0, 0, "auto")] + [(a, *[(v if v == "auto" else int(v)) for v in a.split(",")])
                                                      for a in sys.argv[2:]]
-    results = {}
-    for name, ts, flags, clus, blur in settings:
+    # Round-robin over the settings INSIDE every repetition: the board heats up and power-caps during the run (a column that
+    # is measured later reads ~8 % slower), so every setting is sampled under the same thermal conditions (who goes first rotates); median over reps.
+    def apply(name, ts, flags, clus, blur):
         eng.tc2_cfg = N.tc2_config(ts_mode=ts, flags=flags, cluster_log2=clus)
         eng.blur_variant = blur
         eng.pair_mode = "not on pixel pairs" not in name
-        with torch.no_grad():
+    acc = {s_[0]: {} for s_ in settings}
+    with torch.no_grad():
+        for s_ in settings:                      # warm-up of every variant (layout caches, kernel attributes)
+            apply(*s_)
             for _ in range(2):
                 gen([w], input_is_latent=True, randomize_noise=False)
-            torch.cuda.synchronize()
-            acc = {}
-            for rep in range(5):
+        torch.cuda.synchronize()
+        for rep in range(2 * len(settings)):
+            for s_ in settings[rep % len(settings):] + settings[:rep % len(settings)]:   # rotate who goes first
+                apply(*s_)
                 N.STATS.trace = []
                 gen([w], input_is_latent=True, randomize_noise=False)
                 torch.cuda.synchronize()
                 for call, note, e0, e1 in N.STATS.trace:
                     tag = (note or {}).get("tag") or call
-                    acc.setdefault(tag, []).append(e0.elapsed_time(e1))
+                    acc[s_[0]].setdefault(tag, []).append(e0.elapsed_time(e1))
                 N.STATS.trace = None
-        results[name] = {k: min(v) for k, v in acc.items()}
+    results = {name: {k: sorted(v)[len(v) // 2] for k, v in a.items()} for name, a in acc.items()}   # median
     eng.tc2_cfg = None
     eng.pair_mode = True
     base = results["default"]
