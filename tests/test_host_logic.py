@@ -157,3 +157,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"] and "model" not in j["config"]
+
+
+def test_blend_feature_layers_names_the_maps_a_blended_forward_reads():
+    """attention/attention_model.py:546-561: a blend at a convolution layer is followed by a blend of the next ToRGB image
+    (`this_layer` carry), a blend at a ToRGB layer stands alone"""
+    import where2edit_b200 as w2e
+    gen = w2e.Generator(1024, 512, 8, channel_multiplier=2)
+    kinds = [k for _, k in gen.styled_layers()]
+    assert len(kinds) == 26 and kinds[:5] == ["conv", "rgb", "up", "conv", "rgb"]
+    assert gen.blend_feature_layers(13) == [12, 13]      # the published configuration: conv at 64^2 + its ToRGB
+    assert gen.blend_feature_layers(12) == [11, 13]      # an up-convolution: the next ToRGB comes after the plain conv
+    assert gen.blend_feature_layers(14) == [13]          # a ToRGB layer
+    assert gen.blend_feature_layers(26) == [25]
+    with pytest.raises(ValueError):
+        gen.blend_feature_layers(0)
+    with pytest.raises(ValueError):
+        gen.blend_feature_layers(27)

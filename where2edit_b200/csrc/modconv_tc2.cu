@@ -514,7 +514,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (!ok) break;
         // (no tcgen05 fence: TMA -> mbarrier -> tcgen05.mma needs none, and it was measured to drain the MMA queue)
         const uint32_t a_lo = a_lo0 + ar.idx * a_stage16;
-        if (nmw == 2 && kc == 0) {
+        if (nmw == 2 && kc == 0 && !TR) {
+          // (not for the transposed kernels: their four class accumulators make a tile's issue long enough that two
+          // concurrent issuers win -- up 64->32 @512^2 0.617 -> 0.590 ms in the same binary, while the plain 32 / 64-channel
+          // kernels lose 3...6 % without the token; profiles/r02_ab_issue_token.log)
           // issue token: the other issuer's MMAs of the previous tile are all queued.  Without it the two
           // warps interleave their MMAs, finish together and do their bookkeeping at the same time (measured).
           ok = mbar_wait_warp(&bars->mma_turn[mw], mw == 0 ? (turn & 1u) ^ 1u : (turn & 1u), abort_flag);
