@@ -223,10 +223,10 @@ int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* out_scale, c
  * channels-last input [B,H,W,32] (read as [B,H,W/2,64]); w_pair: bf16 [9][64][64],
  * w_pair[ky*3+dj+1][a*32+o][b*32+c] = w[ky*3+kx][o][c] with kx = 2*dj + b - a + 1 (zero outside 0..2);
  * out_scale [B,32], bias [32], rgb_w [3,32], rgb_style [B,32]: the ordinary 32-channel arrays.  H, W in pixels,
- * W a multiple of 16, H even.  Only the image is produced (rgb, rgb_dtype as above).
+ * W a multiple of 16, H even.  out: bf16 [B,H,W,32] activation or NULL (no modulated copy in this mode); rgb, rgb_dtype as above.
  * models/stylegan2/model.py:234-276, 306-340 (StyledConv) + 343-362 (ToRGB).                                          */
 int w2e_modconv_tc2_rgb_pair(const void* xs, const void* w_pair, const float* out_scale, const float* bias,
-                             const float* noise, const float* noise_w, int noise_batch, int* error_flag, int B,
+                             const float* noise, const float* noise_w, int noise_batch, void* out, int* error_flag, int B,
                              int H, int W, int act, const float* rgb_w, const float* rgb_style,
                              const float* rgb_bias, const float* rgb_skip, const float* host_taps1d, void* rgb,
                              int rgb_dtype, const w2e_tc2_config* cfg, void* stream);

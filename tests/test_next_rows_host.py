@@ -129,8 +129,8 @@ def test_new_entry_points_reject_bad_arguments_without_touching_the_gpu():
     one = 0x1000
     INVALID = 1
     # pair kernel: the width must be a multiple of 16
-    assert lib.w2e_modconv_tc2_rgb_pair(one, one, one, one, None, None, 0, None, 1, 64, 24, 1, one, one, None, None, None, one,
-                                        0, None, None) == INVALID
+    assert lib.w2e_modconv_tc2_rgb_pair(one, one, one, one, None, None, 0, None, None, 1, 64, 24, 1, one, one, None, None, None,
+                                        one, 0, None, None) == INVALID
     assert "multiple of 16" in N.last_error()
     # fused transposed dgrad: null pointers
     assert lib.w2e_modconv_tc2_dgrad_up(None, None, None, None, None, 1, 32, 64, 32, 32, None, None) == INVALID

@@ -219,6 +219,7 @@ def test_bf16_batch_invariance():
     (2, 32, 32, 144, True, False, False),   # RGB-only last layer on pixel pairs (w2e_modconv_tc2_rgb_pair), ragged rows
     (1, 32, 32, 48, False, False, False),   # pixel pairs, no skip image
     (3, 32, 32, 80, True, False, False),    # pixel pairs, 5 x 3 tiles per image
+    (2, 32, 32, 112, True, True, False),    # pixel pairs with the activation kept (the training forward's last layer)
     (1, 64, 64, 64, True, False, True),     # one staging slot per epilogue half
     (3, 128, 128, 48, True, False, True),   # weight ring + staged epilogue, 64-channel units
     (2, 512, 512, 24, True, True, True),    # two channel blocks adding their partial ToRGB sums

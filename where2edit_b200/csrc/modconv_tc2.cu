@@ -1055,40 +1055,62 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int a = 0; a < 2; ++a)
 #pragma unroll
               for (int o = 0; o < 3; ++o) racc[a][o] = 0ull;
+            // optional activation output (the training forward keeps it for the backward): the pair's 2 x 32 channels are
+            // 128 contiguous bytes of the channels-last tensor, written straight from registers (16 bytes per store).  Two
+            // copies of the loop (with / without the stores): the inference copy is the instruction sequence it was before.
+            const int oy_p = j0 + m * kSubTileH + sy, ox_p = 2 * (i0 + sx);
+            auto pair_body = [&](auto out_tag) {
+              constexpr bool OUT = decltype(out_tag)::value;
+              __nv_bfloat16* out_row = nullptr;
+              if (OUT && oy_p < P.OH && ox_p < P.OW_real && ok)
+                out_row = P.out + (((int64_t)b * P.OH + oy_p) * P.OW_real + ox_p) * 32;
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              const uint64_t nz2 = pack2(nzp[a], nzp[a]);
+              for (int a = 0; a < 2; ++a) {
+                const uint64_t nz2 = pack2(nzp[a], nzp[a]);
 #pragma unroll
-              for (int c16 = 0; c16 < 32; c16 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_addr + (uint32_t)(a * 32 + c16), v);
-                tmem_ld_wait();
-                if (a == 1 && c16 == 16) {   // this thread's last TMEM read of the tile: hand the buffer back
-                  tc_fence_before();
-                  mbar_arrive(&bars->acc_empty[ci]);
-                }
-                const uint32_t ca = sc_a + (uint32_t)((a * 32 + c16) * 4);
+                for (int c16 = 0; c16 < 32; c16 += 16) {
+                  uint32_t v[16];
+                  uint32_t po[OUT ? 8 : 1];
+                  tmem_ld16(t_addr + (uint32_t)(a * 32 + c16), v);
+                  tmem_ld_wait();
+                  if (a == 1 && c16 == 16) {   // this thread's last TMEM read of the tile: hand the buffer back
+                    tc_fence_before();
+                    mbar_arrive(&bars->acc_empty[ci]);
+                  }
+                  const uint32_t ca = sc_a + (uint32_t)((a * 32 + c16) * 4);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  uint64_t a01, a23, b01, b23, w01[3], w23[3];
-                  lds_2x2(ca + e * 16, a01, a23);
-                  lds_2x2(ca + 512 + e * 16, b01, b23);
+                  for (int e = 0; e < 4; ++e) {
+                    uint64_t a01, a23, b01, b23, w01[3], w23[3];
+                    lds_2x2(ca + e * 16, a01, a23);
+                    lds_2x2(ca + 512 + e * 16, b01, b23);
 #pragma unroll
-                  for (int o = 0; o < 3; ++o) lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01[o], w23[o]);
-                  uint64_t f01 = add2(fma2(pack2u(v[4 * e], v[4 * e + 1]), a01, b01), nz2);
-                  uint64_t f23 = add2(fma2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23, b23), nz2);
-                  const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
-                  float x0, x1, x2, x3, y0, y1, y2, y3;
-                  unpack2(f01, x0, x1); unpack2(f23, x2, x3);
-                  unpack2(g01, y0, y1); unpack2(g23, y2, y3);
-                  f01 = pack2(fmaxf(x0, y0), fmaxf(x1, y1));
-                  f23 = pack2(fmaxf(x2, y2), fmaxf(x3, y3));
+                    for (int o = 0; o < 3; ++o) lds_2x2(ca + (uint32_t)(1536 + o * 512) + e * 16, w01[o], w23[o]);
+                    uint64_t f01 = add2(fma2(pack2u(v[4 * e], v[4 * e + 1]), a01, b01), nz2);
+                    uint64_t f23 = add2(fma2(pack2u(v[4 * e + 2], v[4 * e + 3]), a23, b23), nz2);
+                    const uint64_t g01 = mul2(f01, slope2), g23 = mul2(f23, slope2);
+                    float x0, x1, x2, x3, y0, y1, y2, y3;
+                    unpack2(f01, x0, x1); unpack2(f23, x2, x3);
+                    unpack2(g01, y0, y1); unpack2(g23, y2, y3);
+                    x0 = fmaxf(x0, y0); x1 = fmaxf(x1, y1); x2 = fmaxf(x2, y2); x3 = fmaxf(x3, y3);
+                    f01 = pack2(x0, x1);
+                    f23 = pack2(x2, x3);
+                    if (OUT) {
+                      po[2 * e] = cvt_bf16x2(x0, x1);
+                      po[2 * e + 1] = cvt_bf16x2(x2, x3);
+                    }
 #pragma unroll
-                  for (int o = 0; o < 3; ++o) racc[a][o] = fma2(f23, w23[o], fma2(f01, w01[o], racc[a][o]));
+                    for (int o = 0; o < 3; ++o) racc[a][o] = fma2(f23, w23[o], fma2(f01, w01[o], racc[a][o]));
+                  }
+                  if (OUT && out_row) {
+                    uint4* dst = reinterpret_cast<uint4*>(out_row + a * 32 + c16);
+                    dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
+                    dst[1] = make_uint4(po[OUT ? 4 : 0], po[OUT ? 5 : 0], po[OUT ? 6 : 0], po[OUT ? 7 : 0]);
+                  }
                 }
               }
-            }
-            const int oy = j0 + m * kSubTileH + sy, ox = 2 * (i0 + sx);
+            };
+            if (P.out) pair_body(std::true_type{}); else pair_body(std::false_type{});
+            const int oy = oy_p, ox = ox_p;
             if (oy < P.OH && ox < P.OW_real && ok) {
               const int64_t plane = (int64_t)P.OH * P.OW_real;
               const int64_t di = ((int64_t)b * 3 * P.OH + oy) * P.OW_real + ox;
@@ -1716,8 +1738,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
   const bool pair = rgb && rgb->pair;
   if (pair) {
-    W2E_CHECK_ARG(!transposed && !out && !out_mod && Cin == 64 && Cout == 64 && in_h > kSubTileH && in_h % 2 == 0 && !tf32 && !view,
-                  "modconv_tc2_rgb_pair: needs the RGB-only 32-channel layer (as 64-channel pixel pairs), even height");
+    W2E_CHECK_ARG(!transposed && !out_mod && Cin == 64 && Cout == 64 && in_h > kSubTileH && in_h % 2 == 0 && !tf32 && !view,
+                  "modconv_tc2_rgb_pair: needs the 32-channel layer without a modulated output (as 64-channel pixel pairs), even height");
     P.pair = 1;
     P.OW_real = 2 * in_w;
   }
@@ -1786,7 +1808,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   const int kchunks = Cin / P.bk;
 
   // TS epilogue eligibility (see the header): staging units of <= 64 channels, TMA-able strides
-  const int n_out = (out ? 1 : 0) + (out_mod ? 1 : 0);
+  const int n_out = pair ? 0 : (out ? 1 : 0) + (out_mod ? 1 : 0);   // (pair mode stores its activation from registers: no staging)
   bool ts = !tf32 && g_ts_mode != 0 && (transposed || P.mt >= 2) && P.bn >= 32 && P.bn <= 128;
   if (rgb && nbuf_plain != 2) ts = false;   // fused ToRGB needs a thread's whole channel row: no unit split
   if (transposed && !fb) ts = ts && !noise && !bias && !next_scale && !out_mod && act == W2E_ACT_NONE;
@@ -1975,7 +1997,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
       const uint64_t ow = view ? (uint64_t)view->out_w : (uint64_t)P.OW, oh = view ? (uint64_t)view->out_h : (uint64_t)P.OH;
       const uint64_t dims[4] = {(uint64_t)Cout, ow, oh, (uint64_t)B};
       const uint64_t strides[3] = {(uint64_t)Cout * 2, ow * Cout * 2, oh * ow * Cout * 2};
-      if (out) {
+      if (out && !pair) {
         int rc = make_bf16_map(&M.st[0], out, 4, dims, strides, sbox, P.ts_unit_ch * 2);
         if (rc) return rc;
       }
@@ -2115,15 +2137,17 @@ extern "C" int w2e_modconv_tc2_rgb(const void* xs, const void* w, const float* o
 // per 256 pixels (1152 vs 1584 cycles).  w_pair: bf16 [9][64][64] pair weights,
 // w_pair[ky*3+dj+1][a*32+o][b*32+c] = W[ky][2dj+b-a+1][o][c] (zero where that tap index falls outside 0..2);
 // out_scale [B,32], bias [32], rgb_w [3,32], rgb_style [B,32]: the ordinary 32-channel arrays (the epilogue indexes them
-// with column & 31); H, W: the image size in pixels (W a multiple of 16); everything else as w2e_modconv_tc2_rgb.
+// with column & 31); out: optional bf16 [B,H,W,32] activation (the training forward keeps it), written from registers; H, W:
+// the image size in pixels (W a multiple of 16); everything else as w2e_modconv_tc2_rgb.
 extern "C" int w2e_modconv_tc2_rgb_pair(const void* xs, const void* w_pair, const float* out_scale, const float* bias,
-                                        const float* noise, const float* noise_w, int noise_batch, int* error_flag, int B,
+                                        const float* noise, const float* noise_w, int noise_batch, void* out, int* error_flag, int B,
                                         int H, int W, int act, const float* rgb_w, const float* rgb_style,
                                         const float* rgb_bias, const float* rgb_skip, const float* host_taps1d, void* rgb,
                                         int rgb_dtype, const w2e_tc2_config* cfg, void* stream) {
   W2E_CHECK_ARG(W > 0 && W % 16 == 0, "modconv_tc2_rgb_pair: the width must be a multiple of 16");
   const RgbArgs a{rgb_w, rgb_style, rgb_bias, rgb_skip, host_taps1d, rgb, rgb_dtype, 1};
-  return run_tc2(xs, w_pair, out_scale, bias, noise, noise_w, noise_batch, nullptr, nullptr, nullptr, error_flag, B, 64, 64,
+  W2E_CHECK_ARG(out == nullptr || (((uintptr_t)out & 15) == 0), "modconv_tc2_rgb_pair: out must be 16-byte aligned");
+  return run_tc2(xs, w_pair, out_scale, bias, noise, noise_w, noise_batch, nullptr, out, nullptr, error_flag, B, 64, 64,
                  H, W / 2, 0, act, &a, cfg, stream);
 }
 

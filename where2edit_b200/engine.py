@@ -202,17 +202,16 @@ class SynthesisEngine:
         rbias = rgb_module.bias.detach().reshape(3).to(torch.float32).contiguous()
         nb = 0 if noise is None else noise.shape[0]
         N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"{pw.cin}->{pw.cout}@{h}x{w}+rgb")
-        if (self.pair_mode and not want_out and not want_mod and pw.cin == 32 and pw.cout == 32 and w % 16 == 0 and h % 2 == 0
-                and h > 16):
+        if self.pair_mode and not want_mod and pw.cin == 32 and pw.cout == 32 and w % 16 == 0 and h % 2 == 0 and h > 16:
             # RGB-only 32-channel layer: on pixel pairs (N = 64 MMAs)
             rc = N.load().w2e_modconv_tc2_rgb_pair(
-                N.ptr(xs), N.ptr(pw.tc_pair()), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb,
+                N.ptr(xs), N.ptr(pw.tc_pair()), N.ptr(d), N.ptr(bias), N.ptr(noise), N.ptr(noise_w), nb, N.ptr(out),
                 N.ptr(self.error_flag(dev)), b, h, w, N.ACT_LRELU, N.ptr(rpw.rgb), N.ptr(rgb_style),
                 N.ptr(rbias), N.ptr(skip), N.host_floats(taps1d) if taps1d is not None else None, N.ptr(rgb),
                 N.dtype_code(rgb), N.tc2_cfg(self.tc2_cfg), N.stream_ptr())
             if rc != N.ERR_UNSUPPORTED:
                 N.check(rc, "modconv_tc2_rgb_pair")
-                return None, None, rgb
+                return out, None, rgb
             N.STATS.launches["w2e_modconv_tc2_rgb_pair"] -= 1   # nothing was launched: the ordinary kernel below runs
             if N.STATS.trace:
                 N.STATS.trace.pop()
