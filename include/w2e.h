@@ -261,6 +261,14 @@ int w2e_modconv_tc2_view(const void* xs, const void* w, const float* out_scale, 
  * next to the four parity-class tiles of gz (use w2e_modconv_tc2_view per class then).                                 */
 int w2e_modconv_tc2_dgrad_up(const void* gz, const void* w, const float* out_scale, void* gx, int* error_flag, int B,
                              int Cin, int Cout, int h, int w_, const w2e_tc2_config* cfg, void* stream);
+/* K-loop form of the same dgrad for the layers whose weights do not fit in shared memory next to four class tiles: the K
+ * loop of one accumulator walks the four parity classes of gz [B,2h+1,2w+1,K] one after the other (class c = py * 2 + px
+ * through its strided view, with the taps `tap_masks >> 9 c & 0x1ff` it feeds), weights streamed through the ring.
+ * w4: bf16 [9][Cout][4 K] = the per-class weights of w2e_modconv_tc2_view concatenated along K in class order.
+ * gx [B,h,w,Cout] is written once.  K % 64 == 0, h >= 16; W2E_ERR_UNSUPPORTED otherwise (use the per-class launches).  */
+int w2e_modconv_tc2_dgrad_up_k(const void* gz, const void* w4, long long tap_masks, const float* out_scale, void* gx,
+                               int* error_flag, int B, int K, int Cout, int h, int w_, const w2e_tc2_config* cfg,
+                               void* stream);
 
 /* tf32 mode (north_star (1): "bf16 and tf32 modes"): the same kernel with fp32 tensors in HBM (channels-last
  * activations xs / out / out_mod, weights [9][Cout][Cin]) read by tcgen05.mma kind::tf32 (10-bit mantissa operands,

@@ -212,9 +212,12 @@ def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     gz = torch.randn(b, 2 * h + 1, 2 * h + 1, cout, device=DEV).to(torch.bfloat16)
     # 64 -> 32 channels: ONE launch (w2e_modconv_tc2_dgrad_up: four class tiles, one accumulator); otherwise per class
     before = N.STATS.launches.get("w2e_modconv_tc2_dgrad_up", 0)
+    before_k = N.STATS.launches.get("w2e_modconv_tc2_dgrad_up_k", 0)
     fused = eng._dgrad_up(gz, pw, h, h)
     eng.assert_ok()
     assert N.STATS.launches.get("w2e_modconv_tc2_dgrad_up", 0) - before == (1 if (cin, cout) == (64, 32) and h > 16 else 0)
+    # >= 64 output channels of the forward, >= 16 rows: the K-loop form (w2e_modconv_tc2_dgrad_up_k), also ONE launch
+    assert (N.STATS.launches.get("w2e_modconv_tc2_dgrad_up_k", 0) - before_k) == (1 if cout in (64, 128) and h >= 16 else 0)
     eng.dgrad_up_fused = False
     got = eng._dgrad_up(gz, pw, h, h)          # (h >= 32: accumulated in place by TMA reduce-add)
     eng.assert_ok()
@@ -230,3 +233,28 @@ def test_transposed_conv_dgrad_by_parity_classes(cin, cout, h):
     assert max_abs(got.double().cpu(), want.cpu()) <= 1.5e-2 * scale
     # the fused launch rounds once (fp32 accumulation of all nine taps), the per-class launches once per class
     assert max_abs(fused.double().cpu(), want.cpu()) <= 8e-3 * scale
+
+
+@pytest.mark.parametrize("cin,cout,h", [(512, 256, 32), (512, 512, 33), (256, 128, 17)])
+def test_transposed_conv_dgrad_k_loop_form_at_every_width(cin, cout, h):
+    """w2e_modconv_tc2_dgrad_up_k directly (the engine only routes 64 / 128-channel layers through it): wide layers and a
+    ragged 17-row grid against the gradient of conv_transpose2d(stride 2)"""
+    from where2edit_b200 import train_engine
+    gen = w2e.Generator(8, 512, 1, precision="bf16").to(DEV)
+    eng = train_engine.TrainEngine(gen)
+    b = 2
+    weight = synth.make_tensor((1, cout, cin, 3, 3), 93).to(DEV)
+    pw = K.PackedWeight(weight, 1 / (cin * 9) ** 0.5, None)
+    gz = torch.randn(b, 2 * h + 1, 2 * h + 1, cout, device=DEV).to(torch.bfloat16)
+    out = torch.empty((b, h, h, cin), device=DEV, dtype=torch.bfloat16)
+    masks = sum(train_engine._CLASS_TAPS[(c >> 1, c & 1)] << (9 * c) for c in range(4))
+    N.check(N.load().w2e_modconv_tc2_dgrad_up_k(N.ptr(gz), N.ptr(pw.tc_dgrad_up_k()), masks, None, N.ptr(out),
+                                                N.ptr(eng.error_flag(gz.device)), b, cout, cin, h, h, None, N.stream_ptr()),
+            "modconv_tc2_dgrad_up_k")
+    eng.assert_ok()
+    x = torch.zeros(b, cin, h, h, device=DEV, dtype=torch.float64, requires_grad=True)
+    wt = (weight[0].double() / (cin * 9) ** 0.5).to(torch.bfloat16).double()
+    y = torch.nn.functional.conv_transpose2d(x, wt.transpose(0, 1), stride=2)
+    (y * gz.double().permute(0, 3, 1, 2)).sum().backward()
+    want = x.grad.permute(0, 2, 3, 1)
+    assert max_abs(out.double().cpu(), want.cpu()) <= 8e-3 * float(want.abs().max())

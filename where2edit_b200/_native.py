@@ -51,6 +51,7 @@ PROTOTYPES = {
     "w2e_attn_heads_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "w2e_attn_heads_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "w2e_modconv_tc2_dgrad_up": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "w2e_modconv_tc2_dgrad_up_k": (_I, [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "w2e_modconv_tc2_view": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P, _P]),
     "w2e_grad_assemble_workspace": (_L, [_I, _L, _I]),
     "w2e_grad_assemble_nhwc": (_I, [_P] * 8 + [_I, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P]),

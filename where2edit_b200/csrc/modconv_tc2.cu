@@ -65,6 +65,8 @@ struct Tc2Params {
   int pair;                 // x-pair mode of the 32-channel RGB-only layer (see run_tc2): accumulator row = TWO adjacent pixels
   int OW_real;              // pair mode: width of the image in pixels (OW counts pixel pairs)
   int skip_box_bytes;       // bytes of one sub-tile's skip patch in the epilogue-input stage
+  int dgk;                  // fused dgrad of the transposed convolution, K-LOOP form (weights in the ring): K chunks per parity class
+  long long dg_masks;       // (0 = off); the K loop walks class 0..3 x chunks, dg_masks = the four 9-bit tap masks (class c at bit 9c)
   int dg4, cls16;           // fused dgrad of the transposed convolution (w2e_modconv_tc2_dgrad_up): an A stage holds the FOUR
                             // parity-class tiles of the upstream gradient, cls16 = bytes of one class tile >> 4
   int percls;               // transposed conv, one accumulator set (4 classes x MT x bn = 512 TMEM columns): the classes
@@ -333,6 +335,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int c = 1; c < 4; ++c)
               tma_load_4d(dst + ((size_t)(c * P.cls16) << 4), &M.a4[c - 1], &bars->a_full[ar.idx], kc * kBK, i0, j0, b);
+          } else if (!TR && P.dgk) {
+            // K-loop form: chunk kc belongs to parity class kc / dgk of the gradient (its own strided view)
+            const int cls = kc / P.dgk;
+            tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, cls == 0 ? &map_a : &M.a4[cls - 1], &bars->a_full[ar.idx],
+                        (kc - cls * P.dgk) * kBK, i0 - 1, j0 - 1, b);
           } else {
             tma_load_4d(a_base + (size_t)ar.idx * P.a_stage_bytes, &map_a, &bars->a_full[ar.idx], kc * kBK, i0 - 1,
                         j0 - 1, b);
@@ -375,10 +382,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // ring was bound by the REQUEST RATE, not by bytes.  (Edge-column tiles use only kx == 2 of each row: the
           // whole row is still fetched.)
           for (int kc = 0; kc < kchunks && ok; ++kc) {
+            const int kmask = (!TR && P.dgk) ? (int)((P.dg_masks >> (9 * (kc / P.dgk))) & 0x1ff) : P.tap_mask;
             for (int gi = 0; gi < 3; ++gi) {
               const int g = TR ? (gi == 0 ? 1 : (gi == 1 ? 0 : 2)) : gi;   // transposed: tap rows in the order 1, 0, 2 (see the issuer)
               if (edge_y && g != 2) continue;
-              if (!TR && !((P.tap_mask >> (3 * g)) & 7)) continue;   // no tap of this row is used
+              if (!TR && !((kmask >> (3 * g)) & 7)) continue;   // no tap of this row is used
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
               mbar_arrive_expect_tx(&bars->b_full[br.idx], 3u * (uint32_t)P.b_block_bytes);
@@ -389,9 +397,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           continue;
         }
         for (int kc = 0; kc < kchunks && ok; ++kc) {
+          const int kmask = (!TR && P.dgk) ? (int)((P.dg_masks >> (9 * (kc / P.dgk))) & 0x1ff) : P.tap_mask;
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;
-            if (!TR && !((P.tap_mask >> t) & 1)) continue;
+            if (!TR && !((kmask >> t) & 1)) continue;
             if (pj == 0) {
               ok = mbar_wait(&bars->b_empty[br.idx], br.phase ^ 1u, abort_flag);
               if (!ok) break;
@@ -597,6 +606,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (leader) umma_commit(&bars->a_empty[ar.idx]);
         } else if (TS && P.bgroup == 3) {
           // grouped weight requests: one b_full / b_empty round trip (and one issue token) per TAP ROW of 3 blocks
+          // (K-loop dgrad of the transposed convolution: the taps of THIS chunk's parity class)
+          const int kmask = (!TR && P.dgk) ? (int)((P.dg_masks >> (9 * (kc / P.dgk))) & 0x1ff) : P.tap_mask;
+          const int last_row = TR ? 2 : (31 - __clz(kmask)) / 3;
 #pragma unroll
           for (int gi = 0; gi < 3; ++gi) {
             const int g = TR ? (gi == 0 ? 1 : (gi == 1 ? 0 : 2)) : gi;
@@ -608,7 +620,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               if (!ok) break;
               tc_fence_after();
             }
-            const bool skip_row = (edge_y && g != 2) || (!TR && !((P.tap_mask >> (3 * g)) & 7));
+            const bool skip_row = (edge_y && g != 2) || (!TR && !((kmask >> (3 * g)) & 7));
             if (TR && P.percls && kc == kchunks - 1 && skip_row && leader && gi != 1) {
               // (a skipped row still is a commit point of its classes: the hand-over protocol is the same for every tile)
               const int c0 = gi == 0 ? 2 : 0;
@@ -628,7 +640,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int kx = 0; kx < 3; ++kx) {
               const int t = g * 3 + kx;
               if (edge_x && kx != 2) continue;
-              if (!TR && !((P.tap_mask >> t) & 1)) continue;
+              if (!TR && !((kmask >> t) & 1)) continue;
               const uint32_t b_lo = b_lo0 + (br.idx + (uint32_t)kx) * b_block16;
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
@@ -652,7 +664,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             if (leader && mine) {
               umma_commit(&bars->b_empty[br.idx]);
-              if (!blk2 && g == last_tap / 3) {
+              if (!blk2 && g == last_row) {
                 umma_commit(&bars->a_empty[ar.idx]);
                 if (kc == kchunks - 1 && !(TR && P.percls)) umma_commit(&bars->acc_full[cr.idx]);
               }
@@ -672,10 +684,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (kc == kchunks - 1 && !(TR && P.percls)) umma_commit(&bars->acc_full[cr.idx]);
           }
         } else {
+          const int kmask = (!TR && TS && P.dgk) ? (int)((P.dg_masks >> (9 * (kc / P.dgk))) & 0x1ff) : P.tap_mask;
+          const int last_tap_k = (!TR && TS && P.dgk) ? 31 - __clz(kmask) : last_tap;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if ((edge_y && t / 3 != 2) || (edge_x && t % 3 != 2)) continue;   // (tap 8 is never skipped)
-            if (!TR && !((P.tap_mask >> t) & 1)) continue;
+            if (!TR && !((kmask >> t) & 1)) continue;
             const bool mine = !blk2 || (int)(nblk & 1u) == mw;
             ++nblk;
             if (mine) {
@@ -710,7 +724,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (leader && mine) {
               if (cl) umma_commit_mc(&bars->b_empty[br.idx], (uint16_t)((1u << (1 << cl)) - 1u));   // free once ALL CTAs consumed it
               else umma_commit(&bars->b_empty[br.idx]);
-              if (!blk2 && t == last_tap) {
+              if (!blk2 && t == last_tap_k) {
                 umma_commit(&bars->a_empty[ar.idx]);
                 if (kc == kchunks - 1) umma_commit(&bars->acc_full[cr.idx]);   // last block of the tile
               }
@@ -1663,8 +1677,11 @@ struct ViewArgs {   // plain conv on a strided view of a channels-last tensor, w
   int tap_mask;
   int out_h, out_w;   // extent of the `out` buffer ([B,out_h,out_w,Cout], <= the convolution grid: the rest is clipped)
   int reduce;         // 1: add the result to `out` (TMA reduce) instead of storing it
-  int dg4;            // fused dgrad of the transposed convolution: xs = the (2 in_h + 1) x (2 in_w + 1) upstream gradient, read
-                      // through its four parity-class views; the strides / tap mask above are not used
+  int dg4;            // fused dgrad of the transposed convolution: xs = the (2 h + 1) x (2 w + 1) upstream gradient, read through
+                      // its four parity-class views; the strides above are not used.  1 = four class tiles per A stage, weights
+                      // resident (in_h x in_w = h x w); 2 = K-loop form, weights [9][Cout][4 K] in the ring, Cin = 4 K,
+                      // in_h x in_w = (h + 1) x (w + 1) = the grid of class (0,0), out_h x out_w = h x w
+  long long dg_masks; // dg4 == 2: the four 9-bit tap masks, class c = py * 2 + px at bit 9 c
 };
 
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
@@ -1712,10 +1729,17 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.pitch = kPitch;
   P.ntaps = 9;
   P.tap_mask = 0x1ff;
-  const bool dg4 = view && view->dg4;
+  const bool dg4 = view && view->dg4 == 1;
+  const bool dgk = view && view->dg4 == 2;
   if (dg4) {
     W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_dgrad_up: plain bf16 convolution only");
     P.dg4 = 1;
+  } else if (dgk) {
+    W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32 && Cin % 256 == 0, "modconv_tc2_dgrad_up: K-loop form needs 4 x 64 k channels");
+    P.dgk = Cin / 4 / 64;
+    P.dg_masks = view->dg_masks;
+    P.tap_mask = (int)(view->dg_masks & 0x1ff);   // class (0,0): its first used tap overwrites the accumulator
+    W2E_CHECK_ARG(P.tap_mask != 0, "modconv_tc2_dgrad_up: empty tap mask of class (0,0)");
   } else if (view) {
     W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_view: plain bf16 convolution only");
     W2E_CHECK_ARG(view->tap_mask > 0 && view->tap_mask <= 0x1ff, "modconv_tc2_view: tap mask %d", view->tap_mask);
@@ -1911,19 +1935,20 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     const uint64_t es = (uint64_t)esize;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
-    if (view && !dg4) {
+    if (view && !dg4 && !dgk) {
       strides[0] = (uint64_t)view->stride_x * es; strides[1] = (uint64_t)view->stride_y * es;
       strides[2] = (uint64_t)view->stride_b * es;
     }
     const uint32_t box[4] = {(uint32_t)P.bk, (uint32_t)P.pitch, (uint32_t)P.box_rows, 1u};
-    if (dg4) {
-      // class (py, px) of the [B, 2h+1, 2w+1, Cin] gradient: pixels (2r+py, 2s+px), extent (h+1-py) x (w+1-px)
-      const uint64_t zh = 2 * (uint64_t)in_h + 1, zw = 2 * (uint64_t)in_w + 1;
-      const uint64_t cstrides[3] = {2 * (uint64_t)Cin * es, 2 * zw * Cin * es, zh * zw * Cin * es};
+    if (dg4 || dgk) {
+      // class (py, px) of the [B, 2h+1, 2w+1, K] gradient: pixels (2r+py, 2s+px), extent (h+1-py) x (w+1-px)
+      const int K = dgk ? Cin / 4 : Cin, h = dgk ? in_h - 1 : in_h, w_ = dgk ? in_w - 1 : in_w;
+      const uint64_t zh = 2 * (uint64_t)h + 1, zw = 2 * (uint64_t)w_ + 1;
+      const uint64_t cstrides[3] = {2 * (uint64_t)K * es, 2 * zw * K * es, zh * zw * K * es};
       for (int c = 0; c < 4; ++c) {
         const int py = c >> 1, px = c & 1;
-        const uint64_t cdims[4] = {(uint64_t)Cin, (uint64_t)(in_w + 1 - px), (uint64_t)(in_h + 1 - py), (uint64_t)B};
-        const __nv_bfloat16* base = (const __nv_bfloat16*)xs + ((int64_t)py * (int64_t)zw + px) * Cin;
+        const uint64_t cdims[4] = {(uint64_t)K, (uint64_t)(w_ + 1 - px), (uint64_t)(h + 1 - py), (uint64_t)B};
+        const __nv_bfloat16* base = (const __nv_bfloat16*)xs + ((int64_t)py * (int64_t)zw + px) * K;
         int rc = make_bf16_map(c == 0 ? &ma : &M.a4[c - 1], base, 4, cdims, cstrides, box, row_bytes);
         if (rc) return rc;
       }
@@ -1970,6 +1995,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // per-class accumulator hand-over (transposed conv with a single accumulator set); flag bit 8 = off (A/B)
   P.percls = (transposed && ts && !fb && P.nbuf == 1 && P.bgroup == 3 && !(g_flags & 256)) ? 1 : 0;
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
+  if (dgk && !(ts && !P.wres && P.bk == 64 && !P.cluster))
+    return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_dgrad_up: the K-loop form needs the staged epilogue with the weight ring");
   if (pair && !(ts && P.wres && P.mt == 2 && P.bk == 64))
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_rgb_pair: needs the staged epilogue with resident weights");
   if (clipped_out && !ts)
@@ -2086,7 +2113,7 @@ extern "C" int w2e_modconv_tc2_view(const void* xs, const void* w, const float* 
                                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                                     int in_w, int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
                                     int out_h, int out_w, int accumulate, const w2e_tc2_config* cfg, void* stream) {
-  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate, 0};
+  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate, 0, 0};
   return run_tc2(xs, w, out_scale, nullptr, nullptr, nullptr, 0, next_scale, out, out_mod, error_flag, B, Cin, Cout, in_h,
                  in_w, 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
@@ -2105,6 +2132,23 @@ extern "C" int w2e_modconv_tc2_dgrad_up(const void* gz, const void* w, const flo
   v.tap_mask = 0x1ff; v.out_h = h; v.out_w = w_; v.dg4 = 1;
   return run_tc2(gz, w, out_scale, nullptr, nullptr, nullptr, 0, nullptr, gx, nullptr, error_flag, B, Cin, Cout, h, w_, 0,
                  W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
+}
+
+// K-LOOP form of the fused dgrad for the layers whose weights do not fit next to four class tiles (>= 64 output channels
+// of the forward): the K loop of ONE accumulator walks the four parity classes of the gradient one after the other --
+// chunk kc reads class kc / (K / 64) through that class's strided view and issues only the taps the class feeds (4 / 2 /
+// 2 / 1) -- so gx is written once instead of stored + three times read-modify-written (w2e_modconv_tc2_view x 4).
+// w4: bf16 [9][Cout][4 K], the per-class weights of w2e_modconv_tc2_view concatenated along K in the order (0,0), (0,1),
+// (1,0), (1,1) (unused taps are never read); tap_masks: class c = py * 2 + px at bit 9 c.  h > 15, K a multiple of 64.
+extern "C" int w2e_modconv_tc2_dgrad_up_k(const void* gz, const void* w4, long long tap_masks, const float* out_scale, void* gx,
+                                          int* error_flag, int B, int K, int Cout, int h, int w_, const w2e_tc2_config* cfg,
+                                          void* stream) {
+  W2E_CHECK_ARG(K > 0 && K % 64 == 0 && h > 0 && w_ > 0, "modconv_tc2_dgrad_up_k: K must be a multiple of 64");
+  ViewArgs v;
+  memset(&v, 0, sizeof(v));
+  v.tap_mask = 0x1ff; v.out_h = h; v.out_w = w_; v.dg4 = 2; v.dg_masks = tap_masks;
+  return run_tc2(gz, w4, out_scale, nullptr, nullptr, nullptr, 0, nullptr, gx, nullptr, error_flag, B, 4 * K, Cout, h + 1, w_ + 1,
+                 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
 
 // tf32 mode (north star item 1: "bf16 and tf32 modes"): xs / w / out / out_mod are fp32 (channels-last activations,

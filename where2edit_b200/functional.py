@@ -99,6 +99,14 @@ class PackedWeight:
             self._tc_dgrad_up_fused = self.fwd.to(torch.bfloat16).contiguous()
         return self._tc_dgrad_up_fused
 
+    def tc_dgrad_up_k(self):
+        """bf16 [9][Cin][4 * Cout]: the four per-class weights of `tc_dgrad_up` concatenated along K in the class order
+        (0,0), (0,1), (1,0), (1,1) -- operand of w2e_modconv_tc2_dgrad_up_k (one accumulator, K loop over the classes)."""
+        if getattr(self, "_tc_dgrad_up_k", None) is None:
+            per = self.tc_dgrad_up()
+            self._tc_dgrad_up_k = torch.cat([per[(0, 0)], per[(0, 1)], per[(1, 0)], per[(1, 1)]], dim=2).contiguous()
+        return self._tc_dgrad_up_k
+
     def tc_dgrad_up(self, dtype=torch.bfloat16):
         """{(py, px): bf16 [9][Cin][Cout]} -- dgrad of the transposed (x2) convolution as four plain convolutions,
         one per output-parity class of the upstream gradient: class (py, px) holds gz[2j+py, 2i+px] and contributes

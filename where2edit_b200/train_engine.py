@@ -180,6 +180,21 @@ class TrainEngine(SynthesisEngine):
             N.STATS.launches["w2e_modconv_tc2_dgrad_up"] -= 1
             if N.STATS.trace:
                 N.STATS.trace.pop()
+        if self.dgrad_up_fused and pw.cout in (64, 128) and h >= 16:
+            # K-loop form: one accumulator, the K loop walks the four parity classes of gz (weights through the ring).
+            # Measured at batch 16: 64->128@256^2 0.53 -> 0.24 ms, 128->256@128^2 0.34 -> 0.26; at 256 / 512 channels the
+            # per-class launches are as fast or faster (0.32 vs 0.30, 0.22 vs 0.24 ms) and stay.
+            masks = sum(_CLASS_TAPS[(c >> 1, c & 1)] << (9 * c) for c in range(4))
+            N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"dgrad up {pw.cout}->{pw.cin}@{h}x{w} fused")
+            rc = lib.w2e_modconv_tc2_dgrad_up_k(N.ptr(gz), N.ptr(pw.tc_dgrad_up_k()), masks, None, N.ptr(out),
+                                                N.ptr(self.error_flag(gz.device)), b, pw.cout, pw.cin, h, w,
+                                                N.tc2_cfg(self.tc2_cfg), N.stream_ptr())
+            if rc != N.ERR_UNSUPPORTED:
+                N.check(rc, "modconv_tc2_dgrad_up_k")
+                return out
+            N.STATS.launches["w2e_modconv_tc2_dgrad_up_k"] -= 1
+            if N.STATS.trace:
+                N.STATS.trace.pop()
         wts = pw.tc_dgrad_up()
         # >= 32 rows: the four class launches accumulate IN PLACE (class 00 stores the h x w region, the others add to
         # it through TMA reduce-add); smaller maps: separate results + w2e_sum4_nhwc
