@@ -230,6 +230,11 @@ int w2e_modconv_tc2_rgb_pair(const void* xs, const void* w_pair, const float* ou
                              int H, int W, int act, const float* rgb_w, const float* rgb_style,
                              const float* rgb_bias, const float* rgb_skip, const float* host_taps1d, void* rgb,
                              int rgb_dtype, const w2e_tc2_config* cfg, void* stream);
+/* Plain 32 -> 32 channel 3x3 convolution on pixel pairs, no epilogue terms (the dgrad of the last layer, model.py:249-274
+ * under autograd): xs bf16 [B,H,W,32], w_pair bf16 [9][64][64] built like w2e_modconv_tc2_rgb_pair's from the [9][32][32]
+ * operand, out bf16 [B,H,W,32].  W a multiple of 16, H > 16.                                                          */
+int w2e_modconv_tc2_pair(const void* xs, const void* w_pair, void* out, int* error_flag, int B, int H, int W,
+                         const w2e_tc2_config* cfg, void* stream);
 /* Fused up-convolution + Blur + NoiseInjection + FusedLeakyReLU (models/stylegan2/model.py:249-260,
  * 279-290; op/fused_act.py:23-39): the transposed x2 modulated convolution of w2e_modconv_tc2 whose
  * (2h+1)^2 pre-blur result stays in shared memory and is filtered by the separable 4x4 FIR host_taps[16]

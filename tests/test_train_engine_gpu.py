@@ -258,3 +258,26 @@ def test_transposed_conv_dgrad_k_loop_form_at_every_width(cin, cout, h):
     (y * gz.double().permute(0, 3, 1, 2)).sum().backward()
     want = x.grad.permute(0, 2, 3, 1)
     assert max_abs(out.double().cpu(), want.cpu()) <= 8e-3 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("b,h", [(2, 48), (1, 144)])
+def test_last_layer_dgrad_on_pixel_pairs_matches_the_pixel_kernel(b, h):
+    """w2e_modconv_tc2_pair (the 32 -> 32 dgrad as N = 64 MMAs on pixel pairs) against the ordinary kernel: same bf16
+    products, only the fp32 summation order inside the tensor core differs"""
+    from where2edit_b200 import train_engine
+    gen = w2e.Generator(8, 512, 1, precision="bf16").to(DEV)
+    eng = train_engine.TrainEngine(gen)
+    weight = synth.make_tensor((1, 32, 32, 3, 3), 95).to(DEV)
+    pw = K.PackedWeight(weight, 1 / (32 * 9) ** 0.5, None)
+    gz = torch.randn(b, h, h, 32, device=DEV).to(torch.bfloat16)
+    before = N.STATS.launches.get("w2e_modconv_tc2_pair", 0)
+    got = eng._dgrad_plain(gz, pw)
+    eng.assert_ok()
+    assert N.STATS.launches.get("w2e_modconv_tc2_pair", 0) - before == 1
+    eng.pair_mode = False
+    want = eng._dgrad_plain(gz, pw)
+    eng.assert_ok()
+    assert N.STATS.launches.get("w2e_modconv_tc2_pair", 0) - before == 1
+    scale = float(want.float().abs().max())
+    assert max_abs(got.float().cpu(), want.float().cpu()) <= 8e-3 * scale      # one bf16 rounding step of the stored value
+    assert float((got.float() - want.float()).abs().mean()) <= 2e-4 * scale

@@ -1682,6 +1682,8 @@ struct ViewArgs {   // plain conv on a strided view of a channels-last tensor, w
                       // resident (in_h x in_w = h x w); 2 = K-loop form, weights [9][Cout][4 K] in the ring, Cin = 4 K,
                       // in_h x in_w = (h + 1) x (w + 1) = the grid of class (0,0), out_h x out_w = h x w
   long long dg_masks; // dg4 == 2: the four 9-bit tap masks, class c = py * 2 + px at bit 9 c
+  int pair;           // plain 32 -> 32 channel convolution on PIXEL PAIRS (w2e_modconv_tc2_pair): tensors described as 64-channel
+                      // pairs, only the K-step skipping of the issue loop differs from an ordinary 64 -> 64 layer
 };
 
 static int run_tc2(const void* xs, const void* w, const float* out_scale, const float* bias, const float* noise,
@@ -1740,7 +1742,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     P.dg_masks = view->dg_masks;
     P.tap_mask = (int)(view->dg_masks & 0x1ff);   // class (0,0): its first used tap overwrites the accumulator
     W2E_CHECK_ARG(P.tap_mask != 0, "modconv_tc2_dgrad_up: empty tap mask of class (0,0)");
-  } else if (view) {
+  } else if (view && !view->pair) {
     W2E_CHECK_ARG(!transposed && !rgb && !fb && !tf32, "modconv_tc2_view: plain bf16 convolution only");
     W2E_CHECK_ARG(view->tap_mask > 0 && view->tap_mask <= 0x1ff, "modconv_tc2_view: tap mask %d", view->tap_mask);
     W2E_CHECK_ARG(view->stride_x > 0 && (view->stride_x * 2) % 16 == 0 && (view->stride_y * 2) % 16 == 0 &&
@@ -1761,9 +1763,17 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   P.mt = (P.grid_h > kSubTileH) ? 2 : 1;
   // the RGB-only last layer (32 -> 32 channels): 512-pixel tiles, two pixels per epilogue thread
   const bool pair = rgb && rgb->pair;
+  const bool pair_plain = view && view->pair;   // no fused ToRGB: the ordinary staged epilogue stores the 64-channel "pairs"
   if (pair) {
     W2E_CHECK_ARG(!transposed && !out_mod && Cin == 64 && Cout == 64 && in_h > kSubTileH && in_h % 2 == 0 && !tf32 && !view,
                   "modconv_tc2_rgb_pair: needs the 32-channel layer without a modulated output (as 64-channel pixel pairs), even height");
+    P.pair = 1;
+    P.OW_real = 2 * in_w;
+  }
+  if (pair_plain) {
+    W2E_CHECK_ARG(!transposed && !rgb && !out_mod && out && !noise && !bias && !out_scale && Cin == 64 && Cout == 64 &&
+                      in_h > kSubTileH && !tf32,
+                  "modconv_tc2_pair: a plain 32 -> 32 channel convolution without epilogue terms, more than 16 rows");
     P.pair = 1;
     P.OW_real = 2 * in_w;
   }
@@ -1779,7 +1789,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   // A 256-pixel x 256-column tile fills the 512 TMEM columns, so MMA and epilogue alternate (measured 0.51 ms against
   // 0.27 ms of MMAs); 128 columns leave room for two accumulator sets and the staged 16-warp epilogue, and the two
   // column tiles add their partial ToRGB sums into the zero-initialised image.  Flag bit 7 = off (A/B).
-  const bool clipped_out = view && !dg4 && (view->reduce || view->out_h != in_h || view->out_w != in_w);   // needs the TMA-store epilogue
+  const bool clipped_out = view && !dg4 && !view->pair && (view->reduce || view->out_h != in_h || view->out_w != in_w);   // needs the TMA-store epilogue
   const bool rgb_split = !transposed && rgb && Cout == 256 && g_ts_mode != 0 && !(g_flags & 128) && in_h > kSubTileH &&
                          rgb->rgb_dtype == W2E_F32;
   const int bn_max = transposed ? ((g_flags & 8) ? 64 : 128) : ((rgb_split || clipped_out) ? 128 : 256);
@@ -1935,7 +1945,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     const uint64_t es = (uint64_t)esize;
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cin * es, (uint64_t)in_w * Cin * es, (uint64_t)in_h * in_w * Cin * es};
-    if (view && !dg4 && !dgk) {
+    if (view && !dg4 && !dgk && !view->pair) {
       strides[0] = (uint64_t)view->stride_x * es; strides[1] = (uint64_t)view->stride_y * es;
       strides[2] = (uint64_t)view->stride_b * es;
     }
@@ -1997,7 +2007,7 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
   if (fb && !ts) return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_upblur: shared memory plan does not fit");
   if (dgk && !(ts && !P.wres && P.bk == 64 && !P.cluster))
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_dgrad_up: the K-loop form needs the staged epilogue with the weight ring");
-  if (pair && !(ts && P.wres && P.mt == 2 && P.bk == 64))
+  if ((pair || pair_plain) && !(ts && P.wres && P.mt == 2 && P.bk == 64))
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_rgb_pair: needs the staged epilogue with resident weights");
   if (clipped_out && !ts)
     return set_error(W2E_ERR_UNSUPPORTED, "modconv_tc2_view: a clipped / accumulating output needs the TMA-store epilogue "
@@ -2021,7 +2031,8 @@ static int run_tc2(const void* xs, const void* w, const float* out_scale, const 
     }
     const uint32_t sbox[4] = {(uint32_t)P.ts_unit_ch, (uint32_t)kTileW, (uint32_t)kSubTileH, 1u};
     if (!transposed) {
-      const uint64_t ow = view ? (uint64_t)view->out_w : (uint64_t)P.OW, oh = view ? (uint64_t)view->out_h : (uint64_t)P.OH;
+      const bool vw = view && !view->pair;
+      const uint64_t ow = vw ? (uint64_t)view->out_w : (uint64_t)P.OW, oh = vw ? (uint64_t)view->out_h : (uint64_t)P.OH;
       const uint64_t dims[4] = {(uint64_t)Cout, ow, oh, (uint64_t)B};
       const uint64_t strides[3] = {(uint64_t)Cout * 2, ow * Cout * 2, oh * ow * Cout * 2};
       if (out && !pair) {
@@ -2113,7 +2124,7 @@ extern "C" int w2e_modconv_tc2_view(const void* xs, const void* w, const float* 
                                     void* out, void* out_mod, int* error_flag, int B, int Cin, int Cout, int in_h,
                                     int in_w, int64_t stride_x, int64_t stride_y, int64_t stride_b, int tap_mask,
                                     int out_h, int out_w, int accumulate, const w2e_tc2_config* cfg, void* stream) {
-  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate, 0, 0};
+  const ViewArgs v{stride_x, stride_y, stride_b, tap_mask, out_h, out_w, accumulate, 0, 0, 0};
   return run_tc2(xs, w, out_scale, nullptr, nullptr, nullptr, 0, next_scale, out, out_mod, error_flag, B, Cin, Cout, in_h,
                  in_w, 0, W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
@@ -2131,6 +2142,19 @@ extern "C" int w2e_modconv_tc2_dgrad_up(const void* gz, const void* w, const flo
   memset(&v, 0, sizeof(v));
   v.tap_mask = 0x1ff; v.out_h = h; v.out_w = w_; v.dg4 = 1;
   return run_tc2(gz, w, out_scale, nullptr, nullptr, nullptr, 0, nullptr, gx, nullptr, error_flag, B, Cin, Cout, h, w_, 0,
+                 W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
+}
+
+// Plain 32 -> 32 channel 3x3 convolution on PIXEL PAIRS (the dgrad of the last layer in the training step: no epilogue
+// terms): xs bf16 [B,H,W,32] read as [B,H,W/2,64], w_pair bf16 [9][64][64] (see w2e_modconv_tc2_rgb_pair), out bf16
+// [B,H,W,32] written as [B,H,W/2,64] by the ordinary staged epilogue.  N = 64 MMAs with the zero K slices skipped.
+extern "C" int w2e_modconv_tc2_pair(const void* xs, const void* w_pair, void* out, int* error_flag, int B, int H, int W,
+                                    const w2e_tc2_config* cfg, void* stream) {
+  W2E_CHECK_ARG(W > 0 && W % 16 == 0, "modconv_tc2_pair: the width must be a multiple of 16");
+  ViewArgs v;
+  memset(&v, 0, sizeof(v));
+  v.tap_mask = 0x1ff; v.pair = 1;
+  return run_tc2(xs, w_pair, nullptr, nullptr, nullptr, nullptr, 0, nullptr, out, nullptr, error_flag, B, 64, 64, H, W / 2, 0,
                  W2E_ACT_NONE, nullptr, cfg, stream, true, nullptr, false, &v);
 }
 

@@ -64,22 +64,32 @@ class PackedWeight:
             self.tc = self.dgr.to(torch.bfloat16).contiguous()
         return self.tc
 
-    def tc_pair(self):
-        """bf16 [9][2*Cout][2*Cin]: the 3x3 kernel over horizontally adjacent PIXEL PAIRS (w2e_modconv_tc2_rgb_pair):
+    @staticmethod
+    def pair_operand(w):
+        """[9][N][K] fp32 (tap = ky*3 + kx) -> bf16 [9][2N][2K]: the 3x3 kernel over horizontally adjacent PIXEL PAIRS --
         pair tap (ky, dj) connects input pixel b of pair i+dj to output pixel a of pair i through kx = 2*dj + b - a + 1."""
+        n, k = w.shape[1], w.shape[2]
+        wp = torch.zeros((9, 2 * n, 2 * k), device=w.device, dtype=torch.float32)
+        for ky in range(3):
+            for dj in (-1, 0, 1):
+                for a in (0, 1):
+                    for b in (0, 1):
+                        kx = 2 * dj + b - a + 1
+                        if 0 <= kx <= 2:
+                            wp[ky * 3 + dj + 1, a * n:(a + 1) * n, b * k:(b + 1) * k] = w[ky * 3 + kx]
+        return wp.to(torch.bfloat16).contiguous()
+
+    def tc_pair(self):
+        """Pair operand of the forward convolution (w2e_modconv_tc2_rgb_pair)."""
         if getattr(self, "_tc_pair", None) is None:
-            w = self.dgr                                   # [9][Cout][Cin] fp32, tap = ky*3 + kx
-            co, ci = self.cout, self.cin
-            wp = torch.zeros((9, 2 * co, 2 * ci), device=w.device, dtype=torch.float32)
-            for ky in range(3):
-                for dj in (-1, 0, 1):
-                    for a in (0, 1):
-                        for b in (0, 1):
-                            kx = 2 * dj + b - a + 1
-                            if 0 <= kx <= 2:
-                                wp[ky * 3 + dj + 1, a * co:(a + 1) * co, b * ci:(b + 1) * ci] = w[ky * 3 + kx]
-            self._tc_pair = wp.to(torch.bfloat16).contiguous()
+            self._tc_pair = self.pair_operand(self.dgr)    # [9][Cout][Cin]
         return self._tc_pair
+
+    def tc_dgrad_pair(self):
+        """Pair operand of the dgrad (flipped taps, channel roles swapped; w2e_modconv_tc2_pair)."""
+        if getattr(self, "_tc_dgrad_pair", None) is None:
+            self._tc_dgrad_pair = self.pair_operand(self.fwd.flip(0))   # [9][Cin][Cout]
+        return self._tc_dgrad_pair
 
     def tc_dgrad(self, dtype=torch.bfloat16):
         """[k*k][Cin][Cout] with the taps flipped: the dgrad of a same-padded 3x3 convolution is the same

@@ -155,6 +155,18 @@ class TrainEngine(SynthesisEngine):
         b, h, w, _ = gz.shape
         out = torch.empty((b, h, w, pw.cin), device=gz.device, dtype=torch.bfloat16)
         N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"dgrad {pw.cout}->{pw.cin}@{h}x{w}")
+        if self.pair_mode and pw.cin == 32 and pw.cout == 32 and w % 16 == 0 and h > 16:
+            # the 32-channel layer on pixel pairs (N = 64 MMAs), as in the forward
+            rc = N.load().w2e_modconv_tc2_pair(N.ptr(gz), N.ptr(pw.tc_dgrad_pair()), N.ptr(out),
+                                               N.ptr(self.error_flag(gz.device)), b, h, w, N.tc2_cfg(self.tc2_cfg),
+                                               N.stream_ptr())
+            if rc != N.ERR_UNSUPPORTED:
+                N.check(rc, "modconv_tc2_pair")
+                return out
+            N.STATS.launches["w2e_modconv_tc2_pair"] -= 1
+            if N.STATS.trace:
+                N.STATS.trace.pop()
+            N.note(kind="modconv", flops=2.0 * 9 * pw.cin * pw.cout * b * h * w, tag=f"dgrad {pw.cout}->{pw.cin}@{h}x{w}")
         N.check(N.load().w2e_modconv_tc2(
             N.ptr(gz), N.ptr(pw.tc_dgrad()), None, None, None, None, 0, None, N.ptr(out), None,
             N.ptr(self.error_flag(gz.device)), b, pw.cout, pw.cin, h, w, 0, N.ACT_NONE, N.tc2_cfg(self.tc2_cfg),
