@@ -7,6 +7,13 @@
 One "step" = one `Generator.forward` over a batch of synthetic W+ latents (configs[1] of
 BASELINE.json: FFHQ-1024 generator, batch 32 per GPU, bf16 tensor-core mode, fixed noise buffers).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+
+Keys beyond the contract: `e2e_fp32_images` / `e2e_u8_images` (the end-to-end number with the reference's fp32 images and
+with uint8 images quantised by the last layer's epilogue), `e2e_d2h_ceiling` (the same device-to-host copies with no
+kernel running: what the host link allows), `gather_ok` (N > 1: the gathered batch checked slot by slot), `kernels`
+(per-kind device time of a traced step), `pipelines` (edit pipeline of config 3 at batch 64, training step of config 4
+eager and as one CUDA graph, tf32 forward, batch-1 latency), `next_rows` (the callers either side of the path).
+`--workload train` is the contract line for config 4 (key `cuda_graph`: the same step as one graph launch).
 """
 import argparse
 import json
